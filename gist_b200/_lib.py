@@ -1,0 +1,106 @@
+"""ctypes binding of the C-ABI shared library (include/gist_b200.h).
+
+The library is built in-tree (``gist_b200/csrc/libgist_b200.so``) by
+``__graft_entry__.build()`` / ``make -C gist_b200/csrc``.  There is NO fallback:
+if the library is missing, or a compute entry point is called on a non-CUDA
+tensor, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libgist_b200.so')
+
+_c_i32p = ctypes.c_void_p
+_P = ctypes.c_void_p
+_I32 = ctypes.c_int32
+_I64 = ctypes.c_int64
+_U32 = ctypes.c_uint32
+_SZ = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/gist_b200.h declares
+SIGNATURES = {
+    'gist_abi_version': (ctypes.c_int, []),
+    'gist_status_string': (ctypes.c_char_p, [ctypes.c_int]),
+    'gist_set_device': (ctypes.c_int, [ctypes.c_int]),
+    'gist_launch_count': (ctypes.c_uint64, []),
+    'gist_spmm_csr_f32': (ctypes.c_int, [_P, _P, _I32, _I32, _P, _I64, _I32, _P, _I64,
+                                         _P, _P, _P, _P, _I64, _P, _I64, _U32, _P]),
+    'gist_spmm_csc_f32': (ctypes.c_int, [_P, _P, _I32, _I32, _P, _I64, _I32, _P, _I64,
+                                         _P, _P, _P, _I64, _U32, _P]),
+    'gist_degree_norm_f32': (ctypes.c_int, [_P, _I32, _I32, _P, _P]),
+    'gist_scan_workspace_bytes': (_SZ, [_I32]),
+    'gist_exclusive_scan_i32': (ctypes.c_int, [_P, _I32, _P, _P, _SZ, _P]),
+    'gist_cluster_batch_build': (ctypes.c_int, [_P, _P, _I32, _P, _I32, _P, _P, _P, _I64, _P, _P,
+                                                _P, _SZ, _P]),
+    'gist_gather_rows': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _P]),
+    'gist_slice_gather_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
+    'gist_slice_scatter_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
+}
+
+SPMM_RELU, SPMM_NARROW, SPMM_WIDE = 1, 2, 4
+NORM_INV, NORM_RSQRT_CLAMP = 0, 1
+
+_lib = None
+_device_set = None
+
+
+class GistLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle; raise loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GistLibraryError(
+            'gist_b200: %s not found. Build it with `python -c "import __graft_entry__ as g; '
+            'g.build()"` or `make -C gist_b200/csrc`. There is no CPU / PyTorch fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.gist_abi_version() != 1:
+        raise GistLibraryError('gist_b200: ABI version mismatch')
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().gist_status_string(status)
+        raise GistLibraryError('gist_b200.%s failed: %s (status %d)'
+                               % (what, msg.decode() if msg else '?', status))
+
+
+def stream_ptr(device):
+    """Raw cudaStream_t of torch's current stream on `device` and bind the runtime."""
+    import torch
+    global _device_set
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if _device_set != idx:
+        check(load().gist_set_device(idx), 'set_device')
+        _device_set = idx
+    return ctypes.c_void_p(torch.cuda.current_stream(idx).cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise GistLibraryError(
+                'gist_b200 has no CPU path: got a %s tensor; move the graph / features to a '
+                'CUDA device (B200, sm_100a)' % t.device)
+
+
+def launch_count():
+    return int(load().gist_launch_count())

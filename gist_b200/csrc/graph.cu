@@ -1,0 +1,345 @@
+// K3 (cluster-batch builder), exclusive scan, row gather and K5 (GIST slice
+// gather / scatter).  All HBM/L2-bound integer and copy work: coalesced index
+// streams, one warp per adjacency row, order-preserving ballot compaction.
+#include "common.cuh"
+
+namespace gist {
+
+// ---------------------------------------------------------------- scan ----
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;  // 2048 elements per CTA pass
+
+// Inclusive scan of one value per thread across a 256-thread CTA; returns the
+// exclusive prefix of this thread and the CTA total.
+__device__ __forceinline__ int block_exclusive_scan(int val, int &total) {
+    __shared__ int warp_sums[kScanThreads / 32];
+    __shared__ int s_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = val;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < kScanThreads / 32) warp_sums[lane] = winc - w;  // exclusive warp offset
+        if (lane == 31) s_total = winc;
+    }
+    __syncthreads();
+    const int excl = inc - val + warp_sums[warp];
+    total = s_total;
+    __syncthreads();  // shared arrays are reused by the caller's next pass
+    return excl;
+}
+
+// Single-CTA scan for small inputs (every cluster batch): loops over tiles with
+// a running carry.  out has n+1 entries.
+__global__ void __launch_bounds__(kScanThreads) scan_small_kernel(const int32_t *in, int32_t n,
+                                                                 int32_t *out) {
+    int carry = 0;
+    for (int base = 0; base < n; base += kScanTile) {
+        int v[kScanItems];
+        int sum = 0;
+        const int i0 = base + threadIdx.x * kScanItems;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            v[k] = (i0 + k < n) ? in[i0 + k] : 0;
+            sum += v[k];
+        }
+        int total;
+        int excl = block_exclusive_scan(sum, total) + carry;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            if (i0 + k < n) out[i0 + k] = excl;
+            excl += v[k];
+        }
+        carry += total;
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const int32_t *in, int32_t n,
+                                                                     int32_t *tile_sums) {
+    const int64_t i0 = (int64_t)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) sum += (i0 + k < n) ? in[i0 + k] : 0;
+    int total;
+    block_exclusive_scan(sum, total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const int32_t *in, int32_t n,
+                                                                 const int32_t *tile_offsets,
+                                                                 int32_t n_tiles, int32_t *out) {
+    const int64_t i0 = (int64_t)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (i0 + k < n) ? in[i0 + k] : 0;
+        sum += v[k];
+    }
+    int total;
+    int excl = block_exclusive_scan(sum, total) + tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (i0 + k < n) out[i0 + k] = excl;
+        excl += v[k];
+    }
+    if (blockIdx.x == n_tiles - 1 && threadIdx.x == 0) out[n] = tile_offsets[n_tiles];
+}
+
+static int scan_launch(const int32_t *in, int32_t n, int32_t *out, void *ws, size_t ws_bytes,
+                       cudaStream_t s) {
+    if (n <= 4 * kScanTile) {
+        scan_small_kernel<<<1, kScanThreads, 0, s>>>(in, n, out);
+        count_launch();
+        return last_error();
+    }
+    const int n_tiles = (n + kScanTile - 1) / kScanTile;
+    if (ws_bytes < gist_scan_workspace_bytes(n) || !ws) return GIST_ERR_WORKSPACE;
+    int32_t *tile_sums = reinterpret_cast<int32_t *>(ws);  // [n_tiles + 1]
+    scan_tile_sums_kernel<<<n_tiles, kScanThreads, 0, s>>>(in, n, tile_sums);
+    scan_small_kernel<<<1, kScanThreads, 0, s>>>(tile_sums, n_tiles, tile_sums);
+    scan_apply_kernel<<<n_tiles, kScanThreads, 0, s>>>(in, n, tile_sums, n_tiles, out);
+    count_launch(3);
+    return last_error();
+}
+
+// ------------------------------------------------------- batch builder ----
+__global__ void batch_mark_kernel(const int64_t *__restrict__ nids, int32_t n_b,
+                                  int32_t *__restrict__ node_map, int32_t value_is_index) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_b) node_map[nids[i]] = value_is_index ? i : -1;
+}
+
+// One warp per batch row: count parent neighbours that are inside the batch.
+__global__ void __launch_bounds__(256) batch_count_kernel(const int32_t *__restrict__ prow,
+                                                          const int32_t *__restrict__ pcol,
+                                                          const int64_t *__restrict__ nids,
+                                                          int32_t n_b,
+                                                          const int32_t *__restrict__ node_map,
+                                                          int32_t *__restrict__ deg) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n_b) return;
+    const int64_t pnode = nids[i];
+    const int rs = prow[pnode], re = prow[pnode + 1];
+    int cnt = 0;
+    for (int e = rs + lane; e < re; e += 32) cnt += node_map[pcol[e]] >= 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) deg[i] = cnt;
+}
+
+// One warp per batch row: write relabelled neighbours, parent order preserved.
+__global__ void __launch_bounds__(256) batch_fill_kernel(const int32_t *__restrict__ prow,
+                                                         const int32_t *__restrict__ pcol,
+                                                         const int64_t *__restrict__ nids,
+                                                         int32_t n_b,
+                                                         const int32_t *__restrict__ node_map,
+                                                         const int32_t *__restrict__ out_rowptr,
+                                                         int32_t *__restrict__ out_col,
+                                                         int64_t col_capacity,
+                                                         float *__restrict__ out_inv_deg,
+                                                         int32_t *__restrict__ overflow_flag) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n_b) return;
+    const int64_t pnode = nids[i];
+    const int rs = prow[pnode], re = prow[pnode + 1];
+    const int obeg = out_rowptr[i], oend = out_rowptr[i + 1];
+    if (lane == 0) {
+        const int dg = oend - obeg;
+        if (out_inv_deg) out_inv_deg[i] = dg > 0 ? 1.0f / (float)dg : 0.f;
+        if (oend > col_capacity && overflow_flag) *overflow_flag = 1;
+    }
+    int64_t pos = obeg;
+    for (int e0 = rs; e0 < re; e0 += 32) {
+        const int e = e0 + lane;
+        const int m = (e < re) ? node_map[pcol[e]] : -1;
+        const unsigned bal = __ballot_sync(0xffffffffu, m >= 0);
+        if (m >= 0) {
+            const int64_t w = pos + __popc(bal & ((1u << lane) - 1u));
+            if (w < col_capacity) out_col[w] = m;
+        }
+        pos += __popc(bal);
+    }
+}
+
+// ----------------------------------------------------------- row gather ----
+template <typename V>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const char *__restrict__ src,
+                                                          int64_t src_stride,
+                                                          const int64_t *__restrict__ idx, int64_t n,
+                                                          char *__restrict__ dst, int64_t dst_stride,
+                                                          int64_t vecs_per_row) {
+    // One warp per destination row, lanes stride over the row's vectors.
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const V *s = reinterpret_cast<const V *>(src + idx[i] * src_stride);
+    V *d = reinterpret_cast<V *>(dst + i * dst_stride);
+    for (int64_t k = lane; k < vecs_per_row; k += 32) d[k] = __ldg(s + k);
+}
+
+// Narrow rows (labels, masks): one thread per row.
+template <typename V>
+__global__ void gather_elems_kernel(const char *__restrict__ src, int64_t src_stride,
+                                    const int64_t *__restrict__ idx, int64_t n,
+                                    char *__restrict__ dst, int64_t dst_stride) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    *reinterpret_cast<V *>(dst + i * dst_stride) =
+        __ldg(reinterpret_cast<const V *>(src + idx[i] * src_stride));
+}
+
+// ------------------------------------------------------- slice (K5) -------
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) slice_kernel(const float *__restrict__ src, int64_t ld_src,
+                                                    const int64_t *__restrict__ ridx, int64_t n_rows,
+                                                    const int64_t *__restrict__ cidx, int64_t n_cols,
+                                                    float *__restrict__ dst, int64_t ld_dst) {
+    // blockIdx.y walks rows (grid-stride), x covers columns: the dense side is
+    // always accessed contiguously, the indexed side stays inside one row.
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    const int64_t cc = cidx ? cidx[c] : c;
+    for (int64_t r = blockIdx.y; r < n_rows; r += gridDim.y) {
+        const int64_t rr = ridx ? ridx[r] : r;
+        if (SCATTER) dst[rr * ld_dst + cc] = src[r * ld_src + c];
+        else dst[r * ld_dst + c] = __ldg(src + rr * ld_src + cc);
+    }
+}
+
+}  // namespace gist
+
+using namespace gist;
+
+extern "C" size_t gist_scan_workspace_bytes(int32_t n) {
+    if (n <= 4 * kScanTile) return 0;
+    const size_t n_tiles = ((size_t)n + kScanTile - 1) / kScanTile;
+    return (n_tiles + 1) * sizeof(int32_t);
+}
+
+extern "C" int gist_exclusive_scan_i32(const int32_t *in, int32_t n, int32_t *out, void *workspace,
+                                       size_t workspace_bytes, gist_stream_t stream) {
+    if (n < 0 || !out || (n > 0 && !in)) return GIST_ERR_BADARG;
+    return scan_launch(in, n, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int gist_cluster_batch_build(const int32_t *parent_rowptr, const int32_t *parent_col,
+                                        int32_t n_parent, const int64_t *nids, int32_t n_b,
+                                        int32_t *node_map, int32_t *out_rowptr, int32_t *out_col,
+                                        int64_t col_capacity, float *out_inv_deg,
+                                        int32_t *overflow_flag, void *scan_ws, size_t scan_ws_bytes,
+                                        gist_stream_t stream) {
+    if (n_parent < 0 || n_b < 0 || col_capacity < 0) return GIST_ERR_BADARG;
+    if (!out_rowptr) return GIST_ERR_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_b == 0) {
+        cudaError_t e = cudaMemsetAsync(out_rowptr, 0, sizeof(int32_t), s);
+        return e == cudaSuccess ? GIST_OK : (int)e;
+    }
+    if (!parent_rowptr || !nids || !node_map) return GIST_ERR_BADARG;
+    if (col_capacity > 0 && !out_col) return GIST_ERR_BADARG;
+    if (scan_ws_bytes < gist_scan_workspace_bytes(n_b)) return GIST_ERR_WORKSPACE;
+    const int tb = 256;
+    const int g_thread = (n_b + tb - 1) / tb;
+    const int g_warp = (int)(((int64_t)n_b * 32 + tb - 1) / tb);
+    batch_mark_kernel<<<g_thread, tb, 0, s>>>(nids, n_b, node_map, 1);
+    // degrees land in out_rowptr[0..n_b) and are scanned in place
+    batch_count_kernel<<<g_warp, tb, 0, s>>>(parent_rowptr, parent_col, nids, n_b, node_map,
+                                             out_rowptr);
+    count_launch(2);
+    int st = scan_launch(out_rowptr, n_b, out_rowptr, scan_ws, scan_ws_bytes, s);
+    if (st != GIST_OK) return st;
+    batch_fill_kernel<<<g_warp, tb, 0, s>>>(parent_rowptr, parent_col, nids, n_b, node_map,
+                                            out_rowptr, out_col, col_capacity, out_inv_deg,
+                                            overflow_flag);
+    batch_mark_kernel<<<g_thread, tb, 0, s>>>(nids, n_b, node_map, 0);
+    count_launch(2);
+    return last_error();
+}
+
+extern "C" int gist_gather_rows(const void *src, int64_t src_stride_bytes, const int64_t *idx,
+                                int64_t n, void *dst, int64_t dst_stride_bytes, int64_t row_bytes,
+                                gist_stream_t stream) {
+    if (n < 0 || row_bytes < 0 || src_stride_bytes < 0 || dst_stride_bytes < row_bytes)
+        return GIST_ERR_BADARG;
+    if (n == 0 || row_bytes == 0) return GIST_OK;
+    if (!src || !idx || !dst) return GIST_ERR_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const char *sp = reinterpret_cast<const char *>(src);
+    char *dp = reinterpret_cast<char *>(dst);
+    auto ok = [&](int64_t a) {
+        return row_bytes % a == 0 && src_stride_bytes % a == 0 && dst_stride_bytes % a == 0 &&
+               aligned(src, (size_t)a) && aligned(dst, (size_t)a);
+    };
+    if (row_bytes <= 8 && (row_bytes == 8 || row_bytes == 4 || row_bytes == 2 || row_bytes == 1) &&
+        ok(row_bytes)) {
+        const unsigned g = (unsigned)((n + 255) / 256);
+        if (row_bytes == 8) gather_elems_kernel<int2><<<g, 256, 0, s>>>(sp, src_stride_bytes, idx, n, dp, dst_stride_bytes);
+        else if (row_bytes == 4) gather_elems_kernel<int><<<g, 256, 0, s>>>(sp, src_stride_bytes, idx, n, dp, dst_stride_bytes);
+        else if (row_bytes == 2) gather_elems_kernel<short><<<g, 256, 0, s>>>(sp, src_stride_bytes, idx, n, dp, dst_stride_bytes);
+        else gather_elems_kernel<char><<<g, 256, 0, s>>>(sp, src_stride_bytes, idx, n, dp, dst_stride_bytes);
+        count_launch();
+        return last_error();
+    }
+    const int64_t blocks = (n * 32 + 255) / 256;
+    if (blocks > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
+    const unsigned g = (unsigned)blocks;
+    if (ok(16)) gather_rows_kernel<int4><<<g, 256, 0, s>>>(sp, src_stride_bytes, idx, n, dp, dst_stride_bytes, row_bytes / 16);
+    else if (ok(8)) gather_rows_kernel<int2><<<g, 256, 0, s>>>(sp, src_stride_bytes, idx, n, dp, dst_stride_bytes, row_bytes / 8);
+    else if (ok(4)) gather_rows_kernel<int><<<g, 256, 0, s>>>(sp, src_stride_bytes, idx, n, dp, dst_stride_bytes, row_bytes / 4);
+    else gather_rows_kernel<char><<<g, 256, 0, s>>>(sp, src_stride_bytes, idx, n, dp, dst_stride_bytes, row_bytes);
+    count_launch();
+    return last_error();
+}
+
+static int slice_launch(bool scatter, const float *src, int64_t ld_src, const int64_t *ridx,
+                        int64_t n_rows, const int64_t *cidx, int64_t n_cols, float *dst,
+                        int64_t ld_dst, cudaStream_t s) {
+    if (n_rows < 0 || n_cols < 0) return GIST_ERR_BADARG;
+    if (n_rows == 0 || n_cols == 0) return GIST_OK;
+    if (!src || !dst) return GIST_ERR_BADARG;
+    const int64_t gx = (n_cols + 255) / 256;
+    if (gx > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
+    // enough row-CTAs to fill the chip a few times over, at most 65535
+    int64_t gy = n_rows;
+    const int64_t target = 8LL * kNumSMs;
+    if (gx * gy > target * 4) gy = (target * 4 + gx - 1) / gx;
+    if (gy > n_rows) gy = n_rows;
+    if (gy > 65535) gy = 65535;
+    if (gy < 1) gy = 1;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (scatter) slice_kernel<true><<<grid, 256, 0, s>>>(src, ld_src, ridx, n_rows, cidx, n_cols, dst, ld_dst);
+    else slice_kernel<false><<<grid, 256, 0, s>>>(src, ld_src, ridx, n_rows, cidx, n_cols, dst, ld_dst);
+    count_launch();
+    return last_error();
+}
+
+extern "C" int gist_slice_gather_f32(const float *src, int64_t ld_src, const int64_t *ridx,
+                                     int64_t n_rows, const int64_t *cidx, int64_t n_cols, float *dst,
+                                     int64_t ld_dst, gist_stream_t stream) {
+    return slice_launch(false, src, ld_src, ridx, n_rows, cidx, n_cols, dst, ld_dst,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int gist_slice_scatter_f32(const float *src, int64_t ld_src, const int64_t *ridx,
+                                      int64_t n_rows, const int64_t *cidx, int64_t n_cols,
+                                      float *dst, int64_t ld_dst, gist_stream_t stream) {
+    return slice_launch(true, src, ld_src, ridx, n_rows, cidx, n_cols, dst, ld_dst,
+                        (cudaStream_t)stream);
+}

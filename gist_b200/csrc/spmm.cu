@@ -1,0 +1,302 @@
+// K1 / K2: CSR SpMM (copy_u / sum message passing) with fused epilogue, sm_100a.
+//
+// Work decomposition:
+//   * a GROUP of LPR lanes (4..32, power of two) owns one (row, feature-chunk);
+//     a warp holds 32/LPR groups, a 256-thread CTA 8 warps of consecutive rows,
+//     so neighbouring rows (which share neighbours inside a cluster) share L1;
+//   * a feature chunk is LPR*VEC*VPL floats; the chunk index is the SLOW grid
+//     dimension, so at any moment the whole chip gathers from one column slab
+//     of X (n_src * chunk * 4 bytes) — for the full Reddit-shape graph that slab
+//     (60-120 MB) is what lives in the 126 MB L2 while the slab is swept;
+//   * the group loads LPR column indices with one coalesced load, then
+//     broadcasts them with shuffles and issues U independent VEC-wide gathers
+//     before touching the accumulators (memory-level parallelism);
+//   * edges are accumulated in CSR order -> deterministic, no atomics.
+#include "common.cuh"
+
+namespace gist {
+
+std::atomic<uint64_t> g_launches{0};
+
+struct SpmmParams {
+    const int32_t *rowptr;
+    const int32_t *col;
+    int32_t n_dst;
+    const float *X;
+    int64_t ldx;
+    int32_t d;
+    float *Y;
+    int64_t ldy;
+    const float *src_scale;
+    const float *dst_scale;
+    const float *bias;
+    const float *addend;
+    int64_t ld_add;
+    float *self_out;
+    int64_t ld_self;
+    int32_t relu;
+    int32_t row_blocks;
+};
+
+template <int VEC>
+__device__ __forceinline__ void ld_vec(float (&r)[VEC], const float *p) {
+    if constexpr (VEC == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+    } else if constexpr (VEC == 2) {
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+        r[0] = v.x; r[1] = v.y;
+    } else {
+        r[0] = __ldg(p);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_vec(float *p, const float (&r)[VEC]) {
+    if constexpr (VEC == 4) {
+        *reinterpret_cast<float4 *>(p) = make_float4(r[0], r[1], r[2], r[3]);
+    } else if constexpr (VEC == 2) {
+        *reinterpret_cast<float2 *>(p) = make_float2(r[0], r[1]);
+    } else {
+        *p = r[0];
+    }
+}
+
+template <int VEC, int LPR, int VPL, bool HAS_SS>
+__global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
+    constexpr int GPW = 32 / LPR;                 // row groups per warp
+    constexpr int ROWS_PER_BLOCK = 8 * GPW;
+    constexpr int CHUNK = LPR * VEC * VPL;        // floats per feature chunk
+    constexpr int UMAX = (VPL == 1) ? 8 : 4;
+    constexpr int U = (LPR < UMAX) ? LPR : UMAX;  // independent gathers in flight per lane
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int grp = lane / LPR;
+    const int lg = lane % LPR;
+    const int chunk = blockIdx.x / p.row_blocks;
+    const int rb = blockIdx.x - chunk * p.row_blocks;
+    const int v = rb * ROWS_PER_BLOCK + warp * GPW + grp;
+    if (v >= p.n_dst) return;  // uniform per group
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
+    const int lane0 = grp * LPR;
+
+    int c[VPL];
+    bool cv[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        c[k] = chunk * CHUNK + k * (LPR * VEC) + lg * VEC;
+        cv[k] = c[k] < p.d;
+    }
+    float acc[VPL][VEC];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[k][i] = 0.f;
+
+    const int rs = __ldg(p.rowptr + v);
+    const int re = __ldg(p.rowptr + v + 1);
+    for (int e0 = rs; e0 < re; e0 += LPR) {
+        const int my = e0 + lg;
+        int u_mine = 0;
+        float s_mine = 0.f;
+        if (my < re) {
+            u_mine = __ldg(p.col + my);
+            if constexpr (HAS_SS) s_mine = __ldg(p.src_scale + u_mine);
+        }
+        const int cnt = min(LPR, re - e0);
+        for (int j = 0; j < cnt; j += U) {
+            float x[U][VPL][VEC];
+            float s[U];
+#pragma unroll
+            for (int jj = 0; jj < U; ++jj) {
+                const int u = __shfl_sync(gmask, u_mine, lane0 + j + jj);
+                if constexpr (HAS_SS) s[jj] = __shfl_sync(gmask, s_mine, lane0 + j + jj);
+                const bool ok = (j + jj) < cnt;
+                const float *xr = p.X + (int64_t)u * p.ldx;
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+                    if (ok && cv[k]) {
+                        ld_vec<VEC>(x[jj][k], xr + c[k]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) x[jj][k][i] = 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < U; ++jj)
+#pragma unroll
+                for (int k = 0; k < VPL; ++k)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        if constexpr (HAS_SS) acc[k][i] = fmaf(s[jj], x[jj][k][i], acc[k][i]);
+                        else acc[k][i] += x[jj][k][i];
+                    }
+        }
+    }
+
+    const float t = p.dst_scale ? __ldg(p.dst_scale + v) : 1.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        if (!cv[k]) continue;
+        float r[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) r[i] = acc[k][i] * t;
+        if (p.addend) {
+            float a[VEC];
+            ld_vec<VEC>(a, p.addend + (int64_t)v * p.ld_add + c[k]);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) r[i] += a[i];
+        }
+        if (p.bias) {
+            float b[VEC];
+            ld_vec<VEC>(b, p.bias + c[k]);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) r[i] += b[i];
+        }
+        if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) r[i] = fmaxf(r[i], 0.f);
+        }
+        st_vec<VEC>(p.Y + (int64_t)v * p.ldy + c[k], r);
+        if (p.self_out) {
+            float sx[VEC];
+            ld_vec<VEC>(sx, p.X + (int64_t)v * p.ldx + c[k]);
+            st_vec<VEC>(p.self_out + (int64_t)v * p.ld_self + c[k], sx);
+        }
+    }
+}
+
+template <int VEC, int LPR, int VPL>
+static int launch_spmm(const SpmmParams &p0, cudaStream_t stream) {
+    SpmmParams p = p0;
+    constexpr int ROWS_PER_BLOCK = 8 * (32 / LPR);
+    constexpr int CHUNK = LPR * VEC * VPL;
+    const int64_t row_blocks = ceil_div64(p.n_dst, ROWS_PER_BLOCK);
+    const int64_t chunks = ceil_div64(p.d, CHUNK);
+    const int64_t grid = row_blocks * chunks;
+    if (grid <= 0) return GIST_OK;
+    if (grid > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
+    p.row_blocks = (int32_t)row_blocks;
+    if (p.src_scale)
+        spmm_csr_kernel<VEC, LPR, VPL, true><<<(unsigned)grid, 256, 0, stream>>>(p);
+    else
+        spmm_csr_kernel<VEC, LPR, VPL, false><<<(unsigned)grid, 256, 0, stream>>>(p);
+    count_launch();
+    return last_error();
+}
+
+template <int VEC>
+static int dispatch_lanes(const SpmmParams &p, uint32_t flags, int32_t n_src, cudaStream_t stream) {
+    const int lanes = (p.d + VEC - 1) / VEC;
+    if (lanes <= 4) return launch_spmm<VEC, 4, 1>(p, stream);
+    if (lanes <= 8) return launch_spmm<VEC, 8, 1>(p, stream);
+    if (lanes <= 16) return launch_spmm<VEC, 16, 1>(p, stream);
+    if (lanes <= 32) return launch_spmm<VEC, 32, 1>(p, stream);
+    bool wide;
+    if (flags & GIST_SPMM_NARROW) wide = false;
+    else if (flags & GIST_SPMM_WIDE) wide = true;
+    else {
+        // auto: two vectors per lane only when there are plenty of rows to fill the
+        // chip AND the gathered operand is small enough that slab-by-slab L2
+        // residency is not what we are after.
+        const int64_t src_bytes = (int64_t)n_src * p.d * 4;
+        const int64_t warps_wide = (int64_t)p.n_dst * ((lanes + 63) / 64);
+        wide = lanes >= 64 && warps_wide >= 4LL * kNumSMs * 64 && src_bytes <= (64LL << 20);
+    }
+    return wide ? launch_spmm<VEC, 32, 2>(p, stream) : launch_spmm<VEC, 32, 1>(p, stream);
+}
+
+static bool vec_ok(int vec, const SpmmParams &p) {
+    const size_t a = 4u * vec;
+    if (p.d % vec) return false;
+    if (!aligned(p.X, a) || p.ldx % vec) return false;
+    if (!aligned(p.Y, a) || p.ldy % vec) return false;
+    if (p.bias && !aligned(p.bias, a)) return false;
+    if (p.addend && (!aligned(p.addend, a) || p.ld_add % vec)) return false;
+    if (p.self_out && (!aligned(p.self_out, a) || p.ld_self % vec)) return false;
+    return true;
+}
+
+__global__ void degree_norm_kernel(const int32_t *__restrict__ rowptr, int32_t n, int32_t mode,
+                                   float *__restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int deg = rowptr[v + 1] - rowptr[v];
+    float r;
+    if (mode == GIST_NORM_INV) r = deg > 0 ? 1.0f / (float)deg : 0.f;
+    else r = 1.0f / sqrtf((float)max(deg, 1));
+    out[v] = r;
+}
+
+}  // namespace gist
+
+using namespace gist;
+
+extern "C" int gist_spmm_csr_f32(const int32_t *rowptr, const int32_t *col, int32_t n_dst,
+                                 int32_t n_src, const float *X, int64_t ldx, int32_t d, float *Y,
+                                 int64_t ldy, const float *src_scale, const float *dst_scale,
+                                 const float *bias, const float *addend, int64_t ld_addend,
+                                 float *self_out, int64_t ld_self, uint32_t flags,
+                                 gist_stream_t stream) {
+    if (n_dst < 0 || n_src < 0 || d < 0) return GIST_ERR_BADARG;
+    if (n_dst == 0 || d == 0) return GIST_OK;
+    if (!rowptr || !X || !Y) return GIST_ERR_BADARG;  // col may be NULL for an edgeless graph
+    if (ldx < d || ldy < d) return GIST_ERR_BADARG;
+    if (addend && ld_addend < d) return GIST_ERR_BADARG;
+    if (self_out && (ld_self < d || n_dst != n_src)) return GIST_ERR_BADARG;
+    if (!aligned(rowptr, 4) || !aligned(col, 4) || !aligned(X, 4) || !aligned(Y, 4))
+        return GIST_ERR_ALIGN;
+    SpmmParams p;
+    p.rowptr = rowptr; p.col = col; p.n_dst = n_dst;
+    p.X = X; p.ldx = ldx; p.d = d; p.Y = Y; p.ldy = ldy;
+    p.src_scale = src_scale; p.dst_scale = dst_scale; p.bias = bias;
+    p.addend = addend; p.ld_add = ld_addend; p.self_out = self_out; p.ld_self = ld_self;
+    p.relu = (flags & GIST_SPMM_RELU) ? 1 : 0;
+    p.row_blocks = 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (vec_ok(4, p)) return dispatch_lanes<4>(p, flags, n_src, s);
+    if (vec_ok(2, p)) return dispatch_lanes<2>(p, flags, n_src, s);
+    return dispatch_lanes<1>(p, flags, n_src, s);
+}
+
+extern "C" int gist_spmm_csc_f32(const int32_t *colptr, const int32_t *row, int32_t n_src,
+                                 int32_t n_dst, const float *dY, int64_t lddy, int32_t d, float *dX,
+                                 int64_t lddx, const float *dst_scale, const float *src_scale,
+                                 const float *addend, int64_t ld_addend, uint32_t flags,
+                                 gist_stream_t stream) {
+    // dX[u] = src_scale[u] * sum_{u->v} dst_scale[v] * dY[v]  (+ addend[u])
+    return gist_spmm_csr_f32(colptr, row, n_src, n_dst, dY, lddy, d, dX, lddx, dst_scale, src_scale,
+                             nullptr, addend, ld_addend, nullptr, 0, flags, stream);
+}
+
+extern "C" int gist_degree_norm_f32(const int32_t *rowptr, int32_t n, int32_t mode, float *out,
+                                    gist_stream_t stream) {
+    if (n < 0 || (mode != GIST_NORM_INV && mode != GIST_NORM_RSQRT_CLAMP)) return GIST_ERR_BADARG;
+    if (n == 0) return GIST_OK;
+    if (!rowptr || !out) return GIST_ERR_BADARG;
+    degree_norm_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rowptr, n, mode, out);
+    count_launch();
+    return last_error();
+}
+
+extern "C" int gist_abi_version(void) { return GIST_ABI_VERSION; }
+
+extern "C" uint64_t gist_launch_count(void) { return g_launches.load(); }
+
+extern "C" int gist_set_device(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    return e == cudaSuccess ? GIST_OK : (int)e;
+}
+
+extern "C" const char *gist_status_string(int status) {
+    switch (status) {
+        case GIST_OK: return "ok";
+        case GIST_ERR_BADARG: return "bad argument";
+        case GIST_ERR_ALIGN: return "misaligned pointer";
+        case GIST_ERR_WORKSPACE: return "workspace / capacity too small";
+        case GIST_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown gist status";
+    }
+}

@@ -1,0 +1,165 @@
+"""GIST (independent sub-network training) partition / dispatch / sync.
+
+Mirrors cluster_gcn/cluster_gcn_ist_distrib.py:51-367 (and its byte-identical
+copy in cluster_gcn_ist_ultra_wide.py).  What changed is the data movement:
+
+  reference                                   here (8x B200, NVSwitch)
+  ---------                                   -----------------------
+  rank 0 is a parameter server holding the    every rank holds a replica of the
+  only full model (on the CPU in ultra-wide)  full model in HBM (fits: 180 GB)
+  dispatch = (2(L+1)-1)(m-1) two-rank         dispatch = local K5 slice gather,
+  broadcasts, a new communicator per tensor   no communication at all
+  sync = the same number of broadcasts back   sync = ONE all-gather of a packed
+  + all_reduce of the last bias               buffer (all slices + last bias),
+                                              then a local K5 scatter of every
+                                              rank's slice into the replica
+
+The partition is never communicated in either design: every rank draws it from
+the same Python ``random`` stream (same seed, same call order).
+"""
+import random
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import ops
+from .modules import GCN
+
+
+def create_partition(num_subnet, size):
+    """cluster_gcn_ist_distrib.py:51-65: shuffle range(size) with Python's
+    ``random``; sub-network j owns the shuffled positions j, j+m, j+2m, ...
+    Returns [(idx, full_idx)] with full_idx = cat(idx, idx + size) (the same
+    columns in the `ah` half of the SAGE concat)."""
+    perm = list(range(size))
+    random.shuffle(perm)
+    out = []
+    for j in range(num_subnet):
+        idx = torch.tensor(perm[j::num_subnet], dtype=torch.int64)
+        out.append((idx, torch.cat((idx, idx + size))))
+    return out
+
+
+def _dist_ready():
+    return dist.is_available() and dist.is_initialized()
+
+
+class DistributedGNNWrapper(torch.nn.Module):
+    """Full ("base") model replica + this rank's sub-model.
+
+    args needs: rank, num_subnet, n_hidden, n_layers, dropout, use_layernorm."""
+
+    def __init__(self, args, g, in_feats, n_classes, device):
+        super().__init__()
+        self.args = args
+        self.g = g
+        self.in_feats = in_feats
+        self.n_classes = n_classes
+        self.device = device
+        mk_base = lambda: GCN(in_feats, args.n_hidden, n_classes, args.n_layers, F.relu,  # noqa: E731
+                              args.dropout, args.use_layernorm, False, False, 1, True)
+        if args.rank == 0:
+            self.base_model = mk_base().to(device)
+        else:
+            # replica: built without disturbing this rank's RNG stream (the reference
+            # builds nothing here), filled from rank 0 below
+            with torch.random.fork_rng(devices=[]):
+                self.base_model = mk_base().to(device)
+        self.sub_model = GCN(in_feats, args.n_hidden, n_classes, args.n_layers, F.relu,
+                             args.dropout, args.use_layernorm, False, True, args.num_subnet,
+                             True).to(device)
+        self.current_partition = None
+        if _dist_ready() and args.num_subnet > 1:
+            flat = torch.cat([p.data.reshape(-1) for p in self.base_model.parameters()])
+            dist.broadcast(flat, src=0)
+            off = 0
+            for p in self.base_model.parameters():
+                p.data.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+
+    # ---------------------------------------------------------- partition --
+    def sample_partitions(self):
+        return [create_partition(self.args.num_subnet, self.args.n_hidden)
+                for _ in range(self.args.n_layers)]
+
+    def _to_dev(self, parts):
+        return [[(i.to(self.device), f.to(self.device)) for (i, f) in layer] for layer in parts]
+
+    # ------------------------------------------------------------ dispatch --
+    def _slice_for(self, layer_idx, site, parts):
+        """(row index, col index) of base layer `layer_idx` owned by `site`."""
+        L = len(parts)
+        if layer_idx == 0:
+            return parts[0][site][0], None
+        if layer_idx == L:
+            return None, parts[L - 1][site][1]
+        return parts[layer_idx][site][0], parts[layer_idx - 1][site][1]
+
+    def _dispatch_local(self, parts):
+        site = self.args.rank
+        L = len(parts)
+        with torch.no_grad():
+            for l in range(L + 1):
+                ridx, cidx = self._slice_for(l, site, parts)
+                base = self.base_model.layers[l].linear
+                sub = self.sub_model.layers[l].linear
+                sub.weight.data = ops.slice_gather(base.weight.data, ridx, cidx)
+                if l == L:
+                    sub.bias.data = base.bias.data.clone()      # shared, full (…distrib.py:217-219)
+                else:
+                    sub.bias.data = ops.slice_gather(base.bias.data, None, ridx)
+
+    def ini_sync_dispatch_model(self):
+        parts = self._to_dev(self.sample_partitions())
+        self._dispatch_local(parts)
+        self.current_partition = parts
+
+    def dispatch_model(self):
+        parts = self._to_dev(self.sample_partitions())
+        self._dispatch_local(parts)
+        self.current_partition = parts
+
+    # ---------------------------------------------------------------- sync --
+    def _pack(self):
+        return torch.cat([t.data.reshape(-1) for lyr in self.sub_model.layers
+                          for t in (lyr.linear.weight, lyr.linear.bias)])
+
+    def sync_model(self):
+        m = self.args.num_subnet
+        parts = self.current_partition
+        L = len(parts)
+        with torch.no_grad():
+            flat = self._pack()
+            if _dist_ready() and m > 1:
+                gathered = torch.empty((m, flat.numel()), dtype=flat.dtype, device=flat.device)
+                dist.all_gather_into_tensor(gathered, flat)
+            else:
+                assert m == 1, 'num_subnet > 1 needs an initialised process group'
+                gathered = flat.unsqueeze(0)
+            self._merge(gathered, parts)
+            # the reference all-reduces the last bias IN PLACE on every rank's sub-model
+            self.sub_model.layers[L].linear.bias.data = self.base_model.layers[L].linear.bias.data.clone()
+
+    def _merge(self, gathered, parts):
+        """Scatter every site's packed slices into the local full-model replica."""
+        m = gathered.shape[0]
+        L = len(parts)
+        shapes = [(tuple(lyr.linear.weight.shape), tuple(lyr.linear.bias.shape))
+                  for lyr in self.sub_model.layers]
+        last_bias = None
+        for site in range(m):
+            off = 0
+            row = gathered[site]
+            for l in range(L + 1):
+                (wr, wc), (bn,) = shapes[l]
+                w = row[off:off + wr * wc].view(wr, wc); off += wr * wc
+                b = row[off:off + bn]; off += bn
+                ridx, cidx = self._slice_for(l, site, parts)
+                base = self.base_model.layers[l].linear
+                ops.slice_scatter_(base.weight.data, w, ridx, cidx)
+                if l == L:
+                    last_bias = b.clone() if last_bias is None else last_bias + b   # rank order
+                else:
+                    ops.slice_scatter_(base.bias.data, b, None, ridx)
+        self.base_model.layers[L].linear.bias.data = last_bias / m

@@ -1,0 +1,238 @@
+"""Drop-in modules for cluster_gcn/modules.py and DGL's GraphConv.
+
+Same constructor signatures, parameter names / shapes / initialisers and
+``forward`` signatures as the reference, so state dicts and the GIST
+split/merge code (which re-assigns ``layer.linear.weight.data`` with tensors of
+a different shape, cluster_gcn_ist_distrib.py:208-226) work unchanged.  The
+aggregation, degree normalisation, concat, bias and ReLU run in the sm_100a
+kernels of ``csrc/``; nothing here falls back to a CPU or library SpMM.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .graph import GistError
+
+
+def _is_relu(act):
+    return act is F.relu or act is torch.relu or isinstance(act, nn.ReLU)
+
+
+class GraphConv(nn.Module):
+    """dgl.nn.pytorch.GraphConv (0.5.x) with norm='both' semantics:
+    weight is [in, out] (Xavier uniform), bias zeros; W is applied first iff in > out.
+    Used by gcn/gcn.py:30-56 and cluster_gcn/modules.py:331-338."""
+
+    def __init__(self, in_feats, out_feats, norm='both', weight=True, bias=True, activation=None,
+                 allow_zero_in_degree=False):
+        super().__init__()
+        if norm not in ('none', 'both', 'right'):
+            raise GistError('Invalid norm value. Must be either "none", "both" or "right".')
+        self._in_feats, self._out_feats, self._norm = in_feats, out_feats, norm
+        self._allow_zero_in_degree = allow_zero_in_degree
+        self.weight = nn.Parameter(torch.Tensor(in_feats, out_feats)) if weight else None
+        self.bias = nn.Parameter(torch.Tensor(out_feats)) if bias else None
+        self.reset_parameters()
+        self._activation = activation
+
+    def reset_parameters(self):
+        if self.weight is not None:
+            nn.init.xavier_uniform_(self.weight)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def forward(self, graph, feat):
+        if not self._allow_zero_in_degree and graph.has_zero_in_degree():
+            raise GistError('There are 0-in-degree nodes in the graph, output for those nodes will '
+                            'be invalid. Add self-loops or set allow_zero_in_degree=True.')
+        s = graph.rsqrt_out_degree() if self._norm == 'both' else None
+        if self._norm == 'both':
+            t = graph.rsqrt_in_degree()
+        elif self._norm == 'right':
+            t = graph.inv_in_degree()
+        else:
+            t = None
+        fuse_relu = _is_relu(self._activation)
+        # the width test uses the CURRENT weight shape: GIST re-assigns .data slices
+        w = self.weight
+        in_f, out_f = (w.shape if w is not None else (self._in_feats, self._out_feats))
+        if in_f > out_f:
+            # (diag(s) X) W == diag(s) (X W): the src-norm moves into the SpMM gather
+            h = feat @ w if w is not None else feat
+            rst = ops.gspmm(graph, h, s, t, self.bias, fuse_relu)
+            if self._activation is not None and not fuse_relu:
+                rst = self._activation(rst)
+            return rst
+        # aggregate first; diag(t) commutes with the right-multiplication by W
+        rst = ops.gspmm(graph, feat, s, t, None, False)
+        if w is not None:
+            rst = torch.addmm(self.bias, rst, w) if self.bias is not None else rst @ w
+        elif self.bias is not None:
+            rst = rst + self.bias
+        if self._activation is not None:
+            rst = self._activation(rst)
+        return rst
+
+
+class GraphSAGELayer(nn.Module):
+    """cluster_gcn/modules.py:100-159."""
+
+    def __init__(self, in_feats, out_feats, activation, dropout, bias=True, use_pp=False,
+                 use_lynorm=True):
+        super().__init__()
+        self.linear = nn.Linear(2 * in_feats, out_feats, bias=bias)
+        self.activation = activation
+        self.use_pp = use_pp
+        self.dropout = nn.Dropout(p=dropout) if dropout else 0.
+        self.lynorm = nn.LayerNorm(out_feats, elementwise_affine=True) if use_lynorm else (lambda x: x)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 1. / math.sqrt(self.linear.weight.size(1))
+        self.linear.weight.data.uniform_(-stdv, stdv)
+        if self.linear.bias is not None:
+            self.linear.bias.data.uniform_(-stdv, stdv)
+
+    def forward(self, g, h):
+        if not self.use_pp or not self.training:
+            h = ops.sage_concat(g, h)       # [h ‖ (A h) / in_deg] in one kernel
+        if self.dropout:
+            h = self.dropout(h)
+        h = self.linear(h)
+        h = self.lynorm(h)
+        if self.activation:
+            h = self.activation(h)
+        return h
+
+    def concat(self, h, ah, norm):
+        return torch.cat((h, ah * norm), dim=1)
+
+    def get_norm(self, g):
+        return g.inv_in_degree().unsqueeze(1)
+
+
+class ISTSAGELayer(nn.Module):
+    """cluster_gcn/modules.py:191-243: Linear(2*in, out), U(+-1/sqrt(2*in)) init for
+    weight and bias, LayerNorm(out, affine=False) when use_lynorm."""
+
+    def __init__(self, in_feats, out_feats, dropout, use_lynorm, activation=None):
+        super().__init__()
+        self.linear = nn.Linear(2 * in_feats, out_feats)
+        self.activation = activation
+        self.init_layer()
+        self.dropout = nn.Dropout(p=dropout) if dropout else 0.
+        self.lynorm = nn.LayerNorm(out_feats, elementwise_affine=False) if use_lynorm else (lambda x: x)
+
+    def init_layer(self):
+        stdv = 1. / math.sqrt(self.linear.weight.size(1))
+        self.linear.weight.data.uniform_(-stdv, stdv)
+        self.linear.bias.data.uniform_(-stdv, stdv)
+
+    def forward(self, g, h):
+        h = ops.sage_concat(g, h)           # get_norm + update_all + `*norm` + cat fused
+        if self.dropout:
+            h = self.dropout(h)
+        # GIST swaps in weight slices of other widths; use the live tensors, and
+        # normalise over the live output width
+        h = F.linear(h, self.linear.weight, self.linear.bias)
+        if isinstance(self.lynorm, nn.LayerNorm):
+            h = F.layer_norm(h, (h.shape[-1],), None, None, self.lynorm.eps)
+        else:
+            h = self.lynorm(h)
+        if self.activation:
+            h = self.activation(h)
+        return h
+
+    def get_norm(self, g):
+        return g.inv_in_degree().unsqueeze(1)
+
+
+class GraphSAGE(nn.Module):
+    """cluster_gcn/modules.py:161-189."""
+
+    def __init__(self, in_feats, n_hidden, n_classes, n_layers, activation, dropout, use_pp):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        self.layers.append(GraphSAGELayer(in_feats, n_hidden, activation=activation, dropout=dropout,
+                                          use_pp=use_pp, use_lynorm=True))
+        for _ in range(n_layers - 1):
+            self.layers.append(GraphSAGELayer(n_hidden, n_hidden, activation=activation,
+                                              dropout=dropout, use_pp=False, use_lynorm=True))
+        self.layers.append(GraphSAGELayer(n_hidden, n_classes, activation=None, dropout=dropout,
+                                          use_pp=False, use_lynorm=False))
+
+    def forward(self, g):
+        h = g.ndata['feat']
+        for layer in self.layers:
+            h = layer(g, h)
+        return h
+
+
+def _split_widths(in_feats, n_hidden, n_classes, n_layers, split_input, split_output, num_subnet):
+    """(in, out, is_output) per layer — the width bookkeeping shared by both GCN
+    containers (cluster_gcn/modules.py:260-308, gcn/gcn.py:27-56)."""
+    k = num_subnet
+    hk = int(n_hidden // k)
+    first_in = int(in_feats // k) if split_input else in_feats
+    first_out = n_hidden if (n_layers <= 1 and not split_output) else hk
+    dims = [(first_in, first_out)]
+    for i in range(n_layers - 1):
+        dims.append((hk, n_hidden if (i == n_layers - 2 and not split_output) else hk))
+    dims.append((hk if split_output else n_hidden, n_classes))
+    return dims
+
+
+class GCN(nn.Module):
+    """The GraphSAGE-style IST container, cluster_gcn/modules.py:245-314.
+    State-dict keys ``layers.{i}.linear.{weight,bias}``."""
+
+    def __init__(self, in_feats, n_hidden, n_classes, n_layers, activation, dropout,
+                 use_layernorm=True, split_input=False, split_output=False, num_subnet=1,
+                 use_aggregation=False):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        self.use_layernorm = use_layernorm
+        self.split_input = split_input
+        self.split_output = split_output
+        if not use_aggregation:
+            raise NotImplementedError('You must use graph sage')
+        dims = _split_widths(in_feats, n_hidden, n_classes, n_layers, split_input, split_output,
+                             num_subnet)
+        for fin, fout in dims[:-1]:
+            self.layers.append(ISTSAGELayer(fin, fout, dropout, use_layernorm, activation=activation))
+        fin, fout = dims[-1]
+        self.layers.append(ISTSAGELayer(fin, fout, dropout, False, activation=None))
+
+    def forward(self, g):
+        h = g.ndata['feat']
+        for layer in self.layers:
+            h = layer(g, h)
+        return h
+
+
+class BaselineGCN(nn.Module):
+    """cluster_gcn/modules.py:316-349: GraphConv stack + whole-tensor layer norm."""
+
+    def __init__(self, in_feats, n_hidden, n_classes, n_layers, activation, dropout,
+                 use_layernorm=True):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        self.use_layernorm = use_layernorm
+        self.layers.append(GraphConv(in_feats, n_hidden, activation=activation))
+        for _ in range(n_layers - 1):
+            self.layers.append(GraphConv(n_hidden, n_hidden, activation=activation))
+        self.layers.append(GraphConv(n_hidden, n_classes))
+        self.dropout = nn.Dropout(p=dropout)
+
+    def forward(self, g):
+        h = g.ndata['feat']
+        for i, layer in enumerate(self.layers):
+            if i != 0:
+                h = self.dropout(h)
+            h = layer(g, h)
+            if i < len(self.layers) - 1 and self.use_layernorm:
+                h = F.layer_norm(h, h.shape)
+        return h

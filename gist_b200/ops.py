@@ -1,0 +1,189 @@
+"""Thin Python wrappers + autograd Functions over the C-ABI kernels.
+
+Every function here enqueues hand-written sm_100a kernels from
+``csrc/libgist_b200.so`` on torch's current stream.  No CPU path exists:
+non-CUDA inputs raise ``GistLibraryError``.
+"""
+import torch
+
+from . import _lib
+from ._lib import check, ptr, require_cuda, stream_ptr
+
+
+def _mat(t, name):
+    if t.dim() != 2 or t.dtype != torch.float32:
+        raise ValueError('%s must be a 2-D float32 tensor, got %s %s' % (name, tuple(t.shape), t.dtype))
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    if t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+def _ld(t):
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+def spmm_raw(rowptr, col, n_dst, n_src, X, out, *, src_scale=None, dst_scale=None, bias=None,
+             addend=None, self_out=None, relu=False, flags=0):
+    """out[v] = act(dst_scale[v] * sum_{e in row v} src_scale[col e] * X[col e] + addend[v] + bias).
+
+    ``out`` (and ``self_out``/``addend``) may be column-block views of wider
+    row-major buffers; leading dimensions are taken from the strides."""
+    require_cuda(rowptr, col, X, out, src_scale, dst_scale, bias, addend, self_out)
+    d = X.shape[1]
+    assert out.shape[0] == n_dst and out.shape[1] == d and X.shape[0] == n_src
+    assert out.stride(1) == 1 or d == 1
+    lib = _lib.load()
+    f = flags | (_lib.SPMM_RELU if relu else 0)
+    st = lib.gist_spmm_csr_f32(
+        ptr(rowptr), ptr(col), n_dst, n_src, ptr(X), _ld(X), d, ptr(out), _ld(out),
+        ptr(src_scale), ptr(dst_scale), ptr(bias),
+        ptr(addend), _ld(addend) if addend is not None else 0,
+        ptr(self_out), _ld(self_out) if self_out is not None else 0,
+        f, stream_ptr(X.device))
+    check(st, 'spmm_csr_f32')
+    return out
+
+
+def degree_norm(rowptr, n, mode):
+    require_cuda(rowptr)
+    out = torch.empty(n, dtype=torch.float32, device=rowptr.device)
+    check(_lib.load().gist_degree_norm_f32(ptr(rowptr), n, mode, ptr(out), stream_ptr(rowptr.device)),
+          'degree_norm_f32')
+    return out
+
+
+def exclusive_scan(x):
+    """int32 exclusive scan; returns n+1 entries (last = total)."""
+    require_cuda(x)
+    assert x.dtype == torch.int32 and x.dim() == 1 and x.is_contiguous()
+    n = x.shape[0]
+    lib = _lib.load()
+    out = torch.empty(n + 1, dtype=torch.int32, device=x.device)
+    wsb = lib.gist_scan_workspace_bytes(n)
+    ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=x.device)
+    check(lib.gist_exclusive_scan_i32(ptr(x), n, ptr(out), ptr(ws), wsb, stream_ptr(x.device)),
+          'exclusive_scan_i32')
+    return out
+
+
+def gather_rows(src, idx):
+    """src[idx] along dim 0 for any dtype / trailing shape (ndata row-gather)."""
+    require_cuda(src, idx)
+    assert idx.dtype == torch.int64 and idx.dim() == 1
+    src = src.contiguous()
+    n = idx.shape[0]
+    out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    row_bytes = src.element_size()
+    for s in src.shape[1:]:
+        row_bytes *= s
+    check(_lib.load().gist_gather_rows(ptr(src), row_bytes, ptr(idx.contiguous()), n, ptr(out),
+                                       row_bytes, row_bytes, stream_ptr(src.device)), 'gather_rows')
+    return out
+
+
+def slice_gather(src, ridx=None, cidx=None, out=None):
+    """out[r, c] = src[ridx[r], cidx[c]] (None = identity). 1-D src is treated as a row."""
+    require_cuda(src, ridx, cidx)
+    one_d = src.dim() == 1
+    s2 = src.unsqueeze(0) if one_d else src
+    s2 = _mat(s2, 'src')
+    nr = ridx.shape[0] if ridx is not None else s2.shape[0]
+    nc = cidx.shape[0] if cidx is not None else s2.shape[1]
+    if out is None:
+        out = torch.empty((nr, nc), dtype=torch.float32, device=src.device)
+    o2 = out.unsqueeze(0) if out.dim() == 1 else out
+    assert tuple(o2.shape) == (nr, nc) and (o2.stride(1) == 1 or nc == 1)
+    check(_lib.load().gist_slice_gather_f32(ptr(s2), _ld(s2), ptr(ridx), nr, ptr(cidx), nc, ptr(o2),
+                                            _ld(o2), stream_ptr(src.device)), 'slice_gather_f32')
+    return out.reshape(nc) if one_d and out.dim() == 2 else out
+
+
+def slice_scatter_(dst, src, ridx=None, cidx=None):
+    """dst[ridx[r], cidx[c]] = src[r, c] in place (indices unique)."""
+    require_cuda(dst, src, ridx, cidx)
+    d2 = dst.unsqueeze(0) if dst.dim() == 1 else dst
+    s2 = src.unsqueeze(0) if src.dim() == 1 else src
+    s2 = _mat(s2, 'src')
+    assert d2.dtype == torch.float32 and (d2.stride(1) == 1 or d2.shape[1] == 1)
+    nr, nc = s2.shape
+    assert nr == (ridx.shape[0] if ridx is not None else d2.shape[0])
+    assert nc == (cidx.shape[0] if cidx is not None else d2.shape[1])
+    check(_lib.load().gist_slice_scatter_f32(ptr(s2), _ld(s2), ptr(ridx), nr, ptr(cidx), nc, ptr(d2),
+                                             _ld(d2), stream_ptr(dst.device)), 'slice_scatter_f32')
+    return dst
+
+
+# --------------------------------------------------------------------------
+# autograd
+# --------------------------------------------------------------------------
+class _ScaledSpMM(torch.autograd.Function):
+    """Y = act(t ⊙ A (s ⊙ X) + bias); backward through K2 on the CSC."""
+
+    @staticmethod
+    def forward(ctx, g, X, src_scale, dst_scale, bias, relu):
+        X = _mat(X, 'X')
+        n = g.number_of_nodes()
+        Y = torch.empty((n, X.shape[1]), dtype=torch.float32, device=X.device)
+        spmm_raw(g.rowptr, g.col_buffer, n, n, X, Y, src_scale=src_scale, dst_scale=dst_scale,
+                 bias=bias, relu=relu)
+        ctx.g, ctx.relu, ctx.has_bias = g, relu, bias is not None
+        ctx.save_for_backward(src_scale, dst_scale, Y if relu else None)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        src_scale, dst_scale, Y = ctx.saved_tensors
+        g = ctx.g
+        dY = _mat(dY, 'dY')
+        if ctx.relu:
+            dY = dY * (Y > 0).to(dY.dtype)
+        dbias = dY.sum(0) if (ctx.has_bias and ctx.needs_input_grad[4]) else None
+        dX = None
+        if ctx.needs_input_grad[1]:
+            n = g.number_of_nodes()
+            colptr, row = g.csc()
+            dX = torch.empty_like(dY)
+            # dX[u] = s[u] * sum_{u->v} t[v] dY[v]
+            spmm_raw(colptr, row, n, n, dY, dX, src_scale=dst_scale, dst_scale=src_scale)
+        return None, dX, None, None, dbias, None
+
+
+def gspmm(g, X, src_scale=None, dst_scale=None, bias=None, relu=False):
+    return _ScaledSpMM.apply(g, X, src_scale, dst_scale, bias, relu)
+
+
+def copy_src_sum(g, X):
+    """update_all(fn.copy_src, fn.sum): Y[v] = sum_{u->v} X[u]."""
+    return _ScaledSpMM.apply(g, X, None, None, None, False)
+
+
+class _SageConcat(torch.autograd.Function):
+    """z = [h ‖ inv_deg ⊙ (A h)] written by ONE kernel into a [n, 2d] buffer
+    (cluster_gcn/modules.py:222-227); backward dh = dz[:, :d] + Aᵀ(inv_deg ⊙ dz[:, d:])."""
+
+    @staticmethod
+    def forward(ctx, g, h):
+        h = _mat(h, 'h')
+        n, d = h.shape
+        z = torch.empty((n, 2 * d), dtype=torch.float32, device=h.device)
+        inv = g.inv_in_degree()
+        spmm_raw(g.rowptr, g.col_buffer, n, n, h, z[:, d:], dst_scale=inv, self_out=z[:, :d])
+        ctx.g = g
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        g = ctx.g
+        dz = _mat(dz, 'dz')
+        n, d2 = dz.shape
+        d = d2 // 2
+        colptr, row = g.csc()
+        dh = torch.empty((n, d), dtype=torch.float32, device=dz.device)
+        spmm_raw(colptr, row, n, n, dz[:, d:], dh, src_scale=g.inv_in_degree(), addend=dz[:, :d])
+        return None, dh
+
+
+def sage_concat(g, h):
+    return _SageConcat.apply(g, h)

@@ -1,0 +1,141 @@
+"""Cluster-batch producer: drop-in for cluster_gcn/sampler.py + partition_utils.py.
+
+Differences from the reference are all *where* the work runs, not *what* it
+computes:
+  * the training graph, its features / labels / masks and the relabel scratch
+    stay resident in HBM; ``get_subgraph`` runs the K3 builder on the device
+    instead of DGL's CPU ``subgraph`` followed by a per-step H2D of structure and
+    ~5 MB of features (cluster_gcn_ist_distrib.py:409);
+  * per step only the batch's node-id list crosses PCIe (``h2d='step'``, from
+    pinned memory) or nothing at all (``h2d='epoch'``: one copy of the epoch's
+    concatenated id lists at ``__iter__``).
+Order of nodes inside a batch, membership, and the Python ``random`` call order
+(shuffle at init and at every StopIteration, sampler.py:55, :92) are identical,
+so batches are bit-identical to the reference's for the same seed and partition.
+
+METIS itself is third-party and out of scope: the node->part assignment is an
+input (``g.ndata['_part']`` on the training graph's parent, a ``partition=``
+list, or the reference's ``../data/{dn}_{psize}.npy`` cache file).
+"""
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import function as fn
+from .graph import NID
+
+
+def get_partition_list(g, psize):
+    """partition_utils.py:11-18 with the METIS call replaced by a given assignment
+    ``g.ndata['_part']`` (int, [n]); returns psize int64 arrays of node ids."""
+    if '_part' not in g.ndata:
+        raise RuntimeError("get_partition_list: METIS is out of scope; provide g.ndata['_part'] "
+                           "(node -> part id) or pass partition= to ClusterIter")
+    part = g.ndata['_part'].detach().cpu().numpy().astype(np.int64)
+    order = np.argsort(part, kind='stable')
+    bounds = np.searchsorted(part[order], np.arange(psize + 1))
+    return [order[bounds[p]:bounds[p + 1]].astype(np.int64) for p in range(psize)]
+
+
+def get_subgraph(g, par_arr, i, psize, batch_size, col_capacity=None):
+    """partition_utils.py:20-25: induced subgraph of the concatenated parts
+    [i*bs, (i+1)*bs), node order = concatenation order."""
+    par_batch_ind_arr = [par_arr[s] for s in range(i * batch_size, (i + 1) * batch_size) if s < psize]
+    nids = np.concatenate(par_batch_ind_arr).reshape(-1).astype(np.int64)
+    return g.subgraph(nids, col_capacity=col_capacity)
+
+
+class ClusterIter(object):
+    """The partition sampler (cluster_gcn/sampler.py:11-93)."""
+
+    def __init__(self, dn, g, psize, batch_size, seed_nid, use_pp=True, partition=None,
+                 h2d='step', cache_dir='../data/'):
+        self.use_pp = use_pp
+        seed_nid = np.asarray(seed_nid).astype(np.int64)
+        self.g = g.subgraph(seed_nid)
+        if use_pp:
+            self.precalc(self.g)
+            print('precalculating')
+        self.psize = psize
+        self.batch_size = batch_size
+        if partition is not None:
+            self.par_li = [np.asarray(p).astype(np.int64) for p in partition]
+        elif dn and os.path.exists(os.path.join(cache_dir, dn + '_{}.npy'.format(psize))):
+            self.par_li = list(np.load(os.path.join(cache_dir, dn + '_{}.npy'.format(psize)),
+                                       allow_pickle=True))
+        else:
+            self.par_li = get_partition_list(self.g, psize)
+        self.max = int((psize) // batch_size)
+        # host-side bound on a batch's edge count: sum of training-graph degrees
+        deg = (self.g.rowptr[1:] - self.g.rowptr[:-1]).cpu().numpy().astype(np.int64)
+        self._deg_sum = {id(p): int(deg[p].sum()) for p in self.par_li}
+        random.shuffle(self.par_li)
+        self.get_fn = get_subgraph
+        assert h2d in ('step', 'epoch')
+        self.h2d = h2d
+        self._pinned = None
+        self._epoch_ids = None
+        self.h2d_bytes = 0      # node-id bytes copied host->device so far
+
+    def precalc(self, g):
+        """sampler.py:58-69 (A·X pre-aggregation on the training graph)."""
+        norm = self.get_norm(g)
+        g.ndata['norm'] = norm
+        features = g.ndata['feat']
+        print("features shape, ", features.shape)
+        with torch.no_grad():
+            g.update_all(fn.copy_src(src='feat', out='m'), fn.sum(msg='m', out='feat'), None)
+            pre_feats = g.ndata['feat'] * norm
+            g.ndata['feat'] = torch.cat([features, pre_feats], dim=1)
+
+    def get_norm(self, g):
+        return g.inv_in_degree().unsqueeze(1)
+
+    def __len__(self):
+        return self.max
+
+    def batch_node_ids(self, i):
+        parts = [self.par_li[s] for s in range(i * self.batch_size, (i + 1) * self.batch_size)
+                 if s < self.psize]
+        return parts, np.concatenate(parts).reshape(-1).astype(np.int64)
+
+    def __iter__(self):
+        self.n = 0
+        if self.h2d == 'epoch':
+            offs, chunks = [0], []
+            for i in range(self.max):
+                _, ids = self.batch_node_ids(i)
+                chunks.append(ids)
+                offs.append(offs[-1] + len(ids))
+            allids = torch.from_numpy(np.concatenate(chunks)) if chunks else torch.zeros(0, dtype=torch.int64)
+            self._epoch_ids = (allids.to(self.g.device), offs)
+            self.h2d_bytes += allids.numel() * 8
+        return self
+
+    def __next__(self):
+        if self.n < self.max:
+            i = self.n
+            parts, ids = self.batch_node_ids(i)
+            cap = sum(self._deg_sum[id(p)] for p in parts)
+            if self.h2d == 'epoch':
+                dev_ids, offs = self._epoch_ids
+                nids = dev_ids[offs[i]:offs[i + 1]]
+            else:
+                n_b = len(ids)
+                if self._pinned is None or self._pinned[0].shape[0] < n_b:
+                    self._pinned = [torch.empty(max(n_b * 2, 1024), dtype=torch.int64).pin_memory()
+                                    for _ in range(4)]
+                    self._pin_slot = 0
+                buf = self._pinned[self._pin_slot]
+                self._pin_slot = (self._pin_slot + 1) % len(self._pinned)
+                buf[:n_b].copy_(torch.from_numpy(ids))
+                nids = buf[:n_b].to(self.g.device, non_blocking=True)
+                self.h2d_bytes += n_b * 8
+            result = self.g.subgraph(nids, col_capacity=cap)
+            self.n += 1
+            return result
+        else:
+            random.shuffle(self.par_li)
+            raise StopIteration

@@ -1,0 +1,164 @@
+/*
+ * gist_b200 — C ABI of the B200-native GIST aggregation hot path.
+ *
+ * The reference (wolfecameron/GIST) has no FFI of its own: its hot path is a
+ * handful of DGL 0.5.3 / PyTorch calls made from Python modules.  Each entry
+ * point below names the reference call site(s) it replaces (paths relative to
+ * the reference root).  The Python side of this repo (gist_b200/_lib.py) binds
+ * these symbols with ctypes; INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t) and returns;
+ *     no implicit synchronisation, no allocation, no global mutable state
+ *     (except the launch counter) — the caller owns all buffers;
+ *   - return value: 0 = OK, <0 = argument error (GIST_ERR_*), >0 = cudaError_t;
+ *   - graph structure is int32 CSR over in-edges: row v lists the sources u of
+ *     all edges u->v (multi-edges repeated, self loops allowed), no values;
+ *   - dense matrices are row-major fp32 with an explicit leading dimension (in
+ *     elements), so a kernel can read/write a column block of a wider buffer.
+ */
+#ifndef GIST_B200_H
+#define GIST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *gist_stream_t; /* cudaStream_t */
+
+#define GIST_ABI_VERSION 1
+
+#define GIST_OK 0
+#define GIST_ERR_BADARG (-1)      /* null pointer / negative size / bad enum      */
+#define GIST_ERR_ALIGN (-2)       /* pointer not aligned for its element type     */
+#define GIST_ERR_WORKSPACE (-3)   /* workspace or output capacity too small       */
+#define GIST_ERR_UNSUPPORTED (-4) /* combination not implemented                  */
+
+/* flags of gist_spmm_csr_f32 */
+#define GIST_SPMM_RELU 1u        /* y = max(y, 0) as the last epilogue step       */
+#define GIST_SPMM_NARROW 2u      /* force 1 vector / lane (narrow feature chunks) */
+#define GIST_SPMM_WIDE 4u        /* force 2 vectors / lane                        */
+
+/* modes of gist_degree_norm_f32 */
+#define GIST_NORM_INV 0       /* 1/deg, deg==0 -> 0   (ISTSAGELayer.get_norm, cluster_gcn/modules.py:239-243) */
+#define GIST_NORM_RSQRT_CLAMP 1 /* clamp(deg,1)^-1/2  (DGL GraphConv norm='both')           */
+
+int gist_abi_version(void);
+const char *gist_status_string(int status);
+
+/* Bind the calling thread's runtime to `device` (one process per GPU; call once
+ * after torch.cuda.set_device). */
+int gist_set_device(int device);
+
+/* Number of kernels this library has launched in this process (bench.py's
+ * gpu_launches evidence). */
+uint64_t gist_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * K1 / K2  CSR SpMM with fused epilogue.
+ *
+ *   acc[v, c]  = sum_{e in [rowptr[v], rowptr[v+1])}  s(col[e]) * X[col[e], c]
+ *   Y[v, c]    = act( t(v) * acc[v, c] + addend[v, c] + bias[c] ),  c in [0, d)
+ *   self_out[v, c] = X[v, c]                     (optional, needs n_dst == n_src)
+ *
+ * s = src_scale (or 1), t = dst_scale (or 1); addend / bias / self_out optional
+ * (NULL).  Edges of a row are accumulated sequentially in CSR order, so the
+ * result is run-to-run deterministic; no atomics.
+ *
+ * Replaces: g.update_all(fn.copy_src, fn.sum)   cluster_gcn/modules.py:136-137, :224-225,
+ *           cluster_gcn/sampler.py:64-66; `ah * norm` + torch.cat  modules.py:226-227;
+ *           DGL GraphConv's src/dst normalisation, bias and activation
+ *           (gcn/gcn.py:30-56, cluster_gcn/modules.py:331-338).
+ * Backward (K2): call it with the CSC arrays (out-edge lists) of the same graph
+ * and src/dst scales swapped — dX[u] = s(u) * sum_{u->v} t(v) dY[v]  (what DGL's
+ * GSpMM.backward does on the reversed graph).
+ *
+ * Vector width (128/64/32-bit gathers) is picked from the alignment of every
+ * pointer / leading dimension involved.
+ */
+int gist_spmm_csr_f32(const int32_t *rowptr, const int32_t *col, int32_t n_dst, int32_t n_src,
+                      const float *X, int64_t ldx, int32_t d,
+                      float *Y, int64_t ldy,
+                      const float *src_scale, const float *dst_scale, const float *bias,
+                      const float *addend, int64_t ld_addend,
+                      float *self_out, int64_t ld_self,
+                      uint32_t flags, gist_stream_t stream);
+
+/* K2 spelled out: identical kernel, arguments named for the transpose.
+ * colptr/row = CSC of the forward graph. */
+int gist_spmm_csc_f32(const int32_t *colptr, const int32_t *row, int32_t n_src, int32_t n_dst,
+                      const float *dY, int64_t lddy, int32_t d,
+                      float *dX, int64_t lddx,
+                      const float *dst_scale, const float *src_scale,
+                      const float *addend, int64_t ld_addend,
+                      uint32_t flags, gist_stream_t stream);
+
+/* out[v] = f(rowptr[v+1]-rowptr[v]);  replaces g.in_degrees() + get_norm
+ * (cluster_gcn/modules.py:155-159, :239-243; sampler.py:72-76) and GraphConv's
+ * degree clamps. */
+int gist_degree_norm_f32(const int32_t *rowptr, int32_t n, int32_t mode, float *out,
+                         gist_stream_t stream);
+
+/* Exclusive prefix sum of n int32 values into out[0..n] (out[n] = total).
+ * workspace: gist_scan_workspace_bytes(n) bytes. in may alias out. */
+size_t gist_scan_workspace_bytes(int32_t n);
+int gist_exclusive_scan_i32(const int32_t *in, int32_t n, int32_t *out, void *workspace,
+                            size_t workspace_bytes, gist_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * K3  device-side cluster-batch builder (node-induced subgraph + relabel).
+ *
+ * new node i <-> nids[i] (order kept; nids must be unique); keeps every parent
+ * edge whose two endpoints are selected, with multiplicity; within a row the
+ * parent's edge order is kept, so the output is deterministic.
+ *
+ *   node_map   [n_parent] int32 scratch, all -1 on entry, all -1 again on exit
+ *   out_rowptr [n_b + 1], out_col [col_capacity]  (capacity >= sum of parent
+ *              degrees of nids is always enough); out_rowptr[n_b] = nnz_b
+ *   out_inv_deg optional [n_b]: 1/in-degree of the batch graph, 0 if isolated
+ *   scan_ws    gist_scan_workspace_bytes(n_b) bytes
+ * If the capacity is exceeded no out-of-bounds write happens and
+ * *overflow_flag (device int32, optional) is set to 1.
+ *
+ * Replaces: DGLGraph.subgraph on the CPU + per-step H2D of structure
+ * (cluster_gcn/partition_utils.py:20-25, cluster_gcn_ist_distrib.py:409).
+ */
+int gist_cluster_batch_build(const int32_t *parent_rowptr, const int32_t *parent_col,
+                             int32_t n_parent, const int64_t *nids, int32_t n_b,
+                             int32_t *node_map, int32_t *out_rowptr, int32_t *out_col,
+                             int64_t col_capacity, float *out_inv_deg, int32_t *overflow_flag,
+                             void *scan_ws, size_t scan_ws_bytes, gist_stream_t stream);
+
+/* dst[i, :] = src[idx[i], :] for rows of row_bytes bytes (features, labels,
+ * masks — the ndata row-gather of DGLGraph.subgraph). Strides in bytes. */
+int gist_gather_rows(const void *src, int64_t src_stride_bytes, const int64_t *idx, int64_t n,
+                     void *dst, int64_t dst_stride_bytes, int64_t row_bytes, gist_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * K5  GIST sub-model split / merge (2-D slice gather / scatter).
+ *
+ *   gather : dst[r, c] = src[ridx[r], cidx[c]]      dst is [n_rows, n_cols]
+ *   scatter: dst[ridx[r], cidx[c]] = src[r, c]      src is [n_rows, n_cols]
+ * ridx / cidx are int64 (torch.LongTensor, as create_partition returns) and
+ * may be NULL = identity.  Indices must be unique for scatter.
+ *
+ * Replaces the advanced-indexing copies of dispatch / sync:
+ * cluster_gcn/cluster_gcn_ist_distrib.py:107-133, :204-226, :291-313 and
+ * gcn/train_ist.py:179-191, :244-285.
+ */
+int gist_slice_gather_f32(const float *src, int64_t ld_src, const int64_t *ridx, int64_t n_rows,
+                          const int64_t *cidx, int64_t n_cols, float *dst, int64_t ld_dst,
+                          gist_stream_t stream);
+int gist_slice_scatter_f32(const float *src, int64_t ld_src, const int64_t *ridx, int64_t n_rows,
+                           const int64_t *cidx, int64_t n_cols, float *dst, int64_t ld_dst,
+                           gist_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIST_B200_H */

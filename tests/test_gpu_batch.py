@@ -1,0 +1,134 @@
+"""K3 parity: device cluster-batch builder vs oracle induced subgraph (bit-exact in
+canonical form), ndata row gathers, scan, K5 slice gather/scatter."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gist_oracle as O
+from tests.util import canonical_csr_from_gist, ograph, random_graph
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('symmetric', [False, True])
+@pytest.mark.parametrize('n_b', [1, 37, 500])
+def test_subgraph_bit_exact(symmetric, n_b):
+    from gist_b200 import GistGraph
+    n, nnz = 2000, 60000
+    src, dst = random_graph(n, nnz, seed=n_b)
+    if symmetric:
+        src, dst = torch.cat([src, dst]), torch.cat([dst, src])
+    g = GistGraph.from_edges(src, dst, n, device='cuda')
+    g.ndata['feat'] = torch.randn(n, 602, device='cuda')
+    g.ndata['label'] = torch.randint(0, 41, (n,), device='cuda')
+    g.ndata['train_mask'] = torch.rand(n, device='cuda') < 0.5
+    rng = np.random.RandomState(0)
+    nids = rng.permutation(n)[:n_b].astype(np.int64)          # arbitrary order, unique
+    sg = g.subgraph(nids)
+    osg = ograph(src, dst, n).subgraph(nids)
+    rp, col = canonical_csr_from_gist(sg)
+    orp, ocol = osg.canonical_csr()
+    assert torch.equal(rp, orp) and torch.equal(col, ocol)
+    assert sg.number_of_edges() == osg.src.shape[0]
+    assert sg.is_symmetric() == symmetric or osg.src.shape[0] == 0
+    # csc of the batch == canonical csr of the reversed oracle graph
+    colptr, row = sg.csc()
+    rev = O.OGraph(osg.dst, osg.src, osg.n).canonical_csr()
+    nn = sg.number_of_nodes()
+    r_of_e = torch.repeat_interleave(torch.arange(nn), colptr.cpu().long()[1:] - colptr.cpu().long()[:-1])
+    key, _ = torch.sort(r_of_e * nn + row.cpu().long()[:r_of_e.shape[0]])
+    assert torch.equal(colptr.cpu().long(), rev[0]) and torch.equal(key % nn, rev[1])
+    # ndata gathered exactly, node order preserved
+    t = torch.from_numpy(nids)
+    assert torch.equal(sg.ndata['feat'].cpu(), g.ndata['feat'].cpu()[t])
+    assert torch.equal(sg.ndata['label'].cpu(), g.ndata['label'].cpu()[t])
+    assert torch.equal(sg.ndata['train_mask'].cpu(), g.ndata['train_mask'].cpu()[t])
+    assert torch.equal(sg.ndata['_ID'].cpu(), t)
+    assert torch.equal(sg.inv_in_degree().cpu(), O.sage_norm(osg).reshape(-1))
+    # scratch restored: a second build gives the same answer
+    sg2 = g.subgraph(nids)
+    assert torch.equal(sg2.rowptr, sg.rowptr) and torch.equal(sg2.col, sg.col)
+
+
+def test_subgraph_empty():
+    from gist_b200 import GistGraph
+    src, dst = random_graph(100, 500, seed=0)
+    g = GistGraph.from_edges(src, dst, 100, device='cuda')
+    sg = g.subgraph(np.zeros(0, dtype=np.int64))
+    assert sg.number_of_nodes() == 0 and sg.number_of_edges() == 0
+
+
+@pytest.mark.parametrize('n', [0, 1, 31, 2048, 2049, 8192, 8193, 100000, 1234567])
+def test_exclusive_scan(n):
+    from gist_b200 import ops
+    x = torch.randint(0, 50, (n,), dtype=torch.int32)
+    got = ops.exclusive_scan(x.cuda()).cpu()
+    ref = torch.zeros(n + 1, dtype=torch.int64)
+    ref[1:] = torch.cumsum(x.long(), 0)
+    assert torch.equal(got.long(), ref)
+
+
+def test_cluster_iter_matches_oracle_batches():
+    import random
+    from gist_b200 import ClusterIter, synth
+    ds = synth.make('reddit', seed=0, device='cpu', scale=0.01)
+    g = synth.to_gist_graph(ds, device='cuda')
+    train_nid = np.nonzero(ds.train_mask.numpy())[0].astype(np.int64)
+    psize, bs = ds.part.max().item() + 1, 3
+    for mode in ('step', 'epoch'):
+        random.seed(3)
+        it = ClusterIter('', g, psize, bs, train_nid, use_pp=False, h2d=mode)
+        # oracle: same training graph, same partition, same python-random stream
+        og = ograph(ds.src, ds.dst, ds.num_nodes).subgraph(train_nid)
+        part = ds.part[torch.from_numpy(train_nid)].numpy()
+        order = np.argsort(part, kind='stable')
+        bounds = np.searchsorted(part[order], np.arange(psize + 1))
+        par_li = [order[bounds[p]:bounds[p + 1]].astype(np.int64) for p in range(psize)]
+        random.seed(3)
+        random.shuffle(par_li)
+        for epoch in range(2):
+            for i, batch in enumerate(it):
+                nids = O.batch_node_ids(par_li, i, psize, bs)
+                assert torch.equal(batch.ndata['_ID'].cpu(), torch.from_numpy(nids))
+                osg = og.subgraph(nids)
+                rp, col = canonical_csr_from_gist(batch)
+                orp, ocol = osg.canonical_csr()
+                assert torch.equal(rp, orp) and torch.equal(col, ocol)
+            assert i == len(it) - 1
+            random.shuffle(par_li)     # sampler.py:92
+
+
+@pytest.mark.parametrize('shape', [(64, 48), (300, 1204), (41, 512)])
+def test_slice_gather_scatter(shape):
+    from gist_b200 import ops
+    R, C = shape
+    torch.manual_seed(0)
+    W = torch.randn(R, C)
+    ridx = torch.randperm(R)[:R // 2]
+    cidx = torch.randperm(C)[:C // 3]
+    Wd = W.cuda()
+    for r, c in [(ridx, cidx), (ridx, None), (None, cidx), (None, None)]:
+        ref = W
+        if r is not None:
+            ref = ref[r, :]
+        if c is not None:
+            ref = ref[:, c]
+        got = ops.slice_gather(Wd, None if r is None else r.cuda(), None if c is None else c.cuda())
+        assert torch.equal(got.cpu(), ref)
+        new = torch.randn_like(ref)
+        D = W.clone()
+        if r is not None and c is not None:
+            tmp = D[:, c]
+            tmp[r, :] = new
+            D[:, c] = tmp
+        elif r is not None:
+            D[r, :] = new
+        elif c is not None:
+            D[:, c] = new
+        else:
+            D = new.clone()
+        Dd = W.clone().cuda()
+        ops.slice_scatter_(Dd, new.cuda(), None if r is None else r.cuda(), None if c is None else c.cuda())
+        assert torch.equal(Dd.cpu(), D)
+    b = torch.randn(R)
+    assert torch.equal(ops.slice_gather(b.cuda(), None, ridx.cuda()).cpu(), b[ridx])

@@ -1,0 +1,166 @@
+"""Module-level parity: drop-in layers / containers on the CUDA path vs the
+functional CPU oracle (forward and gradients), eval mode and injected dropout."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import gist_oracle as O
+from tests.util import assert_close, ograph, random_graph
+
+pytestmark = pytest.mark.gpu
+
+
+def _graphs(n, nnz, seed, loops=True):
+    from gist_b200 import GistGraph
+    src, dst = random_graph(n, nnz, seed=seed)
+    if loops:      # GraphConv refuses zero-in-degree nodes, as DGL does
+        ar = torch.arange(n)
+        src, dst = torch.cat([src, ar]), torch.cat([dst, ar])
+    return GistGraph.from_edges(src, dst, n, device='cuda'), ograph(src, dst, n)
+
+
+def _params64(model):
+    return [(l.linear.weight.detach().double().cpu().requires_grad_(True),
+             l.linear.bias.detach().double().cpu().requires_grad_(True)) for l in model.layers]
+
+
+@pytest.mark.parametrize('cfg', [(602, 256, 41, 2, True), (100, 64, 47, 3, True), (50, 32, 5, 1, False)])
+def test_sage_gcn_forward_backward(cfg):
+    from gist_b200 import SageGCN
+    fin, hid, ncls, L, ln = cfg
+    n = 800
+    g, og = _graphs(n, 12000, seed=L, loops=False)
+    torch.manual_seed(0)
+    model = SageGCN(fin, hid, ncls, L, F.relu, 0.0, ln, False, False, 1, True).cuda()
+    x = torch.randn(n, fin)
+    y = torch.randint(0, ncls, (n,))
+    g.ndata['feat'] = x.cuda()
+    params = _params64(model)
+    ref = O.sage_gcn_forward(og, x.double(), params, ln)
+    F.cross_entropy(ref, y).backward()
+    out = model(g)
+    F.cross_entropy(out, y.cuda()).backward()
+    assert_close(out, ref, rtol=5e-5, what='logits')
+    for l, (w, b) in zip(model.layers, params):
+        assert_close(l.linear.weight.grad, w.grad, rtol=1e-4, what='dW')
+        assert_close(l.linear.bias.grad, b.grad, rtol=1e-4, what='db')
+
+
+def test_ist_sage_layer_train_mode_injected_dropout():
+    """Train-mode parity with the SAME dropout mask: torch's Philox stream cannot be
+    reproduced on the CPU, so the mask is captured from the CUDA run and injected
+    into the oracle."""
+    from gist_b200 import ISTSAGELayer
+    n, fin, fout = 500, 64, 32
+    g, og = _graphs(n, 6000, seed=4, loops=False)
+    torch.manual_seed(0)
+    layer = ISTSAGELayer(fin, fout, 0.5, True, activation=F.relu).cuda().train()
+    masks = []
+    layer.dropout.register_forward_hook(lambda m, i, o: masks.append((o / i[0]).nan_to_num(0.0)))
+    x = torch.randn(n, fin)
+    out = layer(g, x.cuda())
+    mask = masks[0].cpu().double()
+    # entries where the input was exactly 0 give 0/0 -> 0 in the mask; harmless (z*mask = 0)
+    ref = O.ist_sage_layer(og, x.double(), layer.linear.weight.detach().double().cpu(),
+                           layer.linear.bias.detach().double().cpu(), True, F.relu, mask)
+    assert_close(out, ref, rtol=5e-5, what='train-mode layer')
+
+
+@pytest.mark.parametrize('dims', [(1433, 16), (32, 32), (16, 7), (8, 24)])
+@pytest.mark.parametrize('act', [None, 'relu', 'tanh'])
+def test_graph_conv(dims, act):
+    from gist_b200 import GraphConv
+    fin, fout = dims
+    n = 700
+    g, og = _graphs(n, 8000, seed=fin)
+    actf = {None: None, 'relu': F.relu, 'tanh': torch.tanh}[act]
+    torch.manual_seed(0)
+    conv = GraphConv(fin, fout, activation=actf).cuda()
+    with torch.no_grad():
+        conv.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(n, fin)
+    w64 = conv.weight.detach().double().cpu().requires_grad_(True)
+    b64 = conv.bias.detach().double().cpu().requires_grad_(True)
+    x64 = x.double().requires_grad_(True)
+    ref = O.graph_conv(og, x64, w64, b64, actf)
+    wy = torch.randn(n, fout, dtype=torch.double)
+    (ref * wy).sum().backward()
+    xg = x.cuda().requires_grad_(True)
+    out = conv(g, xg)
+    (out * wy.float().cuda()).sum().backward()
+    assert_close(out, ref, rtol=5e-5, what='GraphConv fwd')
+    assert_close(xg.grad, x64.grad, rtol=1e-4, what='dX')
+    assert_close(conv.weight.grad, w64.grad, rtol=1e-4, what='dW')
+    assert_close(conv.bias.grad, b64.grad, rtol=1e-4, what='db')
+
+
+def test_graph_conv_zero_in_degree_raises():
+    from gist_b200 import GistGraph, GraphConv, GistError
+    g = GistGraph.from_edges(torch.tensor([0, 1]), torch.tensor([1, 2]), 3, device='cuda')
+    conv = GraphConv(4, 4).cuda()
+    with pytest.raises(GistError):
+        conv(g, torch.randn(3, 4, device='cuda'))
+
+
+@pytest.mark.parametrize('split', [(False, False, 1), (False, True, 4), (True, True, 2)])
+def test_graphconv_gcn_container(split):
+    from gist_b200 import GCN
+    si, so, k = split
+    fin, hid, ncls, L = 48, 32, 3, 2
+    n = 600
+    g, og = _graphs(n, 7000, seed=9)
+    torch.manual_seed(0)
+    model = GCN(g, fin, hid, ncls, L, F.relu, 0.0, True, si, so, k).cuda()
+    fin_eff = fin // k if si else fin
+    x = torch.randn(n, fin_eff)
+    params = [(l.weight.detach().double().cpu(), l.bias.detach().double().cpu()) for l in model.layers]
+    ref = O.graphconv_gcn_forward(og, x.double(), params, True)
+    out = model(x.cuda())
+    assert_close(out, ref, rtol=5e-5, what='GCN(GraphConv) logits')
+    assert list(model.state_dict().keys())[:2] == ['layers.0.weight', 'layers.0.bias']
+
+
+def test_wrapper_dispatch_sync_single_process_matches_oracle():
+    """m virtual sites simulated on one GPU: dispatch each site with the device K5
+    gather, perturb, merge with the K5 scatter; compare with the oracle algebra."""
+    import random
+    from types import SimpleNamespace
+    from gist_b200.ist import DistributedGNNWrapper, create_partition
+    m, hid, L, fin, ncls = 4, 32, 2, 20, 5
+    args = SimpleNamespace(rank=0, num_subnet=m, n_hidden=hid, n_layers=L, dropout=0.0,
+                           use_layernorm=True)
+    torch.manual_seed(0)
+    w = DistributedGNNWrapper(args, None, fin, ncls, torch.device('cuda'))
+    base0 = [(l.linear.weight.detach().cpu().clone(), l.linear.bias.detach().cpu().clone())
+             for l in w.base_model.layers]
+    random.seed(7)
+    parts = [create_partition(m, hid) for _ in range(L)]
+    random.seed(7)
+    oparts = [O.create_partition(m, hid) for _ in range(L)]
+    for a, b in zip(parts, oparts):
+        for (i1, f1), (i2, f2) in zip(a, b):
+            assert torch.equal(i1, i2) and torch.equal(f1, f2)
+    dparts = w._to_dev(parts)
+    flats, subs = [], []
+    for site in range(m):
+        w.args.rank = site
+        w._dispatch_local(dparts)
+        osub = O.sage_dispatch(base0, oparts, site)
+        for lyr, (ow, ob) in zip(w.sub_model.layers, osub):
+            assert torch.equal(lyr.linear.weight.detach().cpu(), ow)
+            assert torch.equal(lyr.linear.bias.detach().cpu(), ob)
+        # "train": deterministic perturbation
+        trained = []
+        for lyr in w.sub_model.layers:
+            lyr.linear.weight.data = lyr.linear.weight.data * 1.5 + site
+            lyr.linear.bias.data = lyr.linear.bias.data - 0.25 * (site + 1)
+            trained.append((lyr.linear.weight.detach().cpu().clone(), lyr.linear.bias.detach().cpu().clone()))
+        subs.append(trained)
+        flats.append(w._pack().clone())
+    w.args.rank = 0
+    w.current_partition = dparts
+    w._merge(torch.stack(flats), dparts)
+    ref = O.sage_sync(base0, oparts, subs)
+    for lyr, (rw, rb) in zip(w.base_model.layers, ref):
+        assert torch.equal(lyr.linear.weight.detach().cpu(), rw)
+        assert_close(lyr.linear.bias.detach(), rb, rtol=1e-6)

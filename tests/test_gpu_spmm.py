@@ -1,0 +1,162 @@
+"""K1/K2 parity: CUDA SpMM (through the C-ABI) vs the CPU oracle."""
+import pytest
+import torch
+
+from oracle import gist_oracle as O
+from tests.util import assert_close, ograph, powerlaw_graph, random_graph
+
+pytestmark = pytest.mark.gpu
+
+DIMS = [1, 3, 7, 16, 32, 41, 64, 100, 128, 256, 602]
+
+
+def _gist(src, dst, n):
+    from gist_b200 import GistGraph
+    return GistGraph.from_edges(src, dst, n, device='cuda')
+
+
+@pytest.mark.parametrize('d', DIMS)
+def test_copy_src_sum_matches_oracle(d):
+    from gist_b200 import ops
+    n, nnz = 1000, 20000
+    src, dst = random_graph(n, nnz, seed=d, isolated=17)
+    g = _gist(src, dst, n)
+    og = ograph(src, dst, n)
+    torch.manual_seed(d)
+    x = torch.randn(n, d)
+    ref = O.copy_src_sum(og, x)
+    ref64 = O.copy_src_sum(og, x.double())
+    got = ops.copy_src_sum(g, x.cuda())
+    assert_close(got, ref, what='fp32 oracle d=%d' % d)
+    assert_close(got, ref64, what='fp64 oracle d=%d' % d)
+    # zero in-degree rows are exactly zero
+    assert (got[n - 17:] == 0).all()
+
+
+@pytest.mark.parametrize('d', [16, 100, 256, 602])
+def test_powerlaw_rows(d):
+    from gist_b200 import ops
+    n = 3000
+    src, dst = powerlaw_graph(n, 40, seed=5)
+    g = _gist(src, dst, n)
+    og = ograph(src, dst, n)
+    assert int(og.in_degrees().max()) > 2000      # a few very heavy rows
+    x = torch.randn(n, d)
+    assert_close(ops.copy_src_sum(g, x.cuda()), O.copy_src_sum(og, x.double()), what='powerlaw')
+
+
+@pytest.mark.parametrize('d', [7, 64, 130, 602])
+@pytest.mark.parametrize('flags', [0, 2, 4])
+def test_fused_epilogue(d, flags):
+    """act(t * A(s*X) + addend + bias) and the self-copy output, all vector widths."""
+    from gist_b200 import ops
+    n, nnz = 700, 9000
+    src, dst = random_graph(n, nnz, seed=3)
+    g = _gist(src, dst, n)
+    og = ograph(src, dst, n)
+    torch.manual_seed(0)
+    x, s, t = torch.randn(n, d), torch.rand(n) + 0.5, torch.rand(n) + 0.5
+    bias, addend = torch.randn(d), torch.randn(n, d)
+    ref = torch.relu(O.copy_src_sum(og, x.double() * s.double()[:, None]) * t.double()[:, None]
+                     + addend.double() + bias.double())
+    out = torch.full((n, 2 * d + 2), float('nan'), device='cuda')
+    xs = x.cuda()
+    y = out[:, d:2 * d]
+    self_out = out[:, :d]
+    ops.spmm_raw(g.rowptr, g.col_buffer, n, n, xs, y, src_scale=s.cuda(), dst_scale=t.cuda(),
+                 bias=bias.cuda(), addend=addend.cuda(), self_out=self_out, relu=True, flags=flags)
+    assert_close(y, ref, what='epilogue')
+    assert torch.equal(self_out.cpu(), x)
+    assert torch.isnan(out[:, 2 * d:]).all()      # nothing written outside the views
+
+
+def test_empty_and_tiny():
+    from gist_b200 import GistGraph, ops
+    # no edges at all
+    g = GistGraph.from_edges(torch.zeros(0, dtype=torch.long), torch.zeros(0, dtype=torch.long), 5,
+                             device='cuda')
+    y = ops.copy_src_sum(g, torch.ones(5, 8, device='cuda'))
+    assert (y == 0).all()
+    # hand-worked 4-node case: edges 0->1, 2->1, 2->1 (multi), 3->3 (self loop)
+    src = torch.tensor([0, 2, 2, 3])
+    dst = torch.tensor([1, 1, 1, 3])
+    g = GistGraph.from_edges(src, dst, 4, device='cuda')
+    x = torch.tensor([[1., 10.], [2., 20.], [3., 30.], [4., 40.]], device='cuda')
+    y = ops.copy_src_sum(g, x).cpu()
+    assert torch.equal(y, torch.tensor([[0., 0.], [7., 70.], [0., 0.], [4., 40.]]))
+    assert torch.equal(g.in_degrees().cpu(), torch.tensor([0, 3, 0, 1]))
+    assert torch.equal(g.out_degrees().cpu(), torch.tensor([1, 0, 2, 1]))
+    assert torch.equal(g.inv_in_degree().cpu(), torch.tensor([0., 1 / 3., 0., 1.]))
+
+
+@pytest.mark.parametrize('d', [5, 32, 602])
+def test_backward_matches_autograd_of_oracle(d):
+    """K2 (CSC transpose) gradients vs autograd through the oracle, non-symmetric graph."""
+    from gist_b200 import ops
+    n, nnz = 600, 7000
+    src, dst = random_graph(n, nnz, seed=11, isolated=5)
+    g = _gist(src, dst, n)
+    assert not g.is_symmetric()
+    og = ograph(src, dst, n)
+    torch.manual_seed(1)
+    x = torch.randn(n, d, dtype=torch.double, requires_grad=True)
+    w = torch.randn(n, 2 * d, dtype=torch.double)
+    zr = torch.cat((x, O.copy_src_sum(og, x) * O.sage_norm(og, torch.double)), 1)
+    (zr * w).sum().backward()
+    xg = x.detach().float().cuda().requires_grad_(True)
+    z = ops.sage_concat(g, xg)
+    (z * w.float().cuda()).sum().backward()
+    assert_close(z, zr, what='sage_concat fwd')
+    assert_close(xg.grad, x.grad, what='sage_concat bwd')
+
+    # scaled SpMM with bias + relu
+    s, t = torch.rand(n, dtype=torch.double) + .5, torch.rand(n, dtype=torch.double) + .5
+    b = torch.randn(d, dtype=torch.double, requires_grad=True)
+    x2 = torch.randn(n, d, dtype=torch.double, requires_grad=True)
+    yr = torch.relu(O.copy_src_sum(og, x2 * s[:, None]) * t[:, None] + b)
+    wy = torch.randn(n, d, dtype=torch.double)
+    (yr * wy).sum().backward()
+    x2g = x2.detach().float().cuda().requires_grad_(True)
+    bg = b.detach().float().cuda().requires_grad_(True)
+    y = ops.gspmm(g, x2g, s.float().cuda(), t.float().cuda(), bg, True)
+    (y * wy.float().cuda()).sum().backward()
+    assert_close(y, yr, what='gspmm fwd')
+    assert_close(x2g.grad, x2.grad, what='gspmm dX')
+    assert_close(bg.grad, b.grad, rtol=1e-4, what='gspmm dbias')
+
+
+def test_update_all_duck_type():
+    import gist_b200.function as fn
+    n = 300
+    src, dst = random_graph(n, 3000, seed=2)
+    g = _gist(src, dst, n).local_var()
+    x = torch.randn(n, 12)
+    g.ndata['h'] = x.cuda()
+    g.update_all(fn.copy_src(src='h', out='m'), fn.sum(msg='m', out='h'))
+    assert_close(g.ndata.pop('h'), O.copy_src_sum(ograph(src, dst, n), x.double()))
+
+
+def test_no_cpu_path():
+    from gist_b200 import GistGraph, ops
+    from gist_b200._lib import GistLibraryError
+    g = GistGraph.from_edges(torch.tensor([0]), torch.tensor([1]), 2)
+    with pytest.raises(GistLibraryError):
+        ops.copy_src_sum(g, torch.ones(2, 4))
+
+
+def test_full_size_linearity_and_degree_identity():
+    """Size-independent properties at a large size the oracle cannot time: A·1 equals
+    the in-degree vector exactly, and A(ax+by) = aAx + bAy."""
+    from gist_b200 import ops, synth
+    ds = synth.make('reddit', seed=0, device='cuda', scale=0.1)
+    from gist_b200 import GistGraph
+    g = GistGraph.from_edges(ds.src, ds.dst, ds.num_nodes)
+    n = ds.num_nodes
+    ones = torch.ones(n, 64, device='cuda')
+    y = ops.copy_src_sum(g, ones)
+    assert torch.equal(y[:, 0], g.in_degrees().float())       # integers < 2^24: exact
+    assert (y == y[:, :1]).all()
+    x1, x2 = torch.randn(n, 602, device='cuda'), torch.randn(n, 602, device='cuda')
+    lhs = ops.copy_src_sum(g, 2 * x1 - 3 * x2)
+    rhs = 2 * ops.copy_src_sum(g, x1) - 3 * ops.copy_src_sum(g, x2)
+    assert_close(lhs, rhs, rtol=1e-4, what='linearity')
