@@ -50,8 +50,12 @@ class DistributedGNNWrapper(torch.nn.Module):
 
     args needs: rank, num_subnet, n_hidden, n_layers, dropout, use_layernorm."""
 
-    def __init__(self, args, g, in_feats, n_classes, device):
+    def __init__(self, args, g, in_feats, n_classes, device, slice_ops=None):
         super().__init__()
+        # (gather, scatter_) executors for the 2-D slices; the product path is the CUDA
+        # K5 kernels.  Tests of the host-side plan / pack / all-gather logic on CPU
+        # (gloo) inject a checker here; nothing in the package does.
+        self._gather, self._scatter_ = slice_ops or (ops.slice_gather, ops.slice_scatter_)
         self.args = args
         self.g = g
         self.in_feats = in_feats
@@ -104,11 +108,11 @@ class DistributedGNNWrapper(torch.nn.Module):
                 ridx, cidx = self._slice_for(l, site, parts)
                 base = self.base_model.layers[l].linear
                 sub = self.sub_model.layers[l].linear
-                sub.weight.data = ops.slice_gather(base.weight.data, ridx, cidx)
+                sub.weight.data = self._gather(base.weight.data, ridx, cidx)
                 if l == L:
                     sub.bias.data = base.bias.data.clone()      # shared, full (…distrib.py:217-219)
                 else:
-                    sub.bias.data = ops.slice_gather(base.bias.data, None, ridx)
+                    sub.bias.data = self._gather(base.bias.data, None, ridx)
 
     def ini_sync_dispatch_model(self):
         parts = self._to_dev(self.sample_partitions())
@@ -132,8 +136,9 @@ class DistributedGNNWrapper(torch.nn.Module):
         with torch.no_grad():
             flat = self._pack()
             if _dist_ready() and m > 1:
-                gathered = torch.empty((m, flat.numel()), dtype=flat.dtype, device=flat.device)
-                dist.all_gather_into_tensor(gathered, flat)
+                out = torch.empty(m * flat.numel(), dtype=flat.dtype, device=flat.device)
+                dist.all_gather_into_tensor(out, flat)       # ONE collective for all slices
+                gathered = out.view(m, flat.numel())
             else:
                 assert m == 1, 'num_subnet > 1 needs an initialised process group'
                 gathered = flat.unsqueeze(0)
@@ -157,9 +162,9 @@ class DistributedGNNWrapper(torch.nn.Module):
                 b = row[off:off + bn]; off += bn
                 ridx, cidx = self._slice_for(l, site, parts)
                 base = self.base_model.layers[l].linear
-                ops.slice_scatter_(base.weight.data, w, ridx, cidx)
+                self._scatter_(base.weight.data, w, ridx, cidx)
                 if l == L:
                     last_bias = b.clone() if last_bias is None else last_bias + b   # rank order
                 else:
-                    ops.slice_scatter_(base.bias.data, b, None, ridx)
+                    self._scatter_(base.bias.data, b, None, ridx)
         self.base_model.layers[L].linear.bias.data = last_bias / m

@@ -21,7 +21,7 @@ class GraphConv(nn.Module):
             nn.init.zeros_(self.bias)
 
     def forward(self, graph, feat):
-        from .. import DGLError, function as fn
+        from ... import DGLError, function as fn
         graph = graph.local_var()
         if not self._allow_zero_in_degree and (graph.in_degrees() == 0).any():
             raise DGLError('There are 0-in-degree nodes in the graph, output for those nodes '

@@ -95,7 +95,7 @@ def test_cluster_iter_matches_oracle_batches():
                 orp, ocol = osg.canonical_csr()
                 assert torch.equal(rp, orp) and torch.equal(col, ocol)
             assert i == len(it) - 1
-            random.shuffle(par_li)     # sampler.py:92
+            rng.shuffle(par_li)        # sampler.py:92
 
 
 @pytest.mark.parametrize('shape', [(64, 48), (300, 1204), (41, 512)])
