@@ -1,0 +1,470 @@
+#!/usr/bin/env python
+"""bench.py — Reddit-shape GIST GraphSAGE training throughput (epochs/s) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo (CUDA path)
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # CPU port of the reference path
+
+For N > 1 launch under torchrun (one rank per GPU, NCCL):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One STEP = one cluster-batch training step of the rank's sub-GCN (device batch build ->
+forward -> CE -> backward -> Adam), with the GIST sync + re-dispatch every
+--iter-per-site steps inside the timed region.  One EPOCH = psize // batch_size steps.
+With m = N sub-GCNs the reference runs n_epochs // m local epochs per rank
+(cluster_gcn_ist_distrib.py:385), so one local pass on every rank counts as m epochs:
+value = N * K / steps_per_epoch / seconds  (whole job).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'reddit_shape_gist_graphsage_epochs_per_s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=150)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='gist', choices=['gist', 'reference'])
+    ap.add_argument('--shape', default='reddit')
+    ap.add_argument('--scale', type=float, default=1.0, help='<1 shrinks the graph (debug only; reported)')
+    ap.add_argument('--n-hidden', type=int, default=256)
+    ap.add_argument('--n-layers', type=int, default=2)
+    ap.add_argument('--psize', type=int, default=1500)
+    ap.add_argument('--batch-size', type=int, default=20)
+    ap.add_argument('--dropout', type=float, default=0.2)
+    ap.add_argument('--lr', type=float, default=1e-2)
+    ap.add_argument('--weight-decay', type=float, default=5e-4)
+    ap.add_argument('--iter-per-site', type=int, default=100)
+    ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--cpu-steps', type=int, default=6, help='CPU-baseline sample size (steps)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-eval-spmm', action='store_true')
+    ap.add_argument('--ncu', default='', choices=['', 'steps', 'fullgraph'],
+                    help='bracket that region with cudaProfilerStart/Stop (ncu --profile-from-start off)')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.index = index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, names = [], ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out['sm_max_mhz'] = float(r[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.strip().lower() == 'active':
+                    reasons.add(nm)
+        if sm:
+            out['sm_mhz'] = float(np.median(sm))
+        out['reasons'] = sorted(reasons)
+        out['samples'] = len(sm)
+        return out
+
+
+def spmm_bytes(nnz, n_dst, n_src, d, scaled):
+    """Algorithmic bytes of one SpMM launch (SURVEY.md §8d / BASELINE.md §4) and the
+    compulsory lower bound."""
+    alg = 4 * nnz * d + 4 * n_dst * d + 4 * nnz + 4 * (n_dst + 1) + 4 * n_dst * (1 if scaled else 0)
+    comp = 4 * n_src * d + 4 * n_dst * d + 4 * nnz + 4 * (n_dst + 1)
+    return alg, comp
+
+
+# ------------------------------------------------------------------ gist arm --
+def run_gist(a):
+    import torch
+    import torch.distributed as dist
+    import gist_b200 as gb
+    from gist_b200 import _lib, ops, synth
+    from gist_b200.train import make_optimizer, train_step
+    from types import SimpleNamespace
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert world == a.gpus, 'launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)' % (a.gpus, world)
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert a.warmup >= 3, 'timing rules: warm-up >= 3 steps'
+    assert a.n_hidden % world == 0
+
+    # same seeds on every rank (…distrib.py:570-572): partitions and batch order are
+    # derived locally, never communicated
+    torch.manual_seed(a.seed)
+    np.random.seed(a.seed)
+    random.seed(a.seed)
+
+    t_setup = time.time()
+    ds = synth.make(a.shape, seed=0, device=dev, scale=a.scale)
+    g = synth.to_gist_graph(ds)
+    n_nodes, n_edges = ds.num_nodes, int(ds.src.shape[0])
+    in_feats, n_classes = ds.feat.shape[1], ds.num_classes
+    train_nid = torch.nonzero(ds.train_mask).reshape(-1).cpu().numpy().astype(np.int64)
+    psize = a.psize if a.scale == 1.0 else int(ds.part.max().item()) + 1
+    del ds
+    wargs = SimpleNamespace(rank=rank, num_subnet=world, n_hidden=a.n_hidden, n_layers=a.n_layers,
+                            dropout=a.dropout, use_layernorm=True)
+
+    def fresh(h2d):
+        """ClusterIter + wrapper in the state the reference has when train() starts."""
+        random.seed(a.seed)
+        torch.manual_seed(a.seed)
+        it = gb.ClusterIter('', g, psize, a.batch_size, train_nid, use_pp=False, h2d=h2d)
+        w = gb.DistributedGNNWrapper(wargs, g, in_feats, n_classes, dev)
+        w.ini_sync_dispatch_model()
+        return it, w
+
+    class Loop:
+        """The reference's step loop (…distrib.py:394-427) unrolled into next_step()."""
+
+        def __init__(self, it, w, readback):
+            self.it, self.w, self.readback = it, w, readback
+            self.e, self.total_iter, self.opt = 0, 0, None
+            self.iter = iter(it)
+            self.running_loss = 0.0
+            self.loss_acc = torch.zeros((), device=dev)
+            self.nodes = 0
+
+        def next_step(self):
+            try:
+                cluster = next(self.iter)
+            except StopIteration:
+                self.e += 1
+                self.iter = iter(self.it)
+                cluster = next(self.iter)
+            if self.total_iter % a.iter_per_site == 0:
+                if self.e > 0:                            # …distrib.py:401 (never re-dispatched in epoch 0)
+                    if world > 1:
+                        dist.barrier()
+                    self.w.dispatch_model()
+                self.w.sub_model.train()
+                self.opt = make_optimizer(self.w.sub_model.parameters(), a.lr, a.weight_decay)
+            loss = train_step(self.w.sub_model, self.opt, cluster)
+            self.nodes += cluster.number_of_nodes()
+            if self.readback:
+                self.running_loss += float(loss)          # D2H + sync every step, as the reference
+            else:
+                self.loss_acc += loss
+            self.total_iter += 1
+            if self.total_iter % a.iter_per_site == 0:
+                if world > 1:
+                    dist.barrier()
+                self.w.sync_model()
+
+    def timed(loop, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(k):
+            loop.next_step()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        launches = torch.tensor([_lib.launch_count() - l0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+        return ms.item(), int(launches.item())
+
+    steps_per_epoch = psize // a.batch_size
+
+    # ---- device-resident arm: node-id lists already in HBM, no loss readback -------
+    it, w = fresh('epoch')
+    loop = Loop(it, w, readback=False)
+    for _ in range(a.warmup):
+        loop.next_step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if a.ncu == 'steps':
+        torch.cuda.profiler.start()
+    ms, launches = timed(loop, a.steps)
+    if a.ncu == 'steps':
+        torch.cuda.profiler.stop()
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * a.steps / steps_per_epoch / (ms / 1e3)
+    final_loss = float(loop.loss_acc) / max(a.steps + a.warmup, 1)
+
+    # ---- instrumented pass: per-launch SpMM durations with CUDA events --------------
+    ops.SPMM_PROFILE = []
+    prof_steps = min(a.steps, 30)
+    torch.cuda.synchronize()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(prof_steps):
+        loop.next_step()
+    pe1.record()
+    torch.cuda.synchronize()
+    prof, ops.SPMM_PROFILE = ops.SPMM_PROFILE, None
+    prof_ms = pe0.elapsed_time(pe1)
+    alg_b = comp_b = spmm_ms = 0.0
+    by_d = {}
+    nnz_cache = {}
+    for r in prof:
+        key = r['rowptr'].data_ptr()
+        if key not in nnz_cache:
+            nnz_cache[key] = int(r['rowptr'][r['n_dst']].item())
+        nnz = nnz_cache[key]
+        t = r['ev0'].elapsed_time(r['ev1'])
+        ab, cb = spmm_bytes(nnz, r['n_dst'], r['n_src'], r['d'], r['scaled'])
+        alg_b += ab; comp_b += cb; spmm_ms += t
+        e = by_d.setdefault(r['d'], [0, 0.0, 0.0])
+        e[0] += 1; e[1] += ab; e[2] += t
+    peak, peak_src = peaks()
+    n_l = max(len(prof), 1)
+    achieved = alg_b / 1e9 / (spmm_ms / 1e3) if spmm_ms > 0 else 0.0
+    roofline = {
+        'bound': 'hbm', 'kernel': 'spmm_csr_kernel (all %d launches/step, fwd + transpose)' % (len(prof) // max(prof_steps, 1)),
+        'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4),
+        'traffic': None, 'peak_source': peak_src,
+        'bytes_per_launch': round(alg_b / n_l), 'compulsory_bytes_per_launch': round(comp_b / n_l),
+        'us_per_launch': round(spmm_ms * 1e3 / n_l, 2),
+        'share_of_step': round(spmm_ms / prof_ms, 4) if prof_ms > 0 else None,
+        'by_width': {str(d): {'launches_per_step': v[0] / prof_steps, 'GBps': round(v[1] / 1e9 / (v[2] / 1e3), 1),
+                              'us': round(v[2] * 1e3 / v[0], 2)} for d, v in sorted(by_d.items())},
+        'note': 'cluster batches (<=5 MB of features) are L2-resident: algorithmic gather bytes are served by '
+                'L2, so achieved can exceed the HBM copy peak; see roofline_fullgraph for the HBM-bound case',
+    }
+
+    # ---- end-to-end arm: node ids from pinned host memory + loss readback every step --
+    it2, w2 = fresh('step')
+    loop2 = Loop(it2, w2, readback=True)
+    for _ in range(a.warmup):
+        loop2.next_step()
+    h2d0 = it2.h2d_bytes
+    ms2, _ = timed(loop2, a.steps)
+    e2e = {'value': round(world * a.steps / steps_per_epoch / (ms2 / 1e3), 4), 'unit': 'epochs/s',
+           'h2d_bytes_per_step': int((it2.h2d_bytes - h2d0) / a.steps), 'd2h_bytes_per_step': 4,
+           'ms_per_step': round(ms2 / a.steps, 4),
+           'what': 'public API (ClusterIter -> sub_model -> loss): batch node ids copied from pinned host '
+                   'memory every step, float(loss) read back every step; graph + features resident in HBM'}
+
+    # ---- the HBM-bound case: full-graph SpMM that evaluate() runs (rank 0) -------------
+    full = None
+    if rank == 0 and not a.no_eval_spmm:
+        full = {}
+        n = g.number_of_nodes()
+        for d in (in_feats, a.n_hidden):
+            x = torch.randn(n, d, device=dev)
+            y = torch.empty(n, d, device=dev)
+            best = {}
+            for name, fl in (('auto', 0), ('narrow', _lib.SPMM_NARROW), ('wide', _lib.SPMM_WIDE)):
+                for _ in range(2):
+                    ops.spmm_raw(g.rowptr, g.col_buffer, n, n, x, y, dst_scale=g.inv_in_degree(), flags=fl)
+                torch.cuda.synchronize()
+                ts = []
+                if a.ncu == 'fullgraph' and name == 'auto':
+                    torch.cuda.profiler.start()
+                    ops.spmm_raw(g.rowptr, g.col_buffer, n, n, x, y, dst_scale=g.inv_in_degree(), flags=fl)
+                    torch.cuda.synchronize()
+                    torch.cuda.profiler.stop()
+                for _ in range(5):
+                    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    f0.record()
+                    ops.spmm_raw(g.rowptr, g.col_buffer, n, n, x, y, dst_scale=g.inv_in_degree(), flags=fl)
+                    f1.record()
+                    torch.cuda.synchronize()
+                    ts.append(f0.elapsed_time(f1))
+                best[name] = float(np.mean(ts))
+            ab, cb = spmm_bytes(n_edges, n, n, d, True)
+            t = best['auto']
+            full['d%d' % d] = {'ms': round(t, 3), 'achieved': round(ab / 1e9 / (t / 1e3), 1), 'peak': peak,
+                               'unit': 'GB/s', 'frac': round(ab / 1e9 / (t / 1e3) / peak, 4),
+                               'algorithmic_bytes': ab, 'compulsory_bytes': cb,
+                               'ms_by_variant': {k: round(v, 3) for k, v in best.items()},
+                               'flush': 'operand (%.0f MB) larger than L2' % (4 * n * d / 1e6)}
+            del x, y
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_baseline(a, it.g, steps_per_epoch, it)
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': round(value, 4), 'unit': 'epochs/s', 'n_gpus': world,
+            'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': round(ms / a.steps, 4),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {
+                'workload': 'configs[2]: Cluster-GCN GraphSAGE on a Reddit-shaped synthetic graph (%d nodes, %d '
+                            'directed edges, %d feats, %d parts, batch %d parts), hidden %d, %d layers, GIST m=%d '
+                            'sub-GCNs (one per GPU), iter_per_site %d' % (
+                                n_nodes, n_edges, in_feats, psize, a.batch_size, a.n_hidden, a.n_layers + 1,
+                                world, a.iter_per_site),
+                'steps_per_epoch': steps_per_epoch, 'num_subnet': world, 'scale': a.scale,
+                'epoch_accounting': 'm ranks x one local pass = m epochs (reference: local_epochs = n_epochs // num_subnet)',
+                'l2': 'inputs larger than L2: every step gathers a different ~%d-node batch from the %.0f MB '
+                      'training feature matrix' % (loop.nodes // max(loop.total_iter, 1),
+                                                   4.0 * it.g.number_of_nodes() * in_feats / 1e6),
+                'gemm': 'cuBLAS fp32 via torch (library GEMM; tcgen05 GEMM is the ultra-wide config, not this one)',
+                'loss_after': round(final_loss, 4),
+            },
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
+            'clocks': clocks, 'roofline_fullgraph': full,
+            'setup_s': round(time.time() - t_setup, 1),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(a, train_g, steps_per_epoch, it, threads=None):
+    """Oracle-side CPU port of the reference step, timed on this box's host cores on a
+    bounded sample (a.cpu_steps steps) of the same batches."""
+    import torch
+    from oracle import cpu_reference as R
+    if threads:
+        torch.set_num_threads(threads)
+    rowptr = train_g.rowptr.cpu().numpy().astype(np.int64)
+    col = train_g.col.cpu().numpy().astype(np.int64)
+    feat = train_g.ndata['feat'].cpu()
+    label = train_g.ndata['label'].cpu()
+    world = max(int(os.environ.get('WORLD_SIZE', '1')), 1)
+    tr = R.CpuClusterTrainer(rowptr, col, feat, label, feat.shape[1], a.n_hidden, int(label.max()) + 1,
+                             a.n_layers, num_subnet=world, dropout=a.dropout, lr=a.lr,
+                             weight_decay=a.weight_decay, seed=a.seed)
+    batches = [it.batch_node_ids(i)[1] for i in range(min(a.cpu_steps + 1, len(it)))]
+    sec = R.time_steps(tr, batches, warmup=1)
+    return {'value': round(1.0 / (sec * steps_per_epoch), 5), 'unit': 'epochs/s',
+            'cores': torch.get_num_threads(), 'host_cpus': os.cpu_count(), 'kind': 'port',
+            'ms_per_step': round(sec * 1e3, 2),
+            'sample': '%d training steps of the same workload (CPU induced-subgraph per step + torch CSR SpMM '
+                      '+ autograd + Adam), extrapolated to %d steps/epoch' % (len(batches) - 1, steps_per_epoch)}
+
+
+# -------------------------------------------------------------- reference arm --
+def run_reference(a):
+    """The reference's own CPU implementation of the path cannot be installed (DGL 0.5.3
+    wheel absent); this arm times the oracle's CPU port on the host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if rank != 0:
+        return
+    import torch
+    import scipy.sparse as sp
+    from gist_b200 import synth          # synthetic-shape generator only (plain torch ops)
+    from oracle import cpu_reference as R
+    random.seed(a.seed)
+    torch.manual_seed(a.seed)
+    use_cuda = torch.cuda.is_available()
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0'))) if use_cuda else torch.device('cpu')
+    # Setup (not timed).  The same seeded generator as the gist arm, so both arms see the
+    # same graph; everything after generation is host code: none of this repo's kernels,
+    # graph object or sampler is on this arm's path.
+    ds = synth.make(a.shape, seed=0, device=dev, scale=a.scale)
+    n_nodes, n_edges, in_feats = ds.num_nodes, int(ds.src.shape[0]), ds.feat.shape[1]
+    src, dst = ds.src.cpu().numpy(), ds.dst.cpu().numpy()
+    A = sp.csr_matrix((np.ones(len(src), dtype=np.float32), (dst, src)), shape=(n_nodes, n_nodes))
+    del src, dst
+    train_nid = torch.nonzero(ds.train_mask).reshape(-1).cpu().numpy().astype(np.int64)
+    psize = a.psize if a.scale == 1.0 else int(ds.part.max().item()) + 1
+    At = A[train_nid][:, train_nid].tocsr()          # sampler.py:34 training graph
+    At.sort_indices()
+    feat, label = ds.feat.cpu()[train_nid], ds.label.cpu()[train_nid]
+    part = ds.part.cpu().numpy()[train_nid]
+    del ds, A
+    order = np.argsort(part, kind='stable')
+    bounds = np.searchsorted(part[order], np.arange(psize + 1))
+    par_li = [order[bounds[p]:bounds[p + 1]].astype(np.int64) for p in range(psize)]
+    random.shuffle(par_li)                            # sampler.py:55
+    steps_per_epoch = psize // a.batch_size
+    tr = R.CpuClusterTrainer(At.indptr.astype(np.int64), At.indices.astype(np.int64), feat, label, in_feats,
+                             a.n_hidden, int(label.max()) + 1, a.n_layers, num_subnet=world, dropout=a.dropout,
+                             lr=a.lr, weight_decay=a.weight_decay, seed=a.seed)
+
+    def batch_ids(i):
+        return np.concatenate(par_li[i * a.batch_size:(i + 1) * a.batch_size]).astype(np.int64)
+    k = min(a.steps, 40)                       # bounded sample: the CPU step is ~100 ms
+    wu = min(max(a.warmup, 1), 3)
+    batches = [batch_ids(i % steps_per_epoch) for i in range(k + wu)]
+    sec = R.time_steps(tr, batches, warmup=wu)
+    # N sub-GCNs time-share the same host cores: N local passes take N x as long
+    value = 1.0 / (sec * steps_per_epoch)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': round(value, 5), 'unit': 'epochs/s', 'n_gpus': world,
+        'steps': k, 'warmup': wu, 'ms_per_step': round(sec * 1e3, 3), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'configs[2]: Reddit-shaped synthetic graph (%d nodes, %d directed edges, %d feats, '
+                               '%d parts, batch %d), hidden %d/%d, %d layers — CPU port of the reference step '
+                               '(DGL 0.5.3 not installable)' % (n_nodes, n_edges, in_feats, psize, a.batch_size,
+                                                                  a.n_hidden, world, a.n_layers + 1),
+                   'steps_per_epoch': steps_per_epoch, 'scale': a.scale},
+        'cpu_baseline': {'value': round(value, 5), 'unit': 'epochs/s', 'cores': torch.get_num_threads(),
+                         'host_cpus': os.cpu_count(), 'kind': 'port',
+                         'sample': '%d steps (bounded sample of the epoch), all host threads' % k},
+        'e2e': {'value': round(value, 5), 'unit': 'epochs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gist(args)

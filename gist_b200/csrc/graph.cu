@@ -118,29 +118,111 @@ static int scan_launch(const int32_t *in, int32_t n, int32_t *out, void *ws, siz
 }
 
 // ------------------------------------------------------- batch builder ----
+// nids[i] < 0 is a padding sentinel: the row exists but is isolated (lets a caller pad
+// every batch to a fixed node count, e.g. for CUDA-graph replay).
+constexpr int kHeavyParentDeg = 1024;   // parent rows longer than this are split over the CTA
+constexpr int kBuildUnroll = 4;         // 4 x 32 independent (col -> node_map) loads in flight
+
 __global__ void batch_mark_kernel(const int64_t *__restrict__ nids, int32_t n_b,
                                   int32_t *__restrict__ node_map, int32_t value_is_index) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_b) node_map[nids[i]] = value_is_index ? i : -1;
+    if (i < n_b) {
+        const int64_t p = nids[i];
+        if (p >= 0) node_map[p] = value_is_index ? i : -1;
+    }
 }
 
-// One warp per batch row: count parent neighbours that are inside the batch.
+__device__ __forceinline__ int count_range(const int32_t *__restrict__ pcol,
+                                           const int32_t *__restrict__ node_map, int eb, int ee,
+                                           int lane) {
+    int cnt = 0;
+    for (int e0 = eb; e0 < ee; e0 += 32 * kBuildUnroll) {
+        int m[kBuildUnroll];
+#pragma unroll
+        for (int k = 0; k < kBuildUnroll; ++k) {
+            const int e = e0 + k * 32 + lane;
+            m[k] = (e < ee) ? __ldg(node_map + __ldg(pcol + e)) : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < kBuildUnroll; ++k) cnt += m[k] >= 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    return cnt;
+}
+
+// Order-preserving compaction of the in-batch neighbours of edges [eb, ee) to out_col[pos...].
+__device__ __forceinline__ void fill_range(const int32_t *__restrict__ pcol,
+                                           const int32_t *__restrict__ node_map, int eb, int ee,
+                                           int lane, int64_t pos, int32_t *__restrict__ out_col,
+                                           int64_t col_capacity) {
+    for (int e0 = eb; e0 < ee; e0 += 32 * kBuildUnroll) {
+        int m[kBuildUnroll];
+#pragma unroll
+        for (int k = 0; k < kBuildUnroll; ++k) {
+            const int e = e0 + k * 32 + lane;
+            m[k] = (e < ee) ? __ldg(node_map + __ldg(pcol + e)) : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < kBuildUnroll; ++k) {
+            const unsigned bal = __ballot_sync(0xffffffffu, m[k] >= 0);
+            if (m[k] >= 0) {
+                const int64_t w = pos + __popc(bal & ((1u << lane) - 1u));
+                if (w < col_capacity) out_col[w] = m[k];
+            }
+            pos += __popc(bal);
+        }
+    }
+}
+
+__device__ __forceinline__ void heavy_segment(int rs, int re, int warp, int &eb, int &ee) {
+    int seg = (re - rs + 7) / 8;
+    seg = (seg + 31) / 32 * 32;
+    eb = min(re, rs + warp * seg);
+    ee = min(re, eb + seg);
+}
+
+// One warp per batch row (8 rows per CTA); hub rows of the parent are counted by all
+// 8 warps of the CTA in a second phase.
 __global__ void __launch_bounds__(256) batch_count_kernel(const int32_t *__restrict__ prow,
                                                           const int32_t *__restrict__ pcol,
                                                           const int64_t *__restrict__ nids,
                                                           int32_t n_b,
                                                           const int32_t *__restrict__ node_map,
                                                           int32_t *__restrict__ deg) {
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (i >= n_b) return;
-    const int64_t pnode = nids[i];
-    const int rs = prow[pnode], re = prow[pnode + 1];
-    int cnt = 0;
-    for (int e = rs + lane; e < re; e += 32) cnt += node_map[pcol[e]] >= 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) deg[i] = cnt;
+    __shared__ int s_heavy[8], s_cnt[8], s_nheavy;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + warp;
+    if (threadIdx.x == 0) s_nheavy = 0;
+    __syncthreads();
+    if (i < n_b) {
+        const int64_t pnode = nids[i];
+        int rs = 0, re = 0;
+        if (pnode >= 0) { rs = prow[pnode]; re = prow[pnode + 1]; }
+        if (re - rs > kHeavyParentDeg) {
+            if (lane == 0) s_heavy[atomicAdd(&s_nheavy, 1)] = i;
+        } else {
+            const int cnt = count_range(pcol, node_map, rs, re, lane);
+            if (lane == 0) deg[i] = cnt;
+        }
+    }
+    __syncthreads();
+    const int nheavy = s_nheavy;
+    for (int h = 0; h < nheavy; ++h) {
+        const int row = s_heavy[h];
+        const int64_t pnode = nids[row];
+        int eb, ee;
+        heavy_segment(prow[pnode], prow[pnode + 1], warp, eb, ee);
+        const int cnt = count_range(pcol, node_map, eb, ee, lane);
+        if (lane == 0) s_cnt[warp] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 8; ++w) t += s_cnt[w];
+            deg[row] = t;
+        }
+        __syncthreads();
+    }
 }
 
 // One warp per batch row: write relabelled neighbours, parent order preserved.
@@ -154,27 +236,41 @@ __global__ void __launch_bounds__(256) batch_fill_kernel(const int32_t *__restri
                                                          int64_t col_capacity,
                                                          float *__restrict__ out_inv_deg,
                                                          int32_t *__restrict__ overflow_flag) {
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (i >= n_b) return;
-    const int64_t pnode = nids[i];
-    const int rs = prow[pnode], re = prow[pnode + 1];
-    const int obeg = out_rowptr[i], oend = out_rowptr[i + 1];
-    if (lane == 0) {
-        const int dg = oend - obeg;
-        if (out_inv_deg) out_inv_deg[i] = dg > 0 ? 1.0f / (float)dg : 0.f;
-        if (oend > col_capacity && overflow_flag) *overflow_flag = 1;
-    }
-    int64_t pos = obeg;
-    for (int e0 = rs; e0 < re; e0 += 32) {
-        const int e = e0 + lane;
-        const int m = (e < re) ? node_map[pcol[e]] : -1;
-        const unsigned bal = __ballot_sync(0xffffffffu, m >= 0);
-        if (m >= 0) {
-            const int64_t w = pos + __popc(bal & ((1u << lane) - 1u));
-            if (w < col_capacity) out_col[w] = m;
+    __shared__ int s_heavy[8], s_cnt[8], s_nheavy;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + warp;
+    if (threadIdx.x == 0) s_nheavy = 0;
+    __syncthreads();
+    if (i < n_b) {
+        const int64_t pnode = nids[i];
+        int rs = 0, re = 0;
+        if (pnode >= 0) { rs = prow[pnode]; re = prow[pnode + 1]; }
+        const int obeg = out_rowptr[i], oend = out_rowptr[i + 1];
+        if (lane == 0) {
+            const int dg = oend - obeg;
+            if (out_inv_deg) out_inv_deg[i] = dg > 0 ? 1.0f / (float)dg : 0.f;
+            if (oend > col_capacity && overflow_flag) *overflow_flag = 1;
         }
-        pos += __popc(bal);
+        if (re - rs > kHeavyParentDeg) {
+            if (lane == 0) s_heavy[atomicAdd(&s_nheavy, 1)] = i;
+        } else {
+            fill_range(pcol, node_map, rs, re, lane, obeg, out_col, col_capacity);
+        }
+    }
+    __syncthreads();
+    const int nheavy = s_nheavy;
+    for (int h = 0; h < nheavy; ++h) {
+        const int row = s_heavy[h];
+        const int64_t pnode = nids[row];
+        int eb, ee;
+        heavy_segment(prow[pnode], prow[pnode + 1], warp, eb, ee);
+        const int cnt = count_range(pcol, node_map, eb, ee, lane);
+        if (lane == 0) s_cnt[warp] = cnt;
+        __syncthreads();
+        int64_t pos = out_rowptr[row];
+        for (int w = 0; w < warp; ++w) pos += s_cnt[w];
+        fill_range(pcol, node_map, eb, ee, lane, pos, out_col, col_capacity);
+        __syncthreads();
     }
 }
 
@@ -189,8 +285,15 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const char *__restrict
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i >= n) return;
-    const V *s = reinterpret_cast<const V *>(src + idx[i] * src_stride);
+    const int64_t r = idx[i];
     V *d = reinterpret_cast<V *>(dst + i * dst_stride);
+    if (r < 0) {   // padding sentinel: zero row
+        V z;
+        memset(&z, 0, sizeof(V));
+        for (int64_t k = lane; k < vecs_per_row; k += 32) d[k] = z;
+        return;
+    }
+    const V *s = reinterpret_cast<const V *>(src + r * src_stride);
     for (int64_t k = lane; k < vecs_per_row; k += 32) d[k] = __ldg(s + k);
 }
 
@@ -201,8 +304,11 @@ __global__ void gather_elems_kernel(const char *__restrict__ src, int64_t src_st
                                     char *__restrict__ dst, int64_t dst_stride) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    *reinterpret_cast<V *>(dst + i * dst_stride) =
-        __ldg(reinterpret_cast<const V *>(src + idx[i] * src_stride));
+    const int64_t r = idx[i];
+    V v;
+    if (r < 0) memset(&v, 0, sizeof(V));
+    else v = __ldg(reinterpret_cast<const V *>(src + r * src_stride));
+    *reinterpret_cast<V *>(dst + i * dst_stride) = v;
 }
 
 // ------------------------------------------------------- slice (K5) -------
@@ -257,7 +363,7 @@ extern "C" int gist_cluster_batch_build(const int32_t *parent_rowptr, const int3
     if (scan_ws_bytes < gist_scan_workspace_bytes(n_b)) return GIST_ERR_WORKSPACE;
     const int tb = 256;
     const int g_thread = (n_b + tb - 1) / tb;
-    const int g_warp = (int)(((int64_t)n_b * 32 + tb - 1) / tb);
+    const int g_warp = (n_b + 7) / 8;   // 8 warps (rows) per CTA
     batch_mark_kernel<<<g_thread, tb, 0, s>>>(nids, n_b, node_map, 1);
     // degrees land in out_rowptr[0..n_b) and are scanned in place
     batch_count_kernel<<<g_warp, tb, 0, s>>>(parent_rowptr, parent_col, nids, n_b, node_map,

@@ -23,19 +23,20 @@ struct SpmmParams {
     const int32_t *col;
     int32_t n_dst;
     const float *X;
-    int64_t ldx;
-    int32_t d;
+    int32_t ldx;        // leading dimensions fit 32 bits (checked on the host): the row
+    int32_t d;          // address is one IMAD.WIDE instead of a 64-bit multiply
     float *Y;
-    int64_t ldy;
+    int32_t ldy;
     const float *src_scale;
     const float *dst_scale;
     const float *bias;
     const float *addend;
-    int64_t ld_add;
+    int32_t ld_add;
     float *self_out;
-    int64_t ld_self;
+    int32_t ld_self;
     int32_t relu;
     int32_t row_blocks;
+    int32_t heavy_deg;  // rows with more edges are split over the whole CTA (INT_MAX = never)
 };
 
 template <int VEC>
@@ -62,49 +63,30 @@ __device__ __forceinline__ void st_vec(float *p, const float (&r)[VEC]) {
     }
 }
 
+// Accumulate edges [eb, ee) of one row into acc (a group of LPR lanes, lane `lg`).
+// Two-level summation: every block of <= LPR edges is summed on its own and then added
+// to the running total, which keeps the fp32 rounding error of hub rows (10^4 edges)
+// ~sqrt(LPR) lower than one long chain, at the cost of VPL*VEC adds per block.
 template <int VEC, int LPR, int VPL, bool HAS_SS>
-__global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
-    constexpr int GPW = 32 / LPR;                 // row groups per warp
-    constexpr int ROWS_PER_BLOCK = 8 * GPW;
-    constexpr int CHUNK = LPR * VEC * VPL;        // floats per feature chunk
+__device__ __forceinline__ void gather_range(const SpmmParams &p, int eb, int ee, int lg, int lane0,
+                                             unsigned gmask, const int (&c)[VPL], const bool (&cv)[VPL],
+                                             float (&acc)[VPL][VEC]) {
     constexpr int UMAX = (VPL == 1) ? 8 : 4;
     constexpr int U = (LPR < UMAX) ? LPR : UMAX;  // independent gathers in flight per lane
-
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int grp = lane / LPR;
-    const int lg = lane % LPR;
-    const int chunk = blockIdx.x / p.row_blocks;
-    const int rb = blockIdx.x - chunk * p.row_blocks;
-    const int v = rb * ROWS_PER_BLOCK + warp * GPW + grp;
-    if (v >= p.n_dst) return;  // uniform per group
-    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
-    const int lane0 = grp * LPR;
-
-    int c[VPL];
-    bool cv[VPL];
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-        c[k] = chunk * CHUNK + k * (LPR * VEC) + lg * VEC;
-        cv[k] = c[k] < p.d;
-    }
-    float acc[VPL][VEC];
-#pragma unroll
-    for (int k = 0; k < VPL; ++k)
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[k][i] = 0.f;
-
-    const int rs = __ldg(p.rowptr + v);
-    const int re = __ldg(p.rowptr + v + 1);
-    for (int e0 = rs; e0 < re; e0 += LPR) {
+    for (int e0 = eb; e0 < ee; e0 += LPR) {
         const int my = e0 + lg;
         int u_mine = 0;
         float s_mine = 0.f;
-        if (my < re) {
+        if (my < ee) {
             u_mine = __ldg(p.col + my);
             if constexpr (HAS_SS) s_mine = __ldg(p.src_scale + u_mine);
         }
-        const int cnt = min(LPR, re - e0);
+        const int cnt = min(LPR, ee - e0);
+        float blk[VPL][VEC];
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) blk[k][i] = 0.f;
         for (int j = 0; j < cnt; j += U) {
             float x[U][VPL][VEC];
             float s[U];
@@ -130,12 +112,20 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
                 for (int k = 0; k < VPL; ++k)
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) {
-                        if constexpr (HAS_SS) acc[k][i] = fmaf(s[jj], x[jj][k][i], acc[k][i]);
-                        else acc[k][i] += x[jj][k][i];
+                        if constexpr (HAS_SS) blk[k][i] = fmaf(s[jj], x[jj][k][i], blk[k][i]);
+                        else blk[k][i] += x[jj][k][i];
                     }
         }
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[k][i] += blk[k][i];
     }
+}
 
+template <int VEC, int VPL>
+__device__ __forceinline__ void epilogue(const SpmmParams &p, int v, const int (&c)[VPL],
+                                         const bool (&cv)[VPL], const float (&acc)[VPL][VEC]) {
     const float t = p.dst_scale ? __ldg(p.dst_scale + v) : 1.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
@@ -165,6 +155,92 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
             ld_vec<VEC>(sx, p.X + (int64_t)v * p.ldx + c[k]);
             st_vec<VEC>(p.self_out + (int64_t)v * p.ld_self + c[k], sx);
         }
+    }
+}
+
+template <int VEC, int LPR, int VPL, bool HAS_SS>
+__global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
+    constexpr int GPW = 32 / LPR;                 // row groups per warp
+    constexpr int NGROUPS = 8 * GPW;              // row groups (= rows) per CTA
+    constexpr int CHUNK = LPR * VEC * VPL;        // floats per feature chunk
+    __shared__ int s_heavy[NGROUPS];
+    __shared__ int s_nheavy;
+    __shared__ float s_part[NGROUPS][CHUNK];      // 256*VEC*VPL floats = 1..8 KB
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int grp = lane / LPR;
+    const int lg = lane % LPR;
+    const int gid = warp * GPW + grp;             // group index inside the CTA
+    const int chunk = blockIdx.x / p.row_blocks;
+    const int rb = blockIdx.x - chunk * p.row_blocks;
+    const int v = rb * NGROUPS + gid;
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
+    const int lane0 = grp * LPR;
+    const bool coop = p.heavy_deg != 0x7fffffff;  // uniform over the grid
+
+    int c[VPL];
+    bool cv[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        c[k] = chunk * CHUNK + k * (LPR * VEC) + lg * VEC;
+        cv[k] = c[k] < p.d;
+    }
+    float acc[VPL][VEC];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[k][i] = 0.f;
+
+    if (coop) {
+        if (threadIdx.x == 0) s_nheavy = 0;
+        __syncthreads();
+    }
+    if (v < p.n_dst) {
+        const int rs = __ldg(p.rowptr + v);
+        const int re = __ldg(p.rowptr + v + 1);
+        if (coop && re - rs > p.heavy_deg) {
+            if (lg == 0) s_heavy[atomicAdd(&s_nheavy, 1)] = v;   // order irrelevant: rows are independent
+        } else {
+            gather_range<VEC, LPR, VPL, HAS_SS>(p, rs, re, lg, lane0, gmask, c, cv, acc);
+            epilogue<VEC, VPL>(p, v, c, cv, acc);
+        }
+    }
+    if (!coop) return;
+    __syncthreads();
+    const int nheavy = s_nheavy;
+    for (int h = 0; h < nheavy; ++h) {
+        // every group of the CTA takes one contiguous, LPR-aligned slice of the hub row
+        const int hv = s_heavy[h];
+        const int rs = __ldg(p.rowptr + hv);
+        const int re = __ldg(p.rowptr + hv + 1);
+        int seg = (re - rs + NGROUPS - 1) / NGROUPS;
+        seg = (seg + LPR - 1) / LPR * LPR;
+        const int eb = min(re, rs + gid * seg);
+        const int ee = min(re, eb + seg);
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[k][i] = 0.f;
+        gather_range<VEC, LPR, VPL, HAS_SS>(p, eb, ee, lg, lane0, gmask, c, cv, acc);
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) s_part[gid][(k * LPR + lg) * VEC + i] = acc[k][i];
+        __syncthreads();
+        if (gid == 0) {   // fixed summation order over the slices: deterministic
+#pragma unroll
+            for (int k = 0; k < VPL; ++k)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[k][i] = 0.f;
+            for (int g2 = 0; g2 < NGROUPS; ++g2)
+#pragma unroll
+                for (int k = 0; k < VPL; ++k)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) acc[k][i] += s_part[g2][(k * LPR + lg) * VEC + i];
+            epilogue<VEC, VPL>(p, hv, c, cv, acc);
+        }
+        __syncthreads();
     }
 }
 
@@ -244,17 +320,23 @@ extern "C" int gist_spmm_csr_f32(const int32_t *rowptr, const int32_t *col, int3
     if (n_dst == 0 || d == 0) return GIST_OK;
     if (!rowptr || !X || !Y) return GIST_ERR_BADARG;  // col may be NULL for an edgeless graph
     if (ldx < d || ldy < d) return GIST_ERR_BADARG;
+    if (ldx > 0x7fffffffLL || ldy > 0x7fffffffLL || ld_addend > 0x7fffffffLL || ld_self > 0x7fffffffLL)
+        return GIST_ERR_UNSUPPORTED;
     if (addend && ld_addend < d) return GIST_ERR_BADARG;
     if (self_out && (ld_self < d || n_dst != n_src)) return GIST_ERR_BADARG;
     if (!aligned(rowptr, 4) || !aligned(col, 4) || !aligned(X, 4) || !aligned(Y, 4))
         return GIST_ERR_ALIGN;
     SpmmParams p;
     p.rowptr = rowptr; p.col = col; p.n_dst = n_dst;
-    p.X = X; p.ldx = ldx; p.d = d; p.Y = Y; p.ldy = ldy;
+    p.X = X; p.ldx = (int32_t)ldx; p.d = d; p.Y = Y; p.ldy = (int32_t)ldy;
     p.src_scale = src_scale; p.dst_scale = dst_scale; p.bias = bias;
-    p.addend = addend; p.ld_add = ld_addend; p.self_out = self_out; p.ld_self = ld_self;
+    p.addend = addend; p.ld_add = (int32_t)ld_addend; p.self_out = self_out; p.ld_self = (int32_t)ld_self;
     p.relu = (flags & GIST_SPMM_RELU) ? 1 : 0;
     p.row_blocks = 0;
+    // Hub rows are split over the CTA only where rows are scarce (cluster batches): with
+    // >32k rows there are enough warps that one long row is not the critical path.
+    const bool coop = (flags & GIST_SPMM_COOP_ON) || (!(flags & GIST_SPMM_COOP_OFF) && n_dst <= 32768);
+    p.heavy_deg = coop ? 128 : 0x7fffffff;
     cudaStream_t s = (cudaStream_t)stream;
     if (vec_ok(4, p)) return dispatch_lanes<4>(p, flags, n_src, s);
     if (vec_ok(2, p)) return dispatch_lanes<2>(p, flags, n_src, s);

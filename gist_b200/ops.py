@@ -10,6 +10,11 @@ from . import _lib
 from ._lib import check, ptr, require_cuda, stream_ptr
 
 
+# bench.py sets this to a list to time every SpMM launch with a CUDA-event pair on the
+# launching stream (roofline.achieved); None = no instrumentation.
+SPMM_PROFILE = None
+
+
 def _mat(t, name):
     if t.dim() != 2 or t.dtype != torch.float32:
         raise ValueError('%s must be a 2-D float32 tensor, got %s %s' % (name, tuple(t.shape), t.dtype))
@@ -36,6 +41,10 @@ def spmm_raw(rowptr, col, n_dst, n_src, X, out, *, src_scale=None, dst_scale=Non
     assert out.stride(1) == 1 or d == 1
     lib = _lib.load()
     f = flags | (_lib.SPMM_RELU if relu else 0)
+    prof = SPMM_PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     st = lib.gist_spmm_csr_f32(
         ptr(rowptr), ptr(col), n_dst, n_src, ptr(X), _ld(X), d, ptr(out), _ld(out),
         ptr(src_scale), ptr(dst_scale), ptr(bias),
@@ -43,6 +52,10 @@ def spmm_raw(rowptr, col, n_dst, n_src, X, out, *, src_scale=None, dst_scale=Non
         ptr(self_out), _ld(self_out) if self_out is not None else 0,
         f, stream_ptr(X.device))
     check(st, 'spmm_csr_f32')
+    if prof is not None:
+        ev1.record()
+        prof.append(dict(ev0=ev0, ev1=ev1, rowptr=rowptr, n_dst=n_dst, n_src=n_src, d=d,
+                         scaled=(src_scale is not None) + (dst_scale is not None)))
     return out
 
 

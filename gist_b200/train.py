@@ -1,0 +1,44 @@
+"""Training-step helpers shared by the trainers and bench.py (the L4 glue of
+cluster_gcn_ist_distrib.py:370-479, kept thin)."""
+import torch
+import torch.nn.functional as F
+
+
+def masked_cross_entropy(pred, labels, mask):
+    """CrossEntropyLoss()(pred[mask], labels[mask]) (…distrib.py:413-414) without the
+    boolean-index host sync: mean of the per-row losses over the masked rows."""
+    per_row = F.cross_entropy(pred, labels, reduction='none')
+    m = mask.to(per_row.dtype)
+    return (per_row * m).sum() / m.sum()
+
+
+def make_optimizer(params, lr, weight_decay):
+    """torch.optim.Adam as the reference builds it (…distrib.py:405-407); `fused`
+    only changes how many launches the update takes."""
+    return torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, fused=True)
+
+
+def train_step(model, optimizer, cluster):
+    """zero_grad -> forward -> CE on train rows -> backward -> Adam (…distrib.py:408-417).
+    Returns the loss as a 0-d device tensor (no sync)."""
+    optimizer.zero_grad(set_to_none=True)
+    pred = model(cluster)
+    loss = masked_cross_entropy(pred, cluster.ndata['label'], cluster.ndata['train_mask'])
+    loss.backward()
+    optimizer.step()
+    return loss.detach()
+
+
+@torch.no_grad()
+def evaluate(model, g, labels, mask, method='acc'):
+    """cluster_gcn/utils.py:70-80: full-graph inference; accuracy (== micro-F1 for
+    single-label prediction) of argmax over the masked rows."""
+    assert method in ['acc', 'f1'], 'invalid method'
+    model.eval()
+    logits = model(g)
+    pred = logits.argmax(dim=1)
+    m = mask.bool()
+    total = int(m.sum().item())
+    if total == 0:
+        return -1
+    return float(((pred == labels) & m).sum().item()) / total

@@ -43,6 +43,8 @@ typedef void *gist_stream_t; /* cudaStream_t */
 #define GIST_SPMM_RELU 1u        /* y = max(y, 0) as the last epilogue step       */
 #define GIST_SPMM_NARROW 2u      /* force 1 vector / lane (narrow feature chunks) */
 #define GIST_SPMM_WIDE 4u        /* force 2 vectors / lane                        */
+#define GIST_SPMM_COOP_ON 8u     /* force CTA-cooperative hub rows (row split)    */
+#define GIST_SPMM_COOP_OFF 16u   /* never split rows (default: on iff n_dst<=32k) */
 
 /* modes of gist_degree_norm_f32 */
 #define GIST_NORM_INV 0       /* 1/deg, deg==0 -> 0   (ISTSAGELayer.get_norm, cluster_gcn/modules.py:239-243) */

@@ -84,8 +84,8 @@ def test_cluster_iter_matches_oracle_batches():
         order = np.argsort(part, kind='stable')
         bounds = np.searchsorted(part[order], np.arange(psize + 1))
         par_li = [order[bounds[p]:bounds[p + 1]].astype(np.int64) for p in range(psize)]
-        random.seed(3)
-        random.shuffle(par_li)
+        rng = random.Random(3)          # private copy of the stream the sampler draws from
+        rng.shuffle(par_li)
         for epoch in range(2):
             for i, batch in enumerate(it):
                 nids = O.batch_node_ids(par_li, i, psize, bs)
@@ -132,3 +132,38 @@ def test_slice_gather_scatter(shape):
         assert torch.equal(Dd.cpu(), D)
     b = torch.randn(R)
     assert torch.equal(ops.slice_gather(b.cuda(), None, ridx.cuda()).cpu(), b[ridx])
+
+
+def test_subgraph_hub_rows_and_padding_sentinel():
+    """Parent rows far longer than the CTA-cooperative threshold (1024), and nids padded
+    with -1 (isolated, zero-feature rows) as used for fixed-shape replay."""
+    from gist_b200 import GistGraph
+    from tests.util import powerlaw_graph
+    n = 6000
+    src, dst = powerlaw_graph(n, 60, seed=2)
+    g = GistGraph.from_edges(src, dst, n, device='cuda')
+    assert int(g.in_degrees().max()) > 5000
+    g.ndata['feat'] = torch.randn(n, 10, device='cuda')
+    g.ndata['label'] = torch.randint(0, 7, (n,), device='cuda')
+    hubs = torch.argsort(g.in_degrees(), descending=True)[:40].cpu().numpy()
+    rng = np.random.RandomState(1)
+    rest = np.setdiff1d(rng.permutation(n)[:800], hubs)
+    nids = np.concatenate([rest[:300], hubs, rest[300:]]).astype(np.int64)
+    sg = g.subgraph(nids)
+    osg = ograph(src, dst, n).subgraph(nids)
+    rp, col = canonical_csr_from_gist(sg)
+    orp, ocol = osg.canonical_csr()
+    assert torch.equal(rp, orp) and torch.equal(col, ocol)
+    # padded: same structure on the real rows, pad rows isolated with zero ndata
+    pad = 37
+    nids_p = np.concatenate([nids, -np.ones(pad, dtype=np.int64)])
+    cap = int(g.in_degrees()[torch.from_numpy(nids).cuda()].sum().item())
+    sgp = g.subgraph(nids_p, col_capacity=cap)
+    rpp, colp = canonical_csr_from_gist(sgp)
+    assert torch.equal(rpp[:len(nids) + 1], orp) and (rpp[len(nids):] == orp[-1]).all()
+    assert torch.equal(colp, ocol)
+    assert (sgp.ndata['feat'][len(nids):] == 0).all() and (sgp.ndata['label'][len(nids):] == 0).all()
+    assert torch.equal(sgp.ndata['feat'][:len(nids)], sg.ndata['feat'])
+    assert (sgp.inv_in_degree()[len(nids):] == 0).all()
+    # scratch map fully restored
+    assert (g._node_map() == -1).all()
