@@ -53,6 +53,8 @@ def parse():
     ap.add_argument('--cpu-steps', type=int, default=6, help='CPU-baseline sample size (steps)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-eval-spmm', action='store_true')
+    ap.add_argument('--mode', default='graph', choices=['graph', 'eager'],
+                    help='graph: whole training step captured in a CUDA graph; eager: op-by-op')
     ap.add_argument('--ncu', default='', choices=['', 'steps', 'fullgraph'],
                     help='bracket that region with cudaProfilerStart/Stop (ncu --profile-from-start off)')
     return ap.parse_args()
@@ -172,6 +174,40 @@ def run_gist(a):
         w.ini_sync_dispatch_model()
         return it, w
 
+    class GraphLoop:
+        """Same loop with the step body replayed from a CUDA graph (gist_b200/graphed.py)."""
+
+        def __init__(self, it, w, readback):
+            from gist_b200.graphed import GraphedClusterTrainer
+            self.it, self.w, self.readback = it, w, readback
+            w.inplace_dispatch = True
+            w.sub_model.train()
+            self.tr = GraphedClusterTrainer(it, w.sub_model, a.lr, a.weight_decay, h2d=it.h2d).capture()
+            self.total_iter = 0
+            self.running_loss = 0.0
+            self.loss_acc = torch.zeros((), device=dev)
+            self.nodes = 0
+
+        def next_step(self):
+            if self.total_iter % a.iter_per_site == 0 and self.total_iter > 0:
+                e = self.total_iter // len(self.it)
+                if e > 0:                                   # …distrib.py:401
+                    if world > 1:
+                        dist.barrier()
+                    self.w.dispatch_model()
+                self.tr.reset_optimizer()                   # fresh Adam at every round (…distrib.py:405-407)
+            loss = self.tr.step()
+            self.nodes += self.tr.n_pad
+            if self.readback:
+                self.running_loss += float(loss)
+            else:
+                self.loss_acc += loss
+            self.total_iter += 1
+            if self.total_iter % a.iter_per_site == 0:
+                if world > 1:
+                    dist.barrier()
+                self.w.sync_model()
+
     class Loop:
         """The reference's step loop (…distrib.py:394-427) unrolled into next_step()."""
 
@@ -215,6 +251,7 @@ def run_gist(a):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
+        r0 = loop.tr.replays if hasattr(loop, 'tr') else 0
         e0.record()
         for _ in range(k):
             loop.next_step()
@@ -223,7 +260,10 @@ def run_gist(a):
         if world > 1:
             dist.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        launches = torch.tensor([_lib.launch_count() - l0], device=dev, dtype=torch.float64)
+        n_launch = _lib.launch_count() - l0
+        if hasattr(loop, 'tr'):     # kernel nodes of this library replayed from the CUDA graph
+            n_launch += (loop.tr.replays - r0) * loop.tr.gist_launches_per_step
+        launches = torch.tensor([n_launch], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(launches, op=dist.ReduceOp.SUM)
@@ -233,7 +273,8 @@ def run_gist(a):
 
     # ---- device-resident arm: node-id lists already in HBM, no loss readback -------
     it, w = fresh('epoch')
-    loop = Loop(it, w, readback=False)
+    LoopT = GraphLoop if a.mode == 'graph' else Loop
+    loop = LoopT(it, w, readback=False)
     for _ in range(a.warmup):
         loop.next_step()
     sampler = ClockSampler(local)
@@ -249,17 +290,29 @@ def run_gist(a):
     final_loss = float(loop.loss_acc) / max(a.steps + a.warmup, 1)
 
     # ---- instrumented pass: per-launch SpMM durations with CUDA events --------------
+    # Eager steps on the same workload, each preceded by a device-side sleep long enough for
+    # the host to enqueue the whole step first: the event pairs around every SpMM launch then
+    # measure back-to-back GPU execution, not host launch gaps.
+    it3, w3 = fresh('epoch')
+    loop3 = Loop(it3, w3, readback=False)
+    for _ in range(3):
+        loop3.next_step()
+    prof_steps = min(a.steps, 20)
+    sleep_cycles = int(6e-3 * 1.9e9)
     ops.SPMM_PROFILE = []
-    prof_steps = min(a.steps, 30)
+    step_evs = []
     torch.cuda.synchronize()
-    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pe0.record()
     for _ in range(prof_steps):
-        loop.next_step()
-    pe1.record()
-    torch.cuda.synchronize()
+        torch.cuda._sleep(sleep_cycles)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        loop3.next_step()
+        s1.record()
+        step_evs.append((s0, s1))
+        torch.cuda.synchronize()
     prof, ops.SPMM_PROFILE = ops.SPMM_PROFILE, None
-    prof_ms = pe0.elapsed_time(pe1)
+    prof_ms = sum(x.elapsed_time(y) for x, y in step_evs)
+    del loop3, it3, w3
     alg_b = comp_b = spmm_ms = 0.0
     by_d = {}
     nnz_cache = {}
@@ -282,7 +335,7 @@ def run_gist(a):
         'traffic': None, 'peak_source': peak_src,
         'bytes_per_launch': round(alg_b / n_l), 'compulsory_bytes_per_launch': round(comp_b / n_l),
         'us_per_launch': round(spmm_ms * 1e3 / n_l, 2),
-        'share_of_step': round(spmm_ms / prof_ms, 4) if prof_ms > 0 else None,
+        'share_of_step': round((spmm_ms / prof_steps) / (ms / a.steps), 4),
         'by_width': {str(d): {'launches_per_step': v[0] / prof_steps, 'GBps': round(v[1] / 1e9 / (v[2] / 1e3), 1),
                               'us': round(v[2] * 1e3 / v[0], 2)} for d, v in sorted(by_d.items())},
         'note': 'cluster batches (<=5 MB of features) are L2-resident: algorithmic gather bytes are served by '
@@ -291,13 +344,14 @@ def run_gist(a):
 
     # ---- end-to-end arm: node ids from pinned host memory + loss readback every step --
     it2, w2 = fresh('step')
-    loop2 = Loop(it2, w2, readback=True)
+    loop2 = LoopT(it2, w2, readback=True)
     for _ in range(a.warmup):
         loop2.next_step()
-    h2d0 = it2.h2d_bytes
+    h2d_of = (lambda: loop2.tr.h2d_bytes) if a.mode == 'graph' else (lambda: it2.h2d_bytes)
+    h2d0 = h2d_of()
     ms2, _ = timed(loop2, a.steps)
     e2e = {'value': round(world * a.steps / steps_per_epoch / (ms2 / 1e3), 4), 'unit': 'epochs/s',
-           'h2d_bytes_per_step': int((it2.h2d_bytes - h2d0) / a.steps), 'd2h_bytes_per_step': 4,
+           'h2d_bytes_per_step': int((h2d_of() - h2d0) / a.steps), 'd2h_bytes_per_step': 4,
            'ms_per_step': round(ms2 / a.steps, 4),
            'what': 'public API (ClusterIter -> sub_model -> loss): batch node ids copied from pinned host '
                    'memory every step, float(loss) read back every step; graph + features resident in HBM'}
@@ -355,7 +409,7 @@ def run_gist(a):
                             'sub-GCNs (one per GPU), iter_per_site %d' % (
                                 n_nodes, n_edges, in_feats, psize, a.batch_size, a.n_hidden, a.n_layers + 1,
                                 world, a.iter_per_site),
-                'steps_per_epoch': steps_per_epoch, 'num_subnet': world, 'scale': a.scale,
+                'steps_per_epoch': steps_per_epoch, 'num_subnet': world, 'scale': a.scale, 'mode': a.mode,
                 'epoch_accounting': 'm ranks x one local pass = m epochs (reference: local_epochs = n_epochs // num_subnet)',
                 'l2': 'inputs larger than L2: every step gathers a different ~%d-node batch from the %.0f MB '
                       'training feature matrix' % (loop.nodes // max(loop.total_iter, 1),

@@ -158,14 +158,27 @@ __device__ __forceinline__ void epilogue(const SpmmParams &p, int v, const int (
     }
 }
 
-template <int VEC, int LPR, int VPL, bool HAS_SS>
-__global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
+// Resident CTAs per SM the register allocation must allow: the large-graph (non-COOP)
+// variants are gather-latency bound and live on occupancy (40 regs -> 6 CTAs = 48 warps).
+template <int VEC, int VPL, bool HAS_SS, bool COOP>
+constexpr int min_ctas() {
+    if (COOP) return 2;
+    if (VEC * VPL <= 2) return HAS_SS ? 4 : 6;
+    if (VEC * VPL <= 4) return 4;
+    return 3;
+}
+
+// COOP = hub rows (more than heavy_deg edges) are split over all groups of the CTA and
+// reduced through shared memory in a fixed order; used where rows are scarce.
+template <int VEC, int LPR, int VPL, bool HAS_SS, bool COOP>
+__global__ void __launch_bounds__(256, min_ctas<VEC, VPL, HAS_SS, COOP>())
+spmm_csr_kernel(const SpmmParams p) {
     constexpr int GPW = 32 / LPR;                 // row groups per warp
     constexpr int NGROUPS = 8 * GPW;              // row groups (= rows) per CTA
     constexpr int CHUNK = LPR * VEC * VPL;        // floats per feature chunk
-    __shared__ int s_heavy[NGROUPS];
+    __shared__ int s_heavy[COOP ? NGROUPS : 1];
     __shared__ int s_nheavy;
-    __shared__ float s_part[NGROUPS][CHUNK];      // 256*VEC*VPL floats = 1..8 KB
+    __shared__ float s_part[COOP ? NGROUPS : 1][COOP ? CHUNK : 1];   // 256*VEC*VPL floats = 1..8 KB
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -177,7 +190,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
     const int v = rb * NGROUPS + gid;
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
     const int lane0 = grp * LPR;
-    const bool coop = p.heavy_deg != 0x7fffffff;  // uniform over the grid
+    constexpr bool coop = COOP;
 
     int c[VPL];
     bool cv[VPL];
@@ -255,10 +268,14 @@ static int launch_spmm(const SpmmParams &p0, cudaStream_t stream) {
     if (grid <= 0) return GIST_OK;
     if (grid > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
     p.row_blocks = (int32_t)row_blocks;
-    if (p.src_scale)
-        spmm_csr_kernel<VEC, LPR, VPL, true><<<(unsigned)grid, 256, 0, stream>>>(p);
-    else
-        spmm_csr_kernel<VEC, LPR, VPL, false><<<(unsigned)grid, 256, 0, stream>>>(p);
+    const bool coop = p.heavy_deg != 0x7fffffff;
+    if (p.src_scale) {
+        if (coop) spmm_csr_kernel<VEC, LPR, VPL, true, true><<<(unsigned)grid, 256, 0, stream>>>(p);
+        else spmm_csr_kernel<VEC, LPR, VPL, true, false><<<(unsigned)grid, 256, 0, stream>>>(p);
+    } else {
+        if (coop) spmm_csr_kernel<VEC, LPR, VPL, false, true><<<(unsigned)grid, 256, 0, stream>>>(p);
+        else spmm_csr_kernel<VEC, LPR, VPL, false, false><<<(unsigned)grid, 256, 0, stream>>>(p);
+    }
     count_launch();
     return last_error();
 }

@@ -216,7 +216,7 @@ class GistGraph:
             self._cache['node_map'] = torch.full((self._n,), -1, dtype=torch.int32, device=self.device)
         return self._cache['node_map']
 
-    def subgraph(self, nids, col_capacity=None, gather_ndata=True):
+    def subgraph(self, nids, col_capacity=None, gather_ndata=True, ndata_keys=None):
         """Node-induced subgraph built on the device (K3).  new node i <-> nids[i]."""
         _lib.require_cuda(self.rowptr)
         dev = self.device
@@ -231,7 +231,7 @@ class GistGraph:
         n_b = int(nids.shape[0])
         if col_capacity is None:
             deg = (self.rowptr[1:] - self.rowptr[:-1])
-            col_capacity = int(deg[nids].sum().item()) if n_b else 0
+            col_capacity = int(deg[nids.clamp_min(0)].sum().item()) if n_b else 0
 
         def build(prow, pcol, want_inv):
             lib = _lib.load()
@@ -259,7 +259,8 @@ class GistGraph:
             sg._symmetric, sg._csc = False, (cptr, crow)
         if gather_ndata:
             for k, v in self.ndata.items():
-                sg.ndata[k] = ops.gather_rows(v, nids)
+                if ndata_keys is None or k in ndata_keys:
+                    sg.ndata[k] = ops.gather_rows(v, nids)
         sg.ndata[NID] = nids.to(self._idtype)
         return sg
 

@@ -56,6 +56,10 @@ class DistributedGNNWrapper(torch.nn.Module):
         # K5 kernels.  Tests of the host-side plan / pack / all-gather logic on CPU
         # (gloo) inject a checker here; nothing in the package does.
         self._gather, self._scatter_ = slice_ops or (ops.slice_gather, ops.slice_scatter_)
+        # True: dispatch writes the slices INTO the sub-model's existing parameter storage
+        # (same values; keeps addresses stable for CUDA-graph replay) instead of rebinding
+        # `.data` to fresh tensors as the reference does.
+        self.inplace_dispatch = False
         self.args = args
         self.g = g
         self.in_feats = in_feats
@@ -108,6 +112,13 @@ class DistributedGNNWrapper(torch.nn.Module):
                 ridx, cidx = self._slice_for(l, site, parts)
                 base = self.base_model.layers[l].linear
                 sub = self.sub_model.layers[l].linear
+                if self.inplace_dispatch:
+                    self._gather(base.weight.data, ridx, cidx, out=sub.weight.data)
+                    if l == L:
+                        sub.bias.data.copy_(base.bias.data)
+                    else:
+                        self._gather(base.bias.data, None, ridx, out=sub.bias.data)
+                    continue
                 sub.weight.data = self._gather(base.weight.data, ridx, cidx)
                 if l == L:
                     sub.bias.data = base.bias.data.clone()      # shared, full (…distrib.py:217-219)
@@ -144,7 +155,10 @@ class DistributedGNNWrapper(torch.nn.Module):
                 gathered = flat.unsqueeze(0)
             self._merge(gathered, parts)
             # the reference all-reduces the last bias IN PLACE on every rank's sub-model
-            self.sub_model.layers[L].linear.bias.data = self.base_model.layers[L].linear.bias.data.clone()
+            if self.inplace_dispatch:
+                self.sub_model.layers[L].linear.bias.data.copy_(self.base_model.layers[L].linear.bias.data)
+            else:
+                self.sub_model.layers[L].linear.bias.data = self.base_model.layers[L].linear.bias.data.clone()
 
     def _merge(self, gathered, parts):
         """Scatter every site's packed slices into the local full-model replica."""

@@ -51,7 +51,10 @@ class ClusterIter(object):
     """The partition sampler (cluster_gcn/sampler.py:11-93)."""
 
     def __init__(self, dn, g, psize, batch_size, seed_nid, use_pp=True, partition=None,
-                 h2d='step', cache_dir='../data/'):
+                 h2d='step', cache_dir='../data/', rng=None):
+        # the reference draws from Python's GLOBAL random stream (shared with create_partition);
+        # a private random.Random can be injected for tests
+        self._rng = rng if rng is not None else random
         self.use_pp = use_pp
         seed_nid = np.asarray(seed_nid).astype(np.int64)
         self.g = g.subgraph(seed_nid)
@@ -71,7 +74,7 @@ class ClusterIter(object):
         # host-side bound on a batch's edge count: sum of training-graph degrees
         deg = (self.g.rowptr[1:] - self.g.rowptr[:-1]).cpu().numpy().astype(np.int64)
         self._deg_sum = {id(p): int(deg[p].sum()) for p in self.par_li}
-        random.shuffle(self.par_li)
+        self._rng.shuffle(self.par_li)
         self.get_fn = get_subgraph
         assert h2d in ('step', 'epoch')
         self.h2d = h2d
@@ -100,6 +103,30 @@ class ClusterIter(object):
         parts = [self.par_li[s] for s in range(i * self.batch_size, (i + 1) * self.batch_size)
                  if s < self.psize]
         return parts, np.concatenate(parts).reshape(-1).astype(np.int64)
+
+    # ---- fixed-shape (padded) access for CUDA-graph replay -------------------------
+    def max_batch_nodes(self):
+        """Upper bound on a batch's node count over ANY grouping of parts."""
+        sizes = sorted((len(p) for p in self.par_li), reverse=True)
+        return int(sum(sizes[:self.batch_size]))
+
+    def max_batch_edges(self):
+        """Upper bound on a batch's edge count (sum of the largest per-part degree sums)."""
+        sums = sorted(self._deg_sum.values(), reverse=True)
+        return int(sum(sums[:self.batch_size]))
+
+    def padded_epoch_ids(self, n_pad):
+        """[len(self), n_pad] int64 host tensor: batch i's node ids in concatenation order,
+        padded with -1 (the builder's isolated-row sentinel)."""
+        out = np.full((self.max, n_pad), -1, dtype=np.int64)
+        for i in range(self.max):
+            _, ids = self.batch_node_ids(i)
+            out[i, :len(ids)] = ids
+        return torch.from_numpy(out)
+
+    def end_epoch(self):
+        """What StopIteration does in the reference: reshuffle the parts (sampler.py:92)."""
+        self._rng.shuffle(self.par_li)
 
     def __iter__(self):
         self.n = 0
@@ -137,5 +164,5 @@ class ClusterIter(object):
             self.n += 1
             return result
         else:
-            random.shuffle(self.par_li)
+            self._rng.shuffle(self.par_li)
             raise StopIteration
