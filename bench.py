@@ -53,6 +53,8 @@ def parse():
     ap.add_argument('--cpu-steps', type=int, default=6, help='CPU-baseline sample size (steps)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-eval-spmm', action='store_true')
+    ap.add_argument('--matmul', default='tf32', choices=['fp32', 'tf32'],
+                    help='nn.Linear contractions: cuBLAS fp32 sgemm, or the tcgen05 TF32 kernel (K4)')
     ap.add_argument('--mode', default='graph', choices=['graph', 'eager'],
                     help='graph: whole training step captured in a CUDA graph; eager: op-by-op')
     ap.add_argument('--ncu', default='', choices=['', 'steps', 'fullgraph'],
@@ -146,6 +148,7 @@ def run_gist(a):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     assert a.warmup >= 3, 'timing rules: warm-up >= 3 steps'
+    ops.set_matmul_precision(a.matmul)
     assert a.n_hidden % world == 0
 
     # same seeds on every rank (…distrib.py:570-572): partitions and batch order are
@@ -401,7 +404,8 @@ def run_gist(a):
         line = {
             'metric': METRIC, 'value': round(value, 4), 'unit': 'epochs/s', 'n_gpus': world,
             'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': round(ms / a.steps, 4),
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32' if a.matmul == 'fp32' else 'f32 (aggregation, norms, loss, Adam) + tf32 tensor-core GEMM inputs',
             'data': 'synthetic',
             'config': {
                 'workload': 'configs[2]: Cluster-GCN GraphSAGE on a Reddit-shaped synthetic graph (%d nodes, %d '
@@ -414,7 +418,8 @@ def run_gist(a):
                 'l2': 'inputs larger than L2: every step gathers a different ~%d-node batch from the %.0f MB '
                       'training feature matrix' % (loop.nodes // max(loop.total_iter, 1),
                                                    4.0 * it.g.number_of_nodes() * in_feats / 1e6),
-                'gemm': 'cuBLAS fp32 via torch (library GEMM; tcgen05 GEMM is the ultra-wide config, not this one)',
+                'gemm': ('hand-written tcgen05 kernel, TF32 inputs / fp32 accumulate in TMEM (K4)' if a.matmul == 'tf32'
+                         else 'cuBLAS fp32 sgemm via torch'),
                 'loss_after': round(final_loss, 4),
             },
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,

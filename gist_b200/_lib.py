@@ -36,6 +36,8 @@ SIGNATURES = {
     'gist_gather_rows': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _P]),
     'gist_slice_gather_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
     'gist_slice_scatter_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
+    'gist_gemm_tn_tf32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _U32, _P]),
+    'gist_transpose_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P]),
 }
 
 SPMM_RELU, SPMM_NARROW, SPMM_WIDE = 1, 2, 4

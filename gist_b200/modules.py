@@ -101,7 +101,7 @@ class GraphSAGELayer(nn.Module):
             h = ops.sage_concat(g, h)       # [h ‖ (A h) / in_deg] in one kernel
         if self.dropout:
             h = self.dropout(h)
-        h = self.linear(h)
+        h = ops.linear(h, self.linear.weight, self.linear.bias)
         h = self.lynorm(h)
         if self.activation:
             h = self.activation(h)
@@ -137,7 +137,7 @@ class ISTSAGELayer(nn.Module):
             h = self.dropout(h)
         # GIST swaps in weight slices of other widths; use the live tensors, and
         # normalise over the live output width
-        h = F.linear(h, self.linear.weight, self.linear.bias)
+        h = ops.linear(h, self.linear.weight, self.linear.bias)
         if isinstance(self.lynorm, nn.LayerNorm):
             h = F.layer_norm(h, (h.shape[-1],), None, None, self.lynorm.eps)
         else:

@@ -200,3 +200,93 @@ class _SageConcat(torch.autograd.Function):
 
 def sage_concat(g, h):
     return _SageConcat.apply(g, h)
+
+
+# --------------------------------------------------------------------------
+# K4: tensor-core GEMM (tcgen05, TF32 inputs / fp32 accumulate)
+# --------------------------------------------------------------------------
+_MATMUL_PRECISION = 'fp32'
+
+
+def set_matmul_precision(mode):
+    """'fp32' : nn.Linear / matmul through cuBLAS sgemm (bit-for-bit the reference's arithmetic);
+    'tf32' : the hand-written tcgen05 kernel (10-bit mantissa inputs, fp32 accumulate)."""
+    global _MATMUL_PRECISION
+    assert mode in ('fp32', 'tf32')
+    _MATMUL_PRECISION = mode
+
+
+def get_matmul_precision():
+    return _MATMUL_PRECISION
+
+
+def _tma_ok(t):
+    return (t.dim() == 2 and t.dtype == torch.float32 and t.is_cuda and t.stride(1) == 1
+            and t.data_ptr() % 16 == 0 and (t.shape[0] <= 1 or t.stride(0) % 4 == 0)
+            and t.stride(0) >= t.shape[1])
+
+
+def gemm_tn(A, B, bias=None, relu=False, out=None):
+    """C[M,N] = A[M,K] @ B[N,K]^T (+bias) (ReLU) on the tcgen05 kernel.  Raises if an operand is
+    not TMA-addressable (16-byte aligned, leading dimension multiple of 4)."""
+    require_cuda(A, B, bias, out)
+    M, K = A.shape
+    N, K2 = B.shape
+    assert K == K2
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    check(_lib.load().gist_gemm_tn_tf32(ptr(A), _ld(A), ptr(B), _ld(B), ptr(out), _ld(out), M, N, K,
+                                        ptr(bias), 1 if relu else 0, stream_ptr(A.device)),
+          'gemm_tn_tf32')
+    return out
+
+
+def transpose(x):
+    """[rows, cols] -> [cols, rows] whose leading dimension is padded to a multiple of 4
+    floats so the result is TMA-addressable."""
+    require_cuda(x)
+    x = _mat(x, 'x')
+    rows, cols = x.shape
+    ld = (rows + 3) // 4 * 4
+    buf = torch.empty((cols, ld), dtype=torch.float32, device=x.device)
+    check(_lib.load().gist_transpose_f32(ptr(x), _ld(x), rows, cols, ptr(buf), ld, stream_ptr(x.device)),
+          'transpose_f32')
+    return buf[:, :rows]
+
+
+class _LinearTF32(torch.autograd.Function):
+    """y = z W^T + b with all three contractions (y, dz, dW) on the tcgen05 kernel; operands
+    that TMA cannot address (e.g. a 41-wide gradient as the K-major operand) use cuBLAS."""
+
+    @staticmethod
+    def forward(ctx, z, W, b):
+        z = _mat(z, 'z')
+        if _tma_ok(z) and _tma_ok(W):
+            y = gemm_tn(z, W, b)
+        else:
+            y = torch.addmm(b, z, W.t()) if b is not None else z @ W.t()
+        ctx.save_for_backward(z, W)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, W = ctx.saved_tensors
+        dy = _mat(dy, 'dy')
+        dz = dW = db = None
+        if ctx.needs_input_grad[0]:
+            Wt = transpose(W)                                  # [in, out]
+            dz = gemm_tn(dy, Wt) if (_tma_ok(dy) and _tma_ok(Wt)) else dy @ W
+        if ctx.needs_input_grad[1]:
+            dyt, zt = transpose(dy), transpose(z)              # [out, n], [in, n]
+            dW = gemm_tn(dyt, zt)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dz, dW, db
+
+
+def linear(z, W, b=None):
+    """F.linear under the selected matmul precision."""
+    if _MATMUL_PRECISION == 'tf32' and z.is_cuda:
+        return _LinearTF32.apply(z, W, b)
+    return torch.nn.functional.linear(z, W, b)

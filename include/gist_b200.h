@@ -160,6 +160,28 @@ int gist_slice_scatter_f32(const float *src, int64_t ld_src, const int64_t *ridx
                            const int64_t *cidx, int64_t n_cols, float *dst, int64_t ld_dst,
                            gist_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * K4  tensor-core GEMM (tcgen05 / TMEM, TF32 inputs, fp32 accumulate).
+ *
+ *   C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (ReLU)     row-major fp32, K contiguous in A and B
+ *
+ * Replaces the cuBLAS sgemm behind nn.Linear / th.matmul and its autograd
+ * (cluster_gcn/modules.py:144, :233; DGL GraphConv's matmul): forward Y = Z W^T + b
+ * directly; dZ = dY W and dW = dY^T Z by passing explicitly transposed operands
+ * (gist_transpose_f32).  Requires 16-byte aligned A, B and lda, ldb multiples of 4
+ * (TMA global strides); M, N, K themselves are arbitrary (TMA zero-fills the edges).
+ * TF32 keeps 10 mantissa bits of the inputs: ~1e-3 relative on the products; the
+ * aggregation (K1/K2) stays full fp32.
+ */
+#define GIST_GEMM_RELU 1u
+int gist_gemm_tn_tf32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
+                      int32_t M, int32_t N, int32_t K, const float *bias, uint32_t flags,
+                      gist_stream_t stream);
+
+/* dst[c, r] = src[r, c] for a [rows, cols] row-major matrix (dst is [cols, rows]). */
+int gist_transpose_f32(const float *src, int64_t ld_src, int32_t rows, int32_t cols, float *dst,
+                       int64_t ld_dst, gist_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
