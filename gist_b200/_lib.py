@@ -36,12 +36,17 @@ SIGNATURES = {
     'gist_gather_rows': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _P]),
     'gist_slice_gather_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
     'gist_slice_scatter_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
+    'gist_gemm_tf32_workspace_bytes': (_SZ, [_I32, _I32, _I32, _U32]),
+    'gist_gemm_tf32': (ctypes.c_int, [_P, _I64, _I32, _P, _I64, _I32, _P, _I64, _I32, _I32, _I32, _P, _U32,
+                                      _P, _SZ, _P]),
     'gist_gemm_tn_tf32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _U32, _P]),
     'gist_transpose_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P]),
 }
 
 SPMM_RELU, SPMM_NARROW, SPMM_WIDE = 1, 2, 4
 NORM_INV, NORM_RSQRT_CLAMP = 0, 1
+GEMM_RELU, GEMM_NO_SPLITK, GEMM_TILE_N64, GEMM_TILE_N128, GEMM_TILE_N256 = 1, 2, 4, 8, 16
+GEMM_K_MAJOR, GEMM_MN_MAJOR = 0, 1
 
 _lib = None
 _device_set = None

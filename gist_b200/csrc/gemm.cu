@@ -1,18 +1,26 @@
 // K4: TF32 tensor-core GEMM for the dense X·Wᵀ / ∂X / ∂W contractions, sm_100a.
 //
-//   C[M,N] = A[M,K] · B[N,K]ᵀ (+ bias[N]) (ReLU)      all row-major fp32, K contiguous
+//   C[M,N] = op(A)[M,K] · op(B)[N,K]ᵀ (+ bias[N]) (ReLU)        fp32 in HBM, fp32 accumulate
 //
-// tcgen05.mma.kind::tf32 (fp32 operands read straight from shared memory, mantissa
-// truncated to 10 bits by the tensor core, fp32 accumulation in TMEM).  One CTA
-// computes one 128 x BN output tile:
-//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles (128-byte swizzle) of A and B
-//               into a STAGES-deep shared-memory ring, mbarrier complete_tx signalling;
-//   warp 1      TMEM allocator + MMA issuer: one elected lane issues 4 x (128 x BN x 8)
-//               tcgen05.mma per 32-float K block, tcgen05.commit frees the ring slot;
-//   warps 2-5   epilogue: tcgen05.ld the fp32 accumulator (lane = row), bias / ReLU,
-//               64-byte row segments to global memory.
-// TMA zero-fills out-of-bounds rows / K columns, so M, N, K need no padding; only the
-// leading dimensions must be multiples of 4 floats (16-byte global strides).
+// tcgen05.mma.kind::tf32: fp32 operands are read straight from shared memory (the tensor
+// core keeps 10 mantissa bits), accumulators live in TMEM.  Each operand may be stored
+// K-major ([rows, K] row-major) or MN-major ([K, rows] row-major), so the three
+// contractions of a linear layer — y = z Wᵀ, dz = dy W, dW = dyᵀ z — run on the SAME
+// kernel without materialising a transpose.
+//
+// Persistent, warp-specialised CTA (one per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes (128-byte swizzle) of A and B into
+//               a STAGES-deep shared-memory ring, mbarrier complete_tx signalling;
+//   warp 1      TMEM allocator + MMA issuer: one lane issues 4 x (128 x BN x 8) tcgen05.mma per
+//               32-float K block; tcgen05.commit frees the ring slot / publishes the accumulator;
+//   warps 2-5   epilogue: tcgen05.ld (lane = row) -> bias / ReLU -> global.  The accumulator is
+//               double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps
+//               the main loop of tile i+1.
+// Work unit = (m-tile, n-tile, k-split).  Split-K (for the dW contraction: few output tiles,
+// K = batch nodes) writes fp32 partials to a caller-provided workspace which a second kernel
+// sums in a fixed order -> deterministic, no atomics.
+// TMA zero-fills out-of-bounds rows / K columns, so M, N, K need no padding; only base
+// pointers (16 B) and leading dimensions (multiple of 4 floats) are constrained.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -22,8 +30,8 @@ namespace gist {
 constexpr int kBM = 128;       // UMMA M (cta_group::1)
 constexpr int kBK = 32;        // floats per K block = 128 bytes = one swizzle row
 constexpr int kUmmaK = 8;      // tf32: 32 bytes of K per MMA
-constexpr int kStages = 4;
 constexpr int kGemmThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;   // operand ring; barriers etc. on top (227 KB max per CTA)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -37,6 +45,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                  "r"(bytes)
                  : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -63,22 +75,33 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
         : "memory");
 }
 
-// Shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 bytes,
-// 8-row groups 1024 bytes apart (SBO); LBO unused (one swizzle atom along K).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+// Shared-memory matrix descriptors (sm_100 format, 128-byte swizzle).
+//   K-major operand  : rows of 32 floats (128 B), 8-row groups 1024 B apart (SBO); LBO unused.
+//                      One MMA reads 8 floats of K: start address + 32 B per K step.
+//   MN-major operand : 32-bit MN-major operands exist only in the "128B swizzle, 32B atom" layout
+//                      (layout type 1; TMA mode SWIZZLE_128B_ATOM_32B: the four 32-byte chunks of
+//                      a 128-byte row are XORed with the row index mod 4).  The tile is a row of
+//                      [32 floats of MN] x [32 K rows] boxes of 4096 B (what one TMA box writes);
+//                      inside a box K row r is at r*128 B; a swizzle atom is 4 K rows (512 B).
+//                      One MMA reads 8 K rows: start address + 1024 B per K step, SBO = 512
+//                      (next 4 K rows), LBO = 4096 (next 32 floats of MN).
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // [0,14)  start address >> 4
-    d |= (uint64_t)0 << 16;                              // [16,30) leading byte offset >> 4
-    d |= (uint64_t)(1024 >> 4) << 32;                    // [32,46) stride byte offset >> 4
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;    // [16,30) leading byte offset >> 4
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;    // [32,46) stride byte offset >> 4
     d |= (uint64_t)1 << 46;                              // [46,48) descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                              // [61,64) layout: SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;                    // [61,64) swizzle layout
     return d;
 }
 
-// Instruction descriptor, kind::tf32: D = F32, A = B = TF32, both K-major, M x N tile.
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(m >> 4) << 24);
+// Instruction descriptor, kind::tf32: D = F32, A = B = TF32, M x N tile; bit 15 / 16 = A / B is
+// MN-major ("transposed").
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -99,156 +122,247 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
                  : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-          "=r"(r[15])
+          "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+          "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+          "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 struct GemmParams {
-    float *C;
+    float *C;           // final output, or the split-K partial buffer [splits][M][ldc]
     int64_t ldc;
-    const float *bias;
+    const float *bias;  // applied here only when splits == 1
     int32_t M, N, K;
+    int32_t tiles_m, tiles_n, splits, kb_per_split, kblocks;
     int32_t relu;
-    int32_t vec4;   // C rows and bias are 16-byte aligned: float4 epilogue stores
+    int32_t vec4;       // output rows and bias are 16-byte aligned: float4 epilogue stores
 };
 
 template <int BN>
-struct GemmSmem {
-    float a[kStages][kBM * kBK];   // 16 KB per stage, 1024-byte aligned (swizzle atom)
-    float b[kStages][BN * kBK];
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
-    uint64_t tmem_full;
-    uint32_t tmem_base;
+struct GemmCfg {
+    static constexpr int kStageBytes = (kBM + BN) * kBK * 4;
+    static constexpr int kStages = kSmemBudget / kStageBytes;          // 64: 8, 128: 6, 256: 4
+    static constexpr int kTmemCols = 2 * BN;                            // double-buffered accumulator
+    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tn_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmParams p) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int kStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
-    GemmSmem<BN> &sm = *reinterpret_cast<GemmSmem<BN> *>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                                ~static_cast<uintptr_t>(1023));
+    float *sA = reinterpret_cast<float *>(base);                                    // [stages][128*32]
+    float *sB = reinterpret_cast<float *>(base + (size_t)kStages * kBM * kBK * 4);   // [stages][BN*32]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)kStages * Cfg::kStageBytes);
+    uint64_t *full = bars, *empty = bars + kStages;
+    uint64_t *tmem_full = bars + 2 * kStages, *tmem_empty = bars + 2 * kStages + 2;
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * kBM;
-    const int n0 = blockIdx.x * BN;
-    const int kblocks = (p.K + kBK - 1) / kBK;
-    constexpr uint32_t kStageBytes = (kBM + BN) * kBK * sizeof(float);
-    constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;      // power of two >= 32
+    const int n_work = p.tiles_m * p.tiles_n * p.splits;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&sm.full[s], 1);
-            mbar_init(&sm.empty[s], 1);
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
         }
-        mbar_init(&sm.tmem_full, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);     // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // whole warp: allocate the accumulator columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(&sm.tmem_base)),
-                     "r"(kTmemCols)
+                         smem_u32(tmem_base_slot)),
+                     "r"((uint32_t)Cfg::kTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = sm.tmem_base;
+    const uint32_t tmem_d = *tmem_base_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(&sm.empty[s], ph ^ 1);
-                mbar_expect_tx(&sm.full[s], kStageBytes);
-                tma_load_2d(&tmA, &sm.full[s], sm.a[s], kb * kBK, m0);
-                tma_load_2d(&tmB, &sm.full[s], sm.b[s], kb * kBK, n0);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int split = w % p.splits;
+                const int t = w / p.splits;
+                const int m0 = (t % p.tiles_m) * kBM;
+                const int n0 = (t / p.tiles_m) * BN;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], (uint32_t)Cfg::kStageBytes);
+                    float *a = sA + (size_t)s * kBM * kBK;
+                    float *b = sB + (size_t)s * BN * kBK;
+                    if constexpr (A_MN) {
+#pragma unroll
+                        for (int j = 0; j < kBM / 32; ++j)
+                            tma_load_2d(&tmA, &full[s], a + j * 32 * kBK, m0 + 32 * j, kb * kBK);
+                    } else {
+                        tma_load_2d(&tmA, &full[s], a, kb * kBK, m0);
+                    }
+                    if constexpr (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < BN / 32; ++j)
+                            tma_load_2d(&tmB, &full[s], b + j * 32 * kBK, n0 + 32 * j, kb * kBK);
+                    } else {
+                        tma_load_2d(&tmB, &full[s], b, kb * kBK, n0);
+                    }
+                    if (++s == kStages) { s = 0; ph ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(&sm.full[s], ph);
+            constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN, A_MN, B_MN);
+            int s = 0;
+            uint32_t ph = 0;
+            int acc = 0;
+            uint32_t acc_ph = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int split = w % p.splits;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+                mbar_wait(&tmem_empty[acc], acc_ph ^ 1);        // epilogue has drained this buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = smem_u32(sm.a[s]);
-                const uint32_t b_addr = smem_u32(sm.b[s]);
+                const uint32_t d_addr = tmem_d + (uint32_t)(acc * BN);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(sA + (size_t)s * kBM * kBK);
+                    const uint32_t b_addr = smem_u32(sB + (size_t)s * BN * kBK);
 #pragma unroll
-                for (int k = 0; k < kBK / kUmmaK; ++k) {
-                    const uint64_t ad = umma_desc_sw128(a_addr + k * kUmmaK * sizeof(float));
-                    const uint64_t bd = umma_desc_sw128(b_addr + k * kUmmaK * sizeof(float));
-                    umma_tf32(tmem_d, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint64_t ad = A_MN ? umma_desc(a_addr + k * 1024, 4096, 512, kLayoutSw128Base32)
+                                                 : umma_desc(a_addr + k * kUmmaK * 4, 0, 1024, kLayoutSw128);
+                        const uint64_t bd = B_MN ? umma_desc(b_addr + k * 1024, 4096, 512, kLayoutSw128Base32)
+                                                 : umma_desc(b_addr + k * kUmmaK * 4, 0, 1024, kLayoutSw128);
+                        umma_tf32(d_addr, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);          // slot reusable once these MMAs have read it
+                    if (++s == kStages) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&sm.empty[s]);   // slot reusable once these MMAs have read it
+                umma_commit(&tmem_full[acc]);        // accumulator complete
+                acc ^= 1;
+                if (acc == 0) acc_ph ^= 1;
             }
-            umma_commit(&sm.tmem_full);      // accumulator complete
         }
     } else {
         // epilogue warps 2..5: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
         const int q = warp & 3;
-        mbar_wait(&sm.tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = m0 + q * 32 + lane;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int split = w % p.splits;
+            const int t = w / p.splits;
+            const int m0 = (t % p.tiles_m) * kBM;
+            const int n0 = (t / p.tiles_m) * BN;
+            mbar_wait(&tmem_full[acc], acc_ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + q * 32 + lane;
+            float *crow = p.C + ((int64_t)split * p.M + row) * p.ldc;
+            const bool fused = p.splits == 1;
+            const int ncols = min(BN, p.N - n0);     // warp-uniform
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 16) {
-            float v[16];
-            tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            __syncwarp();
-            const bool full = p.vec4 && (n0 + c + 16 <= p.N);   // warp-uniform
-            if (row < p.M) {
-                float *out = p.C + (int64_t)row * p.ldc + n0 + c;
-                if (full) {                                   // 16-byte aligned 64-byte segment
+            for (int c = 0; c < ncols; c += 32) {
+                float v[32];
+                tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
+                if (row < p.M) {
+                    float *out = crow + n0 + c;
+                    if (p.vec4 && c + 32 <= ncols) {             // 16-byte aligned 128-byte segment
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        if (p.bias) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + c + i));
-                            r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+                        for (int i = 0; i < 32; i += 4) {
+                            float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            if (fused) {
+                                if (p.bias) {
+                                    const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + c + i));
+                                    r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+                                }
+                                if (p.relu) {
+                                    r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f);
+                                    r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+                                }
+                            }
+                            *reinterpret_cast<float4 *>(out + i) = r;
                         }
-                        if (p.relu) {
-                            r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f);
-                            r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
-                        }
-                        *reinterpret_cast<float4 *>(out + i) = r;
-                    }
-                } else {
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int col = n0 + c + i;
-                        if (col < p.N) {
-                            float r = v[i];
-                            if (p.bias) r += __ldg(p.bias + col);
-                            if (p.relu) r = fmaxf(r, 0.f);
-                            out[i] = r;
+                        for (int i = 0; i < 32; ++i) {
+                            if (c + i < ncols) {
+                                float r = v[i];
+                                if (fused) {
+                                    if (p.bias) r += __ldg(p.bias + n0 + c + i);
+                                    if (p.relu) r = fmaxf(r, 0.f);
+                                }
+                                out[i] = r;
+                            }
                         }
                     }
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_ph ^= 1;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d),
+                     "r"((uint32_t)Cfg::kTmemCols)
                      : "memory");
+    }
+}
+
+// Split-K second pass: C[r, c] = act(sum_s part[s][r][c] + bias[c]), fixed summation order.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restrict__ part, int64_t ldp,
+                                                            int splits, int M, int N,
+                                                            const float *__restrict__ bias, int relu,
+                                                            float *__restrict__ C, int64_t ldc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nq = (N + 3) >> 2;
+    if (i >= (int64_t)M * nq) return;
+    const int r = (int)(i / nq), c = (int)(i % nq) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {   // ldp is a multiple of 4 and the buffer 16-byte aligned
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(part + ((int64_t)s * M + r) * ldp + c));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float o[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (c + k < N) {
+            float x = o[k];
+            if (bias) x += __ldg(bias + c + k);
+            if (relu) x = fmaxf(x, 0.f);
+            C[(int64_t)r * ldc + c + k] = x;
+        }
     }
 }
 
@@ -290,63 +404,161 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D fp32 tensor map over a row-major [rows, k] matrix: box = [box_rows, 32 floats], 128B swizzle.
-static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t k, int64_t ld, int box_rows) {
+// 2-D fp32 tensor map over a row-major [outer, inner] matrix with row stride ld:
+// box = [box_outer rows, 32 floats], 128B swizzle (16-byte atoms for K-major operands, 32-byte
+// atoms for MN-major ones), zero fill out of bounds.
+static int make_map(CUtensorMap *map, const float *base, int64_t outer, int64_t inner, int64_t ld,
+                    int box_outer, bool mn_major) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return GIST_ERR_UNSUPPORTED;
-    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
     cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? GIST_OK : GIST_ERR_BADARG;
 }
 
-template <int BN>
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = kNumSMs;
+    }
+    return n;
+}
+
+template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &p, cudaStream_t s) {
-    constexpr size_t smem = sizeof(GemmSmem<BN>) + 1024;
+    constexpr size_t smem = GemmCfg<BN>::kSmemBytes;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tn_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM);
-    gemm_tn_tf32_kernel<BN><<<grid, kGemmThreads, smem, s>>>(ta, tb, p);
+    const int n_work = p.tiles_m * p.tiles_n * p.splits;
+    const int grid = n_work < sm_count() ? n_work : sm_count();
+    gemm_tf32_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, smem, s>>>(ta, tb, p);
     count_launch();
     return last_error();
+}
+
+template <int BN>
+static int launch_layout(bool a_mn, bool b_mn, const CUtensorMap &ta, const CUtensorMap &tb,
+                         const GemmParams &p, cudaStream_t s) {
+    if (a_mn) return b_mn ? launch_gemm<BN, true, true>(ta, tb, p, s) : launch_gemm<BN, true, false>(ta, tb, p, s);
+    return b_mn ? launch_gemm<BN, false, true>(ta, tb, p, s) : launch_gemm<BN, false, false>(ta, tb, p, s);
+}
+
+struct GemmPlan {
+    int bn, splits, kb_per_split;
+    int64_t ldp;            // leading dimension of the split-K partial buffer
+    size_t ws_bytes;
+};
+
+// Tile width and split-K factor: the widest tile that still gives most of the 148 SMs a work
+// unit; when even 64-wide tiles leave more than half the chip idle and K is long (the dW
+// contraction), K is split.
+static GemmPlan plan_gemm(int M, int N, int K, uint32_t flags) {
+    GemmPlan pl;
+    const int sms = sm_count();
+    const int64_t tm = (M + kBM - 1) / kBM;
+    auto tiles = [&](int bn) { return tm * ((N + bn - 1) / bn); };
+    if (flags & GIST_GEMM_TILE_N64) pl.bn = 64;
+    else if (flags & GIST_GEMM_TILE_N128) pl.bn = 128;
+    else if (flags & GIST_GEMM_TILE_N256) pl.bn = 256;
+    else if (tiles(256) >= (int64_t)sms * 4 / 5) pl.bn = 256;
+    else if (tiles(128) >= (int64_t)sms * 4 / 5) pl.bn = 128;
+    else pl.bn = 64;
+    const int kblocks = (K + kBK - 1) / kBK;
+    int splits = 1;
+    const int64_t t = tiles(pl.bn);
+    if (!(flags & GIST_GEMM_NO_SPLITK) && t * 2 <= sms) {
+        int64_t want = (sms + t - 1) / t;
+        int64_t cap = kblocks / 4;              // at least 4 K blocks per split
+        if (want > cap) want = cap;
+        if (want > 32) want = 32;
+        if (want > 1) splits = (int)want;
+    }
+    pl.kb_per_split = (kblocks + splits - 1) / splits;
+    pl.splits = (kblocks + pl.kb_per_split - 1) / pl.kb_per_split;   // no empty split
+    pl.ldp = (N + 3) / 4 * 4;
+    pl.ws_bytes = pl.splits > 1 ? (size_t)pl.splits * M * pl.ldp * sizeof(float) : 0;
+    return pl;
 }
 
 }  // namespace gist
 
 using namespace gist;
 
-extern "C" int gist_gemm_tn_tf32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C,
-                                 int64_t ldc, int32_t M, int32_t N, int32_t K, const float *bias,
-                                 uint32_t flags, gist_stream_t stream) {
+extern "C" size_t gist_gemm_tf32_workspace_bytes(int32_t M, int32_t N, int32_t K, uint32_t flags) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return plan_gemm(M, N, K, flags).ws_bytes;
+}
+
+extern "C" int gist_gemm_tf32(const float *A, int64_t lda, int32_t a_layout, const float *B, int64_t ldb,
+                              int32_t b_layout, float *C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                              const float *bias, uint32_t flags, void *workspace, size_t workspace_bytes,
+                              gist_stream_t stream) {
     if (M < 0 || N < 0 || K < 0) return GIST_ERR_BADARG;
     if (M == 0 || N == 0) return GIST_OK;
     if (!A || !B || !C || K == 0) return GIST_ERR_BADARG;
-    if (lda < K || ldb < K || ldc < N) return GIST_ERR_BADARG;
+    if ((a_layout != GIST_GEMM_K_MAJOR && a_layout != GIST_GEMM_MN_MAJOR) ||
+        (b_layout != GIST_GEMM_K_MAJOR && b_layout != GIST_GEMM_MN_MAJOR))
+        return GIST_ERR_BADARG;
+    const bool a_mn = a_layout == GIST_GEMM_MN_MAJOR, b_mn = b_layout == GIST_GEMM_MN_MAJOR;
+    if (lda < (a_mn ? M : K) || ldb < (b_mn ? N : K) || ldc < N) return GIST_ERR_BADARG;
     // TMA: 16-byte aligned base and 16-byte multiple row stride
     if (!aligned(A, 16) || !aligned(B, 16) || (lda % 4) || (ldb % 4) || !aligned(C, 4)) return GIST_ERR_ALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    GemmPlan pl = plan_gemm(M, N, K, flags);
+    if (pl.splits > 1 && (!workspace || workspace_bytes < pl.ws_bytes || !aligned(workspace, 16))) {
+        // no (or too small a) workspace: run unsplit rather than fail
+        pl.splits = 1;
+        pl.kb_per_split = (K + kBK - 1) / kBK;
+    }
     GemmParams p;
-    p.C = C; p.ldc = ldc; p.bias = bias; p.M = M; p.N = N; p.K = K;
+    p.M = M; p.N = N; p.K = K;
+    p.tiles_m = (M + kBM - 1) / kBM;
+    p.tiles_n = (N + pl.bn - 1) / pl.bn;
+    p.splits = pl.splits;
+    p.kb_per_split = pl.kb_per_split;
+    p.kblocks = (K + kBK - 1) / kBK;
     p.relu = (flags & GIST_GEMM_RELU) ? 1 : 0;
-    p.vec4 = (aligned(C, 16) && ldc % 4 == 0 && (!bias || aligned(bias, 16))) ? 1 : 0;
-    // narrow tiles when the grid would otherwise leave most of the 148 SMs idle
-    const int64_t tiles128 = (int64_t)((M + kBM - 1) / kBM) * ((N + 127) / 128);
-    const bool wide = tiles128 >= 2 * kNumSMs;
+    if (pl.splits > 1) {
+        p.C = reinterpret_cast<float *>(workspace); p.ldc = pl.ldp; p.bias = nullptr; p.vec4 = 1;
+    } else {
+        p.C = C; p.ldc = ldc; p.bias = bias;
+        p.vec4 = (aligned(C, 16) && ldc % 4 == 0 && (!bias || aligned(bias, 16))) ? 1 : 0;
+    }
     CUtensorMap ta, tb;
-    int st = make_map(&ta, A, M, K, lda, kBM);
+    int st = a_mn ? make_map(&ta, A, K, M, lda, kBK, true) : make_map(&ta, A, M, K, lda, kBM, false);
     if (st != GIST_OK) return st;
-    st = make_map(&tb, B, N, K, ldb, wide ? 128 : 64);
+    st = b_mn ? make_map(&tb, B, K, N, ldb, kBK, true) : make_map(&tb, B, N, K, ldb, pl.bn, false);
     if (st != GIST_OK) return st;
-    return wide ? launch_gemm<128>(ta, tb, p, (cudaStream_t)stream)
-                : launch_gemm<64>(ta, tb, p, (cudaStream_t)stream);
+    if (pl.bn == 256) st = launch_layout<256>(a_mn, b_mn, ta, tb, p, s);
+    else if (pl.bn == 128) st = launch_layout<128>(a_mn, b_mn, ta, tb, p, s);
+    else st = launch_layout<64>(a_mn, b_mn, ta, tb, p, s);
+    if (st != GIST_OK || pl.splits == 1) return st;
+    const int64_t items = (int64_t)M * ((N + 3) / 4);
+    splitk_reduce_kernel<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const float *>(workspace), pl.ldp, pl.splits, M, N, bias, p.relu, C, ldc);
+    count_launch();
+    return last_error();
+}
+
+extern "C" int gist_gemm_tn_tf32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C,
+                                 int64_t ldc, int32_t M, int32_t N, int32_t K, const float *bias,
+                                 uint32_t flags, gist_stream_t stream) {
+    return gist_gemm_tf32(A, lda, GIST_GEMM_K_MAJOR, B, ldb, GIST_GEMM_K_MAJOR, C, ldc, M, N, K, bias,
+                          flags | GIST_GEMM_NO_SPLITK, nullptr, 0, stream);
 }
 
 extern "C" int gist_transpose_f32(const float *src, int64_t ld_src, int32_t rows, int32_t cols, float *dst,

@@ -226,19 +226,51 @@ def _tma_ok(t):
             and t.stride(0) >= t.shape[1])
 
 
-def gemm_tn(A, B, bias=None, relu=False, out=None):
-    """C[M,N] = A[M,K] @ B[N,K]^T (+bias) (ReLU) on the tcgen05 kernel.  Raises if an operand is
-    not TMA-addressable (16-byte aligned, leading dimension multiple of 4)."""
+def _tma_view(t):
+    """`t` itself when TMA can address it (16-byte aligned base, leading dimension a multiple of
+    4 floats), else a copy into a buffer whose rows are padded to a multiple of 4 floats (e.g. the
+    41-wide logit gradient)."""
+    if _tma_ok(t):
+        return t
+    rows, cols = t.shape
+    buf = torch.empty((rows, (cols + 3) // 4 * 4), dtype=torch.float32, device=t.device)
+    v = buf[:, :cols]
+    v.copy_(t)
+    return v
+
+
+def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, relu=False, out=None, flags=0):
+    """C[M,N] = op(A) @ op(B)^T (+bias) (ReLU) on the tcgen05 TF32 kernel (K4).
+
+    a_mn=False: A is stored [M, K];  a_mn=True: A is stored [K, M] (MN-major, i.e. op(A) = A^T).
+    b_mn=False: B is stored [N, K];  b_mn=True: B is stored [K, N].
+    Raises if an operand is not TMA-addressable (see _tma_view)."""
     require_cuda(A, B, bias, out)
-    M, K = A.shape
-    N, K2 = B.shape
-    assert K == K2
+    if a_mn:
+        K, M = A.shape
+    else:
+        M, K = A.shape
+    if b_mn:
+        K2, N = B.shape
+    else:
+        N, K2 = B.shape
+    assert K == K2, (A.shape, B.shape, a_mn, b_mn)
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=A.device)
-    check(_lib.load().gist_gemm_tn_tf32(ptr(A), _ld(A), ptr(B), _ld(B), ptr(out), _ld(out), M, N, K,
-                                        ptr(bias), 1 if relu else 0, stream_ptr(A.device)),
-          'gemm_tn_tf32')
+    assert tuple(out.shape) == (M, N) and (out.stride(1) == 1 or N == 1)
+    lib = _lib.load()
+    f = flags | (_lib.GEMM_RELU if relu else 0)
+    wsb = lib.gist_gemm_tf32_workspace_bytes(M, N, K, f)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=A.device) if wsb else None
+    check(lib.gist_gemm_tf32(ptr(A), _ld(A), 1 if a_mn else 0, ptr(B), _ld(B), 1 if b_mn else 0,
+                             ptr(out), _ld(out), M, N, K, ptr(bias), f, ptr(ws), wsb,
+                             stream_ptr(A.device)), 'gemm_tf32')
     return out
+
+
+def gemm_tn(A, B, bias=None, relu=False, out=None):
+    """C[M,N] = A[M,K] @ B[N,K]^T (+bias) (ReLU): both operands K-major."""
+    return gemm(A, B, bias=bias, relu=relu, out=out)
 
 
 def transpose(x):
@@ -255,31 +287,27 @@ def transpose(x):
 
 
 class _LinearTF32(torch.autograd.Function):
-    """y = z W^T + b with all three contractions (y, dz, dW) on the tcgen05 kernel; operands
-    that TMA cannot address (e.g. a 41-wide gradient as the K-major operand) use cuBLAS."""
+    """y = z W^T + b with all three contractions (y, dz, dW) on the tcgen05 kernel, no
+    transposed copies: the kernel reads each operand K-major or MN-major as stored."""
 
     @staticmethod
     def forward(ctx, z, W, b):
-        z = _mat(z, 'z')
-        if _tma_ok(z) and _tma_ok(W):
-            y = gemm_tn(z, W, b)
-        else:
-            y = torch.addmm(b, z, W.t()) if b is not None else z @ W.t()
-        ctx.save_for_backward(z, W)
+        z = _tma_view(_mat(z, 'z'))
+        Wv = _tma_view(W)
+        y = gemm(z, Wv, bias=b)
+        ctx.save_for_backward(z, Wv)
         ctx.has_bias = b is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
         z, W = ctx.saved_tensors
-        dy = _mat(dy, 'dy')
+        dy = _tma_view(_mat(dy, 'dy'))
         dz = dW = db = None
         if ctx.needs_input_grad[0]:
-            Wt = transpose(W)                                  # [in, out]
-            dz = gemm_tn(dy, Wt) if (_tma_ok(dy) and _tma_ok(Wt)) else dy @ W
+            dz = gemm(dy, W, b_mn=True)                      # [n, out] x [out, in]: N = in, K = out
         if ctx.needs_input_grad[1]:
-            dyt, zt = transpose(dy), transpose(z)              # [out, n], [in, n]
-            dW = gemm_tn(dyt, zt)
+            dW = gemm(dy, z, a_mn=True, b_mn=True)           # dy^T z: M = out, N = in, K = n
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(0)
         return dz, dW, db

@@ -163,17 +163,40 @@ int gist_slice_scatter_f32(const float *src, int64_t ld_src, const int64_t *ridx
 /* ------------------------------------------------------------------------
  * K4  tensor-core GEMM (tcgen05 / TMEM, TF32 inputs, fp32 accumulate).
  *
- *   C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (ReLU)     row-major fp32, K contiguous in A and B
+ *   C[M,N] = op(A)[M,K] * op(B)[N,K]^T (+ bias[N]) (ReLU)        row-major fp32
+ *
+ * a_layout / b_layout say how each operand is stored:
+ *   GIST_GEMM_K_MAJOR  : A is [M, K] row-major (K contiguous), lda >= K   (B: [N, K], ldb >= K)
+ *   GIST_GEMM_MN_MAJOR : A is [K, M] row-major (M contiguous), lda >= M   (B: [K, N], ldb >= N)
+ * so the three contractions of a linear layer need no transposed copies:
+ *   y  = z W^T + b : A = z  [n, in]  K-major,  B = W [out, in] K-major
+ *   dz = dy W      : A = dy [n, out] K-major,  B = W [out, in] MN-major (N = in, K = out)
+ *   dW = dy^T z    : A = dy [n, out] MN-major (M = out, K = n), B = z [n, in] MN-major
  *
  * Replaces the cuBLAS sgemm behind nn.Linear / th.matmul and its autograd
- * (cluster_gcn/modules.py:144, :233; DGL GraphConv's matmul): forward Y = Z W^T + b
- * directly; dZ = dY W and dW = dY^T Z by passing explicitly transposed operands
- * (gist_transpose_f32).  Requires 16-byte aligned A, B and lda, ldb multiples of 4
- * (TMA global strides); M, N, K themselves are arbitrary (TMA zero-fills the edges).
- * TF32 keeps 10 mantissa bits of the inputs: ~1e-3 relative on the products; the
- * aggregation (K1/K2) stays full fp32.
+ * (cluster_gcn/modules.py:144, :233; DGL GraphConv's matmul).  Requires 16-byte aligned A, B
+ * and lda, ldb multiples of 4 (TMA global strides); M, N, K themselves are arbitrary (TMA
+ * zero-fills the edges).  TF32 keeps 10 mantissa bits of the inputs: ~1e-3 relative on the
+ * products; the aggregation (K1/K2) stays full fp32.
+ *
+ * workspace: gist_gemm_tf32_workspace_bytes(M, N, K, flags) bytes, 16-byte aligned; used for
+ * deterministic split-K when the output has too few tiles to fill the chip (the dW
+ * contraction).  NULL is allowed: the GEMM then runs unsplit.
  */
 #define GIST_GEMM_RELU 1u
+#define GIST_GEMM_NO_SPLITK 2u
+#define GIST_GEMM_TILE_N64 4u     /* force the output-tile width (default: chosen from the grid) */
+#define GIST_GEMM_TILE_N128 8u
+#define GIST_GEMM_TILE_N256 16u
+#define GIST_GEMM_K_MAJOR 0
+#define GIST_GEMM_MN_MAJOR 1
+size_t gist_gemm_tf32_workspace_bytes(int32_t M, int32_t N, int32_t K, uint32_t flags);
+int gist_gemm_tf32(const float *A, int64_t lda, int32_t a_layout, const float *B, int64_t ldb,
+                   int32_t b_layout, float *C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                   const float *bias, uint32_t flags, void *workspace, size_t workspace_bytes,
+                   gist_stream_t stream);
+
+/* Both operands K-major, no workspace (never splits K). */
 int gist_gemm_tn_tf32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
                       int32_t M, int32_t N, int32_t K, const float *bias, uint32_t flags,
                       gist_stream_t stream);

@@ -41,6 +41,58 @@ def test_gemm_tn_tf32(shape):
     assert torch.equal(ops.gemm_tn(Ai, Bi), (Ai.double() @ Bi.double().t()).float())
 
 
+LAYOUT_SHAPES = [(128, 64, 32), (2586, 512, 256), (256, 1204, 2586), (256, 512, 2586), (41, 512, 2586),
+                 (2586, 512, 41), (300, 70, 100), (129, 65, 36), (1000, 300, 520), (2280, 1024, 1056)]
+
+
+@pytest.mark.parametrize('shape', LAYOUT_SHAPES)
+@pytest.mark.parametrize('a_mn', [False, True])
+@pytest.mark.parametrize('b_mn', [False, True])
+def test_gemm_layouts(shape, a_mn, b_mn):
+    """Every storage-layout combination (K-major / MN-major per operand), auto tile width and
+    split-K, against fp64; exact on small-integer (tf32-representable) inputs."""
+    from gist_b200 import ops
+    M, N, K = shape
+    torch.manual_seed(M * 7 + N * 3 + K)
+
+    def stored(rows, cols, mn, gen):
+        # logical [rows, cols] operand; stored transposed when mn; padded leading dimension
+        r, c = (cols, rows) if mn else (rows, cols)
+        buf = gen(r, (c + 3) // 4 * 4)[:, :c]
+        return buf, (buf.t() if mn else buf)
+
+    rnd = lambda r, c: torch.randn(r, c, device='cuda')                      # noqa: E731
+    rint = lambda r, c: torch.randint(-4, 5, (r, c), device='cuda').float()  # noqa: E731
+    A_st, A = stored(M, K, a_mn, rnd)
+    B_st, B = stored(N, K, b_mn, rnd)
+    bias = torch.randn(N, device='cuda')
+    ref = A.double() @ B.double().t()
+    got = ops.gemm(A_st, B_st, a_mn=a_mn, b_mn=b_mn)
+    bound = _err_bound(A, B)
+    assert ((got.double() - ref).abs() <= bound + 1e-6).all(), (got.double() - ref).abs().max().item()
+    assert (got.double() - ref).norm() / ref.norm() < 2e-3
+    got2 = ops.gemm(A_st, B_st, a_mn=a_mn, b_mn=b_mn, bias=bias, relu=True)
+    assert ((got2.double() - torch.relu(ref + bias.double())).abs() <= bound + 1e-6).all()
+    Ai_st, Ai = stored(M, K, a_mn, rint)
+    Bi_st, Bi = stored(N, K, b_mn, rint)
+    exact = (Ai.double() @ Bi.double().t()).float()
+    for fl in (0, 2, 4, 8, 16):      # auto, no split-K, forced 64 / 128 / 256-wide tiles
+        assert torch.equal(ops.gemm(Ai_st, Bi_st, a_mn=a_mn, b_mn=b_mn, flags=fl), exact), fl
+
+
+def test_gemm_splitk_deterministic():
+    from gist_b200 import ops, _lib
+    torch.manual_seed(1)
+    dy = torch.randn(2586, 256, device='cuda')
+    z = torch.randn(2586, 1204, device='cuda')
+    assert _lib.load().gist_gemm_tf32_workspace_bytes(256, 1204, 2586, 0) > 0    # this shape splits K
+    a = ops.gemm(dy, z, a_mn=True, b_mn=True)
+    b = ops.gemm(dy, z, a_mn=True, b_mn=True)
+    assert torch.equal(a, b)
+    ref = dy.double().t() @ z.double()
+    assert (a.double() - ref).norm() / ref.norm() < 2e-3
+
+
 def test_gemm_output_view_and_rejects_unaligned():
     from gist_b200 import ops
     from gist_b200._lib import GistLibraryError
@@ -66,7 +118,13 @@ def test_transpose(shape):
 def test_linear_tf32_autograd():
     from gist_b200 import ops
     torch.manual_seed(0)
-    n, fin, fout = 1000, 1204, 256
+    _check_linear(1000, 1204, 256)
+    _check_linear(2586, 512, 41)       # 41-wide logit gradient: padded copy for TMA
+    _check_linear(777, 64, 32)
+
+
+def _check_linear(n, fin, fout):
+    from gist_b200 import ops
     z = torch.randn(n, fin, device='cuda', requires_grad=True)
     W = (torch.randn(fout, fin, device='cuda') * 0.03).requires_grad_(True)
     b = torch.randn(fout, device='cuda', requires_grad=True)
