@@ -17,6 +17,7 @@ _I32 = ctypes.c_int32
 _I64 = ctypes.c_int64
 _U32 = ctypes.c_uint32
 _SZ = ctypes.c_size_t
+_F32 = ctypes.c_float
 
 # name -> (restype, argtypes); must list every symbol include/gist_b200.h declares
 SIGNATURES = {
@@ -41,12 +42,20 @@ SIGNATURES = {
                                       _P, _SZ, _P]),
     'gist_gemm_tn_tf32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _U32, _P]),
     'gist_transpose_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P]),
+    'gist_layernorm_act_fwd_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _F32, _U32, _P, _I64, _P, _P]),
+    'gist_layernorm_act_bwd_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _U32, _P, _I64, _P]),
+    'gist_colsum_workspace_bytes': (_SZ, [_I32, _I32]),
+    'gist_colsum_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _SZ, _P]),
+    'gist_masked_ce_fwd_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    'gist_masked_ce_bwd_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    'gist_adam_multi_f32': (ctypes.c_int, [_I32, _P, _P, _P, _P, _P, _F32, _F32, _F32, _F32, _F32, _P, _P, _P]),
 }
 
 SPMM_RELU, SPMM_NARROW, SPMM_WIDE = 1, 2, 4
 NORM_INV, NORM_RSQRT_CLAMP = 0, 1
 GEMM_RELU, GEMM_NO_SPLITK, GEMM_TILE_N64, GEMM_TILE_N128, GEMM_TILE_N256 = 1, 2, 4, 8, 16
 GEMM_K_MAJOR, GEMM_MN_MAJOR = 0, 1
+ACT_RELU = 1
 
 _lib = None
 _device_set = None

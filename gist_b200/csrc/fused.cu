@@ -1,0 +1,454 @@
+// Row-wise / elementwise pieces of the training step that sit between the SpMM and GEMM
+// kernels (cluster_gcn/modules.py:233-236, cluster_gcn_ist_distrib.py:405-417), fused so a
+// cluster-batch step is a few launches instead of dozens:
+//   * LayerNorm(affine=False) + ReLU, forward and backward          (modules.py:234-236)
+//   * column sums (bias gradient of nn.Linear)
+//   * masked cross entropy, forward (mean over masked rows) + backward (…distrib.py:413-415)
+//   * Adam over a list of tensors in ONE launch                       (…distrib.py:405-407, :417)
+// All HBM/L2-bound streaming work: one warp per row, 128-bit accesses where the layout allows,
+// fixed-order reductions (deterministic, no float atomics).
+#include "common.cuh"
+
+namespace gist {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------- layer norm ----
+// y[r, :] = act((x[r, :] - mean_r) * rstd_r),  var biased (torch.nn.LayerNorm), no affine.
+// stats[r] = (mean_r, rstd_r) kept for the backward.
+template <bool VEC4>
+__global__ void __launch_bounds__(256) ln_act_fwd_kernel(const float *__restrict__ x, int64_t ldx, int n,
+                                                         int d, float eps, int relu,
+                                                         float *__restrict__ y, int64_t ldy,
+                                                         float2 *__restrict__ stats) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const float *xr = x + (int64_t)r * ldx;
+    float *yr = y + (int64_t)r * ldy;
+    float s = 0.f;
+    if constexpr (VEC4) {
+        for (int c = lane * 4; c < d; c += 128) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(xr + c));
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+    } else {
+        for (int c = lane; c < d; c += 32) s += __ldg(xr + c);
+    }
+    const float mean = warp_sum(s) / (float)d;
+    float q = 0.f;     // two-pass variance: the row is in L1 after the first pass
+    if constexpr (VEC4) {
+        for (int c = lane * 4; c < d; c += 128) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(xr + c));
+            const float a = v.x - mean, b = v.y - mean, e = v.z - mean, f = v.w - mean;
+            q += (a * a + b * b) + (e * e + f * f);
+        }
+    } else {
+        for (int c = lane; c < d; c += 32) {
+            const float a = __ldg(xr + c) - mean;
+            q += a * a;
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+    if (lane == 0 && stats) stats[r] = make_float2(mean, rstd);
+    if constexpr (VEC4) {
+        for (int c = lane * 4; c < d; c += 128) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(xr + c));
+            float4 o = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd,
+                                   (v.w - mean) * rstd);
+            if (relu) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            *reinterpret_cast<float4 *>(yr + c) = o;
+        }
+    } else {
+        for (int c = lane; c < d; c += 32) {
+            float o = (__ldg(xr + c) - mean) * rstd;
+            if (relu) o = fmaxf(o, 0.f);
+            yr[c] = o;
+        }
+    }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * [xhat > 0] (ReLU) or dy.
+template <bool VEC4>
+__global__ void __launch_bounds__(256) ln_act_bwd_kernel(const float *__restrict__ dy, int64_t lddy,
+                                                         const float *__restrict__ x, int64_t ldx,
+                                                         const float2 *__restrict__ stats, int n, int d,
+                                                         int relu, float *__restrict__ dx, int64_t lddx) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const float *xr = x + (int64_t)r * ldx;
+    const float *gr = dy + (int64_t)r * lddy;
+    float *or_ = dx + (int64_t)r * lddx;
+    const float2 st = stats[r];
+    const float mean = st.x, rstd = st.y;
+    float s1 = 0.f, s2 = 0.f;
+    auto acc = [&](float xv, float gv) {
+        const float xh = (xv - mean) * rstd;
+        const float g = (relu && xh <= 0.f) ? 0.f : gv;
+        s1 += g;
+        s2 += g * xh;
+    };
+    if constexpr (VEC4) {
+        for (int c = lane * 4; c < d; c += 128) {
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xr + c));
+            const float4 gv = __ldg(reinterpret_cast<const float4 *>(gr + c));
+            acc(xv.x, gv.x); acc(xv.y, gv.y); acc(xv.z, gv.z); acc(xv.w, gv.w);
+        }
+    } else {
+        for (int c = lane; c < d; c += 32) acc(__ldg(xr + c), __ldg(gr + c));
+    }
+    const float m1 = warp_sum(s1) / (float)d, m2 = warp_sum(s2) / (float)d;
+    auto out = [&](float xv, float gv) {
+        const float xh = (xv - mean) * rstd;
+        const float g = (relu && xh <= 0.f) ? 0.f : gv;
+        return rstd * (g - m1 - xh * m2);
+    };
+    if constexpr (VEC4) {
+        for (int c = lane * 4; c < d; c += 128) {
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xr + c));
+            const float4 gv = __ldg(reinterpret_cast<const float4 *>(gr + c));
+            *reinterpret_cast<float4 *>(or_ + c) =
+                make_float4(out(xv.x, gv.x), out(xv.y, gv.y), out(xv.z, gv.z), out(xv.w, gv.w));
+        }
+    } else {
+        for (int c = lane; c < d; c += 32) or_[c] = out(__ldg(xr + c), __ldg(gr + c));
+    }
+}
+
+// ---------------------------------------------------------------- colsum ----
+// Phase 1: CTA (bx, by) sums rows [by*rows_per, ...) of columns [32*bx, 32*bx+32) -> part[by][c].
+// Phase 2: out[c] = sum_by part[by][c] in index order.
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float *__restrict__ x, int64_t ldx, int n,
+                                                             int d, int rows_per, float *__restrict__ part) {
+    __shared__ float s[8][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const int r0 = blockIdx.y * rows_per;
+    const int r1 = min(n, r0 + rows_per);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (c < d) {
+        int r = r0 + warp;
+        for (; r + 24 < r1; r += 32) {      // 4 independent loads in flight per thread
+            a0 += __ldg(x + (int64_t)r * ldx + c);
+            a1 += __ldg(x + (int64_t)(r + 8) * ldx + c);
+            a2 += __ldg(x + (int64_t)(r + 16) * ldx + c);
+            a3 += __ldg(x + (int64_t)(r + 24) * ldx + c);
+        }
+        for (; r < r1; r += 8) a0 += __ldg(x + (int64_t)r * ldx + c);
+    }
+    s[warp][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (warp == 0 && c < d) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s[w][lane];
+        part[(int64_t)blockIdx.y * d + c] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float *__restrict__ part, int nparts, int d,
+                                                           float *__restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d) return;
+    float t = 0.f;
+#pragma unroll 8
+    for (int p = 0; p < nparts; ++p) t += __ldg(part + (int64_t)p * d + c);
+    out[c] = t;
+}
+
+// ---------------------------------------------------------- cross entropy ----
+// One warp per row: lse_r = logsumexp(logits[r, :]); row_loss[r] = mask_r ? lse_r - logits[r, y_r] : 0.
+__global__ void __launch_bounds__(256) ce_rows_kernel(const float *__restrict__ logits, int64_t ld, int n,
+                                                      int C, const int64_t *__restrict__ labels,
+                                                      const uint8_t *__restrict__ mask,
+                                                      float *__restrict__ lse, float *__restrict__ row_loss) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const float *xr = logits + (int64_t)r * ld;
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, __ldg(xr + c));
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += __expf(__ldg(xr + c) - mx);
+    s = warp_sum(s);
+    if (lane == 0) {
+        const float l = mx + __logf(s);
+        lse[r] = l;
+        const bool m = mask ? (mask[r] != 0) : true;
+        const int64_t y = labels[r];
+        row_loss[r] = (m && y >= 0 && y < C) ? l - __ldg(xr + y) : 0.f;
+    }
+}
+
+// Single CTA: loss = sum(row_loss) / count(mask); out[0] = loss, out[1] = 1 / count.
+__global__ void __launch_bounds__(1024) ce_reduce_kernel(const float *__restrict__ row_loss,
+                                                         const uint8_t *__restrict__ mask, int n,
+                                                         float *__restrict__ out) {
+    __shared__ float s_l[32], s_c[32];
+    float l = 0.f, c = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        l += row_loss[i];
+        c += mask ? (mask[i] != 0 ? 1.f : 0.f) : 1.f;
+    }
+    l = warp_sum(l);
+    c = warp_sum(c);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_l[warp] = l; s_c[warp] = c; }
+    __syncthreads();
+    if (warp == 0) {
+        l = lane < (blockDim.x >> 5) ? s_l[lane] : 0.f;
+        c = lane < (blockDim.x >> 5) ? s_c[lane] : 0.f;
+        l = warp_sum(l);
+        c = warp_sum(c);
+        if (lane == 0) {
+            out[0] = l / c;          // 0/0 = nan, as torch's mean over an empty selection
+            out[1] = 1.f / c;
+        }
+    }
+}
+
+// dlogits[r, c] = mask_r * (softmax(logits[r])_c - [c == y_r]) * gout / count
+__global__ void __launch_bounds__(256) ce_bwd_kernel(const float *__restrict__ logits, int64_t ld, int n, int C,
+                                                     const int64_t *__restrict__ labels,
+                                                     const uint8_t *__restrict__ mask,
+                                                     const float *__restrict__ lse,
+                                                     const float *__restrict__ loss_out,
+                                                     const float *__restrict__ gout,
+                                                     float *__restrict__ dlogits, int64_t ldd, int ldd_fill) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const float *xr = logits + (int64_t)r * ld;
+    float *dr = dlogits + (int64_t)r * ldd;
+    const bool m = mask ? (mask[r] != 0) : true;
+    const float scale = m ? __ldg(gout) * __ldg(loss_out + 1) : 0.f;
+    const float l = lse[r];
+    const int64_t y = labels[r];
+    for (int c = lane; c < ldd_fill; c += 32) {     // columns [C, ldd_fill) are row padding: zeroed
+        float v = 0.f;
+        if (c < C && m) v = (__expf(__ldg(xr + c) - l) - (c == y ? 1.f : 0.f)) * scale;
+        dr[c] = v;
+    }
+}
+
+// -------------------------------------------------------------------- adam ----
+struct AdamTensor {
+    float *p;
+    const float *g;
+    float *m;
+    float *v;
+    int64_t n;
+    int32_t block0;     // first CTA of this tensor
+};
+constexpr int kAdamMaxTensors = 24;
+constexpr int kAdamChunk = 1024;    // elements per CTA (256 threads x float4)
+struct AdamArgs {
+    AdamTensor t[kAdamMaxTensors];
+    int32_t n_tensors;
+    float lr, beta1, beta2, eps, weight_decay;
+};
+
+// torch.optim.Adam (amsgrad=False, L2 weight decay): t = step + 1;
+//   g += wd * p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+//   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// step (a device float, shared by all tensors of the launch) is incremented by the LAST CTA to
+// finish, after every CTA has read it.
+__global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__ AdamArgs a,
+                                                         float *__restrict__ step, int advance_step,
+                                                         unsigned int *__restrict__ counter) {
+    int ti = 0;
+#pragma unroll 1
+    for (int k = 1; k < a.n_tensors; ++k)
+        if ((int)blockIdx.x >= a.t[k].block0) ti = k;
+    const AdamTensor &T = a.t[ti];
+    const float t = *step + 1.f;
+    const float bc1 = 1.f - powf(a.beta1, t);
+    const float bc2 = 1.f - powf(a.beta2, t);
+    const float step_size = a.lr / bc1;
+    const float inv_sqrt_bc2 = rsqrtf(bc2);
+    const int64_t i0 = ((int64_t)(blockIdx.x - T.block0) * 256 + threadIdx.x) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = i0 + k;
+        if (i < T.n) {
+            const float p = T.p[i];
+            const float g = T.g[i] + a.weight_decay * p;
+            const float m = a.beta1 * T.m[i] + (1.f - a.beta1) * g;
+            const float v = a.beta2 * T.v[i] + (1.f - a.beta2) * g * g;
+            T.m[i] = m;
+            T.v[i] = v;
+            T.p[i] = p - step_size * m / (sqrtf(v) * inv_sqrt_bc2 + a.eps);
+        }
+    }
+    if (advance_step) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned prev = atomicAdd(counter, 1u);
+            if (prev == gridDim.x - 1) {
+                *step = t;
+                *counter = 0u;
+            }
+        }
+    }
+}
+
+}  // namespace gist
+
+using namespace gist;
+
+extern "C" int gist_layernorm_act_fwd_f32(const float *x, int64_t ldx, int32_t n, int32_t d, float eps,
+                                          uint32_t flags, float *y, int64_t ldy, float *stats,
+                                          gist_stream_t stream) {
+    if (n < 0 || d < 0) return GIST_ERR_BADARG;
+    if (n == 0 || d == 0) return GIST_OK;
+    if (!x || !y || ldx < d || ldy < d) return GIST_ERR_BADARG;
+    if (stats && !aligned(stats, 8)) return GIST_ERR_ALIGN;
+    const bool v4 = d % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && aligned(x, 16) && aligned(y, 16);
+    const int relu = (flags & GIST_ACT_RELU) ? 1 : 0;
+    const unsigned grid = (unsigned)((n + 7) / 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (v4) ln_act_fwd_kernel<true><<<grid, 256, 0, s>>>(x, ldx, n, d, eps, relu, y, ldy, reinterpret_cast<float2 *>(stats));
+    else ln_act_fwd_kernel<false><<<grid, 256, 0, s>>>(x, ldx, n, d, eps, relu, y, ldy, reinterpret_cast<float2 *>(stats));
+    count_launch();
+    return last_error();
+}
+
+extern "C" int gist_layernorm_act_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx,
+                                          const float *stats, int32_t n, int32_t d, uint32_t flags,
+                                          float *dx, int64_t lddx, gist_stream_t stream) {
+    if (n < 0 || d < 0) return GIST_ERR_BADARG;
+    if (n == 0 || d == 0) return GIST_OK;
+    if (!dy || !x || !stats || !dx || lddy < d || ldx < d || lddx < d) return GIST_ERR_BADARG;
+    if (!aligned(stats, 8)) return GIST_ERR_ALIGN;
+    const bool v4 = d % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && aligned(x, 16) &&
+                    aligned(dy, 16) && aligned(dx, 16);
+    const int relu = (flags & GIST_ACT_RELU) ? 1 : 0;
+    const unsigned grid = (unsigned)((n + 7) / 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    const float2 *st = reinterpret_cast<const float2 *>(stats);
+    if (v4) ln_act_bwd_kernel<true><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, st, n, d, relu, dx, lddx);
+    else ln_act_bwd_kernel<false><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, st, n, d, relu, dx, lddx);
+    count_launch();
+    return last_error();
+}
+
+static int colsum_parts(int32_t n, int32_t d) {
+    const int cx = (d + 31) / 32;
+    int by = (2 * kNumSMs + cx - 1) / cx;        // ~2 CTAs per SM in total
+    const int max_by = (n + 63) / 64;            // at least 64 rows per CTA
+    if (by > max_by) by = max_by;
+    if (by < 1) by = 1;
+    return by;
+}
+
+extern "C" size_t gist_colsum_workspace_bytes(int32_t n, int32_t d) {
+    if (n <= 0 || d <= 0) return 0;
+    return (size_t)colsum_parts(n, d) * d * sizeof(float);
+}
+
+extern "C" int gist_colsum_f32(const float *x, int64_t ldx, int32_t n, int32_t d, float *out,
+                               void *workspace, size_t workspace_bytes, gist_stream_t stream) {
+    if (n < 0 || d < 0) return GIST_ERR_BADARG;
+    if (d == 0) return GIST_OK;
+    if (!out) return GIST_ERR_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        cudaError_t e = cudaMemsetAsync(out, 0, (size_t)d * sizeof(float), s);
+        return e == cudaSuccess ? GIST_OK : (int)e;
+    }
+    if (!x || ldx < d) return GIST_ERR_BADARG;
+    if (!workspace || workspace_bytes < gist_colsum_workspace_bytes(n, d)) return GIST_ERR_WORKSPACE;
+    const int by = colsum_parts(n, d);
+    const int rows_per = (n + by - 1) / by;
+    dim3 grid((d + 31) / 32, by);
+    float *part = reinterpret_cast<float *>(workspace);
+    colsum_partial_kernel<<<grid, 256, 0, s>>>(x, ldx, n, d, rows_per, part);
+    colsum_final_kernel<<<(d + 255) / 256, 256, 0, s>>>(part, by, d, out);
+    count_launch(2);
+    return last_error();
+}
+
+extern "C" int gist_masked_ce_fwd_f32(const float *logits, int64_t ld, int32_t n, int32_t C,
+                                      const int64_t *labels, const uint8_t *mask, float *lse,
+                                      float *row_loss, float *loss_out, gist_stream_t stream) {
+    if (n < 0 || C <= 0) return GIST_ERR_BADARG;
+    if (!loss_out || (n > 0 && (!logits || !labels || !lse || !row_loss || ld < C))) return GIST_ERR_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n > 0) {
+        ce_rows_kernel<<<(n + 7) / 8, 256, 0, s>>>(logits, ld, n, C, labels, mask, lse, row_loss);
+        count_launch();
+    }
+    ce_reduce_kernel<<<1, 1024, 0, s>>>(row_loss, mask, n, loss_out);
+    count_launch();
+    return last_error();
+}
+
+extern "C" int gist_masked_ce_bwd_f32(const float *logits, int64_t ld, int32_t n, int32_t C,
+                                      const int64_t *labels, const uint8_t *mask, const float *lse,
+                                      const float *loss_out, const float *grad_out, float *dlogits,
+                                      int64_t ldd, int32_t fill_cols, gist_stream_t stream) {
+    if (n < 0 || C <= 0) return GIST_ERR_BADARG;
+    if (n == 0) return GIST_OK;
+    if (!logits || !labels || !lse || !loss_out || !grad_out || !dlogits || ld < C || fill_cols < C ||
+        ldd < fill_cols)
+        return GIST_ERR_BADARG;
+    ce_bwd_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(logits, ld, n, C, labels, mask, lse, loss_out,
+                                                                grad_out, dlogits, ldd, fill_cols);
+    count_launch();
+    return last_error();
+}
+
+extern "C" int gist_adam_multi_f32(int32_t n_tensors, float *const *params, const float *const *grads,
+                                   float *const *exp_avg, float *const *exp_avg_sq, const int64_t *numel,
+                                   float lr, float beta1, float beta2, float eps, float weight_decay,
+                                   float *step, uint32_t *counter, gist_stream_t stream) {
+    if (n_tensors < 0) return GIST_ERR_BADARG;
+    if (n_tensors == 0) return GIST_OK;
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !numel || !step || !counter) return GIST_ERR_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int n_live = 0;
+    for (int i = 0; i < n_tensors; ++i) {
+        if (numel[i] < 0) return GIST_ERR_BADARG;
+        if (numel[i] == 0) continue;
+        if (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i]) return GIST_ERR_BADARG;
+        ++n_live;
+    }
+    // non-empty tensors in launches of up to kAdamMaxTensors; only the last launch advances `step`
+    int i = 0, done = 0;
+    while (done < n_live) {
+        AdamArgs a;
+        a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+        int k = 0;
+        int64_t blocks = 0;
+        for (; i < n_tensors && k < kAdamMaxTensors; ++i) {
+            if (numel[i] == 0) continue;
+            a.t[k].p = params[i]; a.t[k].g = grads[i]; a.t[k].m = exp_avg[i]; a.t[k].v = exp_avg_sq[i];
+            a.t[k].n = numel[i]; a.t[k].block0 = (int32_t)blocks;
+            blocks += (numel[i] + kAdamChunk - 1) / kAdamChunk;
+            if (blocks > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
+            ++k;
+        }
+        a.n_tensors = k;
+        done += k;
+        adam_multi_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, step, done >= n_live ? 1 : 0, counter);
+        count_launch();
+        const int st = last_error();
+        if (st != GIST_OK) return st;
+    }
+    return GIST_OK;
+}

@@ -14,7 +14,7 @@ Callers: bench.py and the trainers; mirrors cluster_gcn_ist_distrib.py:398-417.
 """
 import torch
 
-from .train import masked_cross_entropy
+from .train import make_optimizer, masked_cross_entropy
 
 _KEYS = ('feat', 'label', 'train_mask')
 
@@ -29,8 +29,7 @@ class GraphedClusterTrainer:
         self.cap = max(cluster_iter.max_batch_edges(), 1)
         self.nids = torch.full((self.n_pad,), -1, dtype=torch.int64, device=self.dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
-        self.opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay, fused=True,
-                                    capturable=True)
+        self.opt = make_optimizer(model.parameters(), lr, weight_decay)
         self.graph = None
         self._epoch_dev = None          # [steps, n_pad] device ids (h2d='epoch')
         self._epoch_host = None         # pinned host ids (h2d='step')
@@ -101,10 +100,7 @@ class GraphedClusterTrainer:
     def reset_optimizer(self):
         """A fresh Adam, as the reference builds at every dispatch (…distrib.py:405-407), but in
         place: moments and step counters are zeroed so the captured graph's pointers stay valid."""
-        for st in self.opt.state.values():
-            for v in st.values():
-                if torch.is_tensor(v):
-                    v.zero_()
+        self.opt.reset_state()
 
     def step(self):
         """One training step; returns the 0-d device loss tensor (valid until the next step)."""

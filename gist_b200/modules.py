@@ -139,9 +139,13 @@ class ISTSAGELayer(nn.Module):
         # normalise over the live output width
         h = ops.linear(h, self.linear.weight, self.linear.bias)
         if isinstance(self.lynorm, nn.LayerNorm):
-            h = F.layer_norm(h, (h.shape[-1],), None, None, self.lynorm.eps)
-        else:
-            h = self.lynorm(h)
+            # LayerNorm over the live output width + ReLU in one kernel (fwd) / one (bwd)
+            fuse = self.activation is None or _is_relu(self.activation)
+            h = ops.layer_norm_act(h, self.lynorm.eps, relu=fuse and self.activation is not None)
+            if self.activation and not fuse:
+                h = self.activation(h)
+            return h
+        h = self.lynorm(h)
         if self.activation:
             h = self.activation(h)
         return h

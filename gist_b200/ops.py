@@ -309,7 +309,7 @@ class _LinearTF32(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dW = gemm(dy, z, a_mn=True, b_mn=True)           # dy^T z: M = out, N = in, K = n
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum(0)
+            db = colsum(dy)
         return dz, dW, db
 
 
@@ -318,3 +318,93 @@ def linear(z, W, b=None):
     if _MATMUL_PRECISION == 'tf32' and z.is_cuda:
         return _LinearTF32.apply(z, W, b)
     return torch.nn.functional.linear(z, W, b)
+
+
+# --------------------------------------------------------------------------
+# fused row-wise pieces of the training step (csrc/fused.cu)
+# --------------------------------------------------------------------------
+def colsum(x):
+    """x.sum(0) for a 2-D fp32 matrix (bias gradient), fixed-order two-phase reduction."""
+    require_cuda(x)
+    x = _mat(x, 'x')
+    n, d = x.shape
+    lib = _lib.load()
+    out = torch.empty(d, dtype=torch.float32, device=x.device)
+    wsb = lib.gist_colsum_workspace_bytes(n, d)
+    ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=x.device)
+    check(lib.gist_colsum_f32(ptr(x), _ld(x), n, d, ptr(out), ptr(ws), wsb, stream_ptr(x.device)), 'colsum_f32')
+    return out
+
+
+class _LayerNormAct(torch.autograd.Function):
+    """act(LayerNorm(x)) over the last dimension, no affine (modules.py:234-236), one kernel
+    forward and one backward."""
+
+    @staticmethod
+    def forward(ctx, x, eps, relu):
+        x = _mat(x, 'x')
+        n, d = x.shape
+        y = torch.empty((n, d), dtype=torch.float32, device=x.device)
+        stats = torch.empty((n, 2), dtype=torch.float32, device=x.device)
+        fl = _lib.ACT_RELU if relu else 0
+        check(_lib.load().gist_layernorm_act_fwd_f32(ptr(x), _ld(x), n, d, eps, fl, ptr(y), _ld(y), ptr(stats),
+                                                     stream_ptr(x.device)), 'layernorm_act_fwd_f32')
+        ctx.save_for_backward(x, stats)
+        ctx.fl = fl
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats = ctx.saved_tensors
+        dy = _mat(dy, 'dy')
+        n, d = x.shape
+        dx = torch.empty((n, d), dtype=torch.float32, device=x.device)
+        check(_lib.load().gist_layernorm_act_bwd_f32(ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(stats), n, d, ctx.fl,
+                                                     ptr(dx), _ld(dx), stream_ptr(x.device)),
+              'layernorm_act_bwd_f32')
+        return dx, None, None
+
+
+def layer_norm_act(x, eps=1e-5, relu=False):
+    """F.relu(F.layer_norm(x, (x.shape[-1],), eps=eps)) (or without the ReLU) for 2-D fp32 x."""
+    require_cuda(x)
+    return _LayerNormAct.apply(x, float(eps), bool(relu))
+
+
+class _MaskedCrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, mask):
+        logits = _mat(logits, 'logits')
+        n, C = logits.shape
+        assert labels.dtype == torch.int64 and labels.shape == (n,)
+        labels = labels.contiguous()
+        if mask is not None:
+            assert mask.dtype == torch.bool and mask.shape == (n,)
+            mask = mask.contiguous()
+        dev = logits.device
+        lse = torch.empty(n, dtype=torch.float32, device=dev)
+        row_loss = torch.empty(n, dtype=torch.float32, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        check(_lib.load().gist_masked_ce_fwd_f32(ptr(logits), _ld(logits), n, C, ptr(labels), ptr(mask), ptr(lse),
+                                                 ptr(row_loss), ptr(out), stream_ptr(dev)), 'masked_ce_fwd_f32')
+        ctx.save_for_backward(logits, labels, mask, lse, out)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, gout):
+        logits, labels, mask, lse, out = ctx.saved_tensors
+        n, C = logits.shape
+        ldd = (C + 3) // 4 * 4        # padded rows: the gradient feeds the TMA-addressed GEMMs
+        buf = torch.empty((n, ldd), dtype=torch.float32, device=logits.device)
+        gout = gout.contiguous().float()
+        check(_lib.load().gist_masked_ce_bwd_f32(ptr(logits), _ld(logits), n, C, ptr(labels), ptr(mask), ptr(lse),
+                                                 ptr(out), ptr(gout), ptr(buf), ldd, ldd,
+                                                 stream_ptr(logits.device)), 'masked_ce_bwd_f32')
+        return buf[:, :C], None, None
+
+
+def masked_cross_entropy(logits, labels, mask=None):
+    """CrossEntropyLoss()(logits[mask], labels[mask]) (…distrib.py:413-414) as a 0-d tensor: two
+    kernels forward, one backward, no boolean-index gather (hence no host sync)."""
+    require_cuda(logits, labels, mask)
+    return _MaskedCrossEntropy.apply(logits, labels, mask)

@@ -1,21 +1,23 @@
 """Training-step helpers shared by the trainers and bench.py (the L4 glue of
 cluster_gcn_ist_distrib.py:370-479, kept thin)."""
 import torch
-import torch.nn.functional as F
+import torch.nn.functional as F  # noqa: F401
+
+from . import ops
+from .optim import Adam
 
 
 def masked_cross_entropy(pred, labels, mask):
     """CrossEntropyLoss()(pred[mask], labels[mask]) (…distrib.py:413-414) without the
-    boolean-index host sync: mean of the per-row losses over the masked rows."""
-    per_row = F.cross_entropy(pred, labels, reduction='none')
-    m = mask.to(per_row.dtype)
-    return (per_row * m).sum() / m.sum()
+    boolean-index host sync: mean of the per-row losses over the masked rows, in the fused
+    CE kernels (csrc/fused.cu)."""
+    return ops.masked_cross_entropy(pred, labels, mask.bool())
 
 
 def make_optimizer(params, lr, weight_decay):
-    """torch.optim.Adam as the reference builds it (…distrib.py:405-407); `fused`
-    only changes how many launches the update takes."""
-    return torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, fused=True)
+    """Adam as the reference builds it (…distrib.py:405-407: torch.optim.Adam(lr, weight_decay)),
+    with the update of all tensors in one launch."""
+    return Adam(params, lr=lr, weight_decay=weight_decay)
 
 
 def train_step(model, optimizer, cluster):

@@ -205,6 +205,51 @@ int gist_gemm_tn_tf32(const float *A, int64_t lda, const float *B, int64_t ldb, 
 int gist_transpose_f32(const float *src, int64_t ld_src, int32_t rows, int32_t cols, float *dst,
                        int64_t ld_dst, gist_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Row-wise pieces of the training step between the SpMM and the GEMM (fused.cu).
+ */
+#define GIST_ACT_RELU 1u
+
+/* y[r,:] = act((x[r,:] - mean_r) * rstd_r): nn.LayerNorm(d, elementwise_affine=False) followed by
+ * the layer's ReLU (cluster_gcn/modules.py:234-236).  stats (optional) receives (mean_r, rstd_r)
+ * pairs, [n, 2] floats, 8-byte aligned, for the backward. */
+int gist_layernorm_act_fwd_f32(const float *x, int64_t ldx, int32_t n, int32_t d, float eps,
+                               uint32_t flags, float *y, int64_t ldy, float *stats, gist_stream_t stream);
+/* dx = d/dx of the above given dy; x is the forward INPUT, stats from the forward. */
+int gist_layernorm_act_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx,
+                               const float *stats, int32_t n, int32_t d, uint32_t flags, float *dx,
+                               int64_t lddx, gist_stream_t stream);
+
+/* out[c] = sum_r x[r, c] (bias gradient of nn.Linear), two-phase fixed-order reduction.
+ * workspace: gist_colsum_workspace_bytes(n, d) bytes. */
+size_t gist_colsum_workspace_bytes(int32_t n, int32_t d);
+int gist_colsum_f32(const float *x, int64_t ldx, int32_t n, int32_t d, float *out, void *workspace,
+                    size_t workspace_bytes, gist_stream_t stream);
+
+/* CrossEntropyLoss()(pred[mask], labels[mask]) (cluster_gcn_ist_distrib.py:413-414) without the
+ * boolean-index gather: loss_out[0] = mean over masked rows of (logsumexp(logits[r]) -
+ * logits[r, labels[r]]), loss_out[1] = 1 / #masked rows.  mask: one byte per row (torch.bool) or
+ * NULL = all rows.  lse [n] and row_loss [n] are outputs kept for the backward. */
+int gist_masked_ce_fwd_f32(const float *logits, int64_t ld, int32_t n, int32_t C, const int64_t *labels,
+                           const uint8_t *mask, float *lse, float *row_loss, float *loss_out,
+                           gist_stream_t stream);
+/* dlogits[r,c] = mask_r * (softmax(logits[r])_c - [c == labels[r]]) * grad_out[0] / #masked rows;
+ * columns [C, fill_cols) of every row are zeroed (row padding for the TMA-fed GEMMs). */
+int gist_masked_ce_bwd_f32(const float *logits, int64_t ld, int32_t n, int32_t C, const int64_t *labels,
+                           const uint8_t *mask, const float *lse, const float *loss_out,
+                           const float *grad_out, float *dlogits, int64_t ldd, int32_t fill_cols,
+                           gist_stream_t stream);
+
+/* torch.optim.Adam(lr, betas, eps, weight_decay) (amsgrad=False; cluster_gcn_ist_distrib.py:405-407,
+ * :417) over n_tensors tensors in one launch (per 24 tensors).  params / grads / exp_avg /
+ * exp_avg_sq / numel are HOST arrays of device pointers / element counts (read during the call).
+ * step: device float, the number of updates done so far; incremented on the device.
+ * counter: device uint32, zero on entry, zero again on exit. */
+int gist_adam_multi_f32(int32_t n_tensors, float *const *params, const float *const *grads,
+                        float *const *exp_avg, float *const *exp_avg_sq, const int64_t *numel, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, float *step,
+                        uint32_t *counter, gist_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,136 @@
+"""Fused row-wise kernels of the training step (csrc/fused.cu) through the C-ABI against torch
+fp64 references of the same ops.  Tolerance: fp32 round-off of a few-hundred-term row reduction,
+asserted at 2e-6 relative (norm-wise), written next to each check."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(got, ref):
+    return ((got.double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize('n,d', [(1, 4), (2586, 256), (2586, 32), (1000, 41), (333, 100), (64, 4096), (7, 1)])
+@pytest.mark.parametrize('relu', [False, True])
+def test_layer_norm_act(n, d, relu):
+    from gist_b200 import ops
+    torch.manual_seed(n + d)
+    x = (torch.randn(n, d, device='cuda') * 3 + 1).requires_grad_(True)
+    w = torch.randn(n, d, device='cuda')
+    y = ops.layer_norm_act(x, 1e-5, relu=relu)
+    (y * w).sum().backward()
+    x2 = x.detach().double().requires_grad_(True)
+    y2 = F.layer_norm(x2, (d,), eps=1e-5)
+    if relu:
+        y2 = F.relu(y2)
+    (y2 * w.double()).sum().backward()
+    if d > 1:
+        assert _rel(y, y2) < 2e-6
+        assert _rel(x.grad, x2.grad) < 2e-5     # LN backward cancels: looser
+    else:
+        assert torch.equal(y, y2.float())
+
+
+def test_layer_norm_act_strided_views():
+    from gist_b200 import ops
+    buf = torch.randn(500, 300, device='cuda')
+    x = buf[:, 7:107]                   # unaligned column block of a wider buffer
+    y = ops.layer_norm_act(x, 1e-5, relu=True)
+    ref = F.relu(F.layer_norm(x.double(), (100,), eps=1e-5))
+    assert _rel(y, ref) < 2e-6
+
+
+@pytest.mark.parametrize('n,d', [(2586, 256), (2586, 41), (1, 5), (100000, 7), (4096, 4096), (63, 33)])
+def test_colsum(n, d):
+    from gist_b200 import ops
+    torch.manual_seed(n)
+    buf = torch.randn(n, d + 3, device='cuda')
+    x = buf[:, :d]
+    got = ops.colsum(x)
+    ref = x.double().sum(0)
+    scale = x.double().abs().sum(0).max().item()
+    assert (got.double() - ref).abs().max().item() <= 1e-6 * scale
+    assert torch.equal(got, ops.colsum(x))          # deterministic
+    ones = torch.ones(n, d, device='cuda')
+    if n < (1 << 24):
+        assert torch.equal(ops.colsum(ones), torch.full((d,), float(n), device='cuda'))
+
+
+@pytest.mark.parametrize('n,C', [(2586, 41), (1000, 47), (17, 3), (5000, 7), (300, 1000)])
+@pytest.mark.parametrize('use_mask', [True, False])
+def test_masked_cross_entropy(n, C, use_mask):
+    from gist_b200 import ops
+    torch.manual_seed(n + C)
+    logits = (torch.randn(n, C, device='cuda') * 4).requires_grad_(True)
+    labels = torch.randint(0, C, (n,), device='cuda')
+    mask = (torch.rand(n, device='cuda') < 0.6) if use_mask else None
+    loss = ops.masked_cross_entropy(logits, labels, mask)
+    (loss * 1.7).backward()
+    l2 = logits.detach().double().requires_grad_(True)
+    sel = mask if use_mask else torch.ones(n, dtype=torch.bool, device='cuda')
+    ref = F.cross_entropy(l2[sel], labels[sel])
+    (ref * 1.7).backward()
+    assert abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    assert _rel(logits.grad, l2.grad) < 2e-6
+    assert logits.grad.shape == (n, C)
+    if use_mask:
+        assert (logits.grad[~mask] == 0).all()
+
+
+def test_adam_matches_torch():
+    from gist_b200.optim import Adam
+    torch.manual_seed(0)
+    shapes = [(256, 1204), (256,), (256, 512), (256,), (41, 512), (41,), (3, 5), (1,)] + [(17,)] * 30
+    ps = [torch.randn(*s, device='cuda').requires_grad_(True) for s in shapes]
+    qs = [p.detach().clone().double().requires_grad_(True) for p in ps]
+    a = Adam(ps, lr=1e-2, weight_decay=5e-4)
+    b = torch.optim.Adam(qs, lr=1e-2, weight_decay=5e-4)
+    for it in range(12):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p) * (0.1 + it)
+            p.grad = g
+            q.grad = g.double()
+        a.step()
+        b.step()
+    for p, q in zip(ps, qs):
+        assert _rel(p, q) < 2e-6
+    # reset_state == a fresh optimizer
+    a.reset_state()
+    c = torch.optim.Adam(qs, lr=1e-2, weight_decay=5e-4)
+    for p, q in zip(ps, qs):
+        q.data.copy_(p.data.double())
+        g = torch.randn_like(p)
+        p.grad = g
+        q.grad = g.double()
+    a.step()
+    c.step()
+    for p, q in zip(ps, qs):
+        assert _rel(p, q) < 2e-6
+
+
+def test_adam_cuda_graph_replay_advances_step():
+    from gist_b200.optim import Adam
+    torch.manual_seed(1)
+    p = torch.randn(1000, device='cuda').requires_grad_(True)
+    q = p.detach().clone().double().requires_grad_(True)
+    g = torch.randn(1000, device='cuda')
+    p.grad = g.clone()
+    a = Adam([p], lr=1e-2)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        a.step()
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        a.step()
+    for _ in range(5):
+        graph.replay()
+    torch.cuda.synchronize()
+    b = torch.optim.Adam([q], lr=1e-2)
+    for _ in range(6):       # 1 warm-up step + 5 replays (capture itself does not execute)
+        q.grad = g.double()
+        b.step()
+    assert _rel(p, q) < 2e-6
