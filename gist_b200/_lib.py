@@ -48,6 +48,11 @@ SIGNATURES = {
     'gist_colsum_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _SZ, _P]),
     'gist_masked_ce_fwd_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     'gist_masked_ce_bwd_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    'gist_gat_scores_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P]),
+    'gist_gat_aggregate_f32': (ctypes.c_int, [_P, _P, _I32, _P, _I64, _I32, _P, _F32, _P, _I64, _P, _P]),
+    'gist_gat_backward_workspace_bytes': (_SZ, [_I32, _I32]),
+    'gist_gat_backward_f32': (ctypes.c_int, [_P, _P, _P, _P, _I32, _P, _I64, _I32, _P, _P, _P, _F32, _P, _I64,
+                                             _P, _I64, _P, _I64, _P, _P, _SZ, _P]),
     'gist_adam_multi_f32': (ctypes.c_int, [_I32, _P, _P, _P, _P, _P, _F32, _F32, _F32, _F32, _F32, _P, _P, _P]),
 }
 

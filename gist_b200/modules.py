@@ -77,6 +77,71 @@ class GraphConv(nn.Module):
         return rst
 
 
+class GATLayer(nn.Module):
+    """cluster_gcn/modules.py:24-65: one attention head.  fc: Linear(in, out, bias=False),
+    attn_fc: Linear(2*out, 1, bias=False), both Xavier-normal with the ReLU gain.  The edge UDF
+    (leaky_relu(attn_fc([z_u ‖ z_v]))), the mailbox softmax and the weighted sum run as one fused
+    kernel (K6) instead of DGL's degree-bucketed Python UDFs."""
+
+    def __init__(self, in_dim, out_dim):
+        super().__init__()
+        self.fc = nn.Linear(in_dim, out_dim, bias=False)
+        self.attn_fc = nn.Linear(2 * out_dim, 1, bias=False)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        gain = nn.init.calculate_gain('relu')
+        nn.init.xavier_normal_(self.fc.weight, gain=gain)
+        nn.init.xavier_normal_(self.attn_fc.weight, gain=gain)
+
+    def forward(self, g, h):
+        z = ops.linear(h, self.fc.weight, None)
+        return ops.gat_aggregate(g, z, self.attn_fc.weight, 0.01)     # F.leaky_relu default slope
+
+
+class MultiHeadGATLayer(nn.Module):
+    """cluster_gcn/modules.py:67-76.  The committed forward returns
+    ``torch.mean(torch.stack(head_outs))`` with no dim — a 0-d scalar, after which the next
+    layer cannot run.  This implements the intended mean over the HEAD axis
+    (``dim=0``); pass ``reduce='scalar'`` for the literal behaviour of the committed code."""
+
+    def __init__(self, in_dim, out_dim, num_heads, reduce='heads'):
+        super().__init__()
+        assert reduce in ('heads', 'scalar')
+        self.reduce = reduce
+        self.heads = nn.ModuleList()
+        for _ in range(num_heads):
+            self.heads.append(GATLayer(in_dim, out_dim))
+
+    def forward(self, g, h):
+        head_outs = [attn_head(g, h) for attn_head in self.heads]
+        if self.reduce == 'scalar':
+            return torch.mean(torch.stack(head_outs))
+        if len(head_outs) == 1:
+            return head_outs[0]
+        return torch.mean(torch.stack(head_outs), dim=0)
+
+
+class GAT(nn.Module):
+    """cluster_gcn/modules.py:78-98: num_layers MultiHeadGATLayers (the last with one head),
+    ELU after every layer including the last."""
+
+    def __init__(self, num_layers, in_dim, hidden_dim, out_dim, num_heads):
+        super().__init__()
+        layers = [MultiHeadGATLayer(in_dim, hidden_dim, num_heads)]
+        for _ in range(num_layers - 2):
+            layers.append(MultiHeadGATLayer(hidden_dim, hidden_dim, num_heads))
+        layers.append(MultiHeadGATLayer(hidden_dim, out_dim, 1))
+        self.layers = nn.ModuleList(layers)
+
+    def forward(self, g):
+        h = g.ndata['feat']
+        for layer in self.layers:
+            h = layer(g, h)
+            h = F.elu(h)
+        return h
+
+
 class GraphSAGELayer(nn.Module):
     """cluster_gcn/modules.py:100-159."""
 

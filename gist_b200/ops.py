@@ -408,3 +408,55 @@ def masked_cross_entropy(logits, labels, mask=None):
     kernels forward, one backward, no boolean-index gather (hence no host sync)."""
     require_cuda(logits, labels, mask)
     return _MaskedCrossEntropy.apply(logits, labels, mask)
+
+
+# --------------------------------------------------------------------------
+# K6: GAT edge-softmax + weighted aggregation (csrc/gat.cu)
+# --------------------------------------------------------------------------
+class _GatAggregate(torch.autograd.Function):
+    """out[v] = sum_u softmax_u(leaky_relu(a_l.z[u] + a_r.z[v])) z[u]  for one attention head
+    (cluster_gcn/modules.py:40-65).  attn is attn_fc.weight ([1, 2D] or [2D])."""
+
+    @staticmethod
+    def forward(ctx, g, z, attn, negative_slope):
+        z = _mat(z, 'z')
+        n, D = z.shape
+        assert n == g.number_of_nodes() and attn.numel() == 2 * D
+        attn = attn.reshape(-1).contiguous()
+        dev = z.device
+        lib = _lib.load()
+        scores = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        out = torch.empty((n, D), dtype=torch.float32, device=dev)
+        lse = torch.empty(n, dtype=torch.float32, device=dev)
+        check(lib.gist_gat_scores_f32(ptr(z), _ld(z), n, D, ptr(attn), ptr(scores), stream_ptr(dev)),
+              'gat_scores_f32')
+        check(lib.gist_gat_aggregate_f32(ptr(g.rowptr), ptr(g.col_buffer), n, ptr(z), _ld(z), D, ptr(scores),
+                                         negative_slope, ptr(out), _ld(out), ptr(lse), stream_ptr(dev)),
+              'gat_aggregate_f32')
+        ctx.g, ctx.slope = g, negative_slope
+        ctx.save_for_backward(z, attn, scores, lse, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, attn, scores, lse, out = ctx.saved_tensors
+        g = ctx.g
+        dout = _mat(dout, 'dout')
+        n, D = z.shape
+        dev = z.device
+        lib = _lib.load()
+        colptr, row = g.csc()
+        dz = torch.empty((n, D), dtype=torch.float32, device=dev)
+        dattn = torch.empty(2 * D, dtype=torch.float32, device=dev)
+        wsb = lib.gist_gat_backward_workspace_bytes(n, D)
+        ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=dev)
+        check(lib.gist_gat_backward_f32(ptr(g.rowptr), ptr(g.col_buffer), ptr(colptr), ptr(row), n, ptr(z), _ld(z),
+                                        D, ptr(scores), ptr(lse), ptr(attn), ctx.slope, ptr(out), _ld(out),
+                                        ptr(dout), _ld(dout), ptr(dz), _ld(dz), ptr(dattn), ptr(ws), wsb,
+                                        stream_ptr(dev)), 'gat_backward_f32')
+        return None, dz, dattn, None
+
+
+def gat_aggregate(g, z, attn, negative_slope=0.01):
+    require_cuda(z, attn, g.rowptr)
+    return _GatAggregate.apply(g, z, attn.reshape(-1), float(negative_slope))

@@ -250,6 +250,37 @@ int gist_adam_multi_f32(int32_t n_tensors, float *const *params, const float *co
                         float beta1, float beta2, float eps, float weight_decay, float *step,
                         uint32_t *counter, gist_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * K6  graph attention (GAT) message passing: fused edge-softmax + weighted SpMM.
+ *
+ * Replaces GATLayer.forward's apply_edges(edge_attention) + update_all(message_func,
+ * reduce_func) (cluster_gcn/modules.py:10-65; Python UDFs over DGL's degree-bucketed mailboxes).
+ * For one head with z = fc(h) [n, D] and attn = attn_fc.weight [2D] = [a_l | a_r]:
+ *   scores[v] = (a_l.z[v], a_r.z[v])
+ *   e_uv      = leaky_relu(scores[u].x + scores[v].y, negative_slope)     for every edge u -> v
+ *   out[v]    = sum_u softmax_u(e_uv) z[u]          (rows without in-edges: zeros)
+ *   lse[v]    = logsumexp_u e_uv                    (kept for the backward; 0 if no in-edges)
+ * No per-edge tensor is materialised.  D <= 1024.
+ */
+int gist_gat_scores_f32(const float *z, int64_t ldz, int32_t n, int32_t D, const float *attn,
+                        float *scores /* [n,2], 8-byte aligned */, gist_stream_t stream);
+int gist_gat_aggregate_f32(const int32_t *rowptr, const int32_t *col, int32_t n, const float *z,
+                           int64_t ldz, int32_t D, const float *scores, float negative_slope,
+                           float *out, int64_t ldo, float *lse, gist_stream_t stream);
+/* Backward of scores + aggregate together, given dout = dL/dout:
+ *   dz    [n, D] = dL/dz   (through the aggregation AND through the attention scores)
+ *   dattn [2D]   = dL/dattn
+ * (rowptr, col) = in-edge CSR, (colptr, row) = out-edge lists (CSC) of the same graph.
+ * Deterministic: two gather passes (CSR order, then CSC order), no atomics.
+ * workspace: gist_gat_backward_workspace_bytes(n, D) bytes. */
+size_t gist_gat_backward_workspace_bytes(int32_t n, int32_t D);
+int gist_gat_backward_f32(const int32_t *rowptr, const int32_t *col, const int32_t *colptr,
+                          const int32_t *row, int32_t n, const float *z, int64_t ldz, int32_t D,
+                          const float *scores, const float *lse, const float *attn,
+                          float negative_slope, const float *out, int64_t ldo, const float *dout,
+                          int64_t lddo, float *dz, int64_t lddz, float *dattn, void *workspace,
+                          size_t workspace_bytes, gist_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

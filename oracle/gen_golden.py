@@ -356,12 +356,58 @@ def gen_train_ist(out):
         out[p + 'nsplit'] = np.int64(len(sub_loads))
 
 
+def gen_gat(out):
+    """cluster_gcn/modules.py GATLayer (one head) run unmodified on the restated DGL's UDF /
+    degree-bucketing path: output and gradients.  MultiHeadGATLayer / GAT as committed cannot
+    run (scalar mean), so the multi-head golden stacks the reference's own
+    GATLayer heads and takes the intended mean over the head axis."""
+    import dgl
+    import modules
+    cases = [dict(n=50, nnz=400, fin=9, D=8, seed=11, loops=True),
+             dict(n=70, nnz=900, fin=12, D=20, seed=12, loops=False),
+             dict(n=40, nnz=300, fin=5, D=3, seed=13, loops=True)]
+    for ci, c in enumerate(cases):
+        src, dst = small_graph(c['n'], c['nnz'], c['seed'], loops=c['loops'])
+        g = dgl.DGLGraph((src, dst), num_nodes=c['n'])
+        torch.manual_seed(c['seed'])
+        layer = modules.GATLayer(c['fin'], c['D'])
+        x = torch.randn(c['n'], c['fin'], requires_grad=True)
+        wy = torch.randn(c['n'], c['D'])
+        y = layer(g, x)
+        (y * wy).sum().backward()
+        p = 'gat%d_' % ci
+        out[p + 'src'], out[p + 'dst'], out[p + 'n'] = src, dst, np.int64(c['n'])
+        out[p + 'x'], out[p + 'wy'] = x.detach().numpy(), wy.numpy()
+        out[p + 'fc'] = layer.fc.weight.detach().numpy()
+        out[p + 'attn'] = layer.attn_fc.weight.detach().numpy()
+        out[p + 'out'] = y.detach().numpy()
+        out[p + 'dx'] = x.grad.numpy().copy()
+        out[p + 'dfc'] = layer.fc.weight.grad.numpy().copy()
+        out[p + 'dattn'] = layer.attn_fc.weight.grad.numpy().copy()
+    # two layers x two heads, intended head mean + ELU (modules.py:93-98)
+    src, dst = small_graph(60, 600, 14, loops=True)
+    g = dgl.DGLGraph((src, dst), num_nodes=60)
+    torch.manual_seed(14)
+    l0 = [modules.GATLayer(7, 6) for _ in range(2)]
+    l1 = [modules.GATLayer(6, 4)]
+    x = torch.randn(60, 7)
+    h = x
+    for heads in (l0, l1):
+        h = F.elu(torch.stack([hd(g, h) for hd in heads]).mean(dim=0))
+    out['mh_src'], out['mh_dst'], out['mh_n'], out['mh_x'] = src, dst, np.int64(60), x.numpy()
+    for li, heads in enumerate((l0, l1)):
+        for hi, hd in enumerate(heads):
+            out['mh_fc_%d_%d' % (li, hi)] = hd.fc.weight.detach().numpy()
+            out['mh_attn_%d_%d' % (li, hi)] = hd.attn_fc.weight.detach().numpy()
+    out['mh_out'] = h.detach().numpy()
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     bind_reference('cluster_gcn')
-    which = sys.argv[1:] or ['sage', 'graphconv', 'partition', 'cluster_iter', 'wrapper', 'train_ist']
+    which = sys.argv[1:] or ['sage', 'graphconv', 'partition', 'cluster_iter', 'wrapper', 'train_ist', 'gat']
     gens = dict(sage=gen_sage, graphconv=gen_graphconv, partition=gen_partition,
-                cluster_iter=gen_cluster_iter, wrapper=gen_wrapper, train_ist=gen_train_ist)
+                cluster_iter=gen_cluster_iter, wrapper=gen_wrapper, train_ist=gen_train_ist, gat=gen_gat)
     for name in which:
         out = {}
         gens[name](out)

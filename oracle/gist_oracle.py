@@ -133,6 +133,41 @@ def graphconv_gcn_forward(g, feat, params, use_layernorm, activation=F.relu, dro
     return h
 
 
+# -------------------------------------------------------------------- GAT ---
+def gat_layer(g, h, fc_weight, attn_weight, negative_slope=0.01):
+    """GATLayer.forward (modules.py:57-65): z = fc(h); e_uv = leaky_relu(attn_fc([z_u ‖ z_v]))
+    (:40-44, F.leaky_relu default slope 0.01); alpha = softmax over the in-edges of v (:53);
+    h_v = sum_u alpha_uv z_u (:55).  Nodes without in-edges receive no message and keep the
+    zero row DGL's degree bucketing leaves (DGL-recall).  Multi-edges count once each."""
+    z = F.linear(h, fc_weight)
+    D = z.shape[1]
+    a = attn_weight.reshape(-1)
+    el, er = z @ a[:D], z @ a[D:]
+    e = F.leaky_relu(el[g.src] + er[g.dst], negative_slope)
+    m = torch.full((g.n,), -float('inf'), dtype=e.dtype).scatter_reduce(0, g.dst, e.detach(), 'amax',
+                                                                         include_self=True)
+    w = torch.exp(e - m[g.dst])
+    den = torch.zeros(g.n, dtype=e.dtype).index_add(0, g.dst, w)
+    alpha = w / den[g.dst]
+    return torch.zeros((g.n, D), dtype=z.dtype).index_add(0, g.dst, alpha.unsqueeze(1) * z[g.src])
+
+
+def multi_head_gat_layer(g, h, heads, negative_slope=0.01):
+    """MultiHeadGATLayer.forward (modules.py:74-76) with the INTENDED semantics: the mean over
+    the head axis.  The committed code calls torch.mean(torch.stack(head_outs)) without a dim,
+    which collapses everything to a scalar and makes the next layer fail."""
+    return torch.stack([gat_layer(g, h, fw, aw, negative_slope) for fw, aw in heads]).mean(dim=0)
+
+
+def gat_forward(g, feat, layers, negative_slope=0.01):
+    """GAT.forward (modules.py:93-98): ELU after every layer, including the last.
+    layers = [[(fc_weight, attn_weight) per head] per layer]."""
+    h = feat
+    for heads in layers:
+        h = F.elu(multi_head_gat_layer(g, h, heads, negative_slope))
+    return h
+
+
 # ------------------------------------------------------------ cluster iter ---
 def batch_node_ids(par_li, i, psize, batch_size):
     """partition_utils.py:20-25."""

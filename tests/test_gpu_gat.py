@@ -1,0 +1,104 @@
+"""K6 parity (through the C-ABI): fused GAT edge-softmax + aggregation vs the oracle, vs the golden
+produced by the reference's own GATLayer, gradients included.  Tolerance 1e-5 norm-wise relative
+for the forward (fp32, different summation order), 1e-4 for gradients (softmax backward cancels)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import assert_close, powerlaw_graph, random_graph
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _graph(src, dst, n):
+    import gist_b200 as gb
+    return gb.GistGraph.from_edges(torch.as_tensor(src), torch.as_tensor(dst), n, device='cuda')
+
+
+@pytest.mark.parametrize('ci', [0, 1, 2])
+def test_gat_layer_vs_reference_golden(ci):
+    import gist_b200 as gb
+    G = np.load(os.path.join(GOLD, 'gat.npz'))
+    p = 'gat%d_' % ci
+    n = int(G[p + 'n'])
+    g = _graph(G[p + 'src'], G[p + 'dst'], n)
+    layer = gb.GATLayer(G[p + 'fc'].shape[1], G[p + 'fc'].shape[0]).cuda()
+    with torch.no_grad():
+        layer.fc.weight.copy_(torch.from_numpy(G[p + 'fc']))
+        layer.attn_fc.weight.copy_(torch.from_numpy(G[p + 'attn']))
+    x = torch.from_numpy(G[p + 'x']).cuda().requires_grad_(True)
+    y = layer(g, x)
+    assert_close(y, torch.from_numpy(G[p + 'out']), 1e-5, 'out')
+    (y * torch.from_numpy(G[p + 'wy']).cuda()).sum().backward()
+    assert_close(x.grad, torch.from_numpy(G[p + 'dx']), 1e-4, 'dx')
+    assert_close(layer.fc.weight.grad, torch.from_numpy(G[p + 'dfc']), 1e-4, 'dfc')
+    assert_close(layer.attn_fc.weight.grad, torch.from_numpy(G[p + 'dattn']), 1e-4, 'dattn')
+
+
+def test_gat_model_vs_reference_golden():
+    import gist_b200 as gb
+    G = np.load(os.path.join(GOLD, 'gat.npz'))
+    g = _graph(G['mh_src'], G['mh_dst'], int(G['mh_n']))
+    model = gb.GAT(2, 7, 6, 4, 2).cuda()
+    with torch.no_grad():
+        for li, nh in ((0, 2), (1, 1)):
+            for hi in range(nh):
+                model.layers[li].heads[hi].fc.weight.copy_(torch.from_numpy(G['mh_fc_%d_%d' % (li, hi)]))
+                model.layers[li].heads[hi].attn_fc.weight.copy_(torch.from_numpy(G['mh_attn_%d_%d' % (li, hi)]))
+    g.ndata['feat'] = torch.from_numpy(G['mh_x']).cuda()
+    assert_close(model(g), torch.from_numpy(G['mh_out']), 1e-5, 'gat model')
+    assert sorted(model.state_dict().keys())[0] == 'layers.0.heads.0.attn_fc.weight'
+
+
+@pytest.mark.parametrize('n,nnz,D,kind', [(300, 4000, 64, 'rand'), (2000, 30000, 256, 'rand'), (500, 6000, 41, 'rand'),
+                                          (1000, 20, 7, 'power'), (700, 9000, 512, 'rand'), (400, 5000, 1000, 'rand'),
+                                          (257, 3000, 130, 'rand')])
+def test_gat_aggregate_vs_oracle(n, nnz, D, kind):
+    """Forward + all gradients vs fp64 autograd of the oracle; vector widths 4 / 1, every register-slot
+    variant, hub rows, zero-in-degree rows, duplicate edges, asymmetric graphs (CSC != CSR)."""
+    from gist_b200 import ops
+    from oracle import gist_oracle as O
+    if kind == 'power':
+        src, dst = powerlaw_graph(n, nnz, seed=D)
+    else:
+        src, dst = random_graph(n, nnz, seed=n + D, isolated=5)
+    g = _graph(src, dst, n)
+    og = O.OGraph(src, dst, n)
+    torch.manual_seed(D)
+    z = torch.randn(n, D, device='cuda', requires_grad=True)
+    attn = (torch.randn(1, 2 * D, device='cuda') / D ** 0.5).requires_grad_(True)
+    wy = torch.randn(n, D, device='cuda')
+    out = ops.gat_aggregate(g, z, attn, 0.01)
+    (out * wy).sum().backward()
+    z2 = z.detach().double().cpu().requires_grad_(True)
+    a2 = attn.detach().double().cpu().requires_grad_(True)
+    ref = O.gat_layer(og, z2, torch.eye(D, dtype=torch.float64), a2)
+    (ref * wy.double().cpu()).sum().backward()
+    assert_close(out, ref, 1e-5, 'out')
+    assert_close(z.grad, z2.grad, 1e-4, 'dz')
+    assert_close(attn.grad, a2.grad, 1e-4, 'dattn')
+    indeg = torch.bincount(torch.as_tensor(dst), minlength=n)
+    assert (out[(indeg == 0).cuda()] == 0).all()
+    # deterministic
+    z.grad = None
+    out2 = ops.gat_aggregate(g, z, attn, 0.01)
+    assert torch.equal(out, out2)
+
+
+def test_gat_softmax_properties_large():
+    """Size-independent property at a size the oracle would not finish quickly: with a_l = a_r = 0
+    every alpha is 1/deg, so the output equals the mean aggregation the SAGE kernel computes."""
+    import gist_b200 as gb
+    from gist_b200 import ops, synth
+    ds = synth.make('reddit', seed=0, device='cuda', scale=0.05, feat_dim=64)
+    g = synth.to_gist_graph(ds)
+    n = g.number_of_nodes()
+    z = g.ndata['feat']
+    out = ops.gat_aggregate(g, z, torch.zeros(1, 128, device='cuda'), 0.01)
+    mean = ops.gspmm(g, z, None, g.inv_in_degree())
+    assert_close(out, mean, 1e-5, 'uniform attention == mean aggregation')
+    assert gb.GATLayer  # exported

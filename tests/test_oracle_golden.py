@@ -177,3 +177,29 @@ def test_train_ist_split_merge(ci):
         merged = O.graphconv_merge(main, feats_idx, trained, L, bool(si), bool(so))
         for k in keys:
             close(merged[k], G[p + 'r%d_merged.%s' % (r, k)], 1e-6)
+
+
+@pytest.mark.parametrize('ci', [0, 1, 2])
+def test_gat_layer_oracle_vs_reference_golden(ci):
+    """oracle gat_layer == the reference's own GATLayer (modules.py:24-65) run on the restated
+    DGL UDF path: output and all gradients."""
+    G = load('gat')
+    p = 'gat%d_' % ci
+    g = O.OGraph(G[p + 'src'], G[p + 'dst'], int(G[p + 'n']))
+    x = T(G[p + 'x']).requires_grad_(True)
+    fc = T(G[p + 'fc']).requires_grad_(True)
+    attn = T(G[p + 'attn']).requires_grad_(True)
+    out = O.gat_layer(g, x, fc, attn)
+    close(out.detach(), G[p + 'out'])
+    (out * T(G[p + 'wy'])).sum().backward()
+    close(x.grad, G[p + 'dx'], 1e-4)
+    close(fc.grad, G[p + 'dfc'], 1e-4)
+    close(attn.grad, G[p + 'dattn'], 1e-4)
+
+
+def test_gat_multi_head_oracle_vs_golden():
+    G = load('gat')
+    g = O.OGraph(G['mh_src'], G['mh_dst'], int(G['mh_n']))
+    layers = [[(T(G['mh_fc_0_%d' % h]), T(G['mh_attn_0_%d' % h])) for h in range(2)],
+              [(T(G['mh_fc_1_0']), T(G['mh_attn_1_0']))]]
+    close(O.gat_forward(g, T(G['mh_x']), layers), G['mh_out'])
