@@ -7,7 +7,8 @@ from .modules import (GraphConv, GraphSAGELayer, ISTSAGELayer, GraphSAGE, GCN as
 from .gcn import GCN  # noqa: F401
 from .sampler import ClusterIter, get_partition_list, get_subgraph  # noqa: F401
 from .ist import create_partition, DistributedGNNWrapper  # noqa: F401
+from .ist_gat import DistributedGATWrapper  # noqa: F401
 
 __all__ = ['function', 'GistGraph', 'GistError', 'NID', 'GraphConv', 'GraphSAGELayer', 'ISTSAGELayer',
            'GraphSAGE', 'SageGCN', 'BaselineGCN', 'GATLayer', 'MultiHeadGATLayer', 'GAT', 'GCN', 'ClusterIter', 'get_partition_list',
-           'get_subgraph', 'create_partition', 'DistributedGNNWrapper']
+           'get_subgraph', 'create_partition', 'DistributedGNNWrapper', 'DistributedGATWrapper']
