@@ -21,6 +21,13 @@
 // sums in a fixed order -> deterministic, no atomics.
 // TMA zero-fills out-of-bounds rows / K columns, so M, N, K need no padding; only base
 // pointers (16 B) and leading dimensions (multiple of 4 floats) are constrained.
+//
+// NT = 3 ("3xTF32", fp32-accurate): every operand comes as a pair (x, x_lo) with
+// x_lo = tf32(x - trunc_tf32(x)) produced by split_tf32_kernel.  The tensor core drops the low
+// 13 mantissa bits of x, i.e. multiplies trunc_tf32(x); three MMAs per K step
+//     D += A_lo·B + A·B_lo + A·B        (only the A_lo·B_lo term, <= 2^-20 relative, is dropped)
+// recover ~2^-20 relative accuracy per product with fp32 accumulation in TMEM, which keeps the
+// layer outputs and gradients within the 1e-5 parity tolerance of the reference's fp32 sgemm.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -147,27 +154,33 @@ struct GemmParams {
     int32_t tiles_m, tiles_n, splits, kb_per_split, kblocks;
     int32_t relu;
     int32_t vec4;       // output rows and bias are 16-byte aligned: float4 epilogue stores
+    int32_t kc;         // NT == 3: K blocks chained into one TMEM accumulator before it is drained
 };
 
-template <int BN>
+template <int BN, int NT>
 struct GemmCfg {
-    static constexpr int kStageBytes = (kBM + BN) * kBK * 4;
-    static constexpr int kStages = kSmemBudget / kStageBytes;          // 64: 8, 128: 6, 256: 4
+    static constexpr int kOperandCopies = NT == 3 ? 2 : 1;               // (x) or (x, x_lo)
+    static constexpr int kStageBytes = (kBM + BN) * kBK * 4 * kOperandCopies;
+    static constexpr int kStages = kSmemBudget / kStageBytes;          // NT=1: 64: 8, 128: 6, 256: 4
     static constexpr int kTmemCols = 2 * BN;                            // double-buffered accumulator
     static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int NT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmBl,
                  const GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, NT>;
     constexpr int kStages = Cfg::kStages;
+    constexpr size_t kABytes = (size_t)kStages * kBM * kBK * 4, kBBytes = (size_t)kStages * BN * kBK * 4;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                 ~static_cast<uintptr_t>(1023));
-    float *sA = reinterpret_cast<float *>(base);                                    // [stages][128*32]
-    float *sB = reinterpret_cast<float *>(base + (size_t)kStages * kBM * kBK * 4);   // [stages][BN*32]
+    float *sA = reinterpret_cast<float *>(base);                     // [stages][128*32]
+    float *sB = reinterpret_cast<float *>(base + kABytes);           // [stages][BN*32]
+    float *sAl = reinterpret_cast<float *>(base + kABytes + kBBytes);              // NT == 3 only
+    float *sBl = reinterpret_cast<float *>(base + 2 * kABytes + kBBytes);
     uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)kStages * Cfg::kStageBytes);
     uint64_t *full = bars, *empty = bars + kStages;
     uint64_t *tmem_full = bars + 2 * kStages, *tmem_empty = bars + 2 * kStages + 2;
@@ -204,6 +217,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+            if constexpr (NT == 3) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAl)) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBl)) : "memory");
+            }
             int s = 0;
             uint32_t ph = 0;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -216,21 +233,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], (uint32_t)Cfg::kStageBytes);
-                    float *a = sA + (size_t)s * kBM * kBK;
-                    float *b = sB + (size_t)s * BN * kBK;
-                    if constexpr (A_MN) {
 #pragma unroll
-                        for (int j = 0; j < kBM / 32; ++j)
-                            tma_load_2d(&tmA, &full[s], a + j * 32 * kBK, m0 + 32 * j, kb * kBK);
-                    } else {
-                        tma_load_2d(&tmA, &full[s], a, kb * kBK, m0);
-                    }
-                    if constexpr (B_MN) {
+                    for (int part = 0; part < Cfg::kOperandCopies; ++part) {
+                        const CUtensorMap *ma = part ? &tmAl : &tmA, *mb = part ? &tmBl : &tmB;
+                        float *a = (part ? sAl : sA) + (size_t)s * kBM * kBK;
+                        float *b = (part ? sBl : sB) + (size_t)s * BN * kBK;
+                        if constexpr (A_MN) {
 #pragma unroll
-                        for (int j = 0; j < BN / 32; ++j)
-                            tma_load_2d(&tmB, &full[s], b + j * 32 * kBK, n0 + 32 * j, kb * kBK);
-                    } else {
-                        tma_load_2d(&tmB, &full[s], b, kb * kBK, n0);
+                            for (int j = 0; j < kBM / 32; ++j)
+                                tma_load_2d(ma, &full[s], a + j * 32 * kBK, m0 + 32 * j, kb * kBK);
+                        } else {
+                            tma_load_2d(ma, &full[s], a, kb * kBK, m0);
+                        }
+                        if constexpr (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < BN / 32; ++j)
+                                tma_load_2d(mb, &full[s], b + j * 32 * kBK, n0 + 32 * j, kb * kBK);
+                        } else {
+                            tma_load_2d(mb, &full[s], b, kb * kBK, n0);
+                        }
                     }
                     if (++s == kStages) { s = 0; ph ^= 1; }
                 }
@@ -247,28 +268,50 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int split = w % p.splits;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-                mbar_wait(&tmem_empty[acc], acc_ph ^ 1);        // epilogue has drained this buffer
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_addr = tmem_d + (uint32_t)(acc * BN);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&full[s], ph);
+                // The tensor core's fp32 accumulate truncates, so error grows linearly with the
+                // number of MMAs chained into one TMEM accumulator.  NT == 3 therefore closes the
+                // accumulator every p.kc K blocks; the epilogue warps add the chunks in registers
+                // (round-to-nearest fp32), alternating the two TMEM buffers.  NT == 1: one chunk.
+                const int kc = NT == 3 ? p.kc : (kb1 - kb0);
+                for (int kc0 = kb0; kc0 < kb1; kc0 += kc) {
+                    const int kc1 = min(kb1, kc0 + kc);
+                    mbar_wait(&tmem_empty[acc], acc_ph ^ 1);        // epilogue has drained this buffer
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = smem_u32(sA + (size_t)s * kBM * kBK);
-                    const uint32_t b_addr = smem_u32(sB + (size_t)s * BN * kBK);
+                    const uint32_t d_addr = tmem_d + (uint32_t)(acc * BN);
+                    for (int kb = kc0; kb < kc1; ++kb) {
+                        mbar_wait(&full[s], ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_addr = smem_u32(sA + (size_t)s * kBM * kBK);
+                        const uint32_t b_addr = smem_u32(sB + (size_t)s * BN * kBK);
+                        auto a_desc = [](uint32_t addr, int k) {
+                            return A_MN ? umma_desc(addr + k * 1024, 4096, 512, kLayoutSw128Base32)
+                                        : umma_desc(addr + k * kUmmaK * 4, 0, 1024, kLayoutSw128);
+                        };
+                        auto b_desc = [](uint32_t addr, int k) {
+                            return B_MN ? umma_desc(addr + k * 1024, 4096, 512, kLayoutSw128Base32)
+                                        : umma_desc(addr + k * kUmmaK * 4, 0, 1024, kLayoutSw128);
+                        };
 #pragma unroll
-                    for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        const uint64_t ad = A_MN ? umma_desc(a_addr + k * 1024, 4096, 512, kLayoutSw128Base32)
-                                                 : umma_desc(a_addr + k * kUmmaK * 4, 0, 1024, kLayoutSw128);
-                        const uint64_t bd = B_MN ? umma_desc(b_addr + k * 1024, 4096, 512, kLayoutSw128Base32)
-                                                 : umma_desc(b_addr + k * kUmmaK * 4, 0, 1024, kLayoutSw128);
-                        umma_tf32(d_addr, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < kBK / kUmmaK; ++k) {
+                            const uint64_t ad = a_desc(a_addr, k), bd = b_desc(b_addr, k);
+                            const uint32_t first = (kb > kc0 || k > 0) ? 1u : 0u;
+                            if constexpr (NT == 3) {     // small terms first, then the leading product
+                                const uint64_t adl = a_desc(smem_u32(sAl + (size_t)s * kBM * kBK), k);
+                                const uint64_t bdl = b_desc(smem_u32(sBl + (size_t)s * BN * kBK), k);
+                                umma_tf32(d_addr, adl, bd, idesc, first);
+                                umma_tf32(d_addr, ad, bdl, idesc, 1u);
+                                umma_tf32(d_addr, ad, bd, idesc, 1u);
+                            } else {
+                                umma_tf32(d_addr, ad, bd, idesc, first);
+                            }
+                        }
+                        umma_commit(&empty[s]);          // slot reusable once these MMAs have read it
+                        if (++s == kStages) { s = 0; ph ^= 1; }
                     }
-                    umma_commit(&empty[s]);          // slot reusable once these MMAs have read it
-                    if (++s == kStages) { s = 0; ph ^= 1; }
+                    umma_commit(&tmem_full[acc]);        // this chunk's accumulator is complete
+                    acc ^= 1;
+                    if (acc == 0) acc_ph ^= 1;
                 }
-                umma_commit(&tmem_full[acc]);        // accumulator complete
-                acc ^= 1;
-                if (acc == 0) acc_ph ^= 1;
             }
         }
     } else {
@@ -281,54 +324,94 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int t = w / p.splits;
             const int m0 = (t % p.tiles_m) * kBM;
             const int n0 = (t / p.tiles_m) * BN;
-            mbar_wait(&tmem_full[acc], acc_ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = m0 + q * 32 + lane;
             float *crow = p.C + ((int64_t)split * p.M + row) * p.ldc;
             const bool fused = p.splits == 1;
             const int ncols = min(BN, p.N - n0);     // warp-uniform
-#pragma unroll 1
-            for (int c = 0; c < ncols; c += 32) {
-                float v[32];
-                tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
-                if (row < p.M) {
-                    float *out = crow + n0 + c;
-                    if (p.vec4 && c + 32 <= ncols) {             // 16-byte aligned 128-byte segment
+            // one 32-column segment of the finished row: bias / ReLU, then 128-bit or scalar stores
+            auto store32 = [&](const float (&v)[32], int c) {
+                if (row >= p.M) return;
+                float *out = crow + n0 + c;
+                if (p.vec4 && c + 32 <= ncols) {             // 16-byte aligned 128-byte segment
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                            if (fused) {
-                                if (p.bias) {
-                                    const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + c + i));
-                                    r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
-                                }
-                                if (p.relu) {
-                                    r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f);
-                                    r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
-                                }
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        if (fused) {
+                            if (p.bias) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + c + i));
+                                r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
                             }
-                            *reinterpret_cast<float4 *>(out + i) = r;
+                            if (p.relu) {
+                                r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f);
+                                r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+                            }
                         }
-                    } else {
+                        *reinterpret_cast<float4 *>(out + i) = r;
+                    }
+                } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (c + i < ncols) {
-                                float r = v[i];
-                                if (fused) {
-                                    if (p.bias) r += __ldg(p.bias + n0 + c + i);
-                                    if (p.relu) r = fmaxf(r, 0.f);
-                                }
-                                out[i] = r;
+                    for (int i = 0; i < 32; ++i) {
+                        if (c + i < ncols) {
+                            float r = v[i];
+                            if (fused) {
+                                if (p.bias) r += __ldg(p.bias + n0 + c + i);
+                                if (p.relu) r = fmaxf(r, 0.f);
                             }
+                            out[i] = r;
                         }
                     }
                 }
+            };
+            if constexpr (NT == 3) {
+                // sum the K chunks in registers: lane = row, BN fp32 accumulators per thread
+                static_assert(BN <= 128, "3xTF32 keeps the whole row of the tile in registers");
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+                float sum[BN];
+#pragma unroll
+                for (int i = 0; i < BN; ++i) sum[i] = 0.f;
+                for (int kc0 = kb0; kc0 < kb1; kc0 += p.kc) {
+                    mbar_wait(&tmem_full[acc], acc_ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < BN; c += 32) {
+                        if (c < ncols) {
+                            float v[32];
+                            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) sum[c + i] += v[i];
+                        }
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    acc ^= 1;
+                    if (acc == 0) acc_ph ^= 1;
+                }
+#pragma unroll
+                for (int c = 0; c < BN; c += 32) {
+                    if (c < ncols) {
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = sum[c + i];
+                        store32(v, c);
+                    }
+                }
+            } else {
+                mbar_wait(&tmem_full[acc], acc_ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int c = 0; c < ncols; c += 32) {
+                    float v[32];
+                    tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
+                    store32(v, c);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_ph ^= 1;
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_ph ^= 1;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -363,6 +446,43 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restr
             if (relu) x = fmaxf(x, 0.f);
             C[(int64_t)r * ldc + c + k] = x;
         }
+    }
+}
+
+// ------------------------------------------------------------ 3xTF32 split ----
+// lo = tf32_rn(x - trunc_tf32(x)); optionally hi = trunc_tf32(x).  trunc_tf32 clears the 13 low
+// mantissa bits, which is what kind::tf32 does to an fp32 operand, so the GEMM can use x itself as
+// the leading term.  x - trunc(x) is exact in fp32; rounding it to TF32 here (instead of letting
+// the MMA truncate it) halves and unbiases the residual error.  Non-finite x -> lo = 0.
+__device__ __forceinline__ float tf32_lo(float x, float *hi_out) {
+    const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    *hi_out = h;
+    float r = x - h;
+    if (!(fabsf(x) <= 3.402823466e38f)) r = 0.f;
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
+    return __uint_as_float(t);
+}
+
+template <bool V4>
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ x, int64_t ld_x, int rows,
+                                                         int cols, float *__restrict__ hi, int64_t ld_hi,
+                                                         float *__restrict__ lo, int64_t ld_lo) {
+    const int per_row = V4 ? (cols + 3) >> 2 : cols;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows * per_row) return;
+    const int r = (int)(i / per_row), c = (int)(i % per_row) * (V4 ? 4 : 1);
+    if constexpr (V4) {
+        // rows are padded to a multiple of 4 floats (ld % 4 == 0), so a whole float4 is in bounds
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(x + (int64_t)r * ld_x + c));
+        float4 h, l;
+        l.x = tf32_lo(v.x, &h.x); l.y = tf32_lo(v.y, &h.y); l.z = tf32_lo(v.z, &h.z); l.w = tf32_lo(v.w, &h.w);
+        *reinterpret_cast<float4 *>(lo + (int64_t)r * ld_lo + c) = l;
+        if (hi) *reinterpret_cast<float4 *>(hi + (int64_t)r * ld_hi + c) = h;
+    } else {
+        float h;
+        lo[(int64_t)r * ld_lo + c] = tf32_lo(__ldg(x + (int64_t)r * ld_x + c), &h);
+        if (hi) hi[(int64_t)r * ld_hi + c] = h;
     }
 }
 
@@ -433,28 +553,41 @@ static int sm_count() {
     return n;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &p, cudaStream_t s) {
-    constexpr size_t smem = GemmCfg<BN>::kSmemBytes;
+struct GemmMaps {
+    CUtensorMap a, b, al, bl;     // al / bl = the x_lo operands (NT == 3); copies of a / b otherwise
+};
+
+template <int BN, bool A_MN, bool B_MN, int NT>
+static int launch_gemm(const GemmMaps &m, const GemmParams &p, cudaStream_t s) {
+    constexpr size_t smem = GemmCfg<BN, NT>::kSmemBytes;
+    static_assert(GemmCfg<BN, NT>::kStages >= 2, "operand ring needs at least two stages");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN>,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN, NT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     const int n_work = p.tiles_m * p.tiles_n * p.splits;
     const int grid = n_work < sm_count() ? n_work : sm_count();
-    gemm_tf32_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, smem, s>>>(ta, tb, p);
+    gemm_tf32_kernel<BN, A_MN, B_MN, NT><<<grid, kGemmThreads, smem, s>>>(m.a, m.b, m.al, m.bl, p);
     count_launch();
     return last_error();
 }
 
-template <int BN>
-static int launch_layout(bool a_mn, bool b_mn, const CUtensorMap &ta, const CUtensorMap &tb,
-                         const GemmParams &p, cudaStream_t s) {
-    if (a_mn) return b_mn ? launch_gemm<BN, true, true>(ta, tb, p, s) : launch_gemm<BN, true, false>(ta, tb, p, s);
-    return b_mn ? launch_gemm<BN, false, true>(ta, tb, p, s) : launch_gemm<BN, false, false>(ta, tb, p, s);
+template <int BN, int NT>
+static int launch_layout(bool a_mn, bool b_mn, const GemmMaps &m, const GemmParams &p, cudaStream_t s) {
+    if (a_mn) return b_mn ? launch_gemm<BN, true, true, NT>(m, p, s) : launch_gemm<BN, true, false, NT>(m, p, s);
+    return b_mn ? launch_gemm<BN, false, true, NT>(m, p, s) : launch_gemm<BN, false, false, NT>(m, p, s);
+}
+
+template <int NT>
+static int launch_tile(int bn, bool a_mn, bool b_mn, const GemmMaps &m, const GemmParams &p, cudaStream_t s) {
+    if constexpr (NT == 1) {
+        if (bn == 256) return launch_layout<256, NT>(a_mn, b_mn, m, p, s);
+    }
+    if (bn == 128) return launch_layout<128, NT>(a_mn, b_mn, m, p, s);
+    return launch_layout<64, NT>(a_mn, b_mn, m, p, s);
 }
 
 struct GemmPlan {
@@ -466,15 +599,16 @@ struct GemmPlan {
 // Tile width and split-K factor: the widest tile that still gives most of the 148 SMs a work
 // unit; when even 64-wide tiles leave more than half the chip idle and K is long (the dW
 // contraction), K is split.
-static GemmPlan plan_gemm(int M, int N, int K, uint32_t flags) {
+static GemmPlan plan_gemm(int M, int N, int K, uint32_t flags, bool x3) {
     GemmPlan pl;
     const int sms = sm_count();
     const int64_t tm = (M + kBM - 1) / kBM;
     auto tiles = [&](int bn) { return tm * ((N + bn - 1) / bn); };
+    // 3xTF32 sums K chunks in registers (one tile row per epilogue thread): tiles are <= 128 wide
     if (flags & GIST_GEMM_TILE_N64) pl.bn = 64;
     else if (flags & GIST_GEMM_TILE_N128) pl.bn = 128;
-    else if (flags & GIST_GEMM_TILE_N256) pl.bn = 256;
-    else if (tiles(256) >= (int64_t)sms * 4 / 5) pl.bn = 256;
+    else if (flags & GIST_GEMM_TILE_N256) pl.bn = x3 ? 128 : 256;
+    else if (!x3 && tiles(256) >= (int64_t)sms * 4 / 5) pl.bn = 256;
     else if (tiles(128) >= (int64_t)sms * 4 / 5) pl.bn = 128;
     else pl.bn = 64;
     const int kblocks = (K + kBK - 1) / kBK;
@@ -500,25 +634,34 @@ using namespace gist;
 
 extern "C" size_t gist_gemm_tf32_workspace_bytes(int32_t M, int32_t N, int32_t K, uint32_t flags) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    return plan_gemm(M, N, K, flags).ws_bytes;
+    return plan_gemm(M, N, K, flags, false).ws_bytes;
 }
 
-extern "C" int gist_gemm_tf32(const float *A, int64_t lda, int32_t a_layout, const float *B, int64_t ldb,
-                              int32_t b_layout, float *C, int64_t ldc, int32_t M, int32_t N, int32_t K,
-                              const float *bias, uint32_t flags, void *workspace, size_t workspace_bytes,
-                              gist_stream_t stream) {
+extern "C" size_t gist_gemm_3xtf32_workspace_bytes(int32_t M, int32_t N, int32_t K, uint32_t flags) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return plan_gemm(M, N, K, flags, true).ws_bytes;
+}
+
+// Shared body of the 1xTF32 and 3xTF32 entry points (A_lo == B_lo == nullptr selects 1x).
+static int gemm_impl(const float *A, const float *A_lo, int64_t lda, int64_t lda_lo, int32_t a_layout,
+                     const float *B, const float *B_lo, int64_t ldb, int64_t ldb_lo, int32_t b_layout, float *C,
+                     int64_t ldc, int32_t M, int32_t N, int32_t K, const float *bias, uint32_t flags,
+                     void *workspace, size_t workspace_bytes, gist_stream_t stream) {
+    const bool x3 = A_lo != nullptr;
     if (M < 0 || N < 0 || K < 0) return GIST_ERR_BADARG;
     if (M == 0 || N == 0) return GIST_OK;
-    if (!A || !B || !C || K == 0) return GIST_ERR_BADARG;
+    if (!A || !B || !C || K == 0 || (A_lo == nullptr) != (B_lo == nullptr)) return GIST_ERR_BADARG;
     if ((a_layout != GIST_GEMM_K_MAJOR && a_layout != GIST_GEMM_MN_MAJOR) ||
         (b_layout != GIST_GEMM_K_MAJOR && b_layout != GIST_GEMM_MN_MAJOR))
         return GIST_ERR_BADARG;
     const bool a_mn = a_layout == GIST_GEMM_MN_MAJOR, b_mn = b_layout == GIST_GEMM_MN_MAJOR;
     if (lda < (a_mn ? M : K) || ldb < (b_mn ? N : K) || ldc < N) return GIST_ERR_BADARG;
+    if (x3 && (lda_lo < (a_mn ? M : K) || ldb_lo < (b_mn ? N : K))) return GIST_ERR_BADARG;
     // TMA: 16-byte aligned base and 16-byte multiple row stride
     if (!aligned(A, 16) || !aligned(B, 16) || (lda % 4) || (ldb % 4) || !aligned(C, 4)) return GIST_ERR_ALIGN;
+    if (x3 && (!aligned(A_lo, 16) || !aligned(B_lo, 16) || (lda_lo % 4) || (ldb_lo % 4))) return GIST_ERR_ALIGN;
     cudaStream_t s = (cudaStream_t)stream;
-    GemmPlan pl = plan_gemm(M, N, K, flags);
+    GemmPlan pl = plan_gemm(M, N, K, flags, x3);
     if (pl.splits > 1 && (!workspace || workspace_bytes < pl.ws_bytes || !aligned(workspace, 16))) {
         // no (or too small a) workspace: run unsplit rather than fail
         pl.splits = 1;
@@ -532,24 +675,74 @@ extern "C" int gist_gemm_tf32(const float *A, int64_t lda, int32_t a_layout, con
     p.kb_per_split = pl.kb_per_split;
     p.kblocks = (K + kBK - 1) / kBK;
     p.relu = (flags & GIST_GEMM_RELU) ? 1 : 0;
+    p.kc = (int)((flags >> 8) & 0xFFu);
+    if (p.kc == 0) p.kc = 4;          // 128 K elements = 48 chained MMAs per accumulator
     if (pl.splits > 1) {
         p.C = reinterpret_cast<float *>(workspace); p.ldc = pl.ldp; p.bias = nullptr; p.vec4 = 1;
     } else {
         p.C = C; p.ldc = ldc; p.bias = bias;
         p.vec4 = (aligned(C, 16) && ldc % 4 == 0 && (!bias || aligned(bias, 16))) ? 1 : 0;
     }
-    CUtensorMap ta, tb;
-    int st = a_mn ? make_map(&ta, A, K, M, lda, kBK, true) : make_map(&ta, A, M, K, lda, kBM, false);
+    auto map_a = [&](CUtensorMap *t, const float *ptr, int64_t ld) {
+        return a_mn ? make_map(t, ptr, K, M, ld, kBK, true) : make_map(t, ptr, M, K, ld, kBM, false);
+    };
+    auto map_b = [&](CUtensorMap *t, const float *ptr, int64_t ld) {
+        return b_mn ? make_map(t, ptr, K, N, ld, kBK, true) : make_map(t, ptr, N, K, ld, pl.bn, false);
+    };
+    GemmMaps m;
+    int st = map_a(&m.a, A, lda);
     if (st != GIST_OK) return st;
-    st = b_mn ? make_map(&tb, B, K, N, ldb, kBK, true) : make_map(&tb, B, N, K, ldb, pl.bn, false);
+    st = map_b(&m.b, B, ldb);
     if (st != GIST_OK) return st;
-    if (pl.bn == 256) st = launch_layout<256>(a_mn, b_mn, ta, tb, p, s);
-    else if (pl.bn == 128) st = launch_layout<128>(a_mn, b_mn, ta, tb, p, s);
-    else st = launch_layout<64>(a_mn, b_mn, ta, tb, p, s);
+    if (x3) {
+        st = map_a(&m.al, A_lo, lda_lo);
+        if (st != GIST_OK) return st;
+        st = map_b(&m.bl, B_lo, ldb_lo);
+        if (st != GIST_OK) return st;
+        st = launch_tile<3>(pl.bn, a_mn, b_mn, m, p, s);
+    } else {
+        m.al = m.a;
+        m.bl = m.b;
+        st = launch_tile<1>(pl.bn, a_mn, b_mn, m, p, s);
+    }
     if (st != GIST_OK || pl.splits == 1) return st;
     const int64_t items = (int64_t)M * ((N + 3) / 4);
     splitk_reduce_kernel<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(
         reinterpret_cast<const float *>(workspace), pl.ldp, pl.splits, M, N, bias, p.relu, C, ldc);
+    count_launch();
+    return last_error();
+}
+
+extern "C" int gist_gemm_tf32(const float *A, int64_t lda, int32_t a_layout, const float *B, int64_t ldb,
+                              int32_t b_layout, float *C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                              const float *bias, uint32_t flags, void *workspace, size_t workspace_bytes,
+                              gist_stream_t stream) {
+    return gemm_impl(A, nullptr, lda, 0, a_layout, B, nullptr, ldb, 0, b_layout, C, ldc, M, N, K, bias, flags,
+                     workspace, workspace_bytes, stream);
+}
+
+extern "C" int gist_gemm_3xtf32(const float *A, const float *A_lo, int64_t lda, int64_t lda_lo, int32_t a_layout,
+                                const float *B, const float *B_lo, int64_t ldb, int64_t ldb_lo,
+                                int32_t b_layout, float *C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                                const float *bias, uint32_t flags, void *workspace, size_t workspace_bytes,
+                                gist_stream_t stream) {
+    if (!A_lo || !B_lo) return GIST_ERR_BADARG;
+    return gemm_impl(A, A_lo, lda, lda_lo, a_layout, B, B_lo, ldb, ldb_lo, b_layout, C, ldc, M, N, K, bias, flags,
+                     workspace, workspace_bytes, stream);
+}
+
+extern "C" int gist_split_tf32_f32(const float *x, int64_t ld_x, int32_t rows, int32_t cols, float *hi,
+                                   int64_t ld_hi, float *lo, int64_t ld_lo, gist_stream_t stream) {
+    if (rows < 0 || cols < 0) return GIST_ERR_BADARG;
+    if (rows == 0 || cols == 0) return GIST_OK;
+    if (!x || !lo || ld_x < cols || ld_lo < cols || (hi && ld_hi < cols)) return GIST_ERR_BADARG;
+    const bool v4 = aligned(x, 16) && aligned(lo, 16) && (!hi || aligned(hi, 16)) && ld_x % 4 == 0 &&
+                    ld_lo % 4 == 0 && (!hi || ld_hi % 4 == 0);
+    const int per_row = v4 ? (cols + 3) / 4 : cols;
+    const int64_t items = (int64_t)rows * per_row;
+    const unsigned grid = (unsigned)((items + 255) / 256);
+    if (v4) split_tf32_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, ld_x, rows, cols, hi, ld_hi, lo, ld_lo);
+    else split_tf32_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, ld_x, rows, cols, hi, ld_hi, lo, ld_lo);
     count_launch();
     return last_error();
 }

@@ -209,10 +209,13 @@ _MATMUL_PRECISION = 'fp32'
 
 
 def set_matmul_precision(mode):
-    """'fp32' : nn.Linear / matmul through cuBLAS sgemm (bit-for-bit the reference's arithmetic);
-    'tf32' : the hand-written tcgen05 kernel (10-bit mantissa inputs, fp32 accumulate)."""
+    """'fp32'   : nn.Linear / matmul through cuBLAS sgemm (bit-for-bit the reference's arithmetic);
+    '3xtf32' : the hand-written tcgen05 kernel with split operands (x, x_lo): three TF32 MMAs per
+               K step, ~2^-20 relative per product -> fp32-level accuracy (meets the 1e-5 parity
+               tolerance) on the tensor cores;
+    'tf32'   : the same kernel, single pass (10-bit mantissa inputs, fp32 accumulate, ~1e-3)."""
     global _MATMUL_PRECISION
-    assert mode in ('fp32', 'tf32')
+    assert mode in ('fp32', 'tf32', '3xtf32')
     _MATMUL_PRECISION = mode
 
 
@@ -239,13 +242,26 @@ def _tma_view(t):
     return v
 
 
-def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, relu=False, out=None, flags=0):
+def split_tf32(x):
+    """x_lo = tf32(x - trunc_tf32(x)) for a 2-D fp32 matrix, in a TMA-addressable buffer (the
+    second operand half of the 3xTF32 GEMM; the tensor core itself takes trunc_tf32(x) from x)."""
+    require_cuda(x)
+    rows, cols = x.shape
+    buf = torch.empty((rows, (cols + 3) // 4 * 4), dtype=torch.float32, device=x.device)
+    lo = buf[:, :cols]
+    check(_lib.load().gist_split_tf32_f32(ptr(x), _ld(x), rows, cols, None, 0, ptr(lo), _ld(lo),
+                                          stream_ptr(x.device)), 'split_tf32_f32')
+    return lo
+
+
+def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, relu=False, out=None, flags=0, A_lo=None, B_lo=None):
     """C[M,N] = op(A) @ op(B)^T (+bias) (ReLU) on the tcgen05 TF32 kernel (K4).
 
     a_mn=False: A is stored [M, K];  a_mn=True: A is stored [K, M] (MN-major, i.e. op(A) = A^T).
     b_mn=False: B is stored [N, K];  b_mn=True: B is stored [K, N].
+    A_lo / B_lo (from split_tf32, both or neither) select the fp32-accurate 3xTF32 mode.
     Raises if an operand is not TMA-addressable (see _tma_view)."""
-    require_cuda(A, B, bias, out)
+    require_cuda(A, B, bias, out, A_lo, B_lo)
     if a_mn:
         K, M = A.shape
     else:
@@ -260,8 +276,16 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, relu=False, out=None, flags
     assert tuple(out.shape) == (M, N) and (out.stride(1) == 1 or N == 1)
     lib = _lib.load()
     f = flags | (_lib.GEMM_RELU if relu else 0)
-    wsb = lib.gist_gemm_tf32_workspace_bytes(M, N, K, f)
+    x3 = A_lo is not None or B_lo is not None
+    wsb = (lib.gist_gemm_3xtf32_workspace_bytes if x3 else lib.gist_gemm_tf32_workspace_bytes)(M, N, K, f)
     ws = torch.empty(wsb, dtype=torch.uint8, device=A.device) if wsb else None
+    if x3:
+        assert A_lo is not None and B_lo is not None and A_lo.shape == A.shape and B_lo.shape == B.shape
+        check(lib.gist_gemm_3xtf32(ptr(A), ptr(A_lo), _ld(A), _ld(A_lo), 1 if a_mn else 0,
+                                   ptr(B), ptr(B_lo), _ld(B), _ld(B_lo), 1 if b_mn else 0,
+                                   ptr(out), _ld(out), M, N, K, ptr(bias), f, ptr(ws), wsb,
+                                   stream_ptr(A.device)), 'gemm_3xtf32')
+        return out
     check(lib.gist_gemm_tf32(ptr(A), _ld(A), 1 if a_mn else 0, ptr(B), _ld(B), 1 if b_mn else 0,
                              ptr(out), _ld(out), M, N, K, ptr(bias), f, ptr(ws), wsb,
                              stream_ptr(A.device)), 'gemm_tf32')
@@ -313,9 +337,41 @@ class _LinearTF32(torch.autograd.Function):
         return dz, dW, db
 
 
+class _Linear3xTF32(torch.autograd.Function):
+    """y = z W^T + b at fp32 accuracy on the TF32 tensor cores.  Each of z, W, dy is split once
+    (x_lo) and the pair is shared by the contractions that read it: z by y and dW, W by y and dz,
+    dy by dz and dW — three split launches and three GEMMs per layer."""
+
+    @staticmethod
+    def forward(ctx, z, W, b):
+        z = _tma_view(_mat(z, 'z'))
+        Wv = _tma_view(W)
+        z_lo, W_lo = split_tf32(z), split_tf32(Wv)
+        y = gemm(z, Wv, bias=b, A_lo=z_lo, B_lo=W_lo)
+        ctx.save_for_backward(z, z_lo, Wv, W_lo)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, z_lo, W, W_lo = ctx.saved_tensors
+        dy = _tma_view(_mat(dy, 'dy'))
+        dy_lo = split_tf32(dy)
+        dz = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dz = gemm(dy, W, b_mn=True, A_lo=dy_lo, B_lo=W_lo)
+        if ctx.needs_input_grad[1]:
+            dW = gemm(dy, z, a_mn=True, b_mn=True, A_lo=dy_lo, B_lo=z_lo)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy)
+        return dz, dW, db
+
+
 def linear(z, W, b=None):
     """F.linear under the selected matmul precision."""
-    if _MATMUL_PRECISION == 'tf32' and z.is_cuda:
+    if z.is_cuda and _MATMUL_PRECISION == '3xtf32':
+        return _Linear3xTF32.apply(z, W, b)
+    if z.is_cuda and _MATMUL_PRECISION == 'tf32':
         return _LinearTF32.apply(z, W, b)
     return torch.nn.functional.linear(z, W, b)
 

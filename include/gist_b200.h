@@ -188,6 +188,7 @@ int gist_slice_scatter_f32(const float *src, int64_t ld_src, const int64_t *ridx
 #define GIST_GEMM_TILE_N64 4u     /* force the output-tile width (default: chosen from the grid) */
 #define GIST_GEMM_TILE_N128 8u
 #define GIST_GEMM_TILE_N256 16u
+#define GIST_GEMM_KC(n) ((uint32_t)(n) << 8) /* 3xTF32 only: K blocks (of 32) chained per TMEM accumulator, 1..255; 0 = default 4 */
 #define GIST_GEMM_K_MAJOR 0
 #define GIST_GEMM_MN_MAJOR 1
 size_t gist_gemm_tf32_workspace_bytes(int32_t M, int32_t N, int32_t K, uint32_t flags);
@@ -200,6 +201,29 @@ int gist_gemm_tf32(const float *A, int64_t lda, int32_t a_layout, const float *B
 int gist_gemm_tn_tf32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
                       int32_t M, int32_t N, int32_t K, const float *bias, uint32_t flags,
                       gist_stream_t stream);
+
+/* 3xTF32: the same contraction with fp32-level accuracy on the TF32 tensor cores.  Each operand
+ * is passed as (x, x_lo) where x_lo = tf32(x - trunc_tf32(x)) comes from gist_split_tf32_f32 (same
+ * shape and layout as x, own leading dimension, 16-byte aligned, ld % 4 == 0).  The tensor core
+ * reads only the top 19 bits of x, so  A_lo*B + A*B_lo + A*B  (three MMAs per K step, fp32
+ * accumulation in TMEM) equals the fp32 product up to the dropped A_lo*B_lo term: ~2^-20 relative
+ * per product.  This is the mode that meets the reference-parity tolerance (1e-5 relative,
+ * BASELINE north_star) for nn.Linear forward and gradients; gist_gemm_tf32 is the faster,
+ * 1e-3-accurate variant.  The tensor core's fp32 accumulation truncates, so the kernel closes the
+ * TMEM accumulator every GIST_GEMM_KC K blocks and sums the chunks with ordinary fp32 adds in the
+ * epilogue warps' registers: the error does not grow with K.  Tiles are at most 128 wide
+ * (GIST_GEMM_TILE_N256 is served as 128).  Same flags as gist_gemm_tf32; workspace from
+ * gist_gemm_3xtf32_workspace_bytes. */
+size_t gist_gemm_3xtf32_workspace_bytes(int32_t M, int32_t N, int32_t K, uint32_t flags);
+int gist_gemm_3xtf32(const float *A, const float *A_lo, int64_t lda, int64_t lda_lo, int32_t a_layout,
+                     const float *B, const float *B_lo, int64_t ldb, int64_t ldb_lo, int32_t b_layout,
+                     float *C, int64_t ldc, int32_t M, int32_t N, int32_t K, const float *bias,
+                     uint32_t flags, void *workspace, size_t workspace_bytes, gist_stream_t stream);
+
+/* lo[r,c] = tf32_round(x[r,c] - trunc_tf32(x[r,c])) and, if hi != NULL, hi[r,c] = trunc_tf32(x[r,c])
+ * (x with its 13 low mantissa bits cleared) for a [rows, cols] row-major matrix. */
+int gist_split_tf32_f32(const float *x, int64_t ld_x, int32_t rows, int32_t cols, float *hi, int64_t ld_hi,
+                        float *lo, int64_t ld_lo, gist_stream_t stream);
 
 /* dst[c, r] = src[r, c] for a [rows, cols] row-major matrix (dst is [cols, rows]). */
 int gist_transpose_f32(const float *src, int64_t ld_src, int32_t rows, int32_t cols, float *dst,

@@ -141,3 +141,97 @@ def _check_linear(n, fin, fout):
     for got, ref, name in ((y, y2, 'y'), (z.grad, z2.grad, 'dz'), (W.grad, W2.grad, 'dW'), (b.grad, b2.grad, 'db')):
         rel = ((got.double() - ref).norm() / ref.norm()).item()
         assert rel < 2e-3, (name, rel)
+
+
+# ------------------------------------------------------------------ 3xTF32 ----
+# Tolerance: 1e-5 norm-wise relative (the north_star's fp32 parity tolerance); measured ~5e-7,
+# i.e. the level of a plain fp32 sgemm.  A per-entry check against sum_k|a||b| guards the tails.
+X3_TOL = 1e-5
+
+
+def test_split_tf32_is_exact_residual():
+    """x == trunc_tf32(x) + (x - trunc_tf32(x)) exactly; lo is the TF32 rounding of the residual and
+    hi has its 13 low mantissa bits clear."""
+    from gist_b200 import ops, _lib
+    from gist_b200._lib import check, ptr, stream_ptr
+    torch.manual_seed(0)
+    for shape in [(7, 5), (300, 1204), (64, 41)]:
+        x = torch.randn(*shape, device='cuda') * torch.logspace(-6, 6, shape[1], device='cuda')
+        lo = ops.split_tf32(x)
+        hi = torch.empty_like(x)
+        lo2 = torch.empty_like(x)
+        check(_lib.load().gist_split_tf32_f32(ptr(x), x.stride(0), shape[0], shape[1], ptr(hi), hi.stride(0),
+                                              ptr(lo2), lo2.stride(0), stream_ptr(x.device)), 'split')
+        assert torch.equal(lo, lo2)
+        hi_bits = hi.view(torch.int32)
+        assert torch.equal(hi_bits, x.view(torch.int32) & ~0x1FFF)
+        assert (lo.view(torch.int32) & 0x1FFF).eq(0).all()                 # lo is TF32-representable
+        resid = x.double() - hi.double()
+        assert ((lo.double() - resid).abs() <= resid.abs() * 2.0 ** -11 + 1e-45).all()
+    z = torch.tensor([[float('inf'), float('nan'), 0.0, -0.0]], device='cuda')
+    assert torch.equal(ops.split_tf32(z), torch.zeros_like(z))
+
+
+@pytest.mark.parametrize('shape', LAYOUT_SHAPES + [(4096, 512, 1024)])
+@pytest.mark.parametrize('a_mn', [False, True])
+@pytest.mark.parametrize('b_mn', [False, True])
+def test_gemm_3xtf32_layouts(shape, a_mn, b_mn):
+    from gist_b200 import ops
+    M, N, K = shape
+    torch.manual_seed(M * 5 + N * 11 + K)
+
+    def stored(rows, cols, mn):
+        r, c = (cols, rows) if mn else (rows, cols)
+        buf = torch.randn(r, (c + 3) // 4 * 4, device='cuda')[:, :c]
+        return buf, (buf.t() if mn else buf)
+
+    A_st, A = stored(M, K, a_mn)
+    B_st, B = stored(N, K, b_mn)
+    bias = torch.randn(N, device='cuda')
+    ref = A.double() @ B.double().t()
+    absref = A.abs().double() @ B.abs().double().t()
+    A_lo, B_lo = ops.split_tf32(A_st), ops.split_tf32(B_st)
+    for fl in (0, 2, 4, 8, 16):      # auto, no split-K, forced 64 / 128 / 256-wide tiles
+        got = ops.gemm(A_st, B_st, a_mn=a_mn, b_mn=b_mn, A_lo=A_lo, B_lo=B_lo, flags=fl)
+        rel = ((got.double() - ref).norm() / ref.norm()).item()
+        assert rel < X3_TOL, (fl, rel)
+        assert ((got.double() - ref).abs() <= absref * 2.0 ** -18 + 1e-30).all(), fl
+    got2 = ops.gemm(A_st, B_st, a_mn=a_mn, b_mn=b_mn, A_lo=A_lo, B_lo=B_lo, bias=bias, relu=True)
+    ref2 = torch.relu(ref + bias.double())
+    assert ((got2.double() - ref2).norm() / ref2.norm()).item() < X3_TOL
+
+
+def test_gemm_3xtf32_beats_fp32_sgemm_error_class():
+    """Same error class as cuBLAS fp32 on a long contraction with badly scaled columns."""
+    from gist_b200 import ops
+    torch.manual_seed(3)
+    A = torch.randn(512, 8192, device='cuda') * torch.logspace(-3, 3, 8192, device='cuda')
+    B = torch.randn(256, 8192, device='cuda')
+    ref = A.double() @ B.double().t()
+    got = ops.gemm(A, B, A_lo=ops.split_tf32(A), B_lo=ops.split_tf32(B))
+    rel3 = ((got.double() - ref).norm() / ref.norm()).item()
+    rel1 = ((ops.gemm(A, B).double() - ref).norm() / ref.norm()).item()
+    assert rel3 < 2e-6 and rel1 > 50 * rel3, (rel3, rel1)
+
+
+def test_linear_3xtf32_autograd():
+    from gist_b200 import ops
+    torch.manual_seed(0)
+    for n, fin, fout in [(1000, 1204, 256), (2586, 512, 41), (777, 64, 32)]:
+        z = torch.randn(n, fin, device='cuda', requires_grad=True)
+        W = (torch.randn(fout, fin, device='cuda') * 0.03).requires_grad_(True)
+        b = torch.randn(fout, device='cuda', requires_grad=True)
+        wy = torch.randn(n, fout, device='cuda')
+        ops.set_matmul_precision('3xtf32')
+        try:
+            y = ops.linear(z, W, b)
+            (y * wy).sum().backward()
+        finally:
+            ops.set_matmul_precision('fp32')
+        z2, W2, b2 = (t.detach().double().requires_grad_(True) for t in (z, W, b))
+        y2 = torch.nn.functional.linear(z2, W2, b2)
+        (y2 * wy.double()).sum().backward()
+        for got, ref, name in ((y, y2, 'y'), (z.grad, z2.grad, 'dz'), (W.grad, W2.grad, 'dW'),
+                               (b.grad, b2.grad, 'db')):
+            rel = ((got.double() - ref).norm() / ref.norm()).item()
+            assert rel < X3_TOL, (name, rel)

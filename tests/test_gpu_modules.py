@@ -24,8 +24,18 @@ def _params64(model):
              l.linear.bias.detach().double().cpu().requires_grad_(True)) for l in model.layers]
 
 
+@pytest.fixture(params=['fp32', '3xtf32'])
+def matmul_precision(request):
+    """Both fp32-accurate GEMM back ends must meet the same tolerance: cuBLAS sgemm and the
+    tcgen05 kernel in 3xTF32 mode (what bench.py runs)."""
+    from gist_b200 import ops
+    ops.set_matmul_precision(request.param)
+    yield request.param
+    ops.set_matmul_precision('fp32')
+
+
 @pytest.mark.parametrize('cfg', [(602, 256, 41, 2, True), (100, 64, 47, 3, True), (50, 32, 5, 1, False)])
-def test_sage_gcn_forward_backward(cfg):
+def test_sage_gcn_forward_backward(cfg, matmul_precision):
     from gist_b200 import SageGCN
     fin, hid, ncls, L, ln = cfg
     n = 800

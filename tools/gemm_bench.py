@@ -69,13 +69,30 @@ def main():
             res['gist_%s_us' % vn] = round(t * 1e3, 1)
             res['gist_%s_tflops' % vn] = round(fl / t / 1e9, 1)
         res['frac_of_tf32_peak'] = round(res['gist_auto_tflops'] / peak, 3)
+        # 3xTF32 (fp32-accurate): operands pre-split; the split launches are timed separately
+        A_lo, B_lo = ops.split_tf32(A), ops.split_tf32(B)
+        v3 = {'auto': 0, 'kc2': 2 << 8, 'kc8': 8 << 8, 'kc16': 16 << 8}
+        if M * N >= 1 << 22:
+            v3.update({'bn64': 4, 'bn128': 8})
+        for vn, f in v3.items():
+            t = timeit(lambda: ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, out=out, flags=f, A_lo=A_lo, B_lo=B_lo),
+                       10, flush)
+            res['gist3x_%s_us' % vn] = round(t * 1e3, 1)
+            res['gist3x_%s_tflops' % vn] = round(fl / t / 1e9, 1)          # useful (fp32-equivalent) FLOP
+        res['gist3x_mma_frac_of_tf32_peak'] = round(3 * res['gist3x_auto_tflops'] / peak, 3)
+        t = timeit(lambda: (ops.split_tf32(A), ops.split_tf32(B)), 10, flush)
+        res['split_both_us'] = round(t * 1e3, 1)
+        ref = Al[:256].double() @ Bl.double().t()
+        ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, out=out, A_lo=A_lo, B_lo=B_lo)
+        res['rel_err3x_vs_fp64'] = float(((out[:256].double() - ref).norm() / ref.norm()).item())
         torch.backends.cuda.matmul.allow_tf32 = True
         t = timeit(lambda: torch.matmul(Al, Bl.t(), out=out), 10, flush)
         res['cublas_tf32_us'], res['cublas_tf32_tflops'] = round(t * 1e3, 1), round(fl / t / 1e9, 1)
         torch.backends.cuda.matmul.allow_tf32 = False
         t = timeit(lambda: torch.matmul(Al, Bl.t(), out=out), 5, flush)
         res['cublas_fp32_us'], res['cublas_fp32_tflops'] = round(t * 1e3, 1), round(fl / t / 1e9, 1)
-        ref = Al[:256].double() @ Bl.double().t()
+        torch.matmul(Al, Bl.t(), out=out)
+        res['rel_err_cublas_fp32_vs_fp64'] = float(((out[:256].double() - ref).norm() / ref.norm()).item())
         ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, out=out)
         res['rel_err_vs_fp64'] = float(((out[:256].double() - ref).norm() / ref.norm()).item())
         res['tf32_peak_tflops'] = peak
