@@ -30,7 +30,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = 'reddit_shape_gist_graphsage_epochs_per_s'
+def metric_name(shape):
+    return '%s_shape_gist_graphsage_epochs_per_s' % shape
+
+
+CONFIG_OF = {'reddit': 'configs[2]: Cluster-GCN GraphSAGE on a Reddit-shaped',
+             'amazon2m': 'configs[3]: ultra-wide GIST GraphSAGE on an Amazon2M-shaped',
+             'pubmed': 'PubMed-shaped', 'cora': 'Cora-shaped'}
 
 
 def parse():
@@ -39,11 +45,13 @@ def parse():
     ap.add_argument('--steps', type=int, default=150)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='gist', choices=['gist', 'reference'])
-    ap.add_argument('--shape', default='reddit')
+    ap.add_argument('--shape', default='reddit', choices=['reddit', 'amazon2m', 'pubmed', 'cora'],
+                    help='reddit = the headline config; amazon2m with --n-hidden 32768 --psize 15000 --gpus 8 is '
+                         'the ultra-wide config 4 (on one GPU use --n-hidden 4096: the per-rank slice of m = 8)')
     ap.add_argument('--scale', type=float, default=1.0, help='<1 shrinks the graph (debug only; reported)')
     ap.add_argument('--n-hidden', type=int, default=256)
     ap.add_argument('--n-layers', type=int, default=2)
-    ap.add_argument('--psize', type=int, default=1500)
+    ap.add_argument('--psize', type=int, default=None, help='number of parts; default: the shape\'s (reddit 1500, amazon2m 15000)')
     ap.add_argument('--batch-size', type=int, default=20)
     ap.add_argument('--dropout', type=float, default=0.2)
     ap.add_argument('--lr', type=float, default=1e-2)
@@ -70,6 +78,16 @@ def peaks():
         d = json.load(open(p))
         return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def tensor_peak_tf32():
+    """TF32 dense tensor peak = half the bf16 figure (sustained: the GEMMs run inside a long step)."""
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get('bf16_tflops_sustained', d['bf16_tflops'])) / 2, \
+            'measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2: kind::tf32 runs at half the bf16 rate)'
+    return 1590.0 / 2, 'fallback (B200_PROFILING.md 1.59 PF/s bf16 / 2)'
 
 
 class ClockSampler:
@@ -165,7 +183,7 @@ def run_gist(a):
     n_nodes, n_edges = ds.num_nodes, int(ds.src.shape[0])
     in_feats, n_classes = ds.feat.shape[1], ds.num_classes
     train_nid = torch.nonzero(ds.train_mask).reshape(-1).cpu().numpy().astype(np.int64)
-    psize = a.psize if a.scale == 1.0 else int(ds.part.max().item()) + 1
+    psize = a.psize if (a.scale == 1.0 and a.psize) else int(ds.part.max().item()) + 1
     del ds
     wargs = SimpleNamespace(rank=rank, num_subnet=world, n_hidden=a.n_hidden, n_layers=a.n_layers,
                             dropout=a.dropout, use_layernorm=True)
@@ -305,6 +323,7 @@ def run_gist(a):
     prof_steps = min(a.steps, 20)
     sleep_cycles = int(6e-3 * 1.9e9)
     ops.SPMM_PROFILE = []
+    ops.GEMM_PROFILE = []
     step_evs = []
     torch.cuda.synchronize()
     for _ in range(prof_steps):
@@ -316,6 +335,7 @@ def run_gist(a):
         step_evs.append((s0, s1))
         torch.cuda.synchronize()
     prof, ops.SPMM_PROFILE = ops.SPMM_PROFILE, None
+    gprof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
     prof_ms = sum(x.elapsed_time(y) for x, y in step_evs)
     del loop3, it3, w3
     alg_b = comp_b = spmm_ms = 0.0
@@ -346,6 +366,30 @@ def run_gist(a):
         'note': 'cluster batches (<=5 MB of features) are L2-resident: algorithmic gather bytes are served by '
                 'L2, so achieved can exceed the HBM copy peak; see roofline_fullgraph for the HBM-bound case',
     }
+
+    # tensor roofline of the dense contractions (K4): useful FLOP = 2MNK per product; in 3xTF32
+    # mode the tensor core executes three MMAs per useful one
+    roofline_gemm = None
+    if gprof:
+        tpeak, tsrc = tensor_peak_tf32()
+        fl = sum(2.0 * r['M'] * r['N'] * r['K'] for r in gprof)
+        mma_fl = sum(2.0 * r['M'] * r['N'] * r['K'] * r['passes'] for r in gprof)
+        gms = sum(r['ev0'].elapsed_time(r['ev1']) for r in gprof)
+        big = max(gprof, key=lambda r: r['M'] * r['N'] * r['K'])
+        bsel = [r for r in gprof if (r['M'], r['N'], r['K']) == (big['M'], big['N'], big['K'])]
+        bms = sum(r['ev0'].elapsed_time(r['ev1']) for r in bsel) / len(bsel)
+        bfl = 2.0 * big['M'] * big['N'] * big['K']
+        roofline_gemm = {
+            'bound': 'tensor', 'kernel': 'gemm_tf32_kernel (all %d launches/step)' % (len(gprof) // max(prof_steps, 1)),
+            'achieved': round(fl / gms / 1e9, 1), 'peak': tpeak, 'unit': 'TFLOP/s',
+            'frac': round(fl / gms / 1e9 / tpeak, 4), 'peak_source': tsrc,
+            'mma_achieved': round(mma_fl / gms / 1e9, 1), 'mma_frac': round(mma_fl / gms / 1e9 / tpeak, 4),
+            'share_of_step': round((gms / prof_steps) / (ms / a.steps), 4),
+            'largest': {'M': big['M'], 'N': big['N'], 'K': big['K'], 'us': round(bms * 1e3, 1),
+                        'TFLOPs': round(bfl / bms / 1e9, 1), 'mma_TFLOPs': round(bfl * big['passes'] / bms / 1e9, 1)},
+            'note': 'achieved = useful fp32-equivalent FLOP (2MNK) / time; mma_* counts the %d TF32 MMA passes the '
+                    'tensor core actually executes' % big['passes'],
+        }
 
     # ---- end-to-end arm: node ids from pinned host memory + loss readback every step --
     it2, w2 = fresh('step')
@@ -404,18 +448,18 @@ def run_gist(a):
 
     if rank == 0:
         line = {
-            'metric': METRIC, 'value': round(value, 4), 'unit': 'epochs/s', 'n_gpus': world,
+            'metric': metric_name(a.shape), 'value': round(value, 4), 'unit': 'epochs/s', 'n_gpus': world,
             'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': round(ms / a.steps, 4),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'fp32': 'f32', '3xtf32': 'f32 (GEMMs: 3xTF32 split-operand tensor-core products, fp32-accurate)',
                       'tf32': 'f32 (aggregation, norms, loss, Adam) + tf32 tensor-core GEMM inputs'}[a.matmul],
             'data': 'synthetic',
             'config': {
-                'workload': 'configs[2]: Cluster-GCN GraphSAGE on a Reddit-shaped synthetic graph (%d nodes, %d '
+                'workload': '%s synthetic graph (%d nodes, %d '
                             'directed edges, %d feats, %d parts, batch %d parts), hidden %d, %d layers, GIST m=%d '
                             'sub-GCNs (one per GPU), iter_per_site %d' % (
-                                n_nodes, n_edges, in_feats, psize, a.batch_size, a.n_hidden, a.n_layers + 1,
-                                world, a.iter_per_site),
+                                CONFIG_OF[a.shape], n_nodes, n_edges, in_feats, psize, a.batch_size, a.n_hidden,
+                                a.n_layers + 1, world, a.iter_per_site),
                 'steps_per_epoch': steps_per_epoch, 'num_subnet': world, 'scale': a.scale, 'mode': a.mode,
                 'epoch_accounting': 'm ranks x one local pass = m epochs (reference: local_epochs = n_epochs // num_subnet)',
                 'l2': 'inputs larger than L2: every step gathers a different ~%d-node batch from the %.0f MB '
@@ -427,7 +471,7 @@ def run_gist(a):
                          'fp32': 'cuBLAS fp32 sgemm via torch'}[a.matmul],
                 'loss_after': round(final_loss, 4),
             },
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
+            'roofline': roofline, 'roofline_gemm': roofline_gemm, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
             'clocks': clocks, 'roofline_fullgraph': full,
             'setup_s': round(time.time() - t_setup, 1),
         }
@@ -486,7 +530,7 @@ def run_reference(a):
     A = sp.csr_matrix((np.ones(len(src), dtype=np.float32), (dst, src)), shape=(n_nodes, n_nodes))
     del src, dst
     train_nid = torch.nonzero(ds.train_mask).reshape(-1).cpu().numpy().astype(np.int64)
-    psize = a.psize if a.scale == 1.0 else int(ds.part.max().item()) + 1
+    psize = a.psize if (a.scale == 1.0 and a.psize) else int(ds.part.max().item()) + 1
     At = A[train_nid][:, train_nid].tocsr()          # sampler.py:34 training graph
     At.sort_indices()
     feat, label = ds.feat.cpu()[train_nid], ds.label.cpu()[train_nid]
@@ -510,12 +554,13 @@ def run_reference(a):
     # N sub-GCNs time-share the same host cores: N local passes take N x as long
     value = 1.0 / (sec * steps_per_epoch)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': round(value, 5), 'unit': 'epochs/s', 'n_gpus': world,
+        'impl': 'reference', 'metric': metric_name(a.shape), 'value': round(value, 5), 'unit': 'epochs/s', 'n_gpus': world,
         'steps': k, 'warmup': wu, 'ms_per_step': round(sec * 1e3, 3), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'configs[2]: Reddit-shaped synthetic graph (%d nodes, %d directed edges, %d feats, '
+        'config': {'workload': '%s synthetic graph (%d nodes, %d directed edges, %d feats, '
                                '%d parts, batch %d), hidden %d/%d, %d layers — CPU port of the reference step '
-                               '(DGL 0.5.3 not installable)' % (n_nodes, n_edges, in_feats, psize, a.batch_size,
+                               '(DGL 0.5.3 not installable)' % (CONFIG_OF[a.shape], n_nodes, n_edges, in_feats, psize,
+                                                                  a.batch_size,
                                                                   a.n_hidden, world, a.n_layers + 1),
                    'steps_per_epoch': steps_per_epoch, 'scale': a.scale},
         'cpu_baseline': {'value': round(value, 5), 'unit': 'epochs/s', 'cores': torch.get_num_threads(),

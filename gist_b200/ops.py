@@ -13,6 +13,8 @@ from ._lib import check, ptr, require_cuda, stream_ptr
 # bench.py sets this to a list to time every SpMM launch with a CUDA-event pair on the
 # launching stream (roofline.achieved); None = no instrumentation.
 SPMM_PROFILE = None
+# same for every tensor-core GEMM launch (tensor roofline of the ultra-wide config)
+GEMM_PROFILE = None
 
 
 def _mat(t, name):
@@ -279,16 +281,23 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, relu=False, out=None, flags
     x3 = A_lo is not None or B_lo is not None
     wsb = (lib.gist_gemm_3xtf32_workspace_bytes if x3 else lib.gist_gemm_tf32_workspace_bytes)(M, N, K, f)
     ws = torch.empty(wsb, dtype=torch.uint8, device=A.device) if wsb else None
+    prof = GEMM_PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     if x3:
         assert A_lo is not None and B_lo is not None and A_lo.shape == A.shape and B_lo.shape == B.shape
         check(lib.gist_gemm_3xtf32(ptr(A), ptr(A_lo), _ld(A), _ld(A_lo), 1 if a_mn else 0,
                                    ptr(B), ptr(B_lo), _ld(B), _ld(B_lo), 1 if b_mn else 0,
                                    ptr(out), _ld(out), M, N, K, ptr(bias), f, ptr(ws), wsb,
                                    stream_ptr(A.device)), 'gemm_3xtf32')
-        return out
-    check(lib.gist_gemm_tf32(ptr(A), _ld(A), 1 if a_mn else 0, ptr(B), _ld(B), 1 if b_mn else 0,
-                             ptr(out), _ld(out), M, N, K, ptr(bias), f, ptr(ws), wsb,
-                             stream_ptr(A.device)), 'gemm_tf32')
+    else:
+        check(lib.gist_gemm_tf32(ptr(A), _ld(A), 1 if a_mn else 0, ptr(B), _ld(B), 1 if b_mn else 0,
+                                 ptr(out), _ld(out), M, N, K, ptr(bias), f, ptr(ws), wsb,
+                                 stream_ptr(A.device)), 'gemm_tf32')
+    if prof is not None:
+        ev1.record()
+        prof.append(dict(ev0=ev0, ev1=ev1, M=M, N=N, K=K, passes=3 if x3 else 1))
     return out
 
 

@@ -13,9 +13,11 @@ Order of nodes inside a batch, membership, and the Python ``random`` call order
 (shuffle at init and at every StopIteration, sampler.py:55, :92) are identical,
 so batches are bit-identical to the reference's for the same seed and partition.
 
-METIS itself is third-party and out of scope: the node->part assignment is an
-input (``g.ndata['_part']`` on the training graph's parent, a ``partition=``
-list, or the reference's ``../data/{dn}_{psize}.npy`` cache file).
+Where the node->part assignment comes from, in order: a ``partition=`` list, the reference's
+``../data/{dn}_{psize}.npy`` cache file (read and written as sampler.py:44-51 does),
+``g.ndata['_part']`` (the synthetic graphs' planted blocks), else a k-way METIS partition of the
+training graph (gist_b200/partition.py; the partitioner is a seeded third-party heuristic, so its
+assignment is not parity-pinned against DGL's bundled build).
 """
 import os
 import random
@@ -24,19 +26,19 @@ import numpy as np
 import torch
 
 from . import function as fn
+from . import partition as _partition
 from .graph import NID
 
 
-def get_partition_list(g, psize):
-    """partition_utils.py:11-18 with the METIS call replaced by a given assignment
-    ``g.ndata['_part']`` (int, [n]); returns psize int64 arrays of node ids."""
-    if '_part' not in g.ndata:
-        raise RuntimeError("get_partition_list: METIS is out of scope; provide g.ndata['_part'] "
-                           "(node -> part id) or pass partition= to ClusterIter")
-    part = g.ndata['_part'].detach().cpu().numpy().astype(np.int64)
-    order = np.argsort(part, kind='stable')
-    bounds = np.searchsorted(part[order], np.arange(psize + 1))
-    return [order[bounds[p]:bounds[p + 1]].astype(np.int64) for p in range(psize)]
+def get_partition_list(g, psize, seed=0):
+    """partition_utils.py:11-18: psize int64 arrays of node ids (ascending inside a part, parts
+    in id order).  Uses the assignment in ``g.ndata['_part']`` when the graph carries one,
+    otherwise runs METIS on ``g`` (the reference always does the latter)."""
+    if '_part' in g.ndata:
+        part = g.ndata['_part'].detach().cpu().numpy().astype(np.int64)
+    else:
+        part = _partition.metis_assignment(g, psize, seed=seed)
+    return _partition.partition_list(part, psize)
 
 
 def get_subgraph(g, par_arr, i, psize, batch_size, col_capacity=None):
@@ -65,9 +67,13 @@ class ClusterIter(object):
         self.batch_size = batch_size
         if partition is not None:
             self.par_li = [np.asarray(p).astype(np.int64) for p in partition]
-        elif dn and os.path.exists(os.path.join(cache_dir, dn + '_{}.npy'.format(psize))):
-            self.par_li = list(np.load(os.path.join(cache_dir, dn + '_{}.npy'.format(psize)),
-                                       allow_pickle=True))
+        elif dn:                                    # sampler.py:44-51: cache known datasets
+            fn_ = _partition.cache_path(dn, psize, cache_dir)
+            if os.path.exists(fn_):
+                self.par_li = _partition.load_partition(fn_)
+            else:
+                self.par_li = get_partition_list(self.g, psize)
+                _partition.save_partition(fn_, self.par_li)
         else:
             self.par_li = get_partition_list(self.g, psize)
         self.max = int((psize) // batch_size)

@@ -1,5 +1,7 @@
 """K3 parity: device cluster-batch builder vs oracle induced subgraph (bit-exact in
 canonical form), ndata row gathers, scan, K5 slice gather/scatter."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -167,3 +169,42 @@ def test_subgraph_hub_rows_and_padding_sentinel():
     assert (sgp.inv_in_degree()[len(nids):] == 0).all()
     # scratch map fully restored
     assert (g._node_map() == -1).all()
+
+
+def test_cluster_iter_metis_and_partition_cache(tmp_path):
+    """No '_part' on the graph -> get_partition_list runs METIS (partition_utils.py:11-18); with a
+    dataset name the partition is cached in the reference's file format and format-compatible
+    files are replayed (sampler.py:44-51)."""
+    import random
+    from gist_b200 import ClusterIter, partition, synth
+    ds = synth.make('reddit', seed=0, device='cpu', scale=0.01)
+    g = synth.to_gist_graph(ds, device='cuda')
+    del g.ndata['_part']
+    train_nid = np.nonzero(ds.train_mask.numpy())[0].astype(np.int64)
+    psize, bs = 12, 3
+    random.seed(5)
+    it = ClusterIter('synth-reddit', g, psize, bs, train_nid, use_pp=False, cache_dir=str(tmp_path))
+    fn = partition.cache_path('synth-reddit', psize, str(tmp_path))
+    assert os.path.exists(fn)
+    cached = partition.load_partition(fn)
+    n_train = it.g.number_of_nodes()
+    allids = np.sort(np.concatenate(cached))
+    assert np.array_equal(allids, np.arange(n_train))                   # a partition of the training graph
+    assert all(np.all(np.diff(p) > 0) for p in cached)                  # ascending inside a part
+    sizes = np.array([len(p) for p in cached])
+    assert sizes.max() <= 1.05 * n_train / psize + 1
+    # second construction replays the cached file instead of partitioning again: same batches
+    random.seed(5)
+    it2 = ClusterIter('synth-reddit', g, psize, bs, train_nid, use_pp=False, cache_dir=str(tmp_path))
+    for b1, b2 in zip(it, it2):
+        assert torch.equal(b1.ndata['_ID'], b2.ndata['_ID'])
+        assert torch.equal(b1.rowptr, b2.rowptr) and torch.equal(b1.col, b2.col)
+    # METIS cuts far fewer edges than the id-order split of the same sizes
+    rp = it.g.rowptr.cpu().numpy().astype(np.int64)
+    col = it.g.col.cpu().numpy().astype(np.int64)
+    rows = np.repeat(np.arange(n_train), np.diff(rp))
+    part = np.empty(n_train, dtype=np.int64)
+    for k, p in enumerate(cached):
+        part[p] = k
+    naive = np.arange(n_train) * psize // n_train
+    assert (part[rows] != part[col]).sum() < 0.8 * (naive[rows] != naive[col]).sum()
