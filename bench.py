@@ -67,6 +67,9 @@ def parse():
                          'fp32 sgemm through torch')
     ap.add_argument('--mode', default='graph', choices=['graph', 'eager'],
                     help='graph: whole training step captured in a CUDA graph; eager: op-by-op')
+    ap.add_argument('--no-pipeline', action='store_true',
+                    help='graph mode: build batch k inside step k instead of overlapping the build of batch '
+                         'k+1 with the training of batch k')
     ap.add_argument('--ncu', default='', choices=['', 'steps', 'fullgraph'],
                     help='bracket that region with cudaProfilerStart/Stop (ncu --profile-from-start off)')
     return ap.parse_args()
@@ -205,7 +208,8 @@ def run_gist(a):
             self.it, self.w, self.readback = it, w, readback
             w.inplace_dispatch = True
             w.sub_model.train()
-            self.tr = GraphedClusterTrainer(it, w.sub_model, a.lr, a.weight_decay, h2d=it.h2d).capture()
+            self.tr = GraphedClusterTrainer(it, w.sub_model, a.lr, a.weight_decay, h2d=it.h2d,
+                                            pipeline=not a.no_pipeline).capture()
             self.total_iter = 0
             self.running_loss = 0.0
             self.loss_acc = torch.zeros((), device=dev)
@@ -219,17 +223,26 @@ def run_gist(a):
                         dist.barrier()
                     self.w.dispatch_model()
                 self.tr.reset_optimizer()                   # fresh Adam at every round (…distrib.py:405-407)
-            loss = self.tr.step()
-            self.nodes += self.tr.n_pad
             if self.readback:
-                self.running_loss += float(loss)
+                # every step: ids H2D from pinned memory, loss D2H into pinned memory; the host
+                # consumes the value one step late so the readback never stalls the launch queue
+                v = self.tr.step_logged()
+                if v is not None:
+                    self.running_loss += v
             else:
-                self.loss_acc += loss
+                self.loss_acc += self.tr.step()
+            self.nodes += self.tr.n_pad
             self.total_iter += 1
             if self.total_iter % a.iter_per_site == 0:
                 if world > 1:
                     dist.barrier()
                 self.w.sync_model()
+
+        def finish(self):
+            if self.readback:
+                v = self.tr.drain()
+                if v is not None:
+                    self.running_loss += v
 
     class Loop:
         """The reference's step loop (…distrib.py:394-427) unrolled into next_step()."""
@@ -278,6 +291,8 @@ def run_gist(a):
         e0.record()
         for _ in range(k):
             loop.next_step()
+        if hasattr(loop, 'finish'):
+            loop.finish()              # last pending loss readback lands inside the timed region
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -402,8 +417,11 @@ def run_gist(a):
     e2e = {'value': round(world * a.steps / steps_per_epoch / (ms2 / 1e3), 4), 'unit': 'epochs/s',
            'h2d_bytes_per_step': int((h2d_of() - h2d0) / a.steps), 'd2h_bytes_per_step': 4,
            'ms_per_step': round(ms2 / a.steps, 4),
-           'what': 'public API (ClusterIter -> sub_model -> loss): batch node ids copied from pinned host '
-                   'memory every step, float(loss) read back every step; graph + features resident in HBM'}
+           'what': 'public API (ClusterIter -> GraphedClusterTrainer.step_logged): batch node ids copied from '
+                   'pinned host memory every step, the loss copied to pinned host memory every step and summed '
+                   'on the host (consumed one step late in graph mode, float(loss) in eager mode); graph + '
+                   'features resident in HBM',
+           'mean_loss_host': round(loop2.running_loss / max(a.steps + a.warmup, 1), 4)}
 
     # ---- the HBM-bound case: full-graph SpMM that evaluate() runs (rank 0) -------------
     full = None
@@ -461,6 +479,7 @@ def run_gist(a):
                                 CONFIG_OF[a.shape], n_nodes, n_edges, in_feats, psize, a.batch_size, a.n_hidden,
                                 a.n_layers + 1, world, a.iter_per_site),
                 'steps_per_epoch': steps_per_epoch, 'num_subnet': world, 'scale': a.scale, 'mode': a.mode,
+                'pipeline': (a.mode == 'graph' and not a.no_pipeline),
                 'epoch_accounting': 'm ranks x one local pass = m epochs (reference: local_epochs = n_epochs // num_subnet)',
                 'l2': 'inputs larger than L2: every step gathers a different ~%d-node batch from the %.0f MB '
                       'training feature matrix' % (loop.nodes // max(loop.total_iter, 1),

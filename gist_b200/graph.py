@@ -216,8 +216,12 @@ class GistGraph:
             self._cache['node_map'] = torch.full((self._n,), -1, dtype=torch.int32, device=self.device)
         return self._cache['node_map']
 
-    def subgraph(self, nids, col_capacity=None, gather_ndata=True, ndata_keys=None):
-        """Node-induced subgraph built on the device (K3).  new node i <-> nids[i]."""
+    def subgraph(self, nids, col_capacity=None, gather_ndata=True, ndata_keys=None, out=None):
+        """Node-induced subgraph built on the device (K3).  new node i <-> nids[i].
+
+        ``out``: a subgraph previously returned for the same number of ids, capacity and
+        ndata keys; its buffers are overwritten in place (fixed addresses: what the pipelined
+        CUDA-graph trainer needs to build batch k+1 while batch k trains)."""
         _lib.require_cuda(self.rowptr)
         dev = self.device
         if isinstance(nids, np.ndarray):
@@ -233,11 +237,17 @@ class GistGraph:
             deg = (self.rowptr[1:] - self.rowptr[:-1])
             col_capacity = int(deg[nids.clamp_min(0)].sum().item()) if n_b else 0
 
-        def build(prow, pcol, want_inv):
+        if out is not None:
+            assert out.number_of_nodes() == n_b and out.col_buffer.shape[0] == max(col_capacity, 1)
+
+        def build(prow, pcol, want_inv, reuse=None):
             lib = _lib.load()
-            rowptr = torch.empty(n_b + 1, dtype=torch.int32, device=dev)
-            col = torch.empty(max(col_capacity, 1), dtype=torch.int32, device=dev)
-            inv = torch.empty(max(n_b, 1), dtype=torch.float32, device=dev) if want_inv else None
+            if reuse is not None:
+                rowptr, col, inv = reuse
+            else:
+                rowptr = torch.empty(n_b + 1, dtype=torch.int32, device=dev)
+                col = torch.empty(max(col_capacity, 1), dtype=torch.int32, device=dev)
+                inv = torch.empty(max(n_b, 1), dtype=torch.float32, device=dev) if want_inv else None
             wsb = lib.gist_scan_workspace_bytes(n_b)
             ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=dev)
             _lib.check(lib.gist_cluster_batch_build(
@@ -246,9 +256,27 @@ class GistGraph:
                 _lib.ptr(ws), wsb, _lib.stream_ptr(dev)), 'cluster_batch_build')
             return rowptr, col, inv
 
+        if out is not None:
+            sg = out
+            inv_buf = sg._cache['inv_in_buf']
+            build(self.rowptr, self.col_buffer, True, reuse=(sg.rowptr, sg.col_buffer, inv_buf))
+            if not self.is_symmetric():
+                pcolptr, prow_idx = self.csc()
+                build(pcolptr, prow_idx, False, reuse=(sg._csc[0], sg._csc[1], None))
+            if gather_ndata:
+                for k, v in self.ndata.items():
+                    if ndata_keys is None or k in ndata_keys:
+                        ops.gather_rows(v, nids, out=sg.ndata[k])
+            if sg.ndata[NID].data_ptr() != nids.data_ptr():
+                sg.ndata[NID].copy_(nids)
+            sg._nnz = None
+            for k in [k for k in sg._cache if k not in ('inv_in', 'inv_in_buf')]:
+                del sg._cache[k]                 # structure-derived values of the previous batch
+            return sg
         rowptr, col, inv = build(self.rowptr, self.col_buffer, True)
         sg = GistGraph(rowptr, col, n_b, idtype=self._idtype)
         sg._cache['inv_in'] = inv[:n_b]
+        sg._cache['inv_in_buf'] = inv
         if self.is_symmetric():
             # an induced subgraph of a symmetric pattern is symmetric, and it is built
             # from equal arrays in equal order, so CSC == CSR array-for-array

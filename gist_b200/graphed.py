@@ -10,6 +10,20 @@ padded with the builder's `-1` sentinel: pad rows are isolated, have zero
 features and a False train mask, hence contribute exactly 0 to the loss and to
 every gradient.  Results equal the eager step's (tests/test_gpu_graphed.py).
 
+Pipelining (``pipeline=True``, the default).  Three things overlap the training kernels of
+step k instead of sitting between steps:
+  * the batch build of step k+1 (mark / count / scan / fill / ndata gathers — latency-bound
+    walks over hub rows that leave most SMs idle) is captured on a second stream as a parallel
+    branch of the graph that trains step k.  Two graphs alternate: graph j trains on cluster
+    buffer set j while building into set 1-j;
+  * the host->device copy of the ids of batch k+1 (issued while graph k-1 is still running) and
+  * the device->host copy of step k's loss run on a copy stream, fenced with events; node-id
+    and loss buffers are double-buffered with the graphs (graph j reads ``nids[j]``, writes
+    ``loss[j]``), so no copy ever touches a buffer a running graph uses.
+The Python ``random`` call order (epoch-end shuffle, create_partition) is unchanged: the shuffle
+for the next epoch still happens after the dispatch of the epoch's last step and before the next
+dispatch (cluster_gcn/sampler.py:92, cluster_gcn_ist_distrib.py:398-404).
+
 Callers: bench.py and the trainers; mirrors cluster_gcn_ist_distrib.py:398-417.
 """
 import torch
@@ -20,77 +34,132 @@ _KEYS = ('feat', 'label', 'train_mask')
 
 
 class GraphedClusterTrainer:
-    def __init__(self, cluster_iter, model, lr, weight_decay, h2d='epoch'):
+    def __init__(self, cluster_iter, model, lr, weight_decay, h2d='epoch', pipeline=True):
         assert h2d in ('epoch', 'step')
         self.it, self.model, self.h2d = cluster_iter, model, h2d
+        self.pipeline = bool(pipeline)
         g = cluster_iter.g
         self.dev = g.device
         self.n_pad = cluster_iter.max_batch_nodes()
         self.cap = max(cluster_iter.max_batch_edges(), 1)
-        self.nids = torch.full((self.n_pad,), -1, dtype=torch.int64, device=self.dev)
-        self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
+        nbuf = 2 if self.pipeline else 1
+        self.nids = [torch.full((self.n_pad,), -1, dtype=torch.int64, device=self.dev) for _ in range(nbuf)]
+        self.loss = [torch.zeros((), dtype=torch.float32, device=self.dev) for _ in range(nbuf)]
         self.opt = make_optimizer(model.parameters(), lr, weight_decay)
-        self.graph = None
-        self._epoch_dev = None          # [steps, n_pad] device ids (h2d='epoch')
-        self._epoch_host = None         # pinned host ids (h2d='step')
-        self.i = 0
+        self.graphs = None
+        self.clusters = [None, None]    # pipelined: the two cluster buffer sets
+        self.k = 0                      # steps issued so far
+        self.i = 0                      # next row of the epoch's id table to stage
         self.h2d_bytes = 0
+        self.d2h_bytes = 0
         self.replays = 0
         self.gist_launches_per_step = 0
+        # persistent staging: two pinned [steps, n_pad] id tables (alternating per epoch, so a row
+        # still being copied is never overwritten) and, for h2d='epoch', two device tables
+        steps = len(cluster_iter)
+        self._host_tab = [torch.empty((steps, self.n_pad), dtype=torch.int64).pin_memory() for _ in range(2)]
+        self._dev_tab = ([torch.empty((steps, self.n_pad), dtype=torch.int64, device=self.dev) for _ in range(2)]
+                         if h2d == 'epoch' else None)
+        self._tab = 1
+        self._copy = torch.cuda.Stream(device=self.dev)
+        self._ev_ids = [torch.cuda.Event() for _ in range(nbuf)]      # ids landed in nids[j]
+        self._ev_done = [torch.cuda.Event() for _ in range(nbuf)]     # graph j finished
+        self._ev_ring = [torch.cuda.Event() for _ in range(nbuf)]     # loss[j] landed in the host ring
+        self._ring = torch.zeros(nbuf, dtype=torch.float32).pin_memory()
+        self._ring_busy = [False] * nbuf
+        self._pending = None
         g.is_symmetric()                # decided once, outside capture (it syncs)
         self._load_epoch()
 
     # ------------------------------------------------------------------ data --
     def _load_epoch(self):
-        ids = self.it.padded_epoch_ids(self.n_pad)
+        """Fill the other id table with the (re)shuffled epoch; h2d='epoch' uploads it whole."""
+        self._tab ^= 1
+        host = self._host_tab[self._tab]
+        self.it.padded_epoch_ids(self.n_pad, out=host.numpy())
         if self.h2d == 'epoch':
-            self._epoch_dev = ids.to(self.dev)
-            self.h2d_bytes += ids.numel() * 8
-        else:
-            self._epoch_host = ids.pin_memory()
+            with torch.cuda.stream(self._copy):
+                self._dev_tab[self._tab].copy_(host, non_blocking=True)
+            self.h2d_bytes += host.numel() * 8
         self.i = 0
 
-    def _stage_ids(self):
+    def _next_row(self):
         if self.i >= len(self.it):
             self.it.end_epoch()
             self._load_epoch()
-        if self.h2d == 'epoch':
-            self.nids.copy_(self._epoch_dev[self.i])
-        else:
-            self.nids.copy_(self._epoch_host[self.i], non_blocking=True)
-            self.h2d_bytes += self.n_pad * 8
+        row = (self._dev_tab if self.h2d == 'epoch' else self._host_tab)[self._tab][self.i]
         self.i += 1
+        return row
+
+    def _upload(self, j, after=None):
+        """Copy the next batch's ids into nids[j] on the copy stream (after event `after`)."""
+        row = self._next_row()
+        with torch.cuda.stream(self._copy):
+            if after is not None:
+                self._copy.wait_event(after)
+            self.nids[j].copy_(row, non_blocking=True)
+            self._ev_ids[j].record(self._copy)
+        if self.h2d == 'step':
+            self.h2d_bytes += self.n_pad * 8
 
     # ------------------------------------------------------------------ step --
-    def _body(self):
-        cluster = self.it.g.subgraph(self.nids, col_capacity=self.cap, ndata_keys=_KEYS)
+    def _build(self, nids, out=None):
+        return self.it.g.subgraph(nids, col_capacity=self.cap, ndata_keys=_KEYS, out=out)
+
+    def _train(self, cluster, loss_out):
         self.opt.zero_grad(set_to_none=True)
         pred = self.model(cluster)
         loss = masked_cross_entropy(pred, cluster.ndata['label'], cluster.ndata['train_mask'])
         loss.backward()
         self.opt.step()
-        self.loss.copy_(loss.detach())
+        loss_out.copy_(loss.detach())
 
     def capture(self):
         """Warm up on a real batch, capture, then restore parameters / optimizer state so the
         capture itself does not advance training."""
+        from . import _lib
         params = list(self.model.parameters())
         saved = [p.detach().clone() for p in params]
         self.model.train()
-        self.nids.copy_(self._epoch_dev[0] if self.h2d == 'epoch' else self._epoch_host[0].to(self.dev))
+        main = torch.cuda.current_stream(self.dev)
+        self._upload(0)                                  # batch 0
+        main.wait_event(self._ev_ids[0])
         s = torch.cuda.Stream(device=self.dev)
-        s.wait_stream(torch.cuda.current_stream(self.dev))
+        s.wait_stream(main)
         with torch.cuda.stream(s):
             for _ in range(3):
-                self._body()
-        torch.cuda.current_stream(self.dev).wait_stream(s)
+                self._train(self._build(self.nids[0]), self.loss[0])
+        main.wait_stream(s)
         torch.cuda.synchronize(self.dev)
-        from . import _lib
-        l0 = _lib.launch_count()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._body()
-        self.gist_launches_per_step = _lib.launch_count() - l0   # this library's kernel nodes per replay
+        self.graphs = []
+        if self.pipeline:
+            # prologue: batch 0 is built eagerly into buffer set 0; graph j trains on set j and
+            # builds the NEXT batch (ids staged in nids[j] before the replay) into set 1 - j
+            self.clusters[0] = self._build(self.nids[0].clone())
+            torch.cuda.synchronize(self.dev)
+            pool = None
+            for j in (0, 1):
+                gph = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(device=self.dev)
+                l0 = _lib.launch_count()
+                with torch.cuda.graph(gph, pool=pool):
+                    cap_main = torch.cuda.current_stream(self.dev)
+                    side.wait_stream(cap_main)
+                    with torch.cuda.stream(side):
+                        self.clusters[1 - j] = self._build(self.nids[j], out=self.clusters[1 - j])
+                    self._train(self.clusters[j], self.loss[j])
+                    cap_main.wait_stream(side)
+                self.gist_launches_per_step = _lib.launch_count() - l0
+                pool = gph.pool()
+                self.graphs.append(gph)
+        else:
+            l0 = _lib.launch_count()
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                self._train(self._build(self.nids[0]), self.loss[0])
+            self.gist_launches_per_step = _lib.launch_count() - l0   # this library's kernel nodes per replay
+            self.graphs.append(gph)
+        self.k = 0
         with torch.no_grad():
             for p, q in zip(params, saved):
                 p.copy_(q)
@@ -102,11 +171,70 @@ class GraphedClusterTrainer:
         place: moments and step counters are zeroed so the captured graph's pointers stay valid."""
         self.opt.reset_state()
 
-    def step(self):
-        """One training step; returns the 0-d device loss tensor (valid until the next step)."""
-        if self.graph is None:
+    def _issue(self):
+        """Enqueue step k; returns the buffer index j whose loss[j] the step writes."""
+        if self.graphs is None:
             self.capture()
-        self._stage_ids()
-        self.graph.replay()
+        main = torch.cuda.current_stream(self.dev)
+        if not self.pipeline:
+            if self.k > 0:
+                self._upload(0, after=self._ev_done[0])  # graph k-1 was the last reader of nids[0]
+            main.wait_event(self._ev_ids[0])
+            if self._ring_busy[0]:
+                main.wait_event(self._ev_ring[0])        # loss[0] of step k-1 has been copied out
+            self.graphs[0].replay()
+            self._ev_done[0].record(main)
+            j = 0
+        else:
+            j = self.k & 1
+            # ids of batch k+1 (built during this step) go into nids[j], last read by graph k-2.
+            # The host runs at least one step ahead of the GPU, so this copy overlaps graph k-1.
+            # (Fetching the row here, after any dispatch of step k and before the next one, keeps
+            # the epoch-end shuffle in the reference's position in the Python random stream.)
+            self._upload(j, after=self._ev_done[j] if self.k >= 2 else None)
+            main.wait_event(self._ev_ids[j])
+            if self._ring_busy[j]:
+                main.wait_event(self._ev_ring[j])        # loss[j] of step k-2 has been copied out
+            self.graphs[j].replay()
+            self._ev_done[j].record(main)
+        self.k += 1
         self.replays += 1
-        return self.loss
+        return j
+
+    def step(self):
+        """One training step; returns the 0-d device loss tensor (valid until the next step but
+        one is issued)."""
+        return self.loss[self._issue()]
+
+    # -------------------------------------------------------------- readback --
+    def step_logged(self):
+        """step() plus a device->host read of the step's loss EVERY step, without stalling the
+        launch pipeline: the loss is copied into a pinned ring on the copy stream right behind
+        the replay and the value returned is the PREVIOUS step's (None on the first call), whose
+        copy has finished by now.  The reference's ``float(loss)`` (…distrib.py:416) feeds a
+        running-loss log only, so a one-step lag changes nothing it computes; call ``drain()``
+        after the last step for the final value."""
+        j = self._issue()
+        with torch.cuda.stream(self._copy):
+            self._copy.wait_event(self._ev_done[j])
+            self._ring[j:j + 1].copy_(self.loss[j].reshape(1), non_blocking=True)
+            self._ev_ring[j].record(self._copy)
+        self._ring_busy[j] = True
+        self.d2h_bytes += 4
+        if not self.pipeline:           # single buffer set: synchronous, like float(loss)
+            self._ev_ring[j].synchronize()
+            return float(self._ring[j])
+        prev, self._pending = self._pending, j
+        if prev is None:
+            return None
+        self._ev_ring[prev].synchronize()
+        return float(self._ring[prev])
+
+    def drain(self):
+        """Loss of the last step issued through step_logged() (None if already consumed)."""
+        if self._pending is None:
+            return None
+        self._ev_ring[self._pending].synchronize()
+        v = float(self._ring[self._pending])
+        self._pending = None
+        return v

@@ -83,13 +83,15 @@ def exclusive_scan(x):
     return out
 
 
-def gather_rows(src, idx):
+def gather_rows(src, idx, out=None):
     """src[idx] along dim 0 for any dtype / trailing shape (ndata row-gather)."""
-    require_cuda(src, idx)
+    require_cuda(src, idx, out)
     assert idx.dtype == torch.int64 and idx.dim() == 1
     src = src.contiguous()
     n = idx.shape[0]
-    out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    if out is None:
+        out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    assert out.shape == (n,) + tuple(src.shape[1:]) and out.dtype == src.dtype and out.is_contiguous()
     row_bytes = src.element_size()
     for s in src.shape[1:]:
         row_bytes *= s

@@ -121,13 +121,22 @@ class ClusterIter(object):
         sums = sorted(self._deg_sum.values(), reverse=True)
         return int(sum(sums[:self.batch_size]))
 
-    def padded_epoch_ids(self, n_pad):
+    def padded_epoch_ids(self, n_pad, out=None):
         """[len(self), n_pad] int64 host tensor: batch i's node ids in concatenation order,
-        padded with -1 (the builder's isolated-row sentinel)."""
-        out = np.full((self.max, n_pad), -1, dtype=np.int64)
+        padded with -1 (the builder's isolated-row sentinel).  ``out``: a [len(self), n_pad] int64
+        numpy array (e.g. a view of pinned memory) filled in place."""
+        if out is None:
+            out = np.empty((self.max, n_pad), dtype=np.int64)
+        assert out.shape == (self.max, n_pad) and out.dtype == np.int64
+        out.fill(-1)
+        bs = self.batch_size
         for i in range(self.max):
-            _, ids = self.batch_node_ids(i)
-            out[i, :len(ids)] = ids
+            pos = 0
+            row = out[i]
+            for s in range(i * bs, min((i + 1) * bs, self.psize)):
+                p = self.par_li[s]
+                row[pos:pos + len(p)] = p
+                pos += len(p)
         return torch.from_numpy(out)
 
     def end_epoch(self):

@@ -22,15 +22,16 @@ def _setup(seed, h2d):
     return it, model
 
 
+@pytest.mark.parametrize('pipeline', [False, True])
 @pytest.mark.parametrize('h2d', ['epoch', 'step'])
-def test_graphed_matches_eager(h2d):
+def test_graphed_matches_eager(h2d, pipeline):
     from gist_b200.graphed import GraphedClusterTrainer
     from gist_b200.train import train_step
     it_e, model_e = _setup(5, 'step')
     it_g, model_g = _setup(5, h2d)
     model_g.load_state_dict(model_e.state_dict())
     opt = torch.optim.Adam(model_e.parameters(), lr=1e-2, weight_decay=5e-4)
-    tr = GraphedClusterTrainer(it_g, model_g, 1e-2, 5e-4, h2d=h2d).capture()
+    tr = GraphedClusterTrainer(it_g, model_g, 1e-2, 5e-4, h2d=h2d, pipeline=pipeline).capture()
     for p, q in zip(model_g.parameters(), model_e.parameters()):
         assert torch.equal(p, q)                      # capture did not advance training
     model_e.train()
