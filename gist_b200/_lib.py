@@ -47,11 +47,17 @@ SIGNATURES = {
     'gist_gemm_tn_tf32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _U32, _P]),
     'gist_transpose_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P]),
     'gist_layernorm_act_fwd_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _F32, _U32, _P, _I64, _P, _P]),
-    'gist_layernorm_act_bwd_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _U32, _P, _I64, _P]),
+    'gist_layernorm_act_bwd_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _U32, _P, _I64, _P, _I64, _P]),
     'gist_colsum_workspace_bytes': (_SZ, [_I32, _I32]),
     'gist_colsum_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _SZ, _P]),
     'gist_masked_ce_fwd_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
-    'gist_masked_ce_bwd_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    'gist_masked_ce_bwd_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P]),
+    'gist_dropout_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _I32, _P, _I64, _P, _P]),
+    'gist_counter_add_i64': (ctypes.c_int, [_P, _I64, _P]),
+    'gist_spmm_csr_ex_f32': (ctypes.c_int, [_P, _P, _I32, _I32, _P, _I64, _I32, _P, _I64,
+                                            _P, _P, _P, _P, _I64, _P, _I64, _U32, _P, _P]),
+    'gist_gemm_dropmask_f32': (ctypes.c_int, [_P, _P, _I64, _I64, _I32, _P, _P, _I64, _I64, _I32, _P, _I64,
+                                              _I32, _I32, _I32, _U32, _P, _P]),
     'gist_gat_scores_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P]),
     'gist_gat_aggregate_f32': (ctypes.c_int, [_P, _P, _I32, _P, _I64, _I32, _P, _F32, _P, _I64, _P, _P]),
     'gist_gat_backward_workspace_bytes': (_SZ, [_I32, _I32]),
@@ -65,6 +71,21 @@ NORM_INV, NORM_RSQRT_CLAMP = 0, 1
 GEMM_RELU, GEMM_NO_SPLITK, GEMM_TILE_N64, GEMM_TILE_N128, GEMM_TILE_N256 = 1, 2, 4, 8, 16
 GEMM_K_MAJOR, GEMM_MN_MAJOR = 0, 1
 ACT_RELU = 1
+
+
+
+class DropoutDesc(ctypes.Structure):
+    """gist_dropout_t"""
+    _fields_ = [('p', ctypes.c_float), ('seed', ctypes.c_uint64), ('stream_id', ctypes.c_uint32),
+                ('step', ctypes.c_void_p), ('step_saved', ctypes.c_void_p)]
+
+
+class SpmmEx(ctypes.Structure):
+    """gist_spmm_ex_t"""
+    _fields_ = [('y_lo', ctypes.c_void_p), ('ld_y_lo', ctypes.c_int64), ('self_lo', ctypes.c_void_p),
+                ('ld_self_lo', ctypes.c_int64), ('drop', ctypes.POINTER(DropoutDesc)),
+                ('drop_col0_y', ctypes.c_int32), ('drop_col0_self', ctypes.c_int32)]
+
 
 _lib = None
 _device_set = None

@@ -85,13 +85,15 @@ template <bool VEC4>
 __global__ void __launch_bounds__(256) ln_act_bwd_kernel(const float *__restrict__ dy, int64_t lddy,
                                                          const float *__restrict__ x, int64_t ldx,
                                                          const float2 *__restrict__ stats, int n, int d,
-                                                         int relu, float *__restrict__ dx, int64_t lddx) {
+                                                         int relu, float *__restrict__ dx, int64_t lddx,
+                                                         float *__restrict__ dx_lo, int64_t ld_lo) {
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= n) return;
     const float *xr = x + (int64_t)r * ldx;
     const float *gr = dy + (int64_t)r * lddy;
     float *or_ = dx + (int64_t)r * lddx;
+    float *lo_ = dx_lo ? dx_lo + (int64_t)r * ld_lo : nullptr;     // 3xTF32 low half of dx
     const float2 st = stats[r];
     const float mean = st.x, rstd = st.y;
     float s1 = 0.f, s2 = 0.f;
@@ -120,11 +122,18 @@ __global__ void __launch_bounds__(256) ln_act_bwd_kernel(const float *__restrict
         for (int c = lane * 4; c < d; c += 128) {
             const float4 xv = __ldg(reinterpret_cast<const float4 *>(xr + c));
             const float4 gv = __ldg(reinterpret_cast<const float4 *>(gr + c));
-            *reinterpret_cast<float4 *>(or_ + c) =
-                make_float4(out(xv.x, gv.x), out(xv.y, gv.y), out(xv.z, gv.z), out(xv.w, gv.w));
+            const float4 o = make_float4(out(xv.x, gv.x), out(xv.y, gv.y), out(xv.z, gv.z), out(xv.w, gv.w));
+            *reinterpret_cast<float4 *>(or_ + c) = o;
+            if (lo_)
+                *reinterpret_cast<float4 *>(lo_ + c) =
+                    make_float4(tf32_lo(o.x), tf32_lo(o.y), tf32_lo(o.z), tf32_lo(o.w));
         }
     } else {
-        for (int c = lane; c < d; c += 32) or_[c] = out(__ldg(xr + c), __ldg(gr + c));
+        for (int c = lane; c < d; c += 32) {
+            const float o = out(__ldg(xr + c), __ldg(gr + c));
+            or_[c] = o;
+            if (lo_) lo_[c] = tf32_lo(o);
+        }
     }
 }
 
@@ -228,7 +237,8 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float *__restrict__ l
                                                      const float *__restrict__ lse,
                                                      const float *__restrict__ loss_out,
                                                      const float *__restrict__ gout,
-                                                     float *__restrict__ dlogits, int64_t ldd, int ldd_fill) {
+                                                     float *__restrict__ dlogits, int64_t ldd, int ldd_fill,
+                                                     float *__restrict__ dlo) {
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= n) return;
@@ -242,6 +252,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float *__restrict__ l
         float v = 0.f;
         if (c < C && m) v = (__expf(__ldg(xr + c) - l) - (c == y ? 1.f : 0.f)) * scale;
         dr[c] = v;
+        if (dlo) dlo[(int64_t)r * ldd + c] = tf32_lo(v);       // same layout as dlogits
     }
 }
 
@@ -253,6 +264,7 @@ struct AdamTensor {
     float *v;
     int64_t n;
     int32_t block0;     // first CTA of this tensor
+    int32_t vec4;       // all four arrays 16-byte aligned
 };
 constexpr int kAdamMaxTensors = 24;
 constexpr int kAdamChunk = 1024;    // elements per CTA (256 threads x float4)
@@ -281,17 +293,32 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
     const float step_size = a.lr / bc1;
     const float inv_sqrt_bc2 = rsqrtf(bc2);
     const int64_t i0 = ((int64_t)(blockIdx.x - T.block0) * 256 + threadIdx.x) * 4;
+    auto upd = [&](float &p, float g, float &m, float &v) {
+        g += a.weight_decay * p;
+        m = a.beta1 * m + (1.f - a.beta1) * g;
+        v = a.beta2 * v + (1.f - a.beta2) * g * g;
+        p -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + a.eps);
+    };
+    if (T.vec4 && i0 + 3 < T.n) {          // 128-bit accesses: the ultra-wide weights are HBM streams
+        float4 p = *reinterpret_cast<const float4 *>(T.p + i0);
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(T.g + i0));
+        float4 m = *reinterpret_cast<const float4 *>(T.m + i0);
+        float4 v = *reinterpret_cast<const float4 *>(T.v + i0);
+        upd(p.x, g.x, m.x, v.x); upd(p.y, g.y, m.y, v.y); upd(p.z, g.z, m.z, v.z); upd(p.w, g.w, m.w, v.w);
+        *reinterpret_cast<float4 *>(T.m + i0) = m;
+        *reinterpret_cast<float4 *>(T.v + i0) = v;
+        *reinterpret_cast<float4 *>(T.p + i0) = p;
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int64_t i = i0 + k;
-        if (i < T.n) {
-            const float p = T.p[i];
-            const float g = T.g[i] + a.weight_decay * p;
-            const float m = a.beta1 * T.m[i] + (1.f - a.beta1) * g;
-            const float v = a.beta2 * T.v[i] + (1.f - a.beta2) * g * g;
-            T.m[i] = m;
-            T.v[i] = v;
-            T.p[i] = p - step_size * m / (sqrtf(v) * inv_sqrt_bc2 + a.eps);
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = i0 + k;
+            if (i < T.n) {
+                float p = T.p[i], m = T.m[i], v = T.v[i];
+                upd(p, T.g[i], m, v);
+                T.m[i] = m;
+                T.v[i] = v;
+                T.p[i] = p;
+            }
         }
     }
     if (advance_step) {
@@ -307,9 +334,48 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
     }
 }
 
+// ------------------------------------------------------- dropout utilities ----
+// out[r, c] = multiplier (0 or 1/(1-p)) of element (r, col0 + c): the mask the fused kernels apply,
+// materialised (tests, and eager paths that want nn.Dropout as a stand-alone op).
+__global__ void __launch_bounds__(256) dropout_mask_kernel(const DropParams dp, int n, int d, int col0,
+                                                           const float *__restrict__ x, int64_t ldx,
+                                                           float *__restrict__ out, int64_t ldo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n * d) return;
+    const int r = (int)(i / d), c = (int)(i % d);
+    const int64_t step = drop_step(dp);
+    if (dp.step_saved && i == 0) *dp.step_saved = step;
+    const float m = dp.p != 0.f ? drop_mult(dp, step, (uint32_t)r, (uint32_t)(col0 + c)) : 1.f;
+    out[(int64_t)r * ldo + c] = x ? m * __ldg(x + (int64_t)r * ldx + c) : m;
+}
+
+__global__ void counter_add_kernel(int64_t *counter, int64_t delta) { *counter += delta; }
+
 }  // namespace gist
 
 using namespace gist;
+
+extern "C" int gist_dropout_f32(const float *x, int64_t ldx, int32_t n, int32_t d, int32_t col0, float *out,
+                                int64_t ldo, const gist_dropout_t *drop, gist_stream_t stream) {
+    if (n < 0 || d < 0) return GIST_ERR_BADARG;
+    if (n == 0 || d == 0) return GIST_OK;
+    if (!out || ldo < d || (x && ldx < d)) return GIST_ERR_BADARG;
+    DropParams dp;
+    const int st = make_drop_params(drop, &dp);
+    if (st != GIST_OK) return st;
+    const int64_t items = (int64_t)n * d;
+    dropout_mask_kernel<<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dp, n, d, col0, x, ldx,
+                                                                                          out, ldo);
+    count_launch();
+    return last_error();
+}
+
+extern "C" int gist_counter_add_i64(int64_t *counter, int64_t delta, gist_stream_t stream) {
+    if (!counter) return GIST_ERR_BADARG;
+    counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta);
+    count_launch();
+    return last_error();
+}
 
 extern "C" int gist_layernorm_act_fwd_f32(const float *x, int64_t ldx, int32_t n, int32_t d, float eps,
                                           uint32_t flags, float *y, int64_t ldy, float *stats,
@@ -330,19 +396,20 @@ extern "C" int gist_layernorm_act_fwd_f32(const float *x, int64_t ldx, int32_t n
 
 extern "C" int gist_layernorm_act_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx,
                                           const float *stats, int32_t n, int32_t d, uint32_t flags,
-                                          float *dx, int64_t lddx, gist_stream_t stream) {
+                                          float *dx, int64_t lddx, float *dx_lo, int64_t ld_lo,
+                                          gist_stream_t stream) {
     if (n < 0 || d < 0) return GIST_ERR_BADARG;
     if (n == 0 || d == 0) return GIST_OK;
-    if (!dy || !x || !stats || !dx || lddy < d || ldx < d || lddx < d) return GIST_ERR_BADARG;
+    if (!dy || !x || !stats || !dx || lddy < d || ldx < d || lddx < d || (dx_lo && ld_lo < d)) return GIST_ERR_BADARG;
     if (!aligned(stats, 8)) return GIST_ERR_ALIGN;
     const bool v4 = d % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && aligned(x, 16) &&
-                    aligned(dy, 16) && aligned(dx, 16);
+                    aligned(dy, 16) && aligned(dx, 16) && (!dx_lo || (aligned(dx_lo, 16) && ld_lo % 4 == 0));
     const int relu = (flags & GIST_ACT_RELU) ? 1 : 0;
     const unsigned grid = (unsigned)((n + 7) / 8);
     cudaStream_t s = (cudaStream_t)stream;
     const float2 *st = reinterpret_cast<const float2 *>(stats);
-    if (v4) ln_act_bwd_kernel<true><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, st, n, d, relu, dx, lddx);
-    else ln_act_bwd_kernel<false><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, st, n, d, relu, dx, lddx);
+    if (v4) ln_act_bwd_kernel<true><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, st, n, d, relu, dx, lddx, dx_lo, ld_lo);
+    else ln_act_bwd_kernel<false><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, st, n, d, relu, dx, lddx, dx_lo, ld_lo);
     count_launch();
     return last_error();
 }
@@ -401,14 +468,14 @@ extern "C" int gist_masked_ce_fwd_f32(const float *logits, int64_t ld, int32_t n
 extern "C" int gist_masked_ce_bwd_f32(const float *logits, int64_t ld, int32_t n, int32_t C,
                                       const int64_t *labels, const uint8_t *mask, const float *lse,
                                       const float *loss_out, const float *grad_out, float *dlogits,
-                                      int64_t ldd, int32_t fill_cols, gist_stream_t stream) {
+                                      int64_t ldd, int32_t fill_cols, float *dlogits_lo, gist_stream_t stream) {
     if (n < 0 || C <= 0) return GIST_ERR_BADARG;
     if (n == 0) return GIST_OK;
     if (!logits || !labels || !lse || !loss_out || !grad_out || !dlogits || ld < C || fill_cols < C ||
         ldd < fill_cols)
         return GIST_ERR_BADARG;
     ce_bwd_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(logits, ld, n, C, labels, mask, lse, loss_out,
-                                                                grad_out, dlogits, ldd, fill_cols);
+                                                                grad_out, dlogits, ldd, fill_cols, dlogits_lo);
     count_launch();
     return last_error();
 }
@@ -439,6 +506,8 @@ extern "C" int gist_adam_multi_f32(int32_t n_tensors, float *const *params, cons
             if (numel[i] == 0) continue;
             a.t[k].p = params[i]; a.t[k].g = grads[i]; a.t[k].m = exp_avg[i]; a.t[k].v = exp_avg_sq[i];
             a.t[k].n = numel[i]; a.t[k].block0 = (int32_t)blocks;
+            a.t[k].vec4 = (aligned(params[i], 16) && aligned(grads[i], 16) && aligned(exp_avg[i], 16) &&
+                           aligned(exp_avg_sq[i], 16)) ? 1 : 0;
             blocks += (numel[i] + kAdamChunk - 1) / kAdamChunk;
             if (blocks > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
             ++k;

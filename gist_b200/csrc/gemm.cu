@@ -155,6 +155,7 @@ struct GemmParams {
     int32_t relu;
     int32_t vec4;       // output rows and bias are 16-byte aligned: float4 epilogue stores
     int32_t kc;         // NT == 3: K blocks chained into one TMEM accumulator before it is drained
+    DropParams drop;    // p != 0: C[r, c] *= dropout multiplier of (r, c) (the dz = dy W contraction)
 };
 
 template <int BN, int NT>
@@ -329,6 +330,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool fused = p.splits == 1;
             const int ncols = min(BN, p.N - n0);     // warp-uniform
             // one 32-column segment of the finished row: bias / ReLU, then 128-bit or scalar stores
+            const bool masked = fused && p.drop.p != 0.f;
+            const int64_t dstep = masked ? drop_step(p.drop) : 0;
             auto store32 = [&](const float (&v)[32], int c) {
                 if (row >= p.M) return;
                 float *out = crow + n0 + c;
@@ -345,6 +348,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f);
                                 r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
                             }
+                            if (masked) {        // n0 + c + i is a multiple of 4: one Philox call
+                                const uint4 rnd = drop_rand4(p.drop, dstep, (uint32_t)row, (uint32_t)(n0 + c + i) >> 2);
+                                r.x = rnd.x >= p.drop.thresh ? r.x * p.drop.scale : 0.f;
+                                r.y = rnd.y >= p.drop.thresh ? r.y * p.drop.scale : 0.f;
+                                r.z = rnd.z >= p.drop.thresh ? r.z * p.drop.scale : 0.f;
+                                r.w = rnd.w >= p.drop.thresh ? r.w * p.drop.scale : 0.f;
+                            }
                         }
                         *reinterpret_cast<float4 *>(out + i) = r;
                     }
@@ -356,6 +366,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (fused) {
                                 if (p.bias) r += __ldg(p.bias + n0 + c + i);
                                 if (p.relu) r = fmaxf(r, 0.f);
+                                if (masked) r *= drop_mult(p.drop, dstep, (uint32_t)row, (uint32_t)(n0 + c + i));
                             }
                             out[i] = r;
                         }
@@ -454,16 +465,6 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restr
 // mantissa bits, which is what kind::tf32 does to an fp32 operand, so the GEMM can use x itself as
 // the leading term.  x - trunc(x) is exact in fp32; rounding it to TF32 here (instead of letting
 // the MMA truncate it) halves and unbiases the residual error.  Non-finite x -> lo = 0.
-__device__ __forceinline__ float tf32_lo(float x, float *hi_out) {
-    const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    *hi_out = h;
-    float r = x - h;
-    if (!(fabsf(x) <= 3.402823466e38f)) r = 0.f;
-    uint32_t t;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
-    return __uint_as_float(t);
-}
-
 template <bool V4>
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ x, int64_t ld_x, int rows,
                                                          int cols, float *__restrict__ hi, int64_t ld_hi,
@@ -615,7 +616,7 @@ static GemmPlan plan_gemm(int M, int N, int K, uint32_t flags, bool x3) {
     int splits = 1;
     const int64_t t = tiles(pl.bn);
     if (!(flags & GIST_GEMM_NO_SPLITK) && t * 2 <= sms) {
-        int64_t want = (sms + t - 1) / t;
+        int64_t want = sms / t;                 // tiles x splits must fit ONE wave of the chip
         int64_t cap = kblocks / 4;              // at least 4 K blocks per split
         if (want > cap) want = cap;
         if (want > 32) want = 32;
@@ -646,8 +647,14 @@ extern "C" size_t gist_gemm_3xtf32_workspace_bytes(int32_t M, int32_t N, int32_t
 static int gemm_impl(const float *A, const float *A_lo, int64_t lda, int64_t lda_lo, int32_t a_layout,
                      const float *B, const float *B_lo, int64_t ldb, int64_t ldb_lo, int32_t b_layout, float *C,
                      int64_t ldc, int32_t M, int32_t N, int32_t K, const float *bias, uint32_t flags,
-                     void *workspace, size_t workspace_bytes, gist_stream_t stream) {
+                     void *workspace, size_t workspace_bytes, const gist_dropout_t *drop, gist_stream_t stream) {
     const bool x3 = A_lo != nullptr;
+    DropParams dp;
+    {
+        const int st = make_drop_params(drop, &dp);
+        if (st != GIST_OK) return st;
+    }
+    if (dp.p != 0.f) flags |= GIST_GEMM_NO_SPLITK;     // the mask is applied in the GEMM epilogue
     if (M < 0 || N < 0 || K < 0) return GIST_ERR_BADARG;
     if (M == 0 || N == 0) return GIST_OK;
     if (!A || !B || !C || K == 0 || (A_lo == nullptr) != (B_lo == nullptr)) return GIST_ERR_BADARG;
@@ -675,6 +682,7 @@ static int gemm_impl(const float *A, const float *A_lo, int64_t lda, int64_t lda
     p.kb_per_split = pl.kb_per_split;
     p.kblocks = (K + kBK - 1) / kBK;
     p.relu = (flags & GIST_GEMM_RELU) ? 1 : 0;
+    p.drop = dp;
     p.kc = (int)((flags >> 8) & 0xFFu);
     if (p.kc == 0) p.kc = 4;          // 128 K elements = 48 chained MMAs per accumulator
     if (pl.splits > 1) {
@@ -718,7 +726,7 @@ extern "C" int gist_gemm_tf32(const float *A, int64_t lda, int32_t a_layout, con
                               const float *bias, uint32_t flags, void *workspace, size_t workspace_bytes,
                               gist_stream_t stream) {
     return gemm_impl(A, nullptr, lda, 0, a_layout, B, nullptr, ldb, 0, b_layout, C, ldc, M, N, K, bias, flags,
-                     workspace, workspace_bytes, stream);
+                     workspace, workspace_bytes, nullptr, stream);
 }
 
 extern "C" int gist_gemm_3xtf32(const float *A, const float *A_lo, int64_t lda, int64_t lda_lo, int32_t a_layout,
@@ -728,7 +736,17 @@ extern "C" int gist_gemm_3xtf32(const float *A, const float *A_lo, int64_t lda, 
                                 gist_stream_t stream) {
     if (!A_lo || !B_lo) return GIST_ERR_BADARG;
     return gemm_impl(A, A_lo, lda, lda_lo, a_layout, B, B_lo, ldb, ldb_lo, b_layout, C, ldc, M, N, K, bias, flags,
-                     workspace, workspace_bytes, stream);
+                     workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int gist_gemm_dropmask_f32(const float *A, const float *A_lo, int64_t lda, int64_t lda_lo,
+                                      int32_t a_layout, const float *B, const float *B_lo, int64_t ldb,
+                                      int64_t ldb_lo, int32_t b_layout, float *C, int64_t ldc, int32_t M,
+                                      int32_t N, int32_t K, uint32_t flags, const gist_dropout_t *drop,
+                                      gist_stream_t stream) {
+    if ((A_lo == nullptr) != (B_lo == nullptr)) return GIST_ERR_BADARG;
+    return gemm_impl(A, A_lo, lda, lda_lo, a_layout, B, B_lo, ldb, ldb_lo, b_layout, C, ldc, M, N, K, nullptr,
+                     flags | GIST_GEMM_NO_SPLITK, nullptr, 0, drop, stream);
 }
 
 extern "C" int gist_split_tf32_f32(const float *x, int64_t ld_x, int32_t rows, int32_t cols, float *hi,

@@ -37,6 +37,13 @@ struct SpmmParams {
     int32_t relu;
     int32_t row_blocks;
     int32_t heavy_deg;  // rows with more edges are split over the whole CTA (INT_MAX = never)
+    // EX variants only (gist_spmm_csr_ex_f32): dropout on the two outputs and their 3xTF32 halves
+    float *y_lo;
+    int32_t ld_y_lo;
+    float *self_lo;
+    int32_t ld_self_lo;
+    int32_t col0_y, col0_self;   // logical column of output column 0 in the dropout mask
+    DropParams drop;
 };
 
 template <int VEC>
@@ -123,10 +130,43 @@ __device__ __forceinline__ void gather_range(const SpmmParams &p, int eb, int ee
     }
 }
 
-template <int VEC, int VPL>
+// EX: r <- dropout(r) for logical columns [col, col + VEC) of row v, then store r (and tf32_lo(r)).
+template <int VEC>
+__device__ __forceinline__ void drop_store(const SpmmParams &p, int64_t step, int v, int col, float (&r)[VEC],
+                                           float *dst, float *dst_lo) {
+    if (p.drop.p != 0.f) {
+        uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t have = 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const uint32_t cc = (uint32_t)(col + i);
+            if ((cc >> 2) != have) {
+                have = cc >> 2;
+                rnd = drop_rand4(p.drop, step, (uint32_t)v, have);
+            }
+            r[i] = pick4(rnd, cc & 3) >= p.drop.thresh ? r[i] * p.drop.scale : 0.f;
+        }
+    }
+    st_vec<VEC>(dst, r);
+    if (dst_lo) {
+        float l[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) l[i] = tf32_lo(r[i]);
+        st_vec<VEC>(dst_lo, l);
+    }
+}
+
+template <int VEC, int VPL, bool EX>
 __device__ __forceinline__ void epilogue(const SpmmParams &p, int v, const int (&c)[VPL],
                                          const bool (&cv)[VPL], const float (&acc)[VPL][VEC]) {
     const float t = p.dst_scale ? __ldg(p.dst_scale + v) : 1.f;
+    int64_t step = 0;
+    if constexpr (EX) {
+        if (p.drop.p != 0.f) {
+            step = drop_step(p.drop);
+            if (p.drop.step_saved && blockIdx.x == 0 && threadIdx.x == 0) *p.drop.step_saved = step;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
         if (!cv[k]) continue;
@@ -149,11 +189,21 @@ __device__ __forceinline__ void epilogue(const SpmmParams &p, int v, const int (
 #pragma unroll
             for (int i = 0; i < VEC; ++i) r[i] = fmaxf(r[i], 0.f);
         }
-        st_vec<VEC>(p.Y + (int64_t)v * p.ldy + c[k], r);
+        if constexpr (EX) {
+            drop_store<VEC>(p, step, v, p.col0_y + c[k], r, p.Y + (int64_t)v * p.ldy + c[k],
+                            p.y_lo ? p.y_lo + (int64_t)v * p.ld_y_lo + c[k] : nullptr);
+        } else {
+            st_vec<VEC>(p.Y + (int64_t)v * p.ldy + c[k], r);
+        }
         if (p.self_out) {
             float sx[VEC];
             ld_vec<VEC>(sx, p.X + (int64_t)v * p.ldx + c[k]);
-            st_vec<VEC>(p.self_out + (int64_t)v * p.ld_self + c[k], sx);
+            if constexpr (EX) {
+                drop_store<VEC>(p, step, v, p.col0_self + c[k], sx, p.self_out + (int64_t)v * p.ld_self + c[k],
+                                p.self_lo ? p.self_lo + (int64_t)v * p.ld_self_lo + c[k] : nullptr);
+            } else {
+                st_vec<VEC>(p.self_out + (int64_t)v * p.ld_self + c[k], sx);
+            }
         }
     }
 }
@@ -170,7 +220,7 @@ constexpr int min_ctas() {
 
 // COOP = hub rows (more than heavy_deg edges) are split over all groups of the CTA and
 // reduced through shared memory in a fixed order; used where rows are scarce.
-template <int VEC, int LPR, int VPL, bool HAS_SS, bool COOP>
+template <int VEC, int LPR, int VPL, bool HAS_SS, bool COOP, bool EX = false>
 __global__ void __launch_bounds__(256, min_ctas<VEC, VPL, HAS_SS, COOP>())
 spmm_csr_kernel(const SpmmParams p) {
     constexpr int GPW = 32 / LPR;                 // row groups per warp
@@ -216,7 +266,7 @@ spmm_csr_kernel(const SpmmParams p) {
             if (lg == 0) s_heavy[atomicAdd(&s_nheavy, 1)] = v;   // order irrelevant: rows are independent
         } else {
             gather_range<VEC, LPR, VPL, HAS_SS>(p, rs, re, lg, lane0, gmask, c, cv, acc);
-            epilogue<VEC, VPL>(p, v, c, cv, acc);
+            epilogue<VEC, VPL, EX>(p, v, c, cv, acc);
         }
     }
     if (!coop) return;
@@ -251,7 +301,7 @@ spmm_csr_kernel(const SpmmParams p) {
                 for (int k = 0; k < VPL; ++k)
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) acc[k][i] += s_part[g2][(k * LPR + lg) * VEC + i];
-            epilogue<VEC, VPL>(p, hv, c, cv, acc);
+            epilogue<VEC, VPL, EX>(p, hv, c, cv, acc);
         }
         __syncthreads();
     }
@@ -269,6 +319,15 @@ static int launch_spmm(const SpmmParams &p0, cudaStream_t stream) {
     if (grid > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
     p.row_blocks = (int32_t)row_blocks;
     const bool coop = p.heavy_deg != 0x7fffffff;
+    if (p.y_lo || p.self_lo || p.drop.p != 0.f) {
+        // extended epilogue (dropout / 3xTF32 halves): the training-step shapes only — rows are
+        // scarce there, so always the CTA-cooperative variant
+        if (!coop) p.heavy_deg = 128;
+        if (p.src_scale) spmm_csr_kernel<VEC, LPR, VPL, true, true, true><<<(unsigned)grid, 256, 0, stream>>>(p);
+        else spmm_csr_kernel<VEC, LPR, VPL, false, true, true><<<(unsigned)grid, 256, 0, stream>>>(p);
+        count_launch();
+        return last_error();
+    }
     if (p.src_scale) {
         if (coop) spmm_csr_kernel<VEC, LPR, VPL, true, true><<<(unsigned)grid, 256, 0, stream>>>(p);
         else spmm_csr_kernel<VEC, LPR, VPL, true, false><<<(unsigned)grid, 256, 0, stream>>>(p);
@@ -309,6 +368,8 @@ static bool vec_ok(int vec, const SpmmParams &p) {
     if (p.bias && !aligned(p.bias, a)) return false;
     if (p.addend && (!aligned(p.addend, a) || p.ld_add % vec)) return false;
     if (p.self_out && (!aligned(p.self_out, a) || p.ld_self % vec)) return false;
+    if (p.y_lo && (!aligned(p.y_lo, a) || p.ld_y_lo % vec)) return false;
+    if (p.self_lo && (!aligned(p.self_lo, a) || p.ld_self_lo % vec)) return false;
     return true;
 }
 
@@ -333,6 +394,16 @@ extern "C" int gist_spmm_csr_f32(const int32_t *rowptr, const int32_t *col, int3
                                  const float *bias, const float *addend, int64_t ld_addend,
                                  float *self_out, int64_t ld_self, uint32_t flags,
                                  gist_stream_t stream) {
+    return gist_spmm_csr_ex_f32(rowptr, col, n_dst, n_src, X, ldx, d, Y, ldy, src_scale, dst_scale, bias, addend,
+                                ld_addend, self_out, ld_self, flags, nullptr, stream);
+}
+
+extern "C" int gist_spmm_csr_ex_f32(const int32_t *rowptr, const int32_t *col, int32_t n_dst,
+                                    int32_t n_src, const float *X, int64_t ldx, int32_t d, float *Y,
+                                    int64_t ldy, const float *src_scale, const float *dst_scale,
+                                    const float *bias, const float *addend, int64_t ld_addend,
+                                    float *self_out, int64_t ld_self, uint32_t flags,
+                                    const gist_spmm_ex_t *ex, gist_stream_t stream) {
     if (n_dst < 0 || n_src < 0 || d < 0) return GIST_ERR_BADARG;
     if (n_dst == 0 || d == 0) return GIST_OK;
     if (!rowptr || !X || !Y) return GIST_ERR_BADARG;  // col may be NULL for an edgeless graph
@@ -350,6 +421,18 @@ extern "C" int gist_spmm_csr_f32(const int32_t *rowptr, const int32_t *col, int3
     p.addend = addend; p.ld_add = (int32_t)ld_addend; p.self_out = self_out; p.ld_self = (int32_t)ld_self;
     p.relu = (flags & GIST_SPMM_RELU) ? 1 : 0;
     p.row_blocks = 0;
+    p.y_lo = p.self_lo = nullptr;
+    p.ld_y_lo = p.ld_self_lo = p.col0_y = p.col0_self = 0;
+    make_drop_params(nullptr, &p.drop);
+    if (ex) {
+        if ((ex->y_lo && ex->ld_y_lo < d) || (ex->self_lo && (ex->ld_self_lo < d || !self_out))) return GIST_ERR_BADARG;
+        if (ex->ld_y_lo > 0x7fffffffLL || ex->ld_self_lo > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
+        p.y_lo = ex->y_lo; p.ld_y_lo = (int32_t)ex->ld_y_lo;
+        p.self_lo = ex->self_lo; p.ld_self_lo = (int32_t)ex->ld_self_lo;
+        p.col0_y = ex->drop_col0_y; p.col0_self = ex->drop_col0_self;
+        const int st = make_drop_params(ex->drop, &p.drop);
+        if (st != GIST_OK) return st;
+    }
     // Hub rows are split over the CTA only where rows are scarce (cluster batches): with
     // >32k rows there are enough warps that one long row is not the critical path.
     const bool coop = (flags & GIST_SPMM_COOP_ON) || (!(flags & GIST_SPMM_COOP_OFF) && n_dst <= 32768);

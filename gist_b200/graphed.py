@@ -28,6 +28,8 @@ Callers: bench.py and the trainers; mirrors cluster_gcn_ist_distrib.py:398-417.
 """
 import torch
 
+from . import ops
+from .modules import GCN as _SageGCN, SAGE_PRE0
 from .train import make_optimizer, masked_cross_entropy
 
 _KEYS = ('feat', 'label', 'train_mask')
@@ -38,6 +40,7 @@ class GraphedClusterTrainer:
         assert h2d in ('epoch', 'step')
         self.it, self.model, self.h2d = cluster_iter, model, h2d
         self.pipeline = bool(pipeline)
+        self.pre_aggregate = self.pipeline and isinstance(model, _SageGCN)
         g = cluster_iter.g
         self.dev = g.device
         self.n_pad = cluster_iter.max_batch_nodes()
@@ -104,11 +107,19 @@ class GraphedClusterTrainer:
 
     # ------------------------------------------------------------------ step --
     def _build(self, nids, out=None):
-        return self.it.g.subgraph(nids, col_capacity=self.cap, ndata_keys=_KEYS, out=out)
+        prev = out._cache.get(SAGE_PRE0) if out is not None else None
+        sg = self.it.g.subgraph(nids, col_capacity=self.cap, ndata_keys=_KEYS, out=out)
+        if self.pre_aggregate:
+            # layer 0 aggregates raw input features: no dependence on the weights, no gradient,
+            # so it belongs to the batch-preparation branch (what the reference's use_pp idea is
+            # after, but computed per batch on the batch subgraph: identical arithmetic), together
+            # with that layer's dropout and 3xTF32 split, which K1 applies as it writes z
+            sg._cache[SAGE_PRE0] = self.model.layers[0].prepare_input(sg, sg.ndata['feat'], out=prev)
+        return sg
 
     def _train(self, cluster, loss_out):
         self.opt.zero_grad(set_to_none=True)
-        pred = self.model(cluster)
+        pred = self.model(cluster)          # (the dropout clock is ticked by the caller: auto_tick off)
         loss = masked_cross_entropy(pred, cluster.ndata['label'], cluster.ndata['train_mask'])
         loss.backward()
         self.opt.step()
@@ -121,6 +132,22 @@ class GraphedClusterTrainer:
         params = list(self.model.parameters())
         saved = [p.detach().clone() for p in params]
         self.model.train()
+        # the dropout clock (ops.DropoutState) is advanced by one node at the head of every
+        # captured step, BEFORE the build / train branches fork, so both read a stable value
+        clock = ops.dropout_state(self.dev)
+        auto_tick, clock.auto_tick = clock.auto_tick, False
+        try:
+            self._capture(clock, _lib)
+        finally:
+            clock.auto_tick = auto_tick
+        self.k = 0
+        with torch.no_grad():
+            for p, q in zip(params, saved):
+                p.copy_(q)
+        self.reset_optimizer()
+        return self
+
+    def _capture(self, clock, _lib):
         main = torch.cuda.current_stream(self.dev)
         self._upload(0)                                  # batch 0
         main.wait_event(self._ev_ids[0])
@@ -128,6 +155,7 @@ class GraphedClusterTrainer:
         s.wait_stream(main)
         with torch.cuda.stream(s):
             for _ in range(3):
+                clock.tick()
                 self._train(self._build(self.nids[0]), self.loss[0])
         main.wait_stream(s)
         torch.cuda.synchronize(self.dev)
@@ -135,15 +163,23 @@ class GraphedClusterTrainer:
         if self.pipeline:
             # prologue: batch 0 is built eagerly into buffer set 0; graph j trains on set j and
             # builds the NEXT batch (ids staged in nids[j] before the replay) into set 1 - j
+            clock.tick()
             self.clusters[0] = self._build(self.nids[0].clone())
             torch.cuda.synchronize(self.dev)
             pool = None
+            # the training branch is captured on a high-priority stream and the preparation
+            # branch on a low-priority one: kernel nodes inherit the priority, so when both have
+            # CTAs pending (the d = 602 aggregation of the next batch floods the chip) the block
+            # scheduler serves the critical path first and the preparation fills the gaps
+            lo_p, hi_p = torch.cuda.Stream.priority_range()
+            train_stream = torch.cuda.Stream(device=self.dev, priority=hi_p)
             for j in (0, 1):
                 gph = torch.cuda.CUDAGraph()
-                side = torch.cuda.Stream(device=self.dev)
+                side = torch.cuda.Stream(device=self.dev, priority=lo_p)
                 l0 = _lib.launch_count()
-                with torch.cuda.graph(gph, pool=pool):
+                with torch.cuda.graph(gph, pool=pool, stream=train_stream):
                     cap_main = torch.cuda.current_stream(self.dev)
+                    clock.tick()
                     side.wait_stream(cap_main)
                     with torch.cuda.stream(side):
                         self.clusters[1 - j] = self._build(self.nids[j], out=self.clusters[1 - j])
@@ -156,15 +192,10 @@ class GraphedClusterTrainer:
             l0 = _lib.launch_count()
             gph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gph):
+                clock.tick()
                 self._train(self._build(self.nids[0]), self.loss[0])
             self.gist_launches_per_step = _lib.launch_count() - l0   # this library's kernel nodes per replay
             self.graphs.append(gph)
-        self.k = 0
-        with torch.no_grad():
-            for p, q in zip(params, saved):
-                p.copy_(q)
-        self.reset_optimizer()
-        return self
 
     def reset_optimizer(self):
         """A fresh Adam, as the reference builds at every dispatch (…distrib.py:405-407), but in

@@ -17,6 +17,10 @@ from . import ops
 from .graph import GistError
 
 
+# graph-cache key under which a batch may carry the first SAGE layer's prepared input (ops.SagePre)
+SAGE_PRE0 = 'sage_pre0'
+
+
 def _is_relu(act):
     return act is F.relu or act is torch.relu or isinstance(act, nn.ReLU)
 
@@ -190,19 +194,41 @@ class ISTSAGELayer(nn.Module):
         self.init_layer()
         self.dropout = nn.Dropout(p=dropout) if dropout else 0.
         self.lynorm = nn.LayerNorm(out_feats, elementwise_affine=False) if use_lynorm else (lambda x: x)
+        self._drop_stream = ops.new_dropout_stream()      # this layer's slot in the fused dropout clock
 
     def init_layer(self):
         stdv = 1. / math.sqrt(self.linear.weight.size(1))
         self.linear.weight.data.uniform_(-stdv, stdv)
         self.linear.bias.data.uniform_(-stdv, stdv)
 
-    def forward(self, g, h):
-        h = ops.sage_concat(g, h)           # get_norm + update_all + `*norm` + cat fused
-        if self.dropout:
-            h = self.dropout(h)
-        # GIST swaps in weight slices of other widths; use the live tensors, and
-        # normalise over the live output width
-        h = ops.linear(h, self.linear.weight, self.linear.bias)
+    def _p_drop(self):
+        return float(self.dropout.p) if (self.dropout and self.training) else 0.0
+
+    def prepare_input(self, g, h, out=None):
+        """z = dropout([h ‖ (A h) / in_deg]) (+ its 3xTF32 low half) for this layer, outside
+        autograd — the pipelined trainer runs it for the NEXT batch's input features while the
+        current batch trains (they do not depend on the weights and need no gradient)."""
+        return ops.sage_prepare(g, h, self._p_drop(), self._drop_stream, out=out)
+
+    def forward(self, g, h, pre=None):
+        # pre: this layer's prepared input for (g, h) (prepare_input), if already computed
+        if h.is_cuda and ops.get_matmul_precision() != 'fp32':
+            # tensor-core path: aggregation + concat + dropout (+ split) in K1's epilogue, the
+            # dropout backward in the dz GEMM's epilogue (ops._SageLinear)
+            h = ops.sage_linear(g, h, self.linear.weight, self.linear.bias, self._p_drop(), self._drop_stream,
+                                pre=pre)
+        else:
+            if pre is not None:
+                h = pre.z
+                if self.dropout and not pre.dropped:
+                    h = self.dropout(h)
+            else:
+                h = ops.sage_concat(g, h)       # get_norm + update_all + `*norm` + cat fused
+                if self.dropout:
+                    h = self.dropout(h)
+            # GIST swaps in weight slices of other widths; use the live tensors, and
+            # normalise over the live output width
+            h = ops.linear(h, self.linear.weight, self.linear.bias)
         if isinstance(self.lynorm, nn.LayerNorm):
             # LayerNorm over the live output width + ReLU in one kernel (fwd) / one (bwd)
             fuse = self.activation is None or _is_relu(self.activation)
@@ -277,8 +303,13 @@ class GCN(nn.Module):
 
     def forward(self, g):
         h = g.ndata['feat']
-        for layer in self.layers:
-            h = layer(g, h)
+        pre0 = g._cache.get(SAGE_PRE0)      # layer-0 input prepared ahead of time (graphed.py)
+        if self.training and h.is_cuda and ops.get_matmul_precision() != 'fp32':
+            st = ops.dropout_state(h.device)
+            if st.auto_tick:
+                st.tick()                   # one dropout step per training forward
+        for i, layer in enumerate(self.layers):
+            h = layer(g, h, pre=pre0) if (i == 0 and pre0 is not None) else layer(g, h)
         return h
 
 

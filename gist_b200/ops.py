@@ -4,6 +4,8 @@ Every function here enqueues hand-written sm_100a kernels from
 ``csrc/libgist_b200.so`` on torch's current stream.  No CPU path exists:
 non-CUDA inputs raise ``GistLibraryError``.
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -32,12 +34,15 @@ def _ld(t):
 
 
 def spmm_raw(rowptr, col, n_dst, n_src, X, out, *, src_scale=None, dst_scale=None, bias=None,
-             addend=None, self_out=None, relu=False, flags=0):
+             addend=None, self_out=None, relu=False, flags=0, out_lo=None, self_lo=None, drop=None,
+             drop_col0_out=0, drop_col0_self=0):
     """out[v] = act(dst_scale[v] * sum_{e in row v} src_scale[col e] * X[col e] + addend[v] + bias).
 
     ``out`` (and ``self_out``/``addend``) may be column-block views of wider
-    row-major buffers; leading dimensions are taken from the strides."""
-    require_cuda(rowptr, col, X, out, src_scale, dst_scale, bias, addend, self_out)
+    row-major buffers; leading dimensions are taken from the strides.
+    Extended epilogue: ``drop`` (a DropoutDesc) applies dropout to both outputs as they are
+    written, ``out_lo`` / ``self_lo`` receive their 3xTF32 low halves."""
+    require_cuda(rowptr, col, X, out, src_scale, dst_scale, bias, addend, self_out, out_lo, self_lo)
     d = X.shape[1]
     assert out.shape[0] == n_dst and out.shape[1] == d and X.shape[0] == n_src
     assert out.stride(1) == 1 or d == 1
@@ -47,13 +52,18 @@ def spmm_raw(rowptr, col, n_dst, n_src, X, out, *, src_scale=None, dst_scale=Non
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    st = lib.gist_spmm_csr_f32(
+    ex = None
+    if out_lo is not None or self_lo is not None or drop is not None:
+        ex = _lib.SpmmEx(ptr(out_lo), _ld(out_lo) if out_lo is not None else 0,
+                         ptr(self_lo), _ld(self_lo) if self_lo is not None else 0,
+                         ctypes.pointer(drop) if drop is not None else None, drop_col0_out, drop_col0_self)
+    st = lib.gist_spmm_csr_ex_f32(
         ptr(rowptr), ptr(col), n_dst, n_src, ptr(X), _ld(X), d, ptr(out), _ld(out),
         ptr(src_scale), ptr(dst_scale), ptr(bias),
         ptr(addend), _ld(addend) if addend is not None else 0,
         ptr(self_out), _ld(self_out) if self_out is not None else 0,
-        f, stream_ptr(X.device))
-    check(st, 'spmm_csr_f32')
+        f, ctypes.byref(ex) if ex is not None else None, stream_ptr(X.device))
+    check(st, 'spmm_csr_ex_f32')
     if prof is not None:
         ev1.record()
         prof.append(dict(ev0=ev0, ev1=ev1, rowptr=rowptr, n_dst=n_dst, n_src=n_src, d=d,
@@ -206,6 +216,142 @@ def sage_concat(g, h):
     return _SageConcat.apply(g, h)
 
 
+def sage_concat_into(g, h, out, out_lo=None, drop=None):
+    """No-grad z = [h ‖ (A h) / in_deg] into a caller-owned [n, 2d] buffer; optionally with the
+    layer's dropout applied as z is written (``drop``) and z's 3xTF32 low half (``out_lo``)."""
+    h = _mat(h, 'h')
+    n, d = h.shape
+    assert out.shape == (n, 2 * d) and out.dtype == torch.float32 and out.stride(1) == 1
+    spmm_raw(g.rowptr, g.col_buffer, n, n, h, out[:, d:], dst_scale=g.inv_in_degree(), self_out=out[:, :d],
+             out_lo=out_lo[:, d:] if out_lo is not None else None,
+             self_lo=out_lo[:, :d] if out_lo is not None else None,
+             drop=drop, drop_col0_out=d, drop_col0_self=0)
+    return out
+
+
+def _padded_empty(rows, cols, device):
+    """[rows, cols] fp32 view of a buffer whose leading dimension is a multiple of 4 floats (TMA)."""
+    return torch.empty((rows, (cols + 3) // 4 * 4), dtype=torch.float32, device=device)[:, :cols]
+
+
+class SagePre:
+    """A SAGE layer's prepared input: z = dropout([h ‖ mean-agg(h)]), its 3xTF32 low half (or None)
+    and the dropout step the mask was drawn at (or None when no dropout was applied)."""
+    __slots__ = ('z', 'z_lo', 'step_saved', 'dropped')
+
+    def __init__(self, z, z_lo, step_saved, dropped):
+        self.z, self.z_lo, self.step_saved, self.dropped = z, z_lo, step_saved, dropped
+
+
+def sage_prepare(g, h, p_drop, stream_id, out=None):
+    """Aggregation + concat (+ dropout, + 3xTF32 split) of a SAGE layer's input, no autograd.
+    ``out``: a SagePre of the same shape to overwrite in place."""
+    h = _mat(h, 'h')
+    n, d = h.shape
+    x3 = _MATMUL_PRECISION == '3xtf32'
+    if out is None:
+        z = _padded_empty(n, 2 * d, h.device)
+        z_lo = _padded_empty(n, 2 * d, h.device) if x3 else None
+        saved = torch.zeros(1, dtype=torch.int64, device=h.device) if p_drop else None
+        out = SagePre(z, z_lo, saved, bool(p_drop))
+    desc = dropout_state(h.device).desc(p_drop, stream_id, step_saved=out.step_saved) if p_drop else None
+    sage_concat_into(g, h, out.z, out.z_lo, desc)
+    return out
+
+
+# --------------------------------------------------------------------------
+# fused dropout: counter-based mask shared by the kernels on both sides of nn.Dropout
+# --------------------------------------------------------------------------
+class DropoutState:
+    """Per-device dropout clock.  A mask is a pure function of (seed, step, stream_id, row, col)
+    (include/gist_b200.h, gist_dropout_t): ``step`` lives in device memory so captured CUDA graphs
+    draw fresh masks at every replay, and is advanced once per model forward in training mode
+    (``auto_tick``) or by whoever drives the step (GraphedClusterTrainer ticks before its branches
+    fork).  The seed follows ``torch.manual_seed`` (``torch.initial_seed()`` at use)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.step = torch.zeros(1, dtype=torch.int64, device=device)
+        self.auto_tick = True
+
+    def tick(self):
+        check(_lib.load().gist_counter_add_i64(ptr(self.step), 1, stream_ptr(self.device)), 'counter_add_i64')
+
+    def desc(self, p, stream_id, step=None, step_saved=None):
+        """ctypes gist_dropout_t reading ``step`` (default: the live clock)."""
+        step = self.step if step is None else step
+        return _lib.DropoutDesc(float(p), torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, int(stream_id) & 0xFFFFFFFF,
+                                step.data_ptr(), step_saved.data_ptr() if step_saved is not None else None)
+
+
+_DROPOUT_STATES = {}
+_drop_stream_counter = [0]
+
+
+def dropout_state(device):
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _DROPOUT_STATES.get(idx)
+    if st is None:
+        st = _DROPOUT_STATES[idx] = DropoutState(torch.device('cuda', idx))
+    return st
+
+
+def new_dropout_stream():
+    """A fresh stream id (one per dropout site; deterministic in construction order)."""
+    _drop_stream_counter[0] += 1
+    return _drop_stream_counter[0]
+
+
+def dropout(x, desc, col0=0):
+    """desc's mask applied to x as a stand-alone kernel (the same mask the fused kernels apply)."""
+    require_cuda(x)
+    x = _mat(x, 'x')
+    out = torch.empty_like(x)
+    check(_lib.load().gist_dropout_f32(ptr(x), _ld(x), x.shape[0], x.shape[1], col0, ptr(out), _ld(out),
+                                       ctypes.byref(desc), stream_ptr(x.device)), 'dropout_f32')
+    return out
+
+
+# 3xTF32 low halves produced by the kernel that wrote a tensor (layer-norm / cross-entropy backward),
+# handed to the nn.Linear backward that consumes it.  Keyed by data pointer; the entry holds the
+# tensor itself, so the pointer cannot be recycled while the entry lives; consumed on first use.
+_GRAD_LO = {}
+# weight low halves split ahead of time by a trainer (GraphedClusterTrainer: on the side branch)
+_WEIGHT_LO = {}
+
+
+def _lo_put(t, lo):
+    if len(_GRAD_LO) > 16:
+        _GRAD_LO.clear()
+    _GRAD_LO[t.data_ptr()] = (t, lo)
+
+
+def _lo_take(t):
+    e = _GRAD_LO.pop(t.data_ptr(), None)
+    if e is not None and e[0].shape == t.shape and e[0].stride() == t.stride() and e[1].shape == t.shape:
+        return e[1]
+    return None
+
+
+def presplit_weights(params):
+    """Split every 2-D fp32 parameter once (3xTF32 mode) so the layers find W_lo ready."""
+    for p in params:
+        if p.dim() == 2 and p.is_cuda and _tma_ok(p.data):
+            _WEIGHT_LO[p.data_ptr()] = (p, split_tf32(p.data))
+
+
+def clear_presplit():
+    _WEIGHT_LO.clear()
+
+
+def _weight_lo(Wv):
+    e = _WEIGHT_LO.get(Wv.data_ptr())
+    if e is not None and e[1].shape == Wv.shape:
+        return e[1]
+    return split_tf32(Wv)
+
+
 # --------------------------------------------------------------------------
 # K4: tensor-core GEMM (tcgen05, TF32 inputs / fp32 accumulate)
 # --------------------------------------------------------------------------
@@ -303,6 +449,25 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, relu=False, out=None, flags
     return out
 
 
+def gemm_dropmask(A, B, drop, *, a_mn=False, b_mn=False, out=None, A_lo=None, B_lo=None):
+    """C = mask(drop) ⊙ (op(A) op(B)^T): the dz contraction with the forward's dropout mask
+    regenerated in the epilogue (gist_gemm_dropmask_f32)."""
+    require_cuda(A, B, out, A_lo, B_lo)
+    if a_mn:
+        K, M = A.shape
+    else:
+        M, K = A.shape
+    N = B.shape[1] if b_mn else B.shape[0]
+    if out is None:
+        out = _padded_empty(M, N, A.device)
+    assert tuple(out.shape) == (M, N)
+    check(_lib.load().gist_gemm_dropmask_f32(
+        ptr(A), ptr(A_lo), _ld(A), _ld(A_lo) if A_lo is not None else 0, 1 if a_mn else 0,
+        ptr(B), ptr(B_lo), _ld(B), _ld(B_lo) if B_lo is not None else 0, 1 if b_mn else 0,
+        ptr(out), _ld(out), M, N, K, 0, ctypes.byref(drop), stream_ptr(A.device)), 'gemm_dropmask_f32')
+    return out
+
+
 def gemm_tn(A, B, bias=None, relu=False, out=None):
     """C[M,N] = A[M,K] @ B[N,K]^T (+bias) (ReLU): both operands K-major."""
     return gemm(A, B, bias=bias, relu=relu, out=out)
@@ -366,8 +531,12 @@ class _Linear3xTF32(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         z, z_lo, W, W_lo = ctx.saved_tensors
-        dy = _tma_view(_mat(dy, 'dy'))
-        dy_lo = split_tf32(dy)
+        dy = _mat(dy, 'dy')
+        dy_lo = _lo_take(dy)
+        if not _tma_ok(dy):
+            dy, dy_lo = _tma_view(dy), None
+        if dy_lo is None:
+            dy_lo = split_tf32(dy)
         dz = dW = db = None
         if ctx.needs_input_grad[0]:
             dz = gemm(dy, W, b_mn=True, A_lo=dy_lo, B_lo=W_lo)
@@ -376,6 +545,68 @@ class _Linear3xTF32(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy)
         return dz, dW, db
+
+
+class _SageLinear(torch.autograd.Function):
+    """y = dropout([h ‖ (A h) / in_deg]) W^T + b — everything of an IST SAGE layer up to the layer
+    norm (cluster_gcn/modules.py:222-233) as ONE autograd node over fused kernels:
+      forward : K1 writes z with the dropout mask applied and (3xTF32) z_lo beside it -> K4
+      backward: dz = mask ⊙ (dy W) in the K4 epilogue (mask regenerated) -> K2 on the CSC gives dh;
+                dW = dy^T z (K4, split-K); db = column sums.
+    No dropout kernels, no masks in memory, no split passes over z / dy."""
+
+    @staticmethod
+    def forward(ctx, g, h, W, b, p_drop, stream_id, pre):
+        x3 = _MATMUL_PRECISION == '3xtf32'
+        if pre is None:
+            pre = sage_prepare(g, h.detach(), p_drop, stream_id)
+        z, z_lo = pre.z, pre.z_lo
+        if x3 and z_lo is None:
+            z_lo = split_tf32(z)
+        Wv = _tma_view(W)
+        W_lo = _weight_lo(Wv) if x3 else None
+        y = gemm(z, Wv, bias=b, A_lo=z_lo, B_lo=W_lo)
+        ctx.g, ctx.has_bias, ctx.x3 = g, b is not None, x3
+        ctx.drop = (float(p_drop), int(stream_id)) if pre.dropped else None
+        ctx.step_saved = pre.step_saved
+        ctx.save_for_backward(z, z_lo, Wv, W_lo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, z_lo, W, W_lo = ctx.saved_tensors
+        g = ctx.g
+        dy = _mat(dy, 'dy')
+        dy_lo = _lo_take(dy) if ctx.x3 else None
+        if not _tma_ok(dy):
+            dy, dy_lo = _tma_view(dy), None
+        if ctx.x3 and dy_lo is None:
+            dy_lo = split_tf32(dy)
+        n, d2 = z.shape
+        d = d2 // 2
+        dh = dW = db = None
+        if ctx.needs_input_grad[1]:
+            if ctx.drop is not None:
+                desc = dropout_state(dy.device).desc(ctx.drop[0], ctx.drop[1], step=ctx.step_saved)
+                dz = gemm_dropmask(dy, W, desc, b_mn=True, A_lo=dy_lo, B_lo=W_lo)
+            else:
+                dz = gemm(dy, W, b_mn=True, A_lo=dy_lo, B_lo=W_lo, out=_padded_empty(n, d2, dy.device))
+            colptr, row = g.csc()
+            dh = torch.empty((n, d), dtype=torch.float32, device=dy.device)
+            # dh = dz[:, :d] + A^T (inv_deg ⊙ dz[:, d:])
+            spmm_raw(colptr, row, n, n, dz[:, d:], dh, src_scale=g.inv_in_degree(), addend=dz[:, :d])
+        if ctx.needs_input_grad[2]:
+            dW = gemm(dy, z, a_mn=True, b_mn=True, A_lo=dy_lo, B_lo=z_lo)
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            db = colsum(dy)
+        return None, dh, dW, db, None, None, None
+
+
+def sage_linear(g, h, W, b, p_drop=0.0, stream_id=0, pre=None):
+    """Fused SAGE aggregation + dropout + linear on the tensor-core path ('tf32' / '3xtf32')."""
+    assert _MATMUL_PRECISION in ('tf32', '3xtf32')
+    require_cuda(h, W, b)
+    return _SageLinear.apply(g, h, W, b, float(p_drop), int(stream_id), pre)
 
 
 def linear(z, W, b=None):
@@ -425,10 +656,14 @@ class _LayerNormAct(torch.autograd.Function):
         x, stats = ctx.saved_tensors
         dy = _mat(dy, 'dy')
         n, d = x.shape
-        dx = torch.empty((n, d), dtype=torch.float32, device=x.device)
+        x3 = _MATMUL_PRECISION == '3xtf32'
+        dx = _padded_empty(n, d, x.device)
+        dx_lo = _padded_empty(n, d, x.device) if x3 else None       # feeds the nn.Linear backward below
         check(_lib.load().gist_layernorm_act_bwd_f32(ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(stats), n, d, ctx.fl,
-                                                     ptr(dx), _ld(dx), stream_ptr(x.device)),
-              'layernorm_act_bwd_f32')
+                                                     ptr(dx), _ld(dx), ptr(dx_lo), _ld(dx_lo) if x3 else 0,
+                                                     stream_ptr(x.device)), 'layernorm_act_bwd_f32')
+        if x3:
+            _lo_put(dx, dx_lo)
         return dx, None, None
 
 
@@ -463,11 +698,16 @@ class _MaskedCrossEntropy(torch.autograd.Function):
         n, C = logits.shape
         ldd = (C + 3) // 4 * 4        # padded rows: the gradient feeds the TMA-addressed GEMMs
         buf = torch.empty((n, ldd), dtype=torch.float32, device=logits.device)
+        x3 = _MATMUL_PRECISION == '3xtf32'
+        buf_lo = torch.empty((n, ldd), dtype=torch.float32, device=logits.device) if x3 else None
         gout = gout.contiguous().float()
         check(_lib.load().gist_masked_ce_bwd_f32(ptr(logits), _ld(logits), n, C, ptr(labels), ptr(mask), ptr(lse),
-                                                 ptr(out), ptr(gout), ptr(buf), ldd, ldd,
+                                                 ptr(out), ptr(gout), ptr(buf), ldd, ldd, ptr(buf_lo),
                                                  stream_ptr(logits.device)), 'masked_ce_bwd_f32')
-        return buf[:, :C], None, None
+        dl = buf[:, :C]
+        if x3:
+            _lo_put(dl, buf_lo[:, :C])
+        return dl, None, None
 
 
 def masked_cross_entropy(logits, labels, mask=None):

@@ -31,6 +31,23 @@ extern "C" {
 
 typedef void *gist_stream_t; /* cudaStream_t */
 
+/* Counter-based dropout (nn.Dropout as used at cluster_gcn/modules.py:228-229), fused into the
+ * kernels on either side of it instead of running as a kernel of its own.  Whether element
+ * (row, col) of the logical [n, width] matrix is kept is a pure function (Philox4x32-10) of
+ * (seed, *step, stream_id, row, col): the forward kernel that applies the mask and the backward
+ * kernel that needs it again regenerate it, nothing is stored.  `step` is a DEVICE counter read by
+ * the kernel, so a captured CUDA graph draws a fresh mask at every replay (advance it with
+ * gist_counter_add_i64 between steps); `stream_id` separates layers drawing from the same step.
+ * Kept elements are scaled by 1 / (1 - p).  A NULL descriptor or p == 0 disables dropout. */
+typedef struct gist_dropout {
+    float p;               /* drop probability in [0, 1) */
+    uint64_t seed;
+    uint32_t stream_id;
+    const int64_t *step;   /* device pointer; NULL = step 0 */
+    int64_t *step_saved;   /* device pointer, optional: the applying kernel stores the step value it
+                              read, to be passed as `step` to the matching backward call */
+} gist_dropout_t;
+
 #define GIST_ABI_VERSION 1
 
 #define GIST_OK 0
@@ -90,6 +107,29 @@ int gist_spmm_csr_f32(const int32_t *rowptr, const int32_t *col, int32_t n_dst, 
                       const float *addend, int64_t ld_addend,
                       float *self_out, int64_t ld_self,
                       uint32_t flags, gist_stream_t stream);
+
+/* Extended epilogue for the training step (ex == NULL: identical to gist_spmm_csr_f32):
+ *   - dropout applied to Y and to self_out as they are written; the mask is that of the logical
+ *     matrix whose columns [drop_col0_y, +d) / [drop_col0_self, +d) the two outputs are — for the
+ *     SAGE concat z = [h | mean-agg(h)] (cluster_gcn/modules.py:226-229) that is d and 0;
+ *   - y_lo / self_lo (optional): the 3xTF32 low halves tf32(x - trunc_tf32(x)) of the values
+ *     written, so the nn.Linear that consumes z needs no separate split pass.
+ * Replaces nn.Dropout on z (modules.py:228-229) and gist_split_tf32_f32 on z. */
+typedef struct gist_spmm_ex {
+    float *y_lo;
+    int64_t ld_y_lo;
+    float *self_lo;
+    int64_t ld_self_lo;
+    const gist_dropout_t *drop;
+    int32_t drop_col0_y, drop_col0_self;
+} gist_spmm_ex_t;
+int gist_spmm_csr_ex_f32(const int32_t *rowptr, const int32_t *col, int32_t n_dst, int32_t n_src,
+                         const float *X, int64_t ldx, int32_t d,
+                         float *Y, int64_t ldy,
+                         const float *src_scale, const float *dst_scale, const float *bias,
+                         const float *addend, int64_t ld_addend,
+                         float *self_out, int64_t ld_self,
+                         uint32_t flags, const gist_spmm_ex_t *ex, gist_stream_t stream);
 
 /* K2 spelled out: identical kernel, arguments named for the transpose.
  * colptr/row = CSC of the forward graph. */
@@ -220,6 +260,17 @@ int gist_gemm_3xtf32(const float *A, const float *A_lo, int64_t lda, int64_t lda
                      float *C, int64_t ldc, int32_t M, int32_t N, int32_t K, const float *bias,
                      uint32_t flags, void *workspace, size_t workspace_bytes, gist_stream_t stream);
 
+/* C = dropout_mask(seed, *step, stream_id) * (op(A) op(B)^T): the dz = dy W contraction of the layer
+ * whose INPUT z went through dropout (cluster_gcn/modules.py:228-233).  The multiplier of C[r, c] is
+ * the one gist_spmm_csr_ex_f32 applied to z[r, c] in the forward pass (same descriptor, with
+ * step = the forward's step_saved), regenerated in the GEMM epilogue — replaces the masked_scale
+ * kernel of nn.Dropout's backward.  A_lo == B_lo == NULL: single-pass TF32; both given: 3xTF32.
+ * Never splits K. */
+int gist_gemm_dropmask_f32(const float *A, const float *A_lo, int64_t lda, int64_t lda_lo, int32_t a_layout,
+                           const float *B, const float *B_lo, int64_t ldb, int64_t ldb_lo, int32_t b_layout,
+                           float *C, int64_t ldc, int32_t M, int32_t N, int32_t K, uint32_t flags,
+                           const gist_dropout_t *drop, gist_stream_t stream);
+
 /* lo[r,c] = tf32_round(x[r,c] - trunc_tf32(x[r,c])) and, if hi != NULL, hi[r,c] = trunc_tf32(x[r,c])
  * (x with its 13 low mantissa bits cleared) for a [rows, cols] row-major matrix. */
 int gist_split_tf32_f32(const float *x, int64_t ld_x, int32_t rows, int32_t cols, float *hi, int64_t ld_hi,
@@ -242,7 +293,7 @@ int gist_layernorm_act_fwd_f32(const float *x, int64_t ldx, int32_t n, int32_t d
 /* dx = d/dx of the above given dy; x is the forward INPUT, stats from the forward. */
 int gist_layernorm_act_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx,
                                const float *stats, int32_t n, int32_t d, uint32_t flags, float *dx,
-                               int64_t lddx, gist_stream_t stream);
+                               int64_t lddx, float *dx_lo, int64_t ld_lo, gist_stream_t stream);
 
 /* out[c] = sum_r x[r, c] (bias gradient of nn.Linear), two-phase fixed-order reduction.
  * workspace: gist_colsum_workspace_bytes(n, d) bytes. */
@@ -262,7 +313,21 @@ int gist_masked_ce_fwd_f32(const float *logits, int64_t ld, int32_t n, int32_t C
 int gist_masked_ce_bwd_f32(const float *logits, int64_t ld, int32_t n, int32_t C, const int64_t *labels,
                            const uint8_t *mask, const float *lse, const float *loss_out,
                            const float *grad_out, float *dlogits, int64_t ldd, int32_t fill_cols,
-                           gist_stream_t stream);
+                           float *dlogits_lo, gist_stream_t stream);
+
+/* dx_lo (layer norm backward) / dlogits_lo (cross entropy backward): optional (NULL) 3xTF32 low
+ * halves tf32(v - trunc_tf32(v)) of the gradient just written, in the same layout (dlogits_lo: same
+ * leading dimension and padding as dlogits) — the nn.Linear backward that consumes the gradient
+ * then needs no gist_split_tf32_f32 pass over it.
+ *
+ * out[r, c] = m(r, col0 + c) * x[r, c]  (x == NULL: the multiplier itself): nn.Dropout as a
+ * stand-alone kernel with the SAME mask the fused kernels apply (tests; eager fall-backs). */
+int gist_dropout_f32(const float *x, int64_t ldx, int32_t n, int32_t d, int32_t col0, float *out, int64_t ldo,
+                     const gist_dropout_t *drop, gist_stream_t stream);
+
+/* *counter += delta on the device: advances the dropout step between training steps (one node of
+ * the captured step graph, before the build / train branches fork). */
+int gist_counter_add_i64(int64_t *counter, int64_t delta, gist_stream_t stream);
 
 /* torch.optim.Adam(lr, betas, eps, weight_decay) (amsgrad=False; cluster_gcn_ist_distrib.py:405-407,
  * :417) over n_tensors tensors in one launch (per 24 tensors).  params / grads / exp_avg /
