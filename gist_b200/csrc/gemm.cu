@@ -444,8 +444,21 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restr
     if (i >= (int64_t)M * nq) return;
     const int r = (int)(i / nq), c = (int)(i % nq) * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < splits; ++s) {   // ldp is a multiple of 4 and the buffer 16-byte aligned
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(part + ((int64_t)s * M + r) * ldp + c));
+    const float *p0 = part + (int64_t)r * ldp + c;      // ldp is a multiple of 4, buffer 16-byte aligned
+    const int64_t sstride = (int64_t)M * ldp;
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {                   // four loads in flight, summed in split order
+        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)s * sstride));
+        const float4 v1 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)(s + 1) * sstride));
+        const float4 v2 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)(s + 2) * sstride));
+        const float4 v3 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)(s + 3) * sstride));
+        acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+        acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+        acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+        acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+    }
+    for (; s < splits; ++s) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)s * sstride));
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     float o[4] = {acc.x, acc.y, acc.z, acc.w};
@@ -600,30 +613,62 @@ struct GemmPlan {
 // Tile width and split-K factor: the widest tile that still gives most of the 148 SMs a work
 // unit; when even 64-wide tiles leave more than half the chip idle and K is long (the dW
 // contraction), K is split.
+// Tile width and split-K factor from a small cost model (microseconds), fitted to ncu timelines
+// of the training step on B200:
+//   t = fixed + waves x max(K blocks per unit x stage bytes / (per-SM TMA rate), MMA time)
+//       + split-K second pass (launch + partial-buffer traffic)
+// Small problems are bound by the fixed cost and by how many SMs pull operands at once (one CTA
+// streams ~110 GB/s whatever the tile), so the model prefers one full wave of short K loops over
+// few long ones; large problems amortise everything and get the widest tile (least L2 traffic).
 static GemmPlan plan_gemm(int M, int N, int K, uint32_t flags, bool x3) {
     GemmPlan pl;
     const int sms = sm_count();
     const int64_t tm = (M + kBM - 1) / kBM;
-    auto tiles = [&](int bn) { return tm * ((N + bn - 1) / bn); };
-    // 3xTF32 sums K chunks in registers (one tile row per epilogue thread): tiles are <= 128 wide
-    if (flags & GIST_GEMM_TILE_N64) pl.bn = 64;
-    else if (flags & GIST_GEMM_TILE_N128) pl.bn = 128;
-    else if (flags & GIST_GEMM_TILE_N256) pl.bn = x3 ? 128 : 256;
-    else if (!x3 && tiles(256) >= (int64_t)sms * 4 / 5) pl.bn = 256;
-    else if (tiles(128) >= (int64_t)sms * 4 / 5) pl.bn = 128;
-    else pl.bn = 64;
     const int kblocks = (K + kBK - 1) / kBK;
-    int splits = 1;
-    const int64_t t = tiles(pl.bn);
-    if (!(flags & GIST_GEMM_NO_SPLITK) && t * 2 <= sms) {
-        int64_t want = sms / t;                 // tiles x splits must fit ONE wave of the chip
-        int64_t cap = kblocks / 4;              // at least 4 K blocks per split
-        if (want > cap) want = cap;
-        if (want > 32) want = 32;
-        if (want > 1) splits = (int)want;
+    int cand[3], nc = 0;
+    // 3xTF32 sums K chunks in registers (one tile row per epilogue thread): tiles are <= 128 wide
+    if (flags & GIST_GEMM_TILE_N64) cand[nc++] = 64;
+    else if (flags & GIST_GEMM_TILE_N128) cand[nc++] = 128;
+    else if (flags & GIST_GEMM_TILE_N256) cand[nc++] = x3 ? 128 : 256;
+    else {
+        if (!x3) cand[nc++] = 256;
+        cand[nc++] = 128;
+        cand[nc++] = 64;
     }
-    pl.kb_per_split = (kblocks + splits - 1) / splits;
-    pl.splits = (kblocks + pl.kb_per_split - 1) / pl.kb_per_split;   // no empty split
+    int max_splits = 1;
+    if (!(flags & GIST_GEMM_NO_SPLITK)) {
+        max_splits = kblocks / 4;               // at least 4 K blocks per split
+        if (max_splits > 32) max_splits = 32;
+        if (max_splits < 1) max_splits = 1;
+    }
+    double best = 1e30;
+    pl.bn = cand[0]; pl.splits = 1; pl.kb_per_split = kblocks;
+    for (int ci = 0; ci < nc; ++ci) {
+        const int bn = cand[ci];
+        const int64_t t = tm * ((N + bn - 1) / bn);
+        const double stage_bytes = (double)(kBM + bn) * kBK * 4 * (x3 ? 2 : 1);
+        const double kb_load_us = stage_bytes / 110e3;                               // ~110 GB/s per CTA
+        const double kb_mma_us = (x3 ? 3 : 1) * (kBK / kUmmaK) * (bn / 64.0) * 0.017;  // 128x64x8 ~ 32 clk
+        const double kb_us = kb_load_us > kb_mma_us ? kb_load_us : kb_mma_us;
+        const double epi_us = 0.8 * bn / 64.0;
+        for (int sp = 1; sp <= max_splits; ++sp) {
+            const int kbps = (kblocks + sp - 1) / sp;
+            const int s_eff = (kblocks + kbps - 1) / kbps;          // no empty split
+            if (s_eff != sp) continue;
+            const int64_t units = t * s_eff;
+            if (sp > 1 && units > sms) break;                        // splitting past one wave never pays
+            const double waves = (double)((units + sms - 1) / sms);
+            double cost = 6.0 + waves * (kbps * kb_us + epi_us);
+            // chip-wide operand traffic (L2 -> SM) bounds large problems
+            const double agg_us = (double)units * kbps * stage_bytes / 14e6;
+            if (agg_us > cost) cost = agg_us;
+            if (s_eff > 1) cost += 4.0 + (double)(s_eff + 1) * M * N * 4.0 / 3e6;
+            if (cost < best - 0.05) {
+                best = cost;
+                pl.bn = bn; pl.splits = s_eff; pl.kb_per_split = kbps;
+            }
+        }
+    }
     pl.ldp = (N + 3) / 4 * 4;
     pl.ws_bytes = pl.splits > 1 ? (size_t)pl.splits * M * pl.ldp * sizeof(float) : 0;
     return pl;
@@ -636,6 +681,16 @@ using namespace gist;
 extern "C" size_t gist_gemm_tf32_workspace_bytes(int32_t M, int32_t N, int32_t K, uint32_t flags) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     return plan_gemm(M, N, K, flags, false).ws_bytes;
+}
+
+extern "C" int gist_gemm_plan(int32_t M, int32_t N, int32_t K, uint32_t flags, int32_t three_pass, int32_t *tile_n,
+                              int32_t *splits, int32_t *kblocks_per_split) {
+    if (M <= 0 || N <= 0 || K <= 0) return GIST_ERR_BADARG;
+    const GemmPlan pl = plan_gemm(M, N, K, flags, three_pass != 0);
+    if (tile_n) *tile_n = pl.bn;
+    if (splits) *splits = pl.splits;
+    if (kblocks_per_split) *kblocks_per_split = pl.kb_per_split;
+    return GIST_OK;
 }
 
 extern "C" size_t gist_gemm_3xtf32_workspace_bytes(int32_t M, int32_t N, int32_t K, uint32_t flags) {

@@ -252,7 +252,7 @@ def sage_prepare(g, h, p_drop, stream_id, out=None):
     if out is None:
         z = _padded_empty(n, 2 * d, h.device)
         z_lo = _padded_empty(n, 2 * d, h.device) if x3 else None
-        saved = torch.zeros(1, dtype=torch.int64, device=h.device) if p_drop else None
+        saved = torch.empty(1, dtype=torch.int64, device=h.device) if p_drop else None   # K1 writes it
         out = SagePre(z, z_lo, saved, bool(p_drop))
     desc = dropout_state(h.device).desc(p_drop, stream_id, step_saved=out.step_saved) if p_drop else None
     sage_concat_into(g, h, out.z, out.z_lo, desc)
@@ -547,6 +547,53 @@ class _Linear3xTF32(torch.autograd.Function):
         return dz, dW, db
 
 
+# --------------------------------------------------------------------------
+# weight-gradient branch: dW / db never feed the rest of the backward pass (only the optimizer),
+# so they run on a low-priority side stream and the activation-gradient chain
+# (dz GEMM -> K2 -> layer-norm backward -> next dz GEMM ...) is the only thing on the main one.
+# The side stream is joined by an autograd end-of-backward callback, so whoever reads .grad after
+# loss.backward() is ordered behind it — under CUDA-graph capture this becomes a parallel branch.
+# --------------------------------------------------------------------------
+OVERLAP_WEIGHT_GRADS = True
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(idx)
+    if st is None:
+        lo_p, _ = torch.cuda.Stream.priority_range()
+        st = _SIDE_STREAMS[idx] = torch.cuda.Stream(device=idx, priority=lo_p)
+    return st
+
+
+def _weight_grad_branch(device, fn):
+    """Run fn() (returns tensors) on the side stream, forked from the current stream; registers the
+    join.  Falls back to the current stream when overlap is disabled or outside a backward pass."""
+    if not OVERLAP_WEIGHT_GRADS:
+        return fn()
+    cur = torch.cuda.current_stream(device)
+    side = _side_stream(device)
+    if side == cur:
+        return fn()
+    ev = torch.cuda.Event()
+
+    def join():
+        cur.wait_event(ev)
+        now = torch.cuda.current_stream(device)
+        if now != cur:
+            now.wait_event(ev)
+    try:
+        torch.autograd.Variable._execution_engine.queue_callback(join)
+    except RuntimeError:            # not inside a backward pass: nothing would join the branch
+        return fn()
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        out = fn()
+        ev.record(side)
+    return out
+
+
 class _SageLinear(torch.autograd.Function):
     """y = dropout([h ‖ (A h) / in_deg]) W^T + b — everything of an IST SAGE layer up to the layer
     norm (cluster_gcn/modules.py:222-233) as ONE autograd node over fused kernels:
@@ -585,6 +632,13 @@ class _SageLinear(torch.autograd.Function):
         n, d2 = z.shape
         d = d2 // 2
         dh = dW = db = None
+        need_dW, need_db = ctx.needs_input_grad[2], ctx.has_bias and ctx.needs_input_grad[3]
+
+        def weight_grads():
+            return (gemm(dy, z, a_mn=True, b_mn=True, A_lo=dy_lo, B_lo=z_lo) if need_dW else None,
+                    colsum(dy) if need_db else None)
+        if need_dW or need_db:      # forked first: the branch depends on dy only
+            dW, db = _weight_grad_branch(dy.device, weight_grads)
         if ctx.needs_input_grad[1]:
             if ctx.drop is not None:
                 desc = dropout_state(dy.device).desc(ctx.drop[0], ctx.drop[1], step=ctx.step_saved)
@@ -595,10 +649,6 @@ class _SageLinear(torch.autograd.Function):
             dh = torch.empty((n, d), dtype=torch.float32, device=dy.device)
             # dh = dz[:, :d] + A^T (inv_deg ⊙ dz[:, d:])
             spmm_raw(colptr, row, n, n, dz[:, d:], dh, src_scale=g.inv_in_degree(), addend=dz[:, :d])
-        if ctx.needs_input_grad[2]:
-            dW = gemm(dy, z, a_mn=True, b_mn=True, A_lo=dy_lo, B_lo=z_lo)
-        if ctx.has_bias and ctx.needs_input_grad[3]:
-            db = colsum(dy)
         return None, dh, dW, db, None, None, None
 
 

@@ -237,6 +237,11 @@ int gist_gemm_tf32(const float *A, int64_t lda, int32_t a_layout, const float *B
                    const float *bias, uint32_t flags, void *workspace, size_t workspace_bytes,
                    gist_stream_t stream);
 
+/* The launch plan the two GEMMs use for a shape (introspection for tests / tuning): output-tile
+ * width, number of K splits and K blocks (of 32) per split.  Host-only, no launch. */
+int gist_gemm_plan(int32_t M, int32_t N, int32_t K, uint32_t flags, int32_t three_pass, int32_t *tile_n,
+                   int32_t *splits, int32_t *kblocks_per_split);
+
 /* Both operands K-major, no workspace (never splits K). */
 int gist_gemm_tn_tf32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
                       int32_t M, int32_t N, int32_t K, const float *bias, uint32_t flags,
