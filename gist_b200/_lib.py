@@ -57,6 +57,8 @@ SIGNATURES = {
     'gist_counter_add_i64': (ctypes.c_int, [_P, _I64, _P]),
     'gist_spmm_csr_ex_f32': (ctypes.c_int, [_P, _P, _I32, _I32, _P, _I64, _I32, _P, _I64,
                                             _P, _P, _P, _P, _I64, _P, _I64, _U32, _P, _P]),
+    'gist_spmm_schedule_workspace_bytes': (_SZ, [_I32]),
+    'gist_spmm_schedule_build': (ctypes.c_int, [_P, _I32, _I32, _P, _P, _I64, _P, _SZ, _P]),
     'gist_gemm_dropmask_f32': (ctypes.c_int, [_P, _P, _I64, _I64, _I32, _P, _P, _I64, _I64, _I32, _P, _I64,
                                               _I32, _I32, _I32, _U32, _P, _P]),
     'gist_gat_scores_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P]),
@@ -81,11 +83,19 @@ class DropoutDesc(ctypes.Structure):
                 ('step', ctypes.c_void_p), ('step_saved', ctypes.c_void_p)]
 
 
+class SpmmSchedule(ctypes.Structure):
+    """gist_spmm_schedule_t"""
+    _fields_ = [('seg_ptr', ctypes.c_void_p), ('seg_row', ctypes.c_void_p), ('seg_len', ctypes.c_int32),
+                ('max_segments', ctypes.c_int64), ('counters', ctypes.c_void_p), ('workspace', ctypes.c_void_p),
+                ('ld_workspace', ctypes.c_int64)]
+
+
 class SpmmEx(ctypes.Structure):
     """gist_spmm_ex_t"""
     _fields_ = [('y_lo', ctypes.c_void_p), ('ld_y_lo', ctypes.c_int64), ('self_lo', ctypes.c_void_p),
                 ('ld_self_lo', ctypes.c_int64), ('drop', ctypes.POINTER(DropoutDesc)),
-                ('drop_col0_y', ctypes.c_int32), ('drop_col0_self', ctypes.c_int32)]
+                ('drop_col0_y', ctypes.c_int32), ('drop_col0_self', ctypes.c_int32),
+                ('schedule', ctypes.POINTER(SpmmSchedule))]
 
 
 _lib = None

@@ -44,6 +44,14 @@ struct SpmmParams {
     int32_t ld_self_lo;
     int32_t col0_y, col0_self;   // logical column of output column 0 in the dropout mask
     DropParams drop;
+    // segment-balanced variant only (spmm_seg_kernel)
+    const int32_t *seg_ptr;      // [n_dst + 1] first segment of every row; seg_ptr[n_dst] = #segments
+    const int32_t *seg_row;      // [#segments] row of every segment
+    int32_t seg_len;             // edges per segment
+    int32_t seg_blocks;          // CTAs per feature chunk
+    uint32_t *seg_count;         // [chunks][n_dst] arrival counters, zero between launches
+    float *seg_ws;               // [#segments][ld_ws] partial sums of multi-segment rows
+    int32_t ld_ws;
 };
 
 template <int VEC>
@@ -130,6 +138,12 @@ __device__ __forceinline__ void gather_range(const SpmmParams &p, int eb, int ee
     }
 }
 
+// EX: the forward records the dropout step it draws its mask at (once per launch), for the backward
+__device__ __forceinline__ void record_drop_step(const SpmmParams &p) {
+    if (p.drop.p != 0.f && p.drop.step_saved && blockIdx.x == 0 && threadIdx.x == 0)
+        *p.drop.step_saved = drop_step(p.drop);
+}
+
 // EX: r <- dropout(r) for logical columns [col, col + VEC) of row v, then store r (and tf32_lo(r)).
 template <int VEC>
 __device__ __forceinline__ void drop_store(const SpmmParams &p, int64_t step, int v, int col, float (&r)[VEC],
@@ -162,10 +176,7 @@ __device__ __forceinline__ void epilogue(const SpmmParams &p, int v, const int (
     const float t = p.dst_scale ? __ldg(p.dst_scale + v) : 1.f;
     int64_t step = 0;
     if constexpr (EX) {
-        if (p.drop.p != 0.f) {
-            step = drop_step(p.drop);
-            if (p.drop.step_saved && blockIdx.x == 0 && threadIdx.x == 0) *p.drop.step_saved = step;
-        }
+        if (p.drop.p != 0.f) step = drop_step(p.drop);
     }
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
@@ -241,6 +252,7 @@ spmm_csr_kernel(const SpmmParams p) {
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
     const int lane0 = grp * LPR;
     constexpr bool coop = COOP;
+    if constexpr (EX) record_drop_step(p);
 
     int c[VPL];
     bool cv[VPL];
@@ -305,6 +317,156 @@ spmm_csr_kernel(const SpmmParams p) {
         }
         __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Segment-balanced variant for cluster batches (rows are scarce and power-law: with one row per
+// group the launch is as long as its unluckiest CTA — ncu: SMs idle 40-47 % of the kernel).
+// Every row is cut into segments of <= seg_len edges (schedule built once per batch,
+// gist_spmm_schedule_build); a group owns ONE (segment, feature-chunk), so all groups do the same
+// amount of gathering.  A row with one segment is finished by its group.  A longer row's groups
+// write their partial sums to a workspace and bump the row's arrival counter; the group that
+// arrives last re-reads ALL partials and adds them in segment order — the sum does not depend on
+// which group happens to be last, so the result is deterministic without a second launch or float
+// atomics — then runs the epilogue and re-arms the counter.
+template <int VEC, int LPR, int VPL, bool HAS_SS, bool EX>
+__global__ void __launch_bounds__(256, 3) spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
+    constexpr int GPW = 32 / LPR;
+    constexpr int NGROUPS = 8 * GPW;
+    constexpr int CHUNK = LPR * VEC * VPL;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int grp = lane / LPR;
+    const int lg = lane % LPR;
+    const int gid = warp * GPW + grp;
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
+    const int lane0 = grp * LPR;
+    if constexpr (EX) record_drop_step(p);
+    // The number of segments is known on the device only (the host sizes its buffers from the
+    // batch's edge CAPACITY, several times the actual count), so the grid is a fixed number of
+    // resident CTAs striding over the (chunk, segment block) work list — chunk-major, so the
+    // chip sweeps one column slab of X at a time.
+    const int n_seg = __ldg(p.seg_ptr + p.n_dst);
+    const int seg_blocks = (n_seg + NGROUPS - 1) / NGROUPS;
+    const int n_chunks = (p.d + CHUNK - 1) / CHUNK;
+    const int total = seg_blocks * n_chunks;
+    for (int work = blockIdx.x; work < total; work += gridDim.x) {
+        const int chunk = work / seg_blocks;
+        const int seg = (work - chunk * seg_blocks) * NGROUPS + gid;
+        if (seg >= n_seg) continue;                        // whole group skips together
+
+        int c[VPL];
+        bool cv[VPL];
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            c[k] = chunk * CHUNK + k * (LPR * VEC) + lg * VEC;
+            cv[k] = c[k] < p.d;
+        }
+        float acc[VPL][VEC];
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[k][i] = 0.f;
+
+        const int v = __ldg(p.seg_row + seg);
+        const int s0 = __ldg(p.seg_ptr + v);
+        const int nseg = __ldg(p.seg_ptr + v + 1) - s0;
+        const int rs = __ldg(p.rowptr + v), re = __ldg(p.rowptr + v + 1);
+        const int eb = min(re, rs + (seg - s0) * p.seg_len);
+        const int ee = min(re, eb + p.seg_len);
+        gather_range<VEC, LPR, VPL, HAS_SS>(p, eb, ee, lg, lane0, gmask, c, cv, acc);
+        if (nseg == 1) {
+            epilogue<VEC, VPL, EX>(p, v, c, cv, acc);
+            continue;
+        }
+        float *mine = p.seg_ws + (int64_t)seg * p.ld_ws;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+            if (cv[k]) st_vec<VEC>(mine + c[k], acc[k]);
+        __threadfence();                                   // partials visible before the arrival
+        __syncwarp(gmask);
+        unsigned prev = 0;
+        uint32_t *cnt = p.seg_count + (int64_t)chunk * p.n_dst + v;
+        if (lg == 0) prev = atomicAdd(cnt, 1u);
+        prev = __shfl_sync(gmask, prev, lane0);
+        if (prev != (unsigned)(nseg - 1)) continue;
+        __threadfence();
+        if (lg == 0) *cnt = 0u;                            // re-armed for the next launch
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[k][i] = 0.f;
+        for (int j = 0; j < nseg; ++j) {                   // fixed order: segment 0, 1, 2, ...
+            const float *part = p.seg_ws + (int64_t)(s0 + j) * p.ld_ws;
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                if (!cv[k]) continue;
+                float t[VEC];
+                if constexpr (VEC == 4) {
+                    const float4 q = __ldcg(reinterpret_cast<const float4 *>(part + c[k]));   // L2: other SMs wrote it
+                    t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
+                } else if constexpr (VEC == 2) {
+                    const float2 q = __ldcg(reinterpret_cast<const float2 *>(part + c[k]));
+                    t[0] = q.x; t[1] = q.y;
+                } else {
+                    t[0] = __ldcg(part + c[k]);
+                }
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[k][i] += t[i];
+            }
+        }
+        epilogue<VEC, VPL, EX>(p, v, c, cv, acc);
+    }
+}
+
+template <int VEC, int LPR, int VPL>
+static int launch_spmm_seg(const SpmmParams &p0, int64_t max_segments, cudaStream_t stream) {
+    SpmmParams p = p0;
+    constexpr int NGROUPS = 8 * (32 / LPR);
+    constexpr int CHUNK = LPR * VEC * VPL;
+    const int64_t max_work = ceil_div64(max_segments, NGROUPS) * ceil_div64(p.d, CHUNK);
+    if (max_work <= 0) return GIST_OK;
+    if (max_work > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
+    // resident CTAs only (3 per SM by the launch bounds); they stride over the device-side work list
+    int64_t grid = 3LL * kNumSMs;
+    if (grid > max_work) grid = max_work;
+    p.seg_blocks = 0;
+    const bool ex = p.y_lo || p.self_lo || p.drop.p != 0.f;
+    if (p.src_scale) {
+        if (ex) spmm_seg_kernel<VEC, LPR, VPL, true, true><<<(unsigned)grid, 256, 0, stream>>>(p);
+        else spmm_seg_kernel<VEC, LPR, VPL, true, false><<<(unsigned)grid, 256, 0, stream>>>(p);
+    } else {
+        if (ex) spmm_seg_kernel<VEC, LPR, VPL, false, true><<<(unsigned)grid, 256, 0, stream>>>(p);
+        else spmm_seg_kernel<VEC, LPR, VPL, false, false><<<(unsigned)grid, 256, 0, stream>>>(p);
+    }
+    count_launch();
+    return last_error();
+}
+
+template <int VEC>
+static int dispatch_lanes_seg(const SpmmParams &p, int64_t max_segments, cudaStream_t stream) {
+    const int lanes = (p.d + VEC - 1) / VEC;
+    if (lanes <= 4) return launch_spmm_seg<VEC, 4, 1>(p, max_segments, stream);
+    if (lanes <= 8) return launch_spmm_seg<VEC, 8, 1>(p, max_segments, stream);
+    if (lanes <= 16) return launch_spmm_seg<VEC, 16, 1>(p, max_segments, stream);
+    return launch_spmm_seg<VEC, 32, 1>(p, max_segments, stream);
+}
+
+// nseg[v] = max(1, ceil(deg(v) / seg_len)): every row gets at least one segment (its epilogue)
+__global__ void seg_count_kernel(const int32_t *__restrict__ rowptr, int32_t n, int32_t seg_len,
+                                 int32_t *__restrict__ nseg) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int deg = rowptr[v + 1] - rowptr[v];
+    nseg[v] = max(1, (deg + seg_len - 1) / seg_len);
+}
+
+__global__ void seg_fill_kernel(const int32_t *__restrict__ seg_ptr, int32_t n, int64_t capacity,
+                                int32_t *__restrict__ seg_row) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int s0 = seg_ptr[v], s1 = seg_ptr[v + 1];
+    for (int s = s0; s < s1 && s < capacity; ++s) seg_row[s] = v;
 }
 
 template <int VEC, int LPR, int VPL>
@@ -433,6 +595,24 @@ extern "C" int gist_spmm_csr_ex_f32(const int32_t *rowptr, const int32_t *col, i
         const int st = make_drop_params(ex->drop, &p.drop);
         if (st != GIST_OK) return st;
     }
+    p.seg_ptr = p.seg_row = nullptr;
+    p.seg_len = p.seg_blocks = p.ld_ws = 0;
+    p.seg_count = nullptr;
+    p.seg_ws = nullptr;
+    const gist_spmm_schedule_t *sch = ex ? ex->schedule : nullptr;
+    if (sch) {
+        if (!sch->seg_ptr || !sch->seg_row || !sch->counters || !sch->workspace || sch->seg_len <= 0 ||
+            sch->max_segments < n_dst || sch->ld_workspace < d || sch->ld_workspace % 4 || !aligned(sch->workspace, 16))
+            return GIST_ERR_BADARG;
+        if (sch->ld_workspace > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
+        p.seg_ptr = sch->seg_ptr; p.seg_row = sch->seg_row; p.seg_len = sch->seg_len;
+        p.seg_count = sch->counters; p.seg_ws = sch->workspace; p.ld_ws = (int32_t)sch->ld_workspace;
+        p.heavy_deg = 0x7fffffff;
+        cudaStream_t s2 = (cudaStream_t)stream;
+        if (vec_ok(4, p)) return dispatch_lanes_seg<4>(p, sch->max_segments, s2);
+        if (vec_ok(2, p)) return dispatch_lanes_seg<2>(p, sch->max_segments, s2);
+        return dispatch_lanes_seg<1>(p, sch->max_segments, s2);
+    }
     // Hub rows are split over the CTA only where rows are scarce (cluster batches): with
     // >32k rows there are enough warps that one long row is not the critical path.
     const bool coop = (flags & GIST_SPMM_COOP_ON) || (!(flags & GIST_SPMM_COOP_OFF) && n_dst <= 32768);
@@ -451,6 +631,29 @@ extern "C" int gist_spmm_csc_f32(const int32_t *colptr, const int32_t *row, int3
     // dX[u] = src_scale[u] * sum_{u->v} dst_scale[v] * dY[v]  (+ addend[u])
     return gist_spmm_csr_f32(colptr, row, n_src, n_dst, dY, lddy, d, dX, lddx, dst_scale, src_scale,
                              nullptr, addend, ld_addend, nullptr, 0, flags, stream);
+}
+
+extern "C" size_t gist_spmm_schedule_workspace_bytes(int32_t n) { return gist_scan_workspace_bytes(n); }
+
+extern "C" int gist_spmm_schedule_build(const int32_t *rowptr, int32_t n, int32_t seg_len, int32_t *seg_ptr,
+                                        int32_t *seg_row, int64_t max_segments, void *scan_ws,
+                                        size_t scan_ws_bytes, gist_stream_t stream) {
+    if (n < 0 || seg_len <= 0 || max_segments < n) return GIST_ERR_BADARG;
+    if (!seg_ptr) return GIST_ERR_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        cudaError_t e = cudaMemsetAsync(seg_ptr, 0, sizeof(int32_t), s);
+        return e == cudaSuccess ? GIST_OK : (int)e;
+    }
+    if (!rowptr || !seg_row) return GIST_ERR_BADARG;
+    if (scan_ws_bytes < gist_scan_workspace_bytes(n)) return GIST_ERR_WORKSPACE;
+    seg_count_kernel<<<(n + 255) / 256, 256, 0, s>>>(rowptr, n, seg_len, seg_ptr);
+    count_launch();
+    int st = gist_exclusive_scan_i32(seg_ptr, n, seg_ptr, scan_ws, scan_ws_bytes, stream);   // in place
+    if (st != GIST_OK) return st;
+    seg_fill_kernel<<<(n + 255) / 256, 256, 0, s>>>(seg_ptr, n, max_segments, seg_row);
+    count_launch();
+    return last_error();
 }
 
 extern "C" int gist_degree_norm_f32(const int32_t *rowptr, int32_t n, int32_t mode, float *out,

@@ -194,6 +194,23 @@ class GistGraph:
             self._cache['rsqrt_out'] = ops.degree_norm(colptr, self._n, _lib.NORM_RSQRT_CLAMP)
         return self._cache['rsqrt_out']
 
+    # rows are cut into segments for the balanced SpMM only where rows are scarce (cluster batches)
+    SEG_MAX_NODES = 32768
+
+    def seg_schedule(self, transpose=False):
+        """ops.SegSchedule of the in-CSR (or of the CSC for the transpose SpMM), built once per
+        structure; None for large graphs, where one row per warp already balances."""
+        if self._n == 0 or self._n > self.SEG_MAX_NODES or not self.rowptr.is_cuda:
+            return None
+        if transpose and not self.is_symmetric():
+            key, (ptr_, idx_) = 'seg_sched_t', self.csc()
+        else:
+            key, ptr_, idx_ = 'seg_sched', self.rowptr, self.col_buffer
+        sch = self._cache.get(key)
+        if sch is None:
+            sch = self._cache[key] = ops.SegSchedule(ptr_, self._n, int(idx_.shape[0]))
+        return sch
+
     def has_zero_in_degree(self):
         if 'zero_in' not in self._cache:
             self._cache['zero_in'] = bool(((self.rowptr[1:] - self.rowptr[:-1]) == 0).any().item())
@@ -270,8 +287,13 @@ class GistGraph:
             if sg.ndata[NID].data_ptr() != nids.data_ptr():
                 sg.ndata[NID].copy_(nids)
             sg._nnz = None
-            for k in [k for k in sg._cache if k not in ('inv_in', 'inv_in_buf')]:
+            keep = ('inv_in', 'inv_in_buf', 'seg_sched', 'seg_sched_t')
+            for k in [k for k in sg._cache if k not in keep]:
                 del sg._cache[k]                 # structure-derived values of the previous batch
+            if 'seg_sched' in sg._cache:         # same buffers, new contents
+                sg._cache['seg_sched'].rebuild(sg.rowptr)
+            if 'seg_sched_t' in sg._cache:
+                sg._cache['seg_sched_t'].rebuild(sg._csc[0])
             return sg
         rowptr, col, inv = build(self.rowptr, self.col_buffer, True)
         sg = GistGraph(rowptr, col, n_b, idtype=self._idtype)

@@ -204,11 +204,11 @@ class ISTSAGELayer(nn.Module):
     def _p_drop(self):
         return float(self.dropout.p) if (self.dropout and self.training) else 0.0
 
-    def prepare_input(self, g, h, out=None):
+    def prepare_input(self, g, h, out=None, balanced=True):
         """z = dropout([h ‖ (A h) / in_deg]) (+ its 3xTF32 low half) for this layer, outside
         autograd — the pipelined trainer runs it for the NEXT batch's input features while the
         current batch trains (they do not depend on the weights and need no gradient)."""
-        return ops.sage_prepare(g, h, self._p_drop(), self._drop_stream, out=out)
+        return ops.sage_prepare(g, h, self._p_drop(), self._drop_stream, out=out, balanced=balanced)
 
     def forward(self, g, h, pre=None):
         # pre: this layer's prepared input for (g, h) (prepare_input), if already computed

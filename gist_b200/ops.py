@@ -35,13 +35,15 @@ def _ld(t):
 
 def spmm_raw(rowptr, col, n_dst, n_src, X, out, *, src_scale=None, dst_scale=None, bias=None,
              addend=None, self_out=None, relu=False, flags=0, out_lo=None, self_lo=None, drop=None,
-             drop_col0_out=0, drop_col0_self=0):
+             drop_col0_out=0, drop_col0_self=0, schedule=None):
     """out[v] = act(dst_scale[v] * sum_{e in row v} src_scale[col e] * X[col e] + addend[v] + bias).
 
     ``out`` (and ``self_out``/``addend``) may be column-block views of wider
     row-major buffers; leading dimensions are taken from the strides.
     Extended epilogue: ``drop`` (a DropoutDesc) applies dropout to both outputs as they are
-    written, ``out_lo`` / ``self_lo`` receive their 3xTF32 low halves."""
+    written, ``out_lo`` / ``self_lo`` receive their 3xTF32 low halves.  ``schedule`` (a
+    SegSchedule of the same rowptr, see GistGraph.seg_schedule) selects the segment-balanced
+    kernel used for cluster batches."""
     require_cuda(rowptr, col, X, out, src_scale, dst_scale, bias, addend, self_out, out_lo, self_lo)
     d = X.shape[1]
     assert out.shape[0] == n_dst and out.shape[1] == d and X.shape[0] == n_src
@@ -53,10 +55,21 @@ def spmm_raw(rowptr, col, n_dst, n_src, X, out, *, src_scale=None, dst_scale=Non
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     ex = None
-    if out_lo is not None or self_lo is not None or drop is not None:
+    if schedule is not None and d > 384:
+        schedule = None         # wide rows: per-segment overheads outweigh the balance (measured d = 602)
+    if out_lo is not None or self_lo is not None or drop is not None or schedule is not None:
+        sch = None
+        if schedule is not None:
+            assert schedule.n == n_dst
+            ld_ws = (d + 3) // 4 * 4
+            ws = torch.empty((schedule.max_segments, ld_ws), dtype=torch.float32, device=X.device)
+            cnt = schedule.counters(max(1, (d + 31) // 32))
+            sch = _lib.SpmmSchedule(ptr(schedule.seg_ptr), ptr(schedule.seg_row), schedule.seg_len,
+                                    schedule.max_segments, ptr(cnt), ptr(ws), ld_ws)
         ex = _lib.SpmmEx(ptr(out_lo), _ld(out_lo) if out_lo is not None else 0,
                          ptr(self_lo), _ld(self_lo) if self_lo is not None else 0,
-                         ctypes.pointer(drop) if drop is not None else None, drop_col0_out, drop_col0_self)
+                         ctypes.pointer(drop) if drop is not None else None, drop_col0_out, drop_col0_self,
+                         ctypes.pointer(sch) if sch is not None else None)
     st = lib.gist_spmm_csr_ex_f32(
         ptr(rowptr), ptr(col), n_dst, n_src, ptr(X), _ld(X), d, ptr(out), _ld(out),
         ptr(src_scale), ptr(dst_scale), ptr(bias),
@@ -69,6 +82,35 @@ def spmm_raw(rowptr, col, n_dst, n_src, X, out, *, src_scale=None, dst_scale=Non
         prof.append(dict(ev0=ev0, ev1=ev1, rowptr=rowptr, n_dst=n_dst, n_src=n_src, d=d,
                          scaled=(src_scale is not None) + (dst_scale is not None)))
     return out
+
+
+class SegSchedule:
+    """Segment schedule of one CSR (gist_spmm_schedule_t minus the per-launch workspace)."""
+
+    def __init__(self, rowptr, n, capacity, seg_len=64):
+        self.n, self.seg_len = n, seg_len
+        self.max_segments = n + capacity // seg_len + 1
+        dev = rowptr.device
+        self.seg_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        self.seg_row = torch.empty(self.max_segments, dtype=torch.int32, device=dev)
+        self._counters = None
+        self.rebuild(rowptr)
+
+    def rebuild(self, rowptr):
+        """(Re)compute the schedule for the current contents of rowptr, in place."""
+        lib = _lib.load()
+        wsb = lib.gist_spmm_schedule_workspace_bytes(self.n)
+        ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=rowptr.device)
+        check(lib.gist_spmm_schedule_build(ptr(rowptr), self.n, self.seg_len, ptr(self.seg_ptr), ptr(self.seg_row),
+                                           self.max_segments, ptr(ws), wsb, stream_ptr(rowptr.device)),
+              'spmm_schedule_build')
+
+    def counters(self, chunks):
+        """Zeroed arrival counters for `chunks` feature chunks (the kernel leaves them zero)."""
+        need = chunks * max(self.n, 1)
+        if self._counters is None or self._counters.numel() < need:
+            self._counters = torch.zeros(need, dtype=torch.int32, device=self.seg_ptr.device)
+        return self._counters
 
 
 def degree_norm(rowptr, n, mode):
@@ -154,7 +196,7 @@ class _ScaledSpMM(torch.autograd.Function):
         n = g.number_of_nodes()
         Y = torch.empty((n, X.shape[1]), dtype=torch.float32, device=X.device)
         spmm_raw(g.rowptr, g.col_buffer, n, n, X, Y, src_scale=src_scale, dst_scale=dst_scale,
-                 bias=bias, relu=relu)
+                 bias=bias, relu=relu, schedule=g.seg_schedule())
         ctx.g, ctx.relu, ctx.has_bias = g, relu, bias is not None
         ctx.save_for_backward(src_scale, dst_scale, Y if relu else None)
         return Y
@@ -173,7 +215,8 @@ class _ScaledSpMM(torch.autograd.Function):
             colptr, row = g.csc()
             dX = torch.empty_like(dY)
             # dX[u] = s[u] * sum_{u->v} t[v] dY[v]
-            spmm_raw(colptr, row, n, n, dY, dX, src_scale=dst_scale, dst_scale=src_scale)
+            spmm_raw(colptr, row, n, n, dY, dX, src_scale=dst_scale, dst_scale=src_scale,
+                     schedule=g.seg_schedule(transpose=True))
         return None, dX, None, None, dbias, None
 
 
@@ -196,7 +239,8 @@ class _SageConcat(torch.autograd.Function):
         n, d = h.shape
         z = torch.empty((n, 2 * d), dtype=torch.float32, device=h.device)
         inv = g.inv_in_degree()
-        spmm_raw(g.rowptr, g.col_buffer, n, n, h, z[:, d:], dst_scale=inv, self_out=z[:, :d])
+        spmm_raw(g.rowptr, g.col_buffer, n, n, h, z[:, d:], dst_scale=inv, self_out=z[:, :d],
+                 schedule=g.seg_schedule())
         ctx.g = g
         return z
 
@@ -208,7 +252,8 @@ class _SageConcat(torch.autograd.Function):
         d = d2 // 2
         colptr, row = g.csc()
         dh = torch.empty((n, d), dtype=torch.float32, device=dz.device)
-        spmm_raw(colptr, row, n, n, dz[:, d:], dh, src_scale=g.inv_in_degree(), addend=dz[:, :d])
+        spmm_raw(colptr, row, n, n, dz[:, d:], dh, src_scale=g.inv_in_degree(), addend=dz[:, :d],
+                 schedule=g.seg_schedule(transpose=True))
         return None, dh
 
 
@@ -216,16 +261,17 @@ def sage_concat(g, h):
     return _SageConcat.apply(g, h)
 
 
-def sage_concat_into(g, h, out, out_lo=None, drop=None):
+def sage_concat_into(g, h, out, out_lo=None, drop=None, balanced=True):
     """No-grad z = [h ‖ (A h) / in_deg] into a caller-owned [n, 2d] buffer; optionally with the
-    layer's dropout applied as z is written (``drop``) and z's 3xTF32 low half (``out_lo``)."""
+    layer's dropout applied as z is written (``drop``) and z's 3xTF32 low half (``out_lo``).
+    ``balanced``: use the segment-scheduled kernel when the graph has a schedule."""
     h = _mat(h, 'h')
     n, d = h.shape
     assert out.shape == (n, 2 * d) and out.dtype == torch.float32 and out.stride(1) == 1
     spmm_raw(g.rowptr, g.col_buffer, n, n, h, out[:, d:], dst_scale=g.inv_in_degree(), self_out=out[:, :d],
              out_lo=out_lo[:, d:] if out_lo is not None else None,
              self_lo=out_lo[:, :d] if out_lo is not None else None,
-             drop=drop, drop_col0_out=d, drop_col0_self=0)
+             drop=drop, drop_col0_out=d, drop_col0_self=0, schedule=g.seg_schedule() if balanced else None)
     return out
 
 
@@ -243,7 +289,7 @@ class SagePre:
         self.z, self.z_lo, self.step_saved, self.dropped = z, z_lo, step_saved, dropped
 
 
-def sage_prepare(g, h, p_drop, stream_id, out=None):
+def sage_prepare(g, h, p_drop, stream_id, out=None, balanced=True):
     """Aggregation + concat (+ dropout, + 3xTF32 split) of a SAGE layer's input, no autograd.
     ``out``: a SagePre of the same shape to overwrite in place."""
     h = _mat(h, 'h')
@@ -255,7 +301,7 @@ def sage_prepare(g, h, p_drop, stream_id, out=None):
         saved = torch.empty(1, dtype=torch.int64, device=h.device) if p_drop else None   # K1 writes it
         out = SagePre(z, z_lo, saved, bool(p_drop))
     desc = dropout_state(h.device).desc(p_drop, stream_id, step_saved=out.step_saved) if p_drop else None
-    sage_concat_into(g, h, out.z, out.z_lo, desc)
+    sage_concat_into(g, h, out.z, out.z_lo, desc, balanced=balanced)
     return out
 
 
@@ -567,9 +613,14 @@ def _side_stream(device):
     return st
 
 
-def _weight_grad_branch(device, fn):
+def _weight_grad_branch(device, fn, keep):
     """Run fn() (returns tensors) on the side stream, forked from the current stream; registers the
-    join.  Falls back to the current stream when overlap is disabled or outside a backward pass."""
+    join.  Falls back to the current stream when overlap is disabled or outside a backward pass.
+
+    ``keep``: every tensor fn() reads.  They were allocated on the main stream; the caching
+    allocator would hand their memory to the next main-stream allocation as soon as autograd drops
+    them, while the (low-priority, possibly long-delayed) side-stream kernels are still reading —
+    so the join callback holds them until the main stream has been ordered behind the branch."""
     if not OVERLAP_WEIGHT_GRADS:
         return fn()
     cur = torch.cuda.current_stream(device)
@@ -577,12 +628,14 @@ def _weight_grad_branch(device, fn):
     if side == cur:
         return fn()
     ev = torch.cuda.Event()
+    held = [t for t in keep if t is not None]
 
     def join():
         cur.wait_event(ev)
         now = torch.cuda.current_stream(device)
         if now != cur:
             now.wait_event(ev)
+        held.clear()
     try:
         torch.autograd.Variable._execution_engine.queue_callback(join)
     except RuntimeError:            # not inside a backward pass: nothing would join the branch
@@ -638,7 +691,7 @@ class _SageLinear(torch.autograd.Function):
             return (gemm(dy, z, a_mn=True, b_mn=True, A_lo=dy_lo, B_lo=z_lo) if need_dW else None,
                     colsum(dy) if need_db else None)
         if need_dW or need_db:      # forked first: the branch depends on dy only
-            dW, db = _weight_grad_branch(dy.device, weight_grads)
+            dW, db = _weight_grad_branch(dy.device, weight_grads, (dy, dy_lo, z, z_lo))
         if ctx.needs_input_grad[1]:
             if ctx.drop is not None:
                 desc = dropout_state(dy.device).desc(ctx.drop[0], ctx.drop[1], step=ctx.step_saved)
@@ -648,7 +701,8 @@ class _SageLinear(torch.autograd.Function):
             colptr, row = g.csc()
             dh = torch.empty((n, d), dtype=torch.float32, device=dy.device)
             # dh = dz[:, :d] + A^T (inv_deg ⊙ dz[:, d:])
-            spmm_raw(colptr, row, n, n, dz[:, d:], dh, src_scale=g.inv_in_degree(), addend=dz[:, :d])
+            spmm_raw(colptr, row, n, n, dz[:, d:], dh, src_scale=g.inv_in_degree(), addend=dz[:, :d],
+                 schedule=g.seg_schedule(transpose=True))
         return None, dh, dW, db, None, None, None
 
 

@@ -115,6 +115,24 @@ int gist_spmm_csr_f32(const int32_t *rowptr, const int32_t *col, int32_t n_dst, 
  *   - y_lo / self_lo (optional): the 3xTF32 low halves tf32(x - trunc_tf32(x)) of the values
  *     written, so the nn.Linear that consumes z needs no separate split pass.
  * Replaces nn.Dropout on z (modules.py:228-229) and gist_split_tf32_f32 on z. */
+/* Segment schedule of a (small, power-law) graph: every row cut into segments of <= seg_len edges
+ * so that all warps of a launch gather the same amount (gist_spmm_schedule_build, once per cluster
+ * batch; shared by the forward and — for a symmetric pattern — the transpose launches).
+ *   seg_ptr[n+1]  first segment of each row (seg_ptr[n] = number of segments, read on the device)
+ *   seg_row[max_segments]  row of each segment;  max_segments >= n + nnz / seg_len (host bound)
+ *   counters[chunks * n]  uint32, ZERO on entry, left zero on exit (chunks <= ceil(d / 4))
+ *   workspace[max_segments][ld_workspace >= d, % 4 == 0]  fp32 scratch, no initialisation needed
+ * Two launches that share `counters` / `workspace` must not run concurrently. */
+typedef struct gist_spmm_schedule {
+    const int32_t *seg_ptr;
+    const int32_t *seg_row;
+    int32_t seg_len;
+    int64_t max_segments;
+    uint32_t *counters;
+    float *workspace;
+    int64_t ld_workspace;
+} gist_spmm_schedule_t;
+
 typedef struct gist_spmm_ex {
     float *y_lo;
     int64_t ld_y_lo;
@@ -122,7 +140,13 @@ typedef struct gist_spmm_ex {
     int64_t ld_self_lo;
     const gist_dropout_t *drop;
     int32_t drop_col0_y, drop_col0_self;
+    const gist_spmm_schedule_t *schedule; /* NULL: one row per lane group (+ CTA-cooperative hub rows) */
 } gist_spmm_ex_t;
+
+size_t gist_spmm_schedule_workspace_bytes(int32_t n);
+int gist_spmm_schedule_build(const int32_t *rowptr, int32_t n, int32_t seg_len, int32_t *seg_ptr,
+                             int32_t *seg_row, int64_t max_segments, void *scan_ws, size_t scan_ws_bytes,
+                             gist_stream_t stream);
 int gist_spmm_csr_ex_f32(const int32_t *rowptr, const int32_t *col, int32_t n_dst, int32_t n_src,
                          const float *X, int64_t ldx, int32_t d,
                          float *Y, int64_t ldy,

@@ -103,12 +103,27 @@ def test_gemm_dropmask_matches_masked_gemm(shape, x3):
     assert torch.equal(got, ref)
 
 
+def _hub_graph(n, seed):
+    """Power-law multigraph whose row 0 is the heaviest (dozens of 64-edge segments): the first
+    CTA of the segment-balanced kernel is then NOT the one that finishes row 0."""
+    from gist_b200 import GistGraph
+    from tests.util import powerlaw_graph
+    src, dst = powerlaw_graph(n, 30, seed=seed)
+    hub = int(torch.bincount(dst, minlength=n).argmax())
+    swap = lambda t: torch.where(t == hub, torch.zeros_like(t), torch.where(t == 0, torch.full_like(t, hub), t))  # noqa: E731
+    g = GistGraph.from_edges(swap(src), swap(dst), n, device='cuda')
+    assert int(g.rowptr[1]) > 1000
+    return g
+
+
 @pytest.mark.parametrize('precision,tol', [('3xtf32', 1e-5), ('tf32', 2e-3)])
 @pytest.mark.parametrize('p', [0.0, 0.4])
-def test_sage_linear_forward_backward(precision, tol, p):
+@pytest.mark.parametrize('hub', [False, True])
+def test_sage_linear_forward_backward(precision, tol, p, hub):
     from gist_b200 import ops
     n, d, out = 600, 96, 40
-    g = _graph(n, 8000, seed=1)
+    g = _hub_graph(n, seed=1) if hub else _graph(n, 8000, seed=1)
+    ops.dropout_state('cuda').tick()            # a non-zero clock: the saved step must really be recorded
     torch.manual_seed(3)
     h = torch.randn(n, d, device='cuda', requires_grad=True)
     W = (torch.randn(out, 2 * d, device='cuda') * 0.05).requires_grad_(True)

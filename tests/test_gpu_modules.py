@@ -174,3 +174,38 @@ def test_wrapper_dispatch_sync_single_process_matches_oracle():
     for lyr, (rw, rb) in zip(w.base_model.layers, ref):
         assert torch.equal(lyr.linear.weight.detach().cpu(), rw)
         assert_close(lyr.linear.bias.detach(), rb, rtol=1e-6)
+
+
+def test_weight_grad_branch_is_safe_when_the_side_stream_lags():
+    """dW / db run on a low-priority side stream.  Their inputs (dy, z) are main-stream tensors that
+    autograd drops as soon as the layer's backward returns; if the branch lags (here: a sleep
+    queued on the side stream, in production the next batch's aggregation) the allocator must not
+    recycle them under it.  Gradients must equal the single-stream run bit for bit."""
+    from gist_b200 import SageGCN, ops
+    n = 1500
+    g, _ = _graphs(n, 30000, seed=9, loops=False)
+    torch.manual_seed(1)
+    model = SageGCN(128, 64, 10, 2, F.relu, 0.0, True, False, False, 1, True).cuda().train()
+    g.ndata['feat'] = torch.randn(n, 128, device='cuda')
+    y = torch.randint(0, 10, (n,), device='cuda')
+    ops.set_matmul_precision('3xtf32')
+    try:
+        def grads(overlap, lag):
+            ops.OVERLAP_WEIGHT_GRADS = overlap
+            model.zero_grad(set_to_none=True)
+            if lag:
+                with torch.cuda.stream(ops._side_stream(torch.device('cuda', 0))):
+                    torch.cuda._sleep(int(3e6))            # ~1.5 ms head start for the main stream
+            F.cross_entropy(model(g), y).backward()
+            junk = [torch.full((n, 128), float('nan'), device='cuda') for _ in range(8)]   # recycle freed blocks
+            torch.cuda.synchronize()
+            del junk
+            return [p.grad.clone() for p in model.parameters()]
+        ref = grads(False, False)
+        for _ in range(3):
+            got = grads(True, True)
+            for a, b in zip(got, ref):
+                assert torch.equal(a, b)
+    finally:
+        ops.OVERLAP_WEIGHT_GRADS = True
+        ops.set_matmul_precision('fp32')

@@ -160,3 +160,99 @@ def test_full_size_linearity_and_degree_identity():
     lhs = ops.copy_src_sum(g, 2 * x1 - 3 * x2)
     rhs = 2 * ops.copy_src_sum(g, x1) - 3 * ops.copy_src_sum(g, x2)
     assert_close(lhs, rhs, rtol=1e-4, what='linearity')
+
+
+# ------------------------------------------------------------ segment-balanced K1/K2 ----
+@pytest.mark.parametrize('d', [1, 7, 32, 100, 256, 602])
+@pytest.mark.parametrize('has_scale', [False, True])
+def test_segment_balanced_matches_oracle_and_is_deterministic(d, has_scale):
+    """The segment-scheduled kernel (cluster batches) on a power-law graph: hub rows span dozens
+    of segments finished by whichever group arrives last, yet the result is run-to-run identical
+    and within tolerance of the fp64 oracle; arrival counters are left zero."""
+    from gist_b200 import ops
+    n = 3000
+    src, dst = powerlaw_graph(n, 40, seed=7)
+    g = _gist(src, dst, n)
+    og = ograph(src, dst, n)
+    sch = g.seg_schedule()
+    assert sch is not None and sch.seg_len == 64
+    deg = og.in_degrees()
+    nseg = torch.clamp((deg + 63) // 64, min=1)
+    assert int(sch.seg_ptr[n].item()) == int(nseg.sum()) and int(nseg.max()) > 20
+    assert torch.equal(sch.seg_ptr.cpu().long()[1:] - sch.seg_ptr.cpu().long()[:-1], nseg)
+    torch.manual_seed(d)
+    x = torch.randn(n, d)
+    s = (torch.rand(n) + 0.5) if has_scale else None
+    t = (torch.rand(n) + 0.5) if has_scale else None
+    addend, bias = torch.randn(n, d), torch.randn(d)
+    xin = x.double() * s.double()[:, None] if has_scale else x.double()
+    ref = O.copy_src_sum(og, xin)
+    if has_scale:
+        ref = ref * t.double()[:, None]
+    ref = torch.relu(ref + addend.double() + bias.double())
+    cu = lambda v: v.cuda() if v is not None else None      # noqa: E731
+    outs = []
+    for _ in range(3):
+        out = torch.full((n, 2 * d + 1), float('nan'), device='cuda')
+        ops.spmm_raw(g.rowptr, g.col_buffer, n, n, x.cuda(), out[:, d:2 * d], src_scale=cu(s), dst_scale=cu(t),
+                     bias=bias.cuda(), addend=addend.cuda(), self_out=out[:, :d], relu=True, schedule=sch)
+        outs.append(out)
+    assert_close(outs[0][:, d:2 * d], ref, what='segment-balanced')
+    assert torch.equal(outs[0][:, :d].cpu(), x)
+    assert torch.isnan(outs[0][:, 2 * d:]).all()
+    assert torch.equal(outs[0][:, :2 * d], outs[1][:, :2 * d]) and torch.equal(outs[1][:, :2 * d], outs[2][:, :2 * d])
+    assert (sch.counters(1) == 0).all()
+    # same numbers as the row-per-group kernel up to summation order
+    plain = torch.empty(n, d, device='cuda')
+    ops.spmm_raw(g.rowptr, g.col_buffer, n, n, x.cuda(), plain, src_scale=cu(s), dst_scale=cu(t),
+                 bias=bias.cuda(), addend=addend.cuda(), relu=True)
+    assert_close(outs[0][:, d:2 * d], plain, what='vs row-per-group kernel')
+
+
+def test_segment_schedule_edge_cases():
+    from gist_b200 import GistGraph, ops
+    # edgeless graph: one (empty) segment per row, output = epilogue of zero
+    g = GistGraph.from_edges(torch.zeros(0, dtype=torch.long), torch.zeros(0, dtype=torch.long), 9, device='cuda')
+    sch = g.seg_schedule()
+    assert sch.seg_ptr.tolist() == list(range(10))
+    y = torch.empty(9, 5, device='cuda')
+    ops.spmm_raw(g.rowptr, g.col_buffer, 9, 9, torch.ones(9, 5, device='cuda'), y, bias=torch.ones(5, device='cuda'),
+                 schedule=sch)
+    assert (y == 1).all()
+    # a row of exactly 64, 65 and 128 edges: 1, 2 and 2 segments
+    src = torch.cat([torch.arange(64), torch.arange(65), torch.arange(128)])
+    dst = torch.cat([torch.zeros(64), torch.ones(65), torch.full((128,), 2.0)]).long()
+    g = GistGraph.from_edges(src, dst, 130, device='cuda')
+    sch = g.seg_schedule()
+    assert sch.seg_ptr[:4].tolist() == [0, 1, 3, 5]
+    x = torch.arange(130, dtype=torch.float32, device='cuda').unsqueeze(1).repeat(1, 3)
+    y = ops.copy_src_sum(g, x)
+    assert y[0, 0].item() == sum(range(64)) and y[1, 0].item() == sum(range(65)) and y[2, 0].item() == sum(range(128))
+    # large graphs keep the row-per-warp kernel
+    from gist_b200.graph import GistGraph as GG
+    big = GG.from_edges(torch.arange(40000), (torch.arange(40000) + 1) % 40000, 40000, device='cuda')
+    assert big.seg_schedule() is None
+
+
+def test_segment_schedule_rebuilt_in_place_for_reused_batch_buffers():
+    """subgraph(out=...) (the pipelined trainer's buffer reuse) refreshes the schedule."""
+    import numpy as np
+    from gist_b200 import ops
+    n = 4000
+    src, dst = powerlaw_graph(n, 30, seed=2)
+    src, dst = torch.cat([src, dst]), torch.cat([dst, src])
+    g = _gist(src, dst, n)
+    g.ndata['feat'] = torch.randn(n, 16, device='cuda')
+    rng = np.random.RandomState(0)
+    ids1 = torch.from_numpy(rng.choice(n, 600, replace=False)).cuda()
+    ids2 = torch.from_numpy(rng.choice(n, 600, replace=False)).cuda()
+    cap = int((g.rowptr[1:] - g.rowptr[:-1]).max().item()) * 600
+    sg = g.subgraph(ids1, col_capacity=cap)
+    sch = sg.seg_schedule()
+    y1 = ops.copy_src_sum(sg, sg.ndata['feat'])
+    fresh2 = g.subgraph(ids2, col_capacity=cap)
+    want = ops.copy_src_sum(fresh2, fresh2.ndata['feat'])
+    sg2 = g.subgraph(ids2, col_capacity=cap, out=sg)
+    assert sg2 is sg and sg.seg_schedule() is sch
+    got = ops.copy_src_sum(sg, sg.ndata['feat'])
+    assert torch.equal(got, want) and not torch.equal(got, y1)
