@@ -368,11 +368,18 @@ def run_gist(a):
         e[0] += 1; e[1] += ab; e[2] += t
     peak, peak_src = peaks()
     n_l = max(len(prof), 1)
+    # DRAM bytes per SpMM launch from the committed `ncu --set full` capture of the same command
+    # (profiles/README.md); null when the workload is not the one that was captured
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, 'profiles', 'r1_spmm_step_traffic.json')
+    if a.shape == 'reddit' and a.scale == 1.0 and a.n_hidden == 256 and world == 1 and os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj['traffic_bytes_per_launch'], 'profiles/r1_spmm_step_traffic.json: ' + tj['source']
     achieved = alg_b / 1e9 / (spmm_ms / 1e3) if spmm_ms > 0 else 0.0
     roofline = {
         'bound': 'hbm', 'kernel': 'spmm_csr_kernel (all %d launches/step, fwd + transpose)' % (len(prof) // max(prof_steps, 1)),
         'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4),
-        'traffic': None, 'peak_source': peak_src,
+        'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
         'bytes_per_launch': round(alg_b / n_l), 'compulsory_bytes_per_launch': round(comp_b / n_l),
         'us_per_launch': round(spmm_ms * 1e3 / n_l, 2),
         'share_of_step': round((spmm_ms / prof_steps) / (ms / a.steps), 4),

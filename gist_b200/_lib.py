@@ -49,6 +49,9 @@ SIGNATURES = {
     'gist_transpose_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P]),
     'gist_layernorm_act_fwd_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _F32, _U32, _P, _I64, _P, _P]),
     'gist_layernorm_act_bwd_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _U32, _P, _I64, _P, _I64, _P]),
+    'gist_tensor_layernorm_workspace_bytes': (_SZ, [_I32, _I32]),
+    'gist_tensor_layernorm_fwd_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _F32, _P, _I64, _P, _P, _SZ, _P]),
+    'gist_tensor_layernorm_bwd_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _P, _I64, _P, _SZ, _P]),
     'gist_colsum_workspace_bytes': (_SZ, [_I32, _I32]),
     'gist_colsum_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _SZ, _P]),
     'gist_masked_ce_fwd_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),

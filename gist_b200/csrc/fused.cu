@@ -137,6 +137,177 @@ __global__ void __launch_bounds__(256) ln_act_bwd_kernel(const float *__restrict
     }
 }
 
+// ------------------------------------------------- whole-tensor layer norm ----
+// gcn/gcn.py:65-66 normalises with F.layer_norm(h, h.shape): ONE mean / variance over all n*d
+// elements, no affine.  (ATen runs that as a single-CTA row reduction.)  Two launches each way:
+// per-CTA partial moments in fp64 -> every CTA of the second launch folds the partials in the
+// same fixed order (deterministic, no atomics) and streams its share of the elements.
+constexpr int kTlnThreads = 256;
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum of two doubles; result valid in every thread
+__device__ __forceinline__ void block_sum2_d(double &a, double &b) {
+    __shared__ double sa[kTlnThreads / 32], sb[kTlnThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = warp_sum_d(a);
+    b = warp_sum_d(b);
+    __syncthreads();                       // protects reuse of sa/sb between calls
+    if (lane == 0) { sa[warp] = a; sb[warp] = b; }
+    __syncthreads();
+    double ta = 0.0, tb = 0.0;
+#pragma unroll
+    for (int w = 0; w < kTlnThreads / 32; ++w) { ta += sa[w]; tb += sb[w]; }
+    a = ta;
+    b = tb;
+}
+
+// fold the per-CTA partials (a_p, b_p) in a fixed order
+__device__ __forceinline__ void fold_partials(const double2 *__restrict__ part, int nparts, double &a, double &b) {
+    a = 0.0;
+    b = 0.0;
+    for (int p = threadIdx.x; p < nparts; p += kTlnThreads) {
+        const double2 v = part[p];
+        a += v.x;
+        b += v.y;
+    }
+    block_sum2_d(a, b);
+}
+
+// Elements are visited in units of VEC floats (VEC = 4 needs d, ld % 4 == 0 and 16-byte bases);
+// unit u of the tensor is row u / (d / VEC), columns VEC * (u % (d / VEC)) ...
+template <int VEC>
+struct TlnVec;
+template <>
+struct TlnVec<4> {
+    using T = float4;
+    __device__ static void get(const float *p, float (&v)[4]) {
+        const float4 q = __ldg(reinterpret_cast<const float4 *>(p));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+    __device__ static void put(float *p, const float (&v)[4]) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <>
+struct TlnVec<1> {
+    using T = float;
+    __device__ static void get(const float *p, float (&v)[1]) { v[0] = __ldg(p); }
+    __device__ static void put(float *p, const float (&v)[1]) { p[0] = v[0]; }
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kTlnThreads) tln_moments_kernel(const float *__restrict__ x, int64_t ldx,
+                                                                  int64_t units, int upr,
+                                                                  double2 *__restrict__ part) {
+    double s = 0.0, q = 0.0;
+    for (int64_t u = (int64_t)blockIdx.x * kTlnThreads + threadIdx.x; u < units;
+         u += (int64_t)gridDim.x * kTlnThreads) {
+        const int64_t r = u / upr;
+        const int c = (int)(u - r * upr) * VEC;
+        float v[VEC];
+        TlnVec<VEC>::get(x + r * ldx + c, v);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            s += (double)v[i];
+            q += (double)v[i] * (double)v[i];
+        }
+    }
+    block_sum2_d(s, q);
+    if (threadIdx.x == 0) part[blockIdx.x] = make_double2(s, q);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kTlnThreads) tln_apply_kernel(const float *__restrict__ x, int64_t ldx,
+                                                                int64_t units, int upr, double inv_count,
+                                                                float eps, const double2 *__restrict__ part,
+                                                                int nparts, float *__restrict__ y, int64_t ldy,
+                                                                float *__restrict__ stats) {
+    double s, q;
+    fold_partials(part, nparts, s, q);
+    const double mean_d = s * inv_count;
+    const double var_d = fmax(q * inv_count - mean_d * mean_d, 0.0);
+    const float mean = (float)mean_d;
+    const float rstd = (float)(1.0 / sqrt(var_d + (double)eps));
+    if (blockIdx.x == 0 && threadIdx.x == 0 && stats) {
+        stats[0] = mean;
+        stats[1] = rstd;
+    }
+    for (int64_t u = (int64_t)blockIdx.x * kTlnThreads + threadIdx.x; u < units;
+         u += (int64_t)gridDim.x * kTlnThreads) {
+        const int64_t r = u / upr;
+        const int c = (int)(u - r * upr) * VEC;
+        float v[VEC];
+        TlnVec<VEC>::get(x + r * ldx + c, v);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = (v[i] - mean) * rstd;
+        TlnVec<VEC>::put(y + r * ldy + c, v);
+    }
+}
+
+// backward partials: (sum dy, sum dy * xhat), xhat recomputed from the forward input
+template <int VEC>
+__global__ void __launch_bounds__(kTlnThreads) tln_bwd_moments_kernel(const float *__restrict__ dy, int64_t lddy,
+                                                                      const float *__restrict__ x, int64_t ldx,
+                                                                      const float *__restrict__ stats,
+                                                                      int64_t units, int upr,
+                                                                      double2 *__restrict__ part) {
+    const float mean = __ldg(stats), rstd = __ldg(stats + 1);
+    double s = 0.0, q = 0.0;
+    for (int64_t u = (int64_t)blockIdx.x * kTlnThreads + threadIdx.x; u < units;
+         u += (int64_t)gridDim.x * kTlnThreads) {
+        const int64_t r = u / upr;
+        const int c = (int)(u - r * upr) * VEC;
+        float xv[VEC], gv[VEC];
+        TlnVec<VEC>::get(x + r * ldx + c, xv);
+        TlnVec<VEC>::get(dy + r * lddy + c, gv);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            s += (double)gv[i];
+            q += (double)gv[i] * (double)((xv[i] - mean) * rstd);
+        }
+    }
+    block_sum2_d(s, q);
+    if (threadIdx.x == 0) part[blockIdx.x] = make_double2(s, q);
+}
+
+// dx = rstd * (dy - mean(dy) - xhat * mean(dy * xhat))
+template <int VEC>
+__global__ void __launch_bounds__(kTlnThreads) tln_bwd_apply_kernel(const float *__restrict__ dy, int64_t lddy,
+                                                                    const float *__restrict__ x, int64_t ldx,
+                                                                    const float *__restrict__ stats, int64_t units,
+                                                                    int upr, double inv_count,
+                                                                    const double2 *__restrict__ part, int nparts,
+                                                                    float *__restrict__ dx, int64_t lddx) {
+    double s, q;
+    fold_partials(part, nparts, s, q);
+    const float m1 = (float)(s * inv_count), m2 = (float)(q * inv_count);
+    const float mean = __ldg(stats), rstd = __ldg(stats + 1);
+    for (int64_t u = (int64_t)blockIdx.x * kTlnThreads + threadIdx.x; u < units;
+         u += (int64_t)gridDim.x * kTlnThreads) {
+        const int64_t r = u / upr;
+        const int c = (int)(u - r * upr) * VEC;
+        float xv[VEC], gv[VEC];
+        TlnVec<VEC>::get(x + r * ldx + c, xv);
+        TlnVec<VEC>::get(dy + r * lddy + c, gv);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) gv[i] = rstd * (gv[i] - m1 - (xv[i] - mean) * rstd * m2);
+        TlnVec<VEC>::put(dx + r * lddx + c, gv);
+    }
+}
+
+// CTAs of the two-launch scheme: enough to fill the chip twice, never more than the work needs
+static int tln_grid(int64_t count) {
+    int64_t g = ceil_div64(count, (int64_t)kTlnThreads * 16);
+    if (g > 2 * kNumSMs) g = 2 * kNumSMs;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
 // ---------------------------------------------------------------- colsum ----
 // Phase 1: CTA (bx, by) sums rows [by*rows_per, ...) of columns [32*bx, 32*bx+32) -> part[by][c].
 // Phase 2: out[c] = sum_by part[by][c] in index order.
@@ -411,6 +582,64 @@ extern "C" int gist_layernorm_act_bwd_f32(const float *dy, int64_t lddy, const f
     if (v4) ln_act_bwd_kernel<true><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, st, n, d, relu, dx, lddx, dx_lo, ld_lo);
     else ln_act_bwd_kernel<false><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, st, n, d, relu, dx, lddx, dx_lo, ld_lo);
     count_launch();
+    return last_error();
+}
+
+extern "C" size_t gist_tensor_layernorm_workspace_bytes(int32_t n, int32_t d) {
+    if (n <= 0 || d <= 0) return 0;
+    return (size_t)tln_grid((int64_t)n * d) * sizeof(double2);
+}
+
+extern "C" int gist_tensor_layernorm_fwd_f32(const float *x, int64_t ldx, int32_t n, int32_t d, float eps,
+                                             float *y, int64_t ldy, float *stats, void *workspace,
+                                             size_t workspace_bytes, gist_stream_t stream) {
+    if (n < 0 || d < 0) return GIST_ERR_BADARG;
+    if (n == 0 || d == 0) return GIST_OK;
+    if (!x || !y || ldx < d || ldy < d) return GIST_ERR_BADARG;
+    if (workspace_bytes < gist_tensor_layernorm_workspace_bytes(n, d) || !workspace) return GIST_ERR_WORKSPACE;
+    if (!aligned(workspace, 16)) return GIST_ERR_ALIGN;
+    const int64_t count = (int64_t)n * d;
+    const int grid = tln_grid(count);
+    double2 *part = reinterpret_cast<double2 *>(workspace);
+    const double inv = 1.0 / (double)count;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool v4 = d % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && aligned(x, 16) && aligned(y, 16);
+    if (v4) {
+        tln_moments_kernel<4><<<grid, kTlnThreads, 0, s>>>(x, ldx, count / 4, d / 4, part);
+        tln_apply_kernel<4><<<grid, kTlnThreads, 0, s>>>(x, ldx, count / 4, d / 4, inv, eps, part, grid, y, ldy, stats);
+    } else {
+        tln_moments_kernel<1><<<grid, kTlnThreads, 0, s>>>(x, ldx, count, d, part);
+        tln_apply_kernel<1><<<grid, kTlnThreads, 0, s>>>(x, ldx, count, d, inv, eps, part, grid, y, ldy, stats);
+    }
+    count_launch(2);
+    return last_error();
+}
+
+extern "C" int gist_tensor_layernorm_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx,
+                                             const float *stats, int32_t n, int32_t d, float *dx, int64_t lddx,
+                                             void *workspace, size_t workspace_bytes, gist_stream_t stream) {
+    if (n < 0 || d < 0) return GIST_ERR_BADARG;
+    if (n == 0 || d == 0) return GIST_OK;
+    if (!dy || !x || !stats || !dx || lddy < d || ldx < d || lddx < d) return GIST_ERR_BADARG;
+    if (workspace_bytes < gist_tensor_layernorm_workspace_bytes(n, d) || !workspace) return GIST_ERR_WORKSPACE;
+    if (!aligned(workspace, 16)) return GIST_ERR_ALIGN;
+    const int64_t count = (int64_t)n * d;
+    const int grid = tln_grid(count);
+    double2 *part = reinterpret_cast<double2 *>(workspace);
+    const double inv = 1.0 / (double)count;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool v4 = d % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && aligned(x, 16) &&
+                    aligned(dy, 16) && aligned(dx, 16);
+    if (v4) {
+        tln_bwd_moments_kernel<4><<<grid, kTlnThreads, 0, s>>>(dy, lddy, x, ldx, stats, count / 4, d / 4, part);
+        tln_bwd_apply_kernel<4><<<grid, kTlnThreads, 0, s>>>(dy, lddy, x, ldx, stats, count / 4, d / 4, inv, part,
+                                                            grid, dx, lddx);
+    } else {
+        tln_bwd_moments_kernel<1><<<grid, kTlnThreads, 0, s>>>(dy, lddy, x, ldx, stats, count, d, part);
+        tln_bwd_apply_kernel<1><<<grid, kTlnThreads, 0, s>>>(dy, lddy, x, ldx, stats, count, d, inv, part, grid, dx,
+                                                            lddx);
+    }
+    count_launch(2);
     return last_error();
 }
 

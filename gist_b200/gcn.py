@@ -4,6 +4,7 @@ state-dict keys ``layers.{i}.{weight,bias}``)."""
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .modules import GraphConv, _split_widths
 
 
@@ -30,5 +31,5 @@ class GCN(nn.Module):
                 h = self.dropout(h)
             h = layer(self.g, h)
             if i < len(self.layers) - 1 and self.use_layernorm:
-                h = F.layer_norm(h, h.shape)   # ONE mean/var over all n*d elements (gcn/gcn.py:65-66)
+                h = ops.tensor_layer_norm(h)   # F.layer_norm(h, h.shape): ONE mean/var over all n*d elements (gcn/gcn.py:65-66)
         return h

@@ -11,6 +11,8 @@ Structure may live on the CPU (construction, host-side tests) but every compute
 method (``update_all``, ``subgraph``, norms) requires CUDA and raises otherwise —
 there is no CPU path.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -18,6 +20,9 @@ from . import _lib, function as fn, ops
 
 NID = '_ID'
 
+
+# A/B switch for the segment-balanced cluster-batch SpMM (GIST_SPMM_SEG=0: one row per group)
+SEG_ENABLED = os.environ.get('GIST_SPMM_SEG', '1') != '0'
 
 class GistError(RuntimeError):
     """Counterpart of dgl.DGLError."""
@@ -200,7 +205,7 @@ class GistGraph:
     def seg_schedule(self, transpose=False):
         """ops.SegSchedule of the in-CSR (or of the CSC for the transpose SpMM), built once per
         structure; None for large graphs, where one row per warp already balances."""
-        if self._n == 0 or self._n > self.SEG_MAX_NODES or not self.rowptr.is_cuda:
+        if self._n == 0 or self._n > self.SEG_MAX_NODES or not self.rowptr.is_cuda or not SEG_ENABLED:
             return None
         if transpose and not self.is_symmetric():
             key, (ptr_, idx_) = 'seg_sched_t', self.csc()

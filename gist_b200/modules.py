@@ -65,7 +65,7 @@ class GraphConv(nn.Module):
         in_f, out_f = (w.shape if w is not None else (self._in_feats, self._out_feats))
         if in_f > out_f:
             # (diag(s) X) W == diag(s) (X W): the src-norm moves into the SpMM gather
-            h = feat @ w if w is not None else feat
+            h = ops.matmul(feat, w) if w is not None else feat
             rst = ops.gspmm(graph, h, s, t, self.bias, fuse_relu)
             if self._activation is not None and not fuse_relu:
                 rst = self._activation(rst)
@@ -73,7 +73,12 @@ class GraphConv(nn.Module):
         # aggregate first; diag(t) commutes with the right-multiplication by W
         rst = ops.gspmm(graph, feat, s, t, None, False)
         if w is not None:
-            rst = torch.addmm(self.bias, rst, w) if self.bias is not None else rst @ w
+            if ops.get_matmul_precision() == 'fp32':
+                rst = torch.addmm(self.bias, rst, w) if self.bias is not None else rst @ w
+            else:
+                rst = ops.matmul(rst, w)
+                if self.bias is not None:
+                    rst = rst + self.bias
         elif self.bias is not None:
             rst = rst + self.bias
         if self._activation is not None:
@@ -334,5 +339,5 @@ class BaselineGCN(nn.Module):
                 h = self.dropout(h)
             h = layer(g, h)
             if i < len(self.layers) - 1 and self.use_layernorm:
-                h = F.layer_norm(h, h.shape)
+                h = ops.tensor_layer_norm(h)    # F.layer_norm(h, h.shape): ONE mean/var over all n*d elements
         return h

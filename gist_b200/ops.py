@@ -593,6 +593,46 @@ class _Linear3xTF32(torch.autograd.Function):
         return dz, dW, db
 
 
+class _MatmulNN(torch.autograd.Function):
+    """y = x @ W for W stored [in, out] (DGL GraphConv's layout, gcn/gcn.py:30-56) on the tcgen05
+    kernel: W is read MN-major as stored, no transposed copy.  dx = dy W^T reads the same W
+    K-major; dW = x^T dy reads both operands MN-major."""
+
+    @staticmethod
+    def forward(ctx, x, W):
+        x = _tma_view(_mat(x, 'x'))
+        Wv = _tma_view(W)
+        x3 = _MATMUL_PRECISION == '3xtf32'
+        x_lo = split_tf32(x) if x3 else None
+        W_lo = _weight_lo(Wv) if x3 else None
+        y = gemm(x, Wv, b_mn=True, A_lo=x_lo, B_lo=W_lo)
+        ctx.save_for_backward(x, Wv, *((x_lo, W_lo) if x3 else ()))
+        ctx.x3 = x3
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors[:2]
+        x_lo, W_lo = ctx.saved_tensors[2:] if ctx.x3 else (None, None)
+        dy = _tma_view(_mat(dy, 'dy'))
+        dy_lo = split_tf32(dy) if ctx.x3 else None
+        dx = dW = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dy, W, A_lo=dy_lo, B_lo=W_lo)                               # [n,out] x [in,out]^T
+        if ctx.needs_input_grad[1]:
+            dW = gemm(x, dy, a_mn=True, b_mn=True, A_lo=x_lo, B_lo=dy_lo)         # x^T dy: M = in, N = out, K = n
+        return dx, dW
+
+
+def matmul(x, W):
+    """x @ W with W stored [in, out]: cuBLAS sgemm through torch in 'fp32' mode, the tcgen05 kernel
+    (K4) otherwise."""
+    require_cuda(x, W)
+    if _MATMUL_PRECISION == 'fp32':
+        return x @ W
+    return _MatmulNN.apply(x, W)
+
+
 # --------------------------------------------------------------------------
 # weight-gradient branch: dW / db never feed the rest of the backward pass (only the optimizer),
 # so they run on a low-priority side stream and the activation-gradient chain
@@ -775,6 +815,44 @@ def layer_norm_act(x, eps=1e-5, relu=False):
     """F.relu(F.layer_norm(x, (x.shape[-1],), eps=eps)) (or without the ReLU) for 2-D fp32 x."""
     require_cuda(x)
     return _LayerNormAct.apply(x, float(eps), bool(relu))
+
+
+class _TensorLayerNorm(torch.autograd.Function):
+    """F.layer_norm(x, x.shape): one mean / variance over the whole [n, d] tensor, no affine
+    (gcn/gcn.py:65-66, cluster_gcn/modules.py:347-348)."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        x = _mat(x, 'x')
+        n, d = x.shape
+        lib = _lib.load()
+        y = torch.empty((n, d), dtype=torch.float32, device=x.device)
+        stats = torch.empty(2, dtype=torch.float32, device=x.device)
+        wsb = lib.gist_tensor_layernorm_workspace_bytes(n, d)
+        ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=x.device)
+        check(lib.gist_tensor_layernorm_fwd_f32(ptr(x), _ld(x), n, d, eps, ptr(y), _ld(y), ptr(stats), ptr(ws), wsb,
+                                                stream_ptr(x.device)), 'tensor_layernorm_fwd_f32')
+        ctx.save_for_backward(x, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats = ctx.saved_tensors
+        dy = _mat(dy, 'dy')
+        n, d = x.shape
+        lib = _lib.load()
+        dx = torch.empty((n, d), dtype=torch.float32, device=x.device)
+        wsb = lib.gist_tensor_layernorm_workspace_bytes(n, d)
+        ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=x.device)
+        check(lib.gist_tensor_layernorm_bwd_f32(ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(stats), n, d, ptr(dx), _ld(dx),
+                                                ptr(ws), wsb, stream_ptr(x.device)), 'tensor_layernorm_bwd_f32')
+        return dx, None
+
+
+def tensor_layer_norm(x, eps=1e-5):
+    """F.layer_norm(x, x.shape, eps=eps) for a 2-D fp32 matrix."""
+    require_cuda(x)
+    return _TensorLayerNorm.apply(x, float(eps))
 
 
 class _MaskedCrossEntropy(torch.autograd.Function):

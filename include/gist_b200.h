@@ -324,6 +324,21 @@ int gist_layernorm_act_bwd_f32(const float *dy, int64_t lddy, const float *x, in
                                const float *stats, int32_t n, int32_t d, uint32_t flags, float *dx,
                                int64_t lddx, float *dx_lo, int64_t ld_lo, gist_stream_t stream);
 
+/* Whole-tensor layer norm: y = (x - mean) * rstd with ONE mean / biased variance over all n*d
+ * elements, no affine — F.layer_norm(h, h.shape) as gcn/gcn.py:65-66 and
+ * cluster_gcn/modules.py:347-348 (BaselineGCN) apply it between GraphConv layers.
+ * stats (optional, 2 floats) receives (mean, rstd) for the backward.  Two launches, per-CTA fp64
+ * partial moments folded in a fixed order.  workspace: gist_tensor_layernorm_workspace_bytes(n, d)
+ * bytes, 16-byte aligned. */
+size_t gist_tensor_layernorm_workspace_bytes(int32_t n, int32_t d);
+int gist_tensor_layernorm_fwd_f32(const float *x, int64_t ldx, int32_t n, int32_t d, float eps, float *y,
+                                  int64_t ldy, float *stats, void *workspace, size_t workspace_bytes,
+                                  gist_stream_t stream);
+/* dx = rstd * (dy - mean(dy) - xhat * mean(dy * xhat)); x is the forward INPUT, stats from the forward. */
+int gist_tensor_layernorm_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx,
+                                  const float *stats, int32_t n, int32_t d, float *dx, int64_t lddx,
+                                  void *workspace, size_t workspace_bytes, gist_stream_t stream);
+
 /* out[c] = sum_r x[r, c] (bias gradient of nn.Linear), two-phase fixed-order reduction.
  * workspace: gist_colsum_workspace_bytes(n, d) bytes. */
 size_t gist_colsum_workspace_bytes(int32_t n, int32_t d);

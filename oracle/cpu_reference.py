@@ -114,3 +114,128 @@ def time_full_graph_spmm(rowptr, col, n, d, row_sample=None, seed=0):
     torch.sparse.mm(A, x)
     dt = time.perf_counter() - t0
     return dt * (float(rowptr[n]) / max(nnz, 1)), nnz
+
+
+# ---------------------------------------------------------------------------------------------
+# Full-graph GraphConv trainers (configs 1 and 2): gcn/train.py:86-121 and gcn/train_ist.py:140-286
+# with DGL's GraphConv(norm='both') restated as one torch CSR product with the symmetric
+# normalisation folded into the edge values, whole-tensor layer norm
+# (gcn/gcn.py:65-66), dropout before every layer but the first (:62-63).
+# ---------------------------------------------------------------------------------------------
+def _normalised_adj(rowptr, col, n):
+    indeg = np.diff(rowptr).astype(np.float64)
+    outdeg = np.bincount(col, minlength=n).astype(np.float64)
+    t = np.maximum(indeg, 1.0) ** -0.5
+    s = np.maximum(outdeg, 1.0) ** -0.5
+    row = np.repeat(np.arange(n), np.diff(rowptr))
+    vals = (t[row] * s[col]).astype(np.float32)
+    A = sp.csr_matrix((vals, col, rowptr), shape=(n, n))
+
+    def tcsr(m):
+        m = m.tocsr()
+        return torch.sparse_csr_tensor(torch.from_numpy(m.indptr.astype(np.int64)),
+                                       torch.from_numpy(m.indices.astype(np.int64)),
+                                       torch.from_numpy(m.data.astype(np.float32)), size=m.shape)
+    return tcsr(A), tcsr(A.T)
+
+
+def _graphconv_forward(A, At, h, params, dropout, use_layernorm, training):
+    L = len(params)
+    for i, (W, b) in enumerate(params):
+        if i != 0:
+            h = F.dropout(h, dropout, training)
+        if W.shape[0] > W.shape[1]:
+            h = _SpMM.apply(A, At, h @ W) + b
+        else:
+            h = _SpMM.apply(A, At, h) @ W + b
+        if i < L - 1:
+            h = F.relu(h)
+            if use_layernorm:
+                h = F.layer_norm(h, h.shape)
+    return h
+
+
+def _xavier(fin, fout):
+    W = torch.empty(fin, fout)
+    torch.nn.init.xavier_uniform_(W)
+    return W.requires_grad_(True), torch.zeros(fout, requires_grad=True)
+
+
+class CpuGCNTrainer:
+    """gcn/train.py: one Adam step on the full graph per epoch."""
+
+    def __init__(self, rowptr, col, feat, label, train_mask, n_hidden, n_classes, n_layers, dropout=0.5,
+                 use_layernorm=True, lr=1e-3, weight_decay=5e-4, seed=0):
+        n = rowptr.shape[0] - 1
+        self.A, self.At = _normalised_adj(np.asarray(rowptr, np.int64), np.asarray(col, np.int64), n)
+        self.feat, self.label, self.mask = feat, label, train_mask.bool()
+        torch.manual_seed(seed)
+        dims = [(feat.shape[1], n_hidden)] + [(n_hidden, n_hidden)] * (n_layers - 1) + [(n_hidden, n_classes)]
+        self.params = [_xavier(a, b) for a, b in dims]
+        self.dropout, self.use_layernorm = dropout, use_layernorm
+        self.opt = torch.optim.Adam([t for p in self.params for t in p], lr=lr, weight_decay=weight_decay)
+
+    def epoch(self, e=0):
+        self.opt.zero_grad()
+        out = _graphconv_forward(self.A, self.At, self.feat, self.params, self.dropout, self.use_layernorm, True)
+        loss = F.cross_entropy(out[self.mask], self.label[self.mask])
+        loss.backward()
+        self.opt.step()
+        return float(loss.detach())
+
+
+class CpuISTGCNTrainer:
+    """gcn/train_ist.py: m sub-GCNs trained one after the other every epoch, split / merged every
+    iter_per_site epochs (split_input False, split_output True: the config-2 flags of
+    script/sweep.py:12-13; index algebra from oracle/gist_oracle.py)."""
+
+    def __init__(self, rowptr, col, feat, label, train_mask, n_hidden, n_classes, n_layers, num_subnet,
+                 iter_per_site=5, dropout=0.5, use_layernorm=True, lr=1e-2, weight_decay=5e-4, seed=0):
+        from oracle import gist_oracle as O
+        self.O = O
+        n = rowptr.shape[0] - 1
+        self.A, self.At = _normalised_adj(np.asarray(rowptr, np.int64), np.asarray(col, np.int64), n)
+        self.feat, self.label, self.mask = feat, label, train_mask.bool()
+        torch.manual_seed(seed)
+        self.L, self.m, self.h, self.ips = n_layers, num_subnet, n_hidden, iter_per_site
+        dims = [(feat.shape[1], n_hidden)] + [(n_hidden, n_hidden)] * (n_layers - 1) + [(n_hidden, n_classes)]
+        self.main = {}
+        for l, (a, b) in enumerate(dims):
+            W, bb = _xavier(a, b)
+            self.main['layers.%d.weight' % l], self.main['layers.%d.bias' % l] = W.detach(), bb.detach()
+        self.dropout, self.use_layernorm, self.lr, self.wd = dropout, use_layernorm, lr, weight_decay
+
+    def epoch(self, e):
+        O, L, m = self.O, self.L, self.m
+        if e % self.ips == 0:
+            self.feats_idx = [None] + [torch.chunk(torch.randperm(self.h), m) for _ in range(1, L)] + \
+                             [torch.chunk(torch.randperm(self.h), m)]
+            self.subs, self.opts = [], []
+            for s in range(m):
+                sd = O.graphconv_split(self.main, self.feats_idx, s, L, False, True)
+                ps = [(sd['layers.%d.weight' % l].clone().requires_grad_(True),
+                       sd['layers.%d.bias' % l].clone().requires_grad_(True)) for l in range(L + 1)]
+                self.subs.append(ps)
+                self.opts.append(torch.optim.Adam([t for p in ps for t in p], lr=self.lr, weight_decay=self.wd))
+        loss = None
+        for s in range(m):
+            self.opts[s].zero_grad()
+            out = _graphconv_forward(self.A, self.At, self.feat, self.subs[s], self.dropout, self.use_layernorm, True)
+            loss = F.cross_entropy(out[self.mask], self.label[self.mask])
+            loss.backward()
+            self.opts[s].step()
+        if (e + 1) % self.ips == 0:
+            sds = [{('layers.%d.%s' % (l, nm)): t.detach() for l, p in enumerate(ps) for nm, t in zip(('weight', 'bias'), p)}
+                   for ps in self.subs]
+            self.main = O.graphconv_merge(self.main, self.feats_idx, sds, L, False, True)
+        return float(loss.detach())
+
+
+def time_epochs(trainer, n_epochs, warmup=1):
+    """Seconds per epoch of a Cpu*GCNTrainer after `warmup` epochs."""
+    for e in range(warmup):
+        trainer.epoch(e)
+    t0 = time.perf_counter()
+    for e in range(warmup, warmup + n_epochs):
+        trainer.epoch(e)
+    return (time.perf_counter() - t0) / max(n_epochs, 1)

@@ -356,6 +356,24 @@ def gen_train_ist(out):
         out[p + 'nsplit'] = np.int64(len(sub_loads))
 
 
+def gen_train_ist_data(out):
+    """The tiny dataset gen_train_ist's loader hands to gcn/train_ist.py (so the GPU trainer test
+    does not depend on networkx reproducing the same random graph): directed edge list after the
+    reference's self-loop step (train_ist.py:110-113), features, labels, masks."""
+    import networkx as nx
+    rng = np.random.RandomState(0)
+    n, f, c = 60, 12, 3
+    gnx = nx.gnm_random_graph(n, 150, seed=0)
+    feats = rng.rand(n, f).astype(np.float32)
+    labels = rng.randint(0, c, n)
+    gnx.remove_edges_from(nx.selfloop_edges(gnx))
+    gnx.add_edges_from(zip(gnx.nodes(), gnx.nodes()))
+    e = np.asarray(list(gnx.to_directed().edges()), dtype=np.int64)
+    out['src'], out['dst'] = e[:, 0].copy(), e[:, 1].copy()
+    out['features'], out['labels'] = feats, labels.astype(np.int64)
+    out['n'], out['num_labels'] = np.int64(n), np.int64(c)
+
+
 def gen_gat(out):
     """cluster_gcn/modules.py GATLayer (one head) run unmodified on the restated DGL's UDF /
     degree-bucketing path: output and gradients.  MultiHeadGATLayer / GAT as committed cannot
@@ -405,9 +423,9 @@ def gen_gat(out):
 def main():
     os.makedirs(OUT, exist_ok=True)
     bind_reference('cluster_gcn')
-    which = sys.argv[1:] or ['sage', 'graphconv', 'partition', 'cluster_iter', 'wrapper', 'train_ist', 'gat']
+    which = sys.argv[1:] or ['sage', 'graphconv', 'partition', 'cluster_iter', 'wrapper', 'train_ist', 'train_ist_data', 'gat']
     gens = dict(sage=gen_sage, graphconv=gen_graphconv, partition=gen_partition,
-                cluster_iter=gen_cluster_iter, wrapper=gen_wrapper, train_ist=gen_train_ist, gat=gen_gat)
+                cluster_iter=gen_cluster_iter, wrapper=gen_wrapper, train_ist=gen_train_ist, train_ist_data=gen_train_ist_data, gat=gen_gat)
     for name in which:
         out = {}
         gens[name](out)
