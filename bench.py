@@ -30,8 +30,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-def metric_name(shape):
-    return '%s_shape_gist_graphsage_epochs_per_s' % shape
+def metric_name(shape, model='sage'):
+    return '%s_shape_gist_%s_epochs_per_s' % (shape, 'gat' if model == 'gat' else 'graphsage')
 
 
 CONFIG_OF = {'reddit': 'configs[2]: Cluster-GCN GraphSAGE on a Reddit-shaped',
@@ -49,6 +49,10 @@ def parse():
                     help='reddit = the headline config; amazon2m with --n-hidden 32768 --psize 15000 --gpus 8 is '
                          'the ultra-wide config 4 (on one GPU use --n-hidden 4096: the per-rank slice of m = 8)')
     ap.add_argument('--scale', type=float, default=1.0, help='<1 shrinks the graph (debug only; reported)')
+    ap.add_argument('--model', default='sage', choices=['sage', 'gat'],
+                    help='sage: cluster_gcn_ist_distrib.py (the headline); gat: cluster_gcn_ist_distrib_gat.py '
+                         '(config 5; use --n-hidden 512 --n-heads 4 --n-layers 1)')
+    ap.add_argument('--n-heads', type=int, default=4)
     ap.add_argument('--n-hidden', type=int, default=256)
     ap.add_argument('--n-layers', type=int, default=2)
     ap.add_argument('--psize', type=int, default=None, help='number of parts; default: the shape\'s (reddit 1500, amazon2m 15000)')
@@ -189,14 +193,15 @@ def run_gist(a):
     psize = a.psize if (a.scale == 1.0 and a.psize) else int(ds.part.max().item()) + 1
     del ds
     wargs = SimpleNamespace(rank=rank, num_subnet=world, n_hidden=a.n_hidden, n_layers=a.n_layers,
-                            dropout=a.dropout, use_layernorm=True)
+                            dropout=a.dropout, use_layernorm=True, n_heads=a.n_heads)
+    Wrapper = gb.DistributedGATWrapper if a.model == 'gat' else gb.DistributedGNNWrapper
 
     def fresh(h2d):
         """ClusterIter + wrapper in the state the reference has when train() starts."""
         random.seed(a.seed)
         torch.manual_seed(a.seed)
         it = gb.ClusterIter('', g, psize, a.batch_size, train_nid, use_pp=False, h2d=h2d)
-        w = gb.DistributedGNNWrapper(wargs, g, in_feats, n_classes, dev)
+        w = Wrapper(wargs, g, in_feats, n_classes, dev)
         w.ini_sync_dispatch_model()
         return it, w
 
@@ -339,6 +344,7 @@ def run_gist(a):
     sleep_cycles = int(6e-3 * 1.9e9)
     ops.SPMM_PROFILE = []
     ops.GEMM_PROFILE = []
+    ops.GAT_PROFILE = []
     step_evs = []
     torch.cuda.synchronize()
     for _ in range(prof_steps):
@@ -351,6 +357,7 @@ def run_gist(a):
         torch.cuda.synchronize()
     prof, ops.SPMM_PROFILE = ops.SPMM_PROFILE, None
     gprof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    aprof, ops.GAT_PROFILE = ops.GAT_PROFILE, None
     prof_ms = sum(x.elapsed_time(y) for x, y in step_evs)
     del loop3, it3, w3
     alg_b = comp_b = spmm_ms = 0.0
@@ -388,6 +395,25 @@ def run_gist(a):
         'note': 'cluster batches (<=5 MB of features) are L2-resident: algorithmic gather bytes are served by '
                 'L2, so achieved can exceed the HBM copy peak; see roofline_fullgraph for the HBM-bound case',
     }
+
+    if a.model == 'gat' and aprof:
+        # K6 forward (edge softmax + weighted gather in one pass): per launch one D-wide source row
+        # and one score per edge, the destination's score / output row / log-sum-exp per row
+        gb_, gms = 0.0, 0.0
+        for r in aprof:
+            key = r['rowptr'].data_ptr()
+            if key not in nnz_cache:
+                nnz_cache[key] = int(r['rowptr'][r['n']].item())
+            nnz = nnz_cache[key]
+            gb_ += 4.0 * nnz * r['D'] + 4.0 * nnz + 4.0 * nnz + 4.0 * r['n'] * r['D'] + 4.0 * (r['n'] + 1) + 8.0 * r['n']
+            gms += r['ev0'].elapsed_time(r['ev1'])
+        roofline = {'bound': 'hbm', 'kernel': 'gat_aggregate_kernel (K6 forward, %d launches/step)' % (len(aprof) // max(prof_steps, 1)),
+                    'achieved': round(gb_ / 1e9 / (gms / 1e3), 1), 'peak': peak, 'unit': 'GB/s',
+                    'frac': round(gb_ / 1e9 / (gms / 1e3) / peak, 4), 'traffic': None, 'peak_source': peak_src,
+                    'bytes_per_launch': round(gb_ / len(aprof)), 'us_per_launch': round(gms * 1e3 / len(aprof), 2),
+                    'share_of_step': round((gms / prof_steps) / (ms / a.steps), 4),
+                    'note': 'algorithmic bytes = 4*nnz*D (source rows) + 8*nnz (col, source score) + 4*n*D (out) + '
+                            'rowptr + per-row score/lse; batches are L2-resident (see the SAGE note)'}
 
     # tensor roofline of the dense contractions (K4): useful FLOP = 2MNK per product; in 3xTF32
     # mode the tensor core executes three MMAs per useful one
@@ -466,14 +492,47 @@ def run_gist(a):
                                'flush': 'operand (%.0f MB) larger than L2' % (4 * n * d / 1e6)}
             del x, y
 
+    # ---- evaluate() on the full graph (a12; outside the reference's epoch timer) ---------
+    # reference structure: two full forward passes (val, test), aggregate-first in every layer;
+    # here: one pass for both masks, project-first wherever the output is narrower than the input
+    ev = None
+    if rank == 0 and not a.no_eval_spmm and getattr(w, 'base_model', None) is not None:
+        from gist_b200.train import evaluate_masks
+        labels, vm, tm = g.ndata['label'], g.ndata['val_mask'], g.ndata['test_mask']
+
+        def timed_eval(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(reps):
+                fn()
+            f1.record()
+            torch.cuda.synchronize()
+            return f0.elapsed_time(f1) / reps
+
+        def ref_structure():
+            w.base_model.eval()
+            for m_ in (vm, tm):
+                with torch.enable_grad():           # grad mode on = the aggregate-first training form
+                    pred = w.base_model(g).argmax(dim=1)
+                ((pred == labels) & m_).sum()
+        ms_fast = timed_eval(lambda: evaluate_masks(w.base_model, g, labels, [vm, tm]))
+        ms_ref = timed_eval(ref_structure)
+        ev = {'ms_val_plus_test': round(ms_fast, 2), 'ms_reference_structure': round(ms_ref, 2),
+              'what': 'full-graph inference of the full-width model for the val and test masks: one pass, '
+                      'project-first layers (aggregate at the output width) vs two aggregate-first passes '
+                      '(utils.py:70-80 called twice, cluster_gcn_ist_distrib.py:439-446)'}
+        w.base_model.train()
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---------
     cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and a.model == 'sage':
         cpu = cpu_baseline(a, it.g, steps_per_epoch, it)
 
     if rank == 0:
         line = {
-            'metric': metric_name(a.shape), 'value': round(value, 4), 'unit': 'epochs/s', 'n_gpus': world,
+            'metric': metric_name(a.shape, a.model), 'value': round(value, 4), 'unit': 'epochs/s', 'n_gpus': world,
             'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': round(ms / a.steps, 4),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'fp32': 'f32', '3xtf32': 'f32 (GEMMs: 3xTF32 split-operand tensor-core products, fp32-accurate)',
@@ -485,6 +544,8 @@ def run_gist(a):
                             'sub-GCNs (one per GPU), iter_per_site %d' % (
                                 CONFIG_OF[a.shape], n_nodes, n_edges, in_feats, psize, a.batch_size, a.n_hidden,
                                 a.n_layers + 1, world, a.iter_per_site),
+                'model': ('GAT (cluster_gcn_ist_distrib_gat.py), %d heads, fused edge-softmax + weighted SpMM (K6)' % a.n_heads
+                          if a.model == 'gat' else 'GraphSAGE (cluster_gcn_ist_distrib.py)'),
                 'steps_per_epoch': steps_per_epoch, 'num_subnet': world, 'scale': a.scale, 'mode': a.mode,
                 'pipeline': (a.mode == 'graph' and not a.no_pipeline),
                 'epoch_accounting': 'm ranks x one local pass = m epochs (reference: local_epochs = n_epochs // num_subnet)',
@@ -498,7 +559,7 @@ def run_gist(a):
                 'loss_after': round(final_loss, 4),
             },
             'roofline': roofline, 'roofline_gemm': roofline_gemm, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
-            'clocks': clocks, 'roofline_fullgraph': full,
+            'clocks': clocks, 'roofline_fullgraph': full, 'evaluate': ev,
             'setup_s': round(time.time() - t_setup, 1),
         }
         print(json.dumps(line), flush=True)

@@ -217,7 +217,12 @@ class ISTSAGELayer(nn.Module):
 
     def forward(self, g, h, pre=None):
         # pre: this layer's prepared input for (g, h) (prepare_input), if already computed
-        if h.is_cuda and ops.get_matmul_precision() != 'fp32':
+        W = self.linear.weight
+        if (pre is None and not self.training and not torch.is_grad_enabled() and h.is_cuda
+                and W.shape[0] < h.shape[1] and self.linear.bias is not None):
+            # inference (evaluate(), utils.py:70-80): project first, aggregate at the output width
+            h = ops.sage_project_first(g, h, W, self.linear.bias)
+        elif h.is_cuda and ops.get_matmul_precision() != 'fp32':
             # tensor-core path: aggregation + concat + dropout (+ split) in K1's epilogue, the
             # dropout backward in the dz GEMM's epilogue (ops._SageLinear)
             h = ops.sage_linear(g, h, self.linear.weight, self.linear.bias, self._p_drop(), self._drop_stream,

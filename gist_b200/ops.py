@@ -17,6 +17,7 @@ from ._lib import check, ptr, require_cuda, stream_ptr
 SPMM_PROFILE = None
 # same for every tensor-core GEMM launch (tensor roofline of the ultra-wide config)
 GEMM_PROFILE = None
+GAT_PROFILE = None     # bench.py: list of dicts (event pair, n, D, rowptr) per K6 forward aggregation
 
 
 def _mat(t, name):
@@ -753,6 +754,31 @@ def sage_linear(g, h, W, b, p_drop=0.0, stream_id=0, pre=None):
     return _SageLinear.apply(g, h, W, b, float(p_drop), int(stream_id), pre)
 
 
+@torch.no_grad()
+def sage_project_first(g, h, W, b):
+    """Inference-only form of a SAGE layer whose output is narrower than its input:
+    [h ‖ D^-1 A h] W^T + b  ==  h W_l^T + b + D^-1 A (h W_r^T)   (W = [W_l ‖ W_r]),
+    so the aggregation runs at the OUTPUT width (full Reddit-shape graph, layer 0: a 256-wide
+    gather instead of a 602-wide one; last layer: 41 instead of 256).  One GEMM produces
+    P = h [W_l; W_r]^T, one SpMM adds the self term and the bias in its epilogue."""
+    require_cuda(h, W, b)
+    h = _mat(h, 'h')
+    n, d = h.shape
+    out_f = W.shape[0]
+    assert W.shape[1] == 2 * d
+    W2 = torch.cat((W[:, :d], W[:, d:]), dim=0)                  # [2*out, d]
+    if _MATMUL_PRECISION == 'fp32':
+        P = h @ W2.t()
+    else:
+        hv, Wv = _tma_view(h), _tma_view(W2)
+        x3 = _MATMUL_PRECISION == '3xtf32'
+        P = gemm(hv, Wv, A_lo=split_tf32(hv) if x3 else None, B_lo=split_tf32(Wv) if x3 else None)
+    y = torch.empty((n, out_f), dtype=torch.float32, device=h.device)
+    spmm_raw(g.rowptr, g.col_buffer, n, n, P[:, out_f:], y, dst_scale=g.inv_in_degree(), addend=P[:, :out_f],
+             bias=b, schedule=g.seg_schedule())
+    return y
+
+
 def linear(z, W, b=None):
     """F.linear under the selected matmul precision."""
     if z.is_cuda and _MATMUL_PRECISION == '3xtf32':
@@ -919,9 +945,16 @@ class _GatAggregate(torch.autograd.Function):
         lse = torch.empty(n, dtype=torch.float32, device=dev)
         check(lib.gist_gat_scores_f32(ptr(z), _ld(z), n, D, ptr(attn), ptr(scores), stream_ptr(dev)),
               'gat_scores_f32')
+        prof = GAT_PROFILE
+        if prof is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         check(lib.gist_gat_aggregate_f32(ptr(g.rowptr), ptr(g.col_buffer), n, ptr(z), _ld(z), D, ptr(scores),
                                          negative_slope, ptr(out), _ld(out), ptr(lse), stream_ptr(dev)),
               'gat_aggregate_f32')
+        if prof is not None:
+            ev1.record()
+            prof.append(dict(ev0=ev0, ev1=ev1, rowptr=g.rowptr, n=n, D=D))
         ctx.g, ctx.slope = g, negative_slope
         ctx.save_for_backward(z, attn, scores, lse, out)
         return out

@@ -44,3 +44,17 @@ def evaluate(model, g, labels, mask, method='acc'):
     if total == 0:
         return -1
     return float(((pred == labels) & m).sum().item()) / total
+
+
+@torch.no_grad()
+def evaluate_masks(model, g, labels, masks, method='acc'):
+    """The reference evaluates val and test with TWO full-graph forward passes per eval point
+    (cluster_gcn_ist_distrib.py:439-446 -> utils.py:70-80).  One pass serves any number of masks:
+    returns [accuracy over mask_i].  Counts stay on the device until one final readback."""
+    assert method in ['acc', 'f1'], 'invalid method'
+    model.eval()
+    pred = model(g).argmax(dim=1)
+    hit = pred == labels
+    M = torch.stack([m.bool() for m in masks])                        # [k, n]
+    cnt = torch.stack(((M & hit).sum(1), M.sum(1))).cpu()             # one D2H
+    return [float(cnt[0, i]) / int(cnt[1, i]) if int(cnt[1, i]) else -1 for i in range(len(masks))]

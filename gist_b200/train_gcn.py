@@ -16,14 +16,17 @@ from .train_ist import _flag, add_self_loops, evaluate
 class GCNTrainer:
     """model / optimizer state of gcn/train.py::main between epochs."""
 
-    def __init__(self, g, features, labels, train_mask, n_classes, args, device=None):
+    def __init__(self, g, features, labels, train_mask, n_classes, args, device=None, use_graph=False):
         assert isinstance(g, GistGraph)
         self.args = args
+        self.use_graph = bool(use_graph)        # replay the (static) full-graph step from a CUDA graph
+        self._captured, self._captured_lr = None, None
         self.device = torch.device(device) if device is not None else features.device
         self.features, self.labels, self.train_mask = features, labels, train_mask.bool()
         self.model = GCN(g, features.shape[1], args.n_hidden, n_classes, args.n_layers, F.relu, args.dropout,
                          _flag(args.use_layernorm)).to(self.device)                 # train.py:80-83
         self.optimizer = Adam(self.model.parameters(), lr=args.lr, weight_decay=args.weight_decay)   # :87
+        self._loss = torch.zeros((), dtype=torch.float32, device=self.device)
 
     def train_epoch(self, epoch):
         a = self.args
@@ -32,15 +35,28 @@ class GCNTrainer:
                 for pg in self.optimizer.param_groups:
                     pg['lr'] = pg['lr'] / 10
         self.model.train()
+        if self.use_graph:
+            lr = self.optimizer.param_groups[0]['lr']
+            if self._captured is None or self._captured_lr != lr:       # lr is a kernel argument of Adam
+                from .graph_capture import CapturedStep
+                self._captured = CapturedStep(self._step, list(self.model.parameters()), [self.optimizer],
+                                              self.device)
+                self._captured_lr = lr
+            self._captured.replay()
+        else:
+            self._step()
+        return self._loss
+
+    def _step(self):
         self.optimizer.zero_grad(set_to_none=True)
         logits = self.model(self.features)
         loss = ops.masked_cross_entropy(logits, self.labels, self.train_mask)
         loss.backward()
         self.optimizer.step()
-        return loss.detach()
+        self._loss.copy_(loss.detach())
 
 
-def main(args, data, device='cuda', log=print, eval_every=1):
+def main(args, data, device='cuda', log=print, eval_every=1, use_graph=False):
     """gcn/train.py::main on an already-loaded dataset (fields as gist_b200.train_ist.main)."""
     device = torch.device(device)
     features = torch.as_tensor(data.features, dtype=torch.float32)
@@ -54,7 +70,7 @@ def main(args, data, device='cuda', log=print, eval_every=1):
             src, dst = add_self_loops(src, dst, n)
         g = GistGraph.from_edges(src, dst, n, device=device)
     features = features.to(device)
-    tr = GCNTrainer(g, features, labels, masks[0], data.num_labels, args, device)
+    tr = GCNTrainer(g, features, labels, masks[0], data.num_labels, args, device, use_graph=use_graph)
     dur, record = [], []
     for epoch in range(args.n_epochs):
         if epoch >= 3:

@@ -66,9 +66,14 @@ class ISTGCNTrainer:
     names: n_hidden, n_layers, num_subnet, iter_per_site, dropout, lr, weight_decay, n_epochs,
     split_input, split_output, use_layernorm."""
 
-    def __init__(self, g, features, labels, train_mask, n_classes, args, device=None):
+    def __init__(self, g, features, labels, train_mask, n_classes, args, device=None, use_graph=False):
         assert isinstance(g, GistGraph)
         self.args = args
+        # use_graph: the m sub-network steps of one epoch are captured ONCE into a CUDA graph (the
+        # step is static: whole graph, whole feature matrix) and replayed per epoch; dispatch then
+        # loads the new slices into the SAME sub-model / optimizer tensors instead of building new ones
+        self.use_graph = bool(use_graph)
+        self._captured, self._captured_lr, self._streams = None, None, None
         self.device = torch.device(device) if device is not None else features.device
         self.g = g
         self.features, self.labels = features, labels
@@ -85,6 +90,7 @@ class ISTGCNTrainer:
         self.sub_models, self.opt_list, self.model_inputs = [], [], []
         self.main_dict = self.feats_idx = None
         self.last_loss = None
+        self._loss = torch.zeros(args.num_subnet, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ one epoch --
     def _lr(self, epoch):
@@ -101,20 +107,31 @@ class ISTGCNTrainer:
         self.main_dict = {k: v.detach() for k, v in self.model.state_dict().items()}
         self.feats_idx = IG.sample_feature_partitions(self.in_feats, a.n_hidden, a.n_layers, a.num_subnet,
                                                       self.split_input, self.split_output)
-        self.sub_models, self.opt_list, self.model_inputs = [], [], []
+        persistent = self.use_graph and len(self.sub_models) == a.num_subnet
+        if not persistent:
+            self.sub_models, self.opt_list, self.model_inputs = [], [], []
         for s in range(a.num_subnet):
+            # the reference builds a fresh narrow GCN per sub-network here; its Xavier init draws
+            # from the global RNG before the slice overwrites it, so the draw is kept either way
             sub = GCN(self.g, self.in_feats, a.n_hidden, self.n_classes, a.n_layers, F.relu, a.dropout,
-                      self.use_layernorm, self.split_input, self.split_output, a.num_subnet).to(self.device)
+                      self.use_layernorm, self.split_input, self.split_output, a.num_subnet)
             sd = IG.split_state_dict(self.main_dict, self.feats_idx, s, a.n_layers, self.split_input,
                                      self.split_output)
+            idx = self.feats_idx[0][s].to(self.device) if self.split_input else None
+            if persistent:
+                self.sub_models[s].load_state_dict(sd)                  # in place: captured pointers stay valid
+                self.opt_list[s].reset_state()                          # a fresh Adam (train_ist.py:207-209)
+                for pg in self.opt_list[s].param_groups:
+                    pg['lr'] = self._lr(epoch)
+                if idx is not None:
+                    ops.slice_gather(self.features, None, idx, out=self.model_inputs[s])
+                continue
+            sub = sub.to(self.device)
             sub.load_state_dict(sd)
             self.sub_models.append(sub)
             self.opt_list.append(Adam(sub.parameters(), lr=self._lr(epoch), weight_decay=a.weight_decay))
-            if self.split_input:
-                idx = self.feats_idx[0][s].to(self.device)
-                self.model_inputs.append(ops.slice_gather(self.features, None, idx))   # features[:, idx]
-            else:
-                self.model_inputs.append(self.features)
+            self.model_inputs.append(ops.slice_gather(self.features, None, idx) if idx is not None   # features[:, idx]
+                                     else self.features)
 
     def _merge(self):
         a = self.args
@@ -130,22 +147,54 @@ class ISTGCNTrainer:
         self.model.eval()                                               # train_ist.py:144
         if epoch % a.iter_per_site == 0:
             self._dispatch(epoch)
-        loss = None
-        for s in range(a.num_subnet):
-            sub, opt = self.sub_models[s], self.opt_list[s]
-            opt.zero_grad(set_to_none=True)
-            sub.train()
-            logits = sub(self.model_inputs[s])
-            loss = ops.masked_cross_entropy(logits, self.labels, self.train_mask)
-            loss.backward()
-            opt.step()
+        if self.use_graph:
+            lr = self.opt_list[0].param_groups[0]['lr']
+            if self._captured is None or self._captured_lr != lr:       # lr is a kernel argument of Adam
+                from .graph_capture import CapturedStep
+                params = [p for sub in self.sub_models for p in sub.parameters()]
+                self._captured = CapturedStep(self._sub_steps, params, self.opt_list, self.device)
+                self._captured_lr = lr
+            self._captured.replay()
+        else:
+            self._sub_steps()
         if (epoch + 1) % a.iter_per_site == 0 or epoch == a.n_epochs - 1:
             self._merge()
-        self.last_loss = loss.detach()
+        self.last_loss = self._loss[a.num_subnet - 1]
         return self.last_loss
 
+    def _sub_steps(self):
+        """train_ist.py:212-229 for every sub-network.  The m sub-networks of one epoch share only
+        read-only inputs (graph, features, labels) — parameters, gradients and optimizer state are
+        disjoint — so in graph mode each runs on its own stream: m parallel branches of the captured
+        graph instead of a chain of m x ~60 small kernels.  Results are independent of the overlap."""
+        m = self.args.num_subnet
+        if not self.use_graph:
+            for s in range(m):
+                self._sub_step(s)
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(m)]
+        for s in range(m):
+            st = self._streams[s]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                self._sub_step(s)
+        for st in self._streams:
+            main.wait_stream(st)
 
-def main(args, data, device='cuda', log=print, eval_every=1):
+    def _sub_step(self, s):
+        sub, opt = self.sub_models[s], self.opt_list[s]
+        opt.zero_grad(set_to_none=True)
+        sub.train()
+        logits = sub(self.model_inputs[s])
+        loss = ops.masked_cross_entropy(logits, self.labels, self.train_mask)
+        loss.backward()
+        opt.step()
+        self._loss[s].copy_(loss.detach())
+
+
+def main(args, data, device='cuda', log=print, eval_every=1, use_graph=False):
     """train_ist.main(args) on an already-loaded dataset (``data``: graph edges ``src``/``dst`` or
     a GistGraph ``graph``, ``features``, ``labels``, ``train_mask``/``val_mask``/``test_mask``,
     ``num_labels`` — the fields of DGL's citation datasets the reference reads, :66-92).
@@ -168,7 +217,7 @@ def main(args, data, device='cuda', log=print, eval_every=1):
             src, dst = add_self_loops(src, dst, n)
         g = GistGraph.from_edges(src, dst, n, device=device)
     features = features.to(device)
-    tr = ISTGCNTrainer(g, features, labels, masks[0], data.num_labels, args, device)
+    tr = ISTGCNTrainer(g, features, labels, masks[0], data.num_labels, args, device, use_graph=use_graph)
     dur, record = [], []
     for epoch in range(args.n_epochs):
         if epoch >= 3:

@@ -209,3 +209,41 @@ def test_weight_grad_branch_is_safe_when_the_side_stream_lags():
     finally:
         ops.OVERLAP_WEIGHT_GRADS = True
         ops.set_matmul_precision('fp32')
+
+
+@pytest.mark.parametrize('cfg', [(602, 256, 41, 2, True), (100, 64, 47, 3, True), (50, 64, 5, 1, False)])
+def test_sage_gcn_inference_project_first_vs_oracle(cfg, matmul_precision):
+    """evaluate()'s no-grad eval forward takes the project-first form of every layer whose output is
+    narrower than its input (ops.sage_project_first); it must meet the oracle like the training form,
+    and agree with the aggregate-first forward of the same module."""
+    from gist_b200 import SageGCN
+    fin, hid, ncls, L, ln = cfg
+    n = 900
+    g, og = _graphs(n, 15000, seed=10 + L, loops=False)
+    torch.manual_seed(1)
+    model = SageGCN(fin, hid, ncls, L, F.relu, 0.3, ln, False, False, 1, True).cuda().eval()
+    x = torch.randn(n, fin)
+    g.ndata['feat'] = x.cuda()
+    ref = O.sage_gcn_forward(og, x.double(), _params64(model), ln)
+    with torch.no_grad():
+        fast = model(g)
+    slow = model(g)                         # grad enabled: aggregate-first path
+    assert_close(fast, ref, rtol=5e-5, what='project-first logits')
+    assert_close(fast, slow, rtol=5e-5, what='project-first vs aggregate-first')
+
+
+def test_evaluate_masks_one_pass_equals_two_evaluate_calls():
+    from gist_b200 import SageGCN
+    from gist_b200.train import evaluate, evaluate_masks
+    n = 1200
+    g, _ = _graphs(n, 20000, seed=3, loops=False)
+    torch.manual_seed(2)
+    model = SageGCN(64, 32, 7, 2, F.relu, 0.2, True, False, False, 1, True).cuda()
+    g.ndata['feat'] = torch.randn(n, 64, device='cuda')
+    labels = torch.randint(0, 7, (n,), device='cuda')
+    r = torch.rand(n, device='cuda')
+    val, test, empty = r < 0.3, r > 0.6, torch.zeros(n, dtype=torch.bool, device='cuda')
+    both = evaluate_masks(model, g, labels, [val, test, empty])
+    assert both[0] == evaluate(model, g, labels, val)
+    assert both[1] == evaluate(model, g, labels, test)
+    assert both[2] == -1 == evaluate(model, g, labels, empty)

@@ -84,9 +84,10 @@ def _data():
                            test_mask=torch.from_numpy(te), num_labels=int(D['num_labels']))
 
 
+@pytest.mark.parametrize('use_graph', [False, True])
 @pytest.mark.parametrize('mode', ['fp32', '3xtf32'])
 @pytest.mark.parametrize('ci', [0, 1, 2, 3])
-def test_train_ist_trainer_vs_reference_golden(ci, mode):
+def test_train_ist_trainer_vs_reference_golden(ci, mode, use_graph):
     """Same seed, same data: the trainer must draw the reference's partitions bit-exactly, start
     every round from the reference's weights, and after every round hold the reference's trained
     sub-models and merged model (fp32 training, 2 Adam steps per round: 2e-5 norm-wise)."""
@@ -107,7 +108,8 @@ def test_train_ist_trainer_vs_reference_golden(ci, mode):
                                weight_decay=5e-4, use_layernorm='True')
         g = GistGraph.from_edges(d.src, d.dst, d.features.shape[0], device=dev)
         torch.manual_seed(ci)                      # gen_train_ist seeds right before ref.main(args)
-        tr = ISTGCNTrainer(g, d.features.to(dev), d.labels.to(dev), d.train_mask.to(dev), ncls, args, dev)
+        tr = ISTGCNTrainer(g, d.features.to(dev), d.labels.to(dev), d.train_mask.to(dev), ncls, args, dev,
+                           use_graph=use_graph)
         nper = int(G[p + 'nperm']) // int(G[p + 'nrounds'])
         for r in range(int(G[p + 'nrounds'])):
             sd = tr.model.state_dict()
@@ -157,3 +159,28 @@ def test_train_ist_main_runs_pubmed_shape_slice():
     assert len(out.record) == 20 and n == data.features.shape[0]
     assert losses[-1] < losses[0]
     assert all(np.isfinite(losses))
+
+
+def test_gcn_trainer_graph_replay_equals_eager():
+    """gcn/train.py mirror: the CUDA-graph replayed step gives the eager step's weights (dropout 0)."""
+    from gist_b200 import synth
+    from gist_b200.graph import GistGraph
+    from gist_b200.train_gcn import GCNTrainer
+    from gist_b200.train_ist import add_self_loops
+    ds = synth.make('cora', seed=0)
+    dev = torch.device('cuda')
+    src, dst = add_self_loops(ds.src, ds.dst, ds.num_nodes)
+    g = GistGraph.from_edges(src, dst, ds.num_nodes, device=dev)
+    args = SimpleNamespace(n_hidden=16, n_layers=1, dropout=0.0, lr=1e-2, weight_decay=5e-4, n_epochs=8,
+                           use_layernorm='True', lr_scheduler=True)
+    out = []
+    for use_graph in (False, True):
+        torch.manual_seed(1)
+        tr = GCNTrainer(g, ds.feat.to(dev), ds.label.to(dev), ds.train_mask.to(dev), ds.num_classes, args, dev,
+                        use_graph=use_graph)
+        losses = [float(tr.train_epoch(e)) for e in range(8)]      # lr drops at epochs 4 and 6: two re-captures
+        out.append((losses, [p.detach().clone() for p in tr.model.parameters()]))
+    for a, b in zip(out[0][0], out[1][0]):
+        assert abs(a - b) <= 1e-5 * max(abs(a), 1.0)
+    for p, q in zip(out[0][1], out[1][1]):
+        assert _rel(q, p) < 1e-5

@@ -36,7 +36,11 @@ def time_gpu(tr, k, w):
         loss = tr.train_epoch(e)
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / k, float(loss), _lib.launch_count() - l0
+    n_l = _lib.launch_count() - l0
+    cap = getattr(tr, '_captured', None)
+    if cap is not None:
+        n_l += k * cap.gist_launches              # kernel nodes of this library replayed from the graph
+    return e0.elapsed_time(e1) / k, float(loss), n_l
 
 
 def main():
@@ -46,6 +50,7 @@ def main():
     ap.add_argument('--cpu-epochs', type=int, default=5)
     ap.add_argument('--matmul', default='3xtf32', choices=['fp32', 'tf32', '3xtf32'])
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='op-by-op instead of one CUDA-graph replay per epoch')
     a = ap.parse_args()
     ops.set_matmul_precision(a.matmul)
     dev = torch.device('cuda', 0)
@@ -64,13 +69,13 @@ def main():
         if cfg == 0:
             args = SimpleNamespace(n_hidden=16, n_layers=1, dropout=0.5, lr=1e-3, weight_decay=5e-4, n_epochs=400,
                                    use_layernorm='True', lr_scheduler=False)
-            tr = GCNTrainer(g, x, y, tm, ds.num_classes, args, dev)
+            tr = GCNTrainer(g, x, y, tm, ds.num_classes, args, dev, use_graph=not a.eager)
             what = 'configs[0]: gcn/train.py 2-layer GCN, Cora-shaped synthetic graph'
         else:
             args = SimpleNamespace(n_hidden=256, n_layers=2, num_subnet=8, iter_per_site=5, dropout=0.5, lr=1e-2,
                                    weight_decay=5e-4, n_epochs=10 ** 6, split_input='False', split_output='True',
                                    use_layernorm='True')
-            tr = ISTGCNTrainer(g, x, y, tm, ds.num_classes, args, dev)
+            tr = ISTGCNTrainer(g, x, y, tm, ds.num_classes, args, dev, use_graph=not a.eager)
             what = 'configs[1]: gcn/train_ist.py 3-layer GCN, PubMed-shaped synthetic graph, 8 sub-GCNs, iter_per_site 5'
         ms, loss, launches = time_gpu(tr, a.epochs, a.warmup)
         line = {'metric': '%s_shape_gcn_epochs_per_s' % shape, 'value': round(1e3 / ms, 2), 'unit': 'epochs/s',
@@ -78,7 +83,8 @@ def main():
                 'higher_is_better': True, 'dtype': 'f32' if a.matmul == 'fp32' else 'f32 (GEMMs %s)' % a.matmul,
                 'data': 'synthetic',
                 'config': {'workload': '%s (%d nodes, %d directed edges incl. self loops, %d feats)' % (
-                    what, ds.num_nodes, int(src.shape[0]), x.shape[1]), 'eval': 'excluded (as the reference timer)'},
+                    what, ds.num_nodes, int(src.shape[0]), x.shape[1]), 'eval': 'excluded (as the reference timer)',
+                           'mode': 'eager' if a.eager else 'graph (one replay per epoch)'},
                 'loss_after': round(loss, 4), 'gpu_launches': launches}
         if not a.no_cpu:
             rp, cl = g.rowptr.cpu().numpy(), g.col.cpu().numpy()
