@@ -332,27 +332,39 @@ spmm_csr_kernel(const SpmmParams p) {
 template <int VEC, int LPR, int VPL, bool HAS_SS, bool EX>
 __global__ void __launch_bounds__(256, 3) spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
     constexpr int GPW = 32 / LPR;
-    constexpr int NGROUPS = 8 * GPW;
     constexpr int CHUNK = LPR * VEC * VPL;
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
     const int grp = lane / LPR;
     const int lg = lane % LPR;
-    const int gid = warp * GPW + grp;
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
     const int lane0 = grp * LPR;
     if constexpr (EX) record_drop_step(p);
     // The number of segments is known on the device only (the host sizes its buffers from the
     // batch's edge CAPACITY, several times the actual count), so the grid is a fixed number of
-    // resident CTAs striding over the (chunk, segment block) work list — chunk-major, so the
-    // chip sweeps one column slab of X at a time.
+    // resident CTAs that pull work from a queue: a warp item is GPW consecutive segments of one
+    // feature chunk — chunk-major, so the chip sweeps one column slab of X at a time.  Segments
+    // differ in length (most rows of a cluster batch are one short segment), so a static
+    // round-robin leaves warps idle behind the unlucky ones (ncu: 22 % of the warp slots active);
+    // the queue hands the next item to whichever warp is free.  Its head is seg_count[0]: each of
+    // the W warps makes exactly one failing fetch, so the fetch that returns total + W - 1 is the
+    // last access of the launch and re-arms the head for the next one.
     const int n_seg = __ldg(p.seg_ptr + p.n_dst);
-    const int seg_blocks = (n_seg + NGROUPS - 1) / NGROUPS;
+    const int wipc = (n_seg + GPW - 1) / GPW;              // warp items per chunk
     const int n_chunks = (p.d + CHUNK - 1) / CHUNK;
-    const int total = seg_blocks * n_chunks;
-    for (int work = blockIdx.x; work < total; work += gridDim.x) {
-        const int chunk = work / seg_blocks;
-        const int seg = (work - chunk * seg_blocks) * NGROUPS + gid;
+    const unsigned total = (unsigned)(wipc * n_chunks);
+    const unsigned n_warps = gridDim.x * 8u;
+    uint32_t *head = p.seg_count;
+    uint32_t *arrivals = p.seg_count + 1;
+    while (true) {
+        unsigned work = 0;
+        if (lane == 0) work = atomicAdd(head, 1u);
+        work = __shfl_sync(0xffffffffu, work, 0);
+        if (work >= total) {
+            if (work == total + n_warps - 1u && lane == 0) *head = 0u;
+            break;
+        }
+        const int chunk = (int)work / wipc;
+        const int seg = ((int)work - chunk * wipc) * GPW + grp;
         if (seg >= n_seg) continue;                        // whole group skips together
 
         int c[VPL];
@@ -386,7 +398,7 @@ __global__ void __launch_bounds__(256, 3) spmm_seg_kernel(const __grid_constant_
         __threadfence();                                   // partials visible before the arrival
         __syncwarp(gmask);
         unsigned prev = 0;
-        uint32_t *cnt = p.seg_count + (int64_t)chunk * p.n_dst + v;
+        uint32_t *cnt = arrivals + (int64_t)chunk * p.n_dst + v;
         if (lg == 0) prev = atomicAdd(cnt, 1u);
         prev = __shfl_sync(gmask, prev, lane0);
         if (prev != (unsigned)(nseg - 1)) continue;
@@ -424,12 +436,13 @@ static int launch_spmm_seg(const SpmmParams &p0, int64_t max_segments, cudaStrea
     SpmmParams p = p0;
     constexpr int NGROUPS = 8 * (32 / LPR);
     constexpr int CHUNK = LPR * VEC * VPL;
-    const int64_t max_work = ceil_div64(max_segments, NGROUPS) * ceil_div64(p.d, CHUNK);
+    constexpr int GPW = 32 / LPR;
+    const int64_t max_work = ceil_div64(max_segments, GPW) * ceil_div64(p.d, CHUNK);     // warp items
     if (max_work <= 0) return GIST_OK;
-    if (max_work > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
-    // resident CTAs only (3 per SM by the launch bounds); they stride over the device-side work list
+    if (max_work > 0x3fffffffLL) return GIST_ERR_UNSUPPORTED;
+    // resident CTAs only (3 per SM by the launch bounds); their warps pull from the device-side queue
     int64_t grid = 3LL * kNumSMs;
-    if (grid > max_work) grid = max_work;
+    if (grid > ceil_div64(max_work, 8)) grid = ceil_div64(max_work, 8);
     p.seg_blocks = 0;
     const bool ex = p.y_lo || p.self_lo || p.drop.p != 0.f;
     if (p.src_scale) {

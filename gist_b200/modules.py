@@ -108,6 +108,18 @@ class GATLayer(nn.Module):
         return ops.gat_aggregate(g, z, self.attn_fc.weight, 0.01)     # F.leaky_relu default slope
 
 
+PARALLEL_HEADS = True
+_HEAD_STREAMS = {}
+
+
+def _head_streams(device, k):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    pool = _HEAD_STREAMS.setdefault(idx, [])
+    while len(pool) < k:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:k]
+
+
 class MultiHeadGATLayer(nn.Module):
     """cluster_gcn/modules.py:67-76.  The committed forward returns
     ``torch.mean(torch.stack(head_outs))`` with no dim — a 0-d scalar, after which the next
@@ -123,7 +135,22 @@ class MultiHeadGATLayer(nn.Module):
             self.heads.append(GATLayer(in_dim, out_dim))
 
     def forward(self, g, h):
-        head_outs = [attn_head(g, h) for attn_head in self.heads]
+        if h.is_cuda and len(self.heads) > 1 and PARALLEL_HEADS:
+            # the heads share only read-only inputs (graph, h): one stream per head, so their
+            # projection GEMMs and row-per-warp attention kernels (tail-bound on a cluster batch's hub
+            # rows) overlap — parallel branches under CUDA-graph capture; autograd runs each head's
+            # backward on its forward stream.  fork: side waits for main; join: main waits for side.
+            main = torch.cuda.current_stream(h.device)
+            streams = _head_streams(h.device, len(self.heads))
+            head_outs = []
+            for attn_head, st in zip(self.heads, streams):
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    head_outs.append(attn_head(g, h))
+            for st in streams:
+                main.wait_stream(st)
+        else:
+            head_outs = [attn_head(g, h) for attn_head in self.heads]
         if self.reduce == 'scalar':
             return torch.mean(torch.stack(head_outs))
         if len(head_outs) == 1:

@@ -107,8 +107,9 @@ class SegSchedule:
               'spmm_schedule_build')
 
     def counters(self, chunks):
-        """Zeroed arrival counters for `chunks` feature chunks (the kernel leaves them zero)."""
-        need = chunks * max(self.n, 1)
+        """Zeroed work-queue head + arrival counters for `chunks` feature chunks (the kernel leaves
+        them zero)."""
+        need = 1 + chunks * max(self.n, 1)
         if self._counters is None or self._counters.numel() < need:
             self._counters = torch.zeros(need, dtype=torch.int32, device=self.seg_ptr.device)
         return self._counters

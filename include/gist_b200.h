@@ -120,7 +120,8 @@ int gist_spmm_csr_f32(const int32_t *rowptr, const int32_t *col, int32_t n_dst, 
  * batch; shared by the forward and — for a symmetric pattern — the transpose launches).
  *   seg_ptr[n+1]  first segment of each row (seg_ptr[n] = number of segments, read on the device)
  *   seg_row[max_segments]  row of each segment;  max_segments >= n + nnz / seg_len (host bound)
- *   counters[chunks * n]  uint32, ZERO on entry, left zero on exit (chunks <= ceil(d / 4))
+ *   counters[1 + chunks * n]  uint32, ZERO on entry, left zero on exit (chunks <= ceil(d / 4)):
+ *                  [0] head of the launch's work queue, then one arrival counter per (chunk, row)
  *   workspace[max_segments][ld_workspace >= d, % 4 == 0]  fp32 scratch, no initialisation needed
  * Two launches that share `counters` / `workspace` must not run concurrently. */
 typedef struct gist_spmm_schedule {

@@ -24,18 +24,22 @@ from gist_b200.train_gcn import GCNTrainer                  # noqa: E402
 from gist_b200.train_ist import ISTGCNTrainer, add_self_loops, random_projection   # noqa: E402
 
 
-def time_gpu(tr, k, w):
+def time_gpu(tr, k, w, ncu=False):
     for e in range(w):
         tr.train_epoch(e)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = _lib.launch_count()
+    if ncu:
+        torch.cuda.profiler.start()
     e0.record()
     loss = None
     for e in range(w, w + k):
         loss = tr.train_epoch(e)
     e1.record()
     torch.cuda.synchronize()
+    if ncu:
+        torch.cuda.profiler.stop()
     n_l = _lib.launch_count() - l0
     cap = getattr(tr, '_captured', None)
     if cap is not None:
@@ -50,13 +54,15 @@ def main():
     ap.add_argument('--cpu-epochs', type=int, default=5)
     ap.add_argument('--matmul', default='3xtf32', choices=['fp32', 'tf32', '3xtf32'])
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--ncu', action='store_true', help='bracket the timed epochs with cudaProfilerStart/Stop')
+    ap.add_argument('--only', type=int, default=None, help='run only this config (0 or 1)')
     ap.add_argument('--eager', action='store_true', help='op-by-op instead of one CUDA-graph replay per epoch')
     a = ap.parse_args()
     ops.set_matmul_precision(a.matmul)
     dev = torch.device('cuda', 0)
     from oracle import cpu_reference as R                   # CPU baseline leg only
 
-    for cfg in (0, 1):
+    for cfg in ((0, 1) if a.only is None else (a.only,)):
         shape = 'cora' if cfg == 0 else 'pubmed'
         ds = synth.make(shape, seed=0)
         feat = ds.feat
@@ -77,7 +83,7 @@ def main():
                                    use_layernorm='True')
             tr = ISTGCNTrainer(g, x, y, tm, ds.num_classes, args, dev, use_graph=not a.eager)
             what = 'configs[1]: gcn/train_ist.py 3-layer GCN, PubMed-shaped synthetic graph, 8 sub-GCNs, iter_per_site 5'
-        ms, loss, launches = time_gpu(tr, a.epochs, a.warmup)
+        ms, loss, launches = time_gpu(tr, a.epochs, a.warmup, a.ncu)
         line = {'metric': '%s_shape_gcn_epochs_per_s' % shape, 'value': round(1e3 / ms, 2), 'unit': 'epochs/s',
                 'n_gpus': 1, 'steps': a.epochs, 'warmup': a.warmup, 'ms_per_step': round(ms, 4),
                 'higher_is_better': True, 'dtype': 'f32' if a.matmul == 'fp32' else 'f32 (GEMMs %s)' % a.matmul,
