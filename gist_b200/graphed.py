@@ -64,7 +64,11 @@ class GraphedClusterTrainer:
         self._dev_tab = ([torch.empty((steps, self.n_pad), dtype=torch.int64, device=self.dev) for _ in range(2)]
                          if h2d == 'epoch' else None)
         self._tab = 1
+        # two copy streams: uploads must never queue behind a loss readback, which waits for the
+        # running graph to finish (one shared stream delayed the ids of batch k+1 — and with them
+        # graph k+1 — until graph k had completed and its loss had been copied out)
         self._copy = torch.cuda.Stream(device=self.dev)
+        self._copy_out = torch.cuda.Stream(device=self.dev)
         self._ev_ids = [torch.cuda.Event() for _ in range(nbuf)]      # ids landed in nids[j]
         self._ev_done = [torch.cuda.Event() for _ in range(nbuf)]     # graph j finished
         self._ev_ring = [torch.cuda.Event() for _ in range(nbuf)]     # loss[j] landed in the host ring
@@ -253,10 +257,10 @@ class GraphedClusterTrainer:
         running-loss log only, so a one-step lag changes nothing it computes; call ``drain()``
         after the last step for the final value."""
         j = self._issue()
-        with torch.cuda.stream(self._copy):
-            self._copy.wait_event(self._ev_done[j])
+        with torch.cuda.stream(self._copy_out):
+            self._copy_out.wait_event(self._ev_done[j])
             self._ring[j:j + 1].copy_(self.loss[j].reshape(1), non_blocking=True)
-            self._ev_ring[j].record(self._copy)
+            self._ev_ring[j].record(self._copy_out)
         self._ring_busy[j] = True
         self.d2h_bytes += 4
         if not self.pipeline:           # single buffer set: synchronous, like float(loss)

@@ -94,7 +94,7 @@ class SegSchedule:
         dev = rowptr.device
         self.seg_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
         self.seg_row = torch.empty(self.max_segments, dtype=torch.int32, device=dev)
-        self._counters = None
+        self._counters = {}
         self.rebuild(rowptr)
 
     def rebuild(self, rowptr):
@@ -108,11 +108,16 @@ class SegSchedule:
 
     def counters(self, chunks):
         """Zeroed work-queue head + arrival counters for `chunks` feature chunks (the kernel leaves
-        them zero)."""
+        them zero).  One set PER STREAM: launches on one stream are ordered, but the same structure
+        is aggregated concurrently from parallel streams / graph branches (the m sub-networks of
+        train_ist share the graph), and two running launches must never share a queue head."""
         need = 1 + chunks * max(self.n, 1)
-        if self._counters is None or self._counters.numel() < need:
-            self._counters = torch.zeros(need, dtype=torch.int32, device=self.seg_ptr.device)
-        return self._counters
+        dev = self.seg_ptr.device
+        key = torch.cuda.current_stream(dev).cuda_stream
+        cnt = self._counters.get(key)
+        if cnt is None or cnt.numel() < need:
+            cnt = self._counters[key] = torch.zeros(need, dtype=torch.int32, device=dev)
+        return cnt
 
 
 def degree_norm(rowptr, n, mode):
