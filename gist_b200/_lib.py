@@ -56,6 +56,8 @@ SIGNATURES = {
     'gist_colsum_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _SZ, _P]),
     'gist_masked_ce_fwd_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     'gist_masked_ce_bwd_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P]),
+    'gist_masked_ce_fused_workspace_bytes': (_SZ, [_I32]),
+    'gist_masked_ce_fused_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _SZ, _P, _P]),
     'gist_dropout_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _I32, _P, _I64, _P, _P]),
     'gist_counter_add_i64': (ctypes.c_int, [_P, _I64, _P]),
     'gist_spmm_csr_ex_f32': (ctypes.c_int, [_P, _P, _I32, _I32, _P, _I64, _I32, _P, _I64,

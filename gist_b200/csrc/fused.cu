@@ -427,6 +427,82 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float *__restrict__ l
     }
 }
 
+// Forward AND gradient seed in one launch (the trainers' loss + loss.backward() seed): every CTA
+// counts the masked rows itself (n bytes, L2-resident), so dlogits is final as it is written and
+// nothing waits on a reduction; the scalar loss is folded by the last CTA to arrive, over the
+// per-CTA partial sums in CTA order (deterministic).  sync[0] is the arrival counter (left 0).
+__global__ void __launch_bounds__(256) ce_fused_kernel(const float *__restrict__ logits, int64_t ld, int n,
+                                                       int C, const int64_t *__restrict__ labels,
+                                                       const uint8_t *__restrict__ mask,
+                                                       float *__restrict__ dlogits, int64_t ldd, int ldd_fill,
+                                                       float *__restrict__ dlo, float *__restrict__ partial,
+                                                       unsigned int *__restrict__ sync,
+                                                       float *__restrict__ out) {
+    __shared__ int s_cnt[8];
+    __shared__ float s_loss[8];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int cnt = 0;
+    if (mask) {
+        for (int i = threadIdx.x; i < n; i += 256) cnt += mask[i] != 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) s_cnt[warp] = cnt;
+        __syncthreads();
+        cnt = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) cnt += s_cnt[w];
+    } else {
+        cnt = n;
+    }
+    const float inv = 1.f / (float)cnt;         // cnt == 0: inf, and no row is masked in
+    const int r = blockIdx.x * 8 + warp;
+    float row_loss = 0.f;
+    if (r < n) {
+        const float *xr = logits + (int64_t)r * ld;
+        float mx = -INFINITY;
+        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, __ldg(xr + c));
+        mx = warp_max(mx);
+        float se = 0.f;
+        for (int c = lane; c < C; c += 32) se += __expf(__ldg(xr + c) - mx);
+        se = warp_sum(se);
+        const float l = mx + __logf(se);
+        const bool m = mask ? (mask[r] != 0) : true;
+        const int64_t y = labels[r];
+        if (m && y >= 0 && y < C) row_loss = l - __ldg(xr + y);
+        float *dr = dlogits + (int64_t)r * ldd;
+        for (int c = lane; c < ldd_fill; c += 32) {     // columns [C, ldd_fill) are row padding: zeroed
+            float v = 0.f;
+            if (c < C && m) v = (__expf(__ldg(xr + c) - l) - (c == y ? 1.f : 0.f)) * inv;
+            dr[c] = v;
+            if (dlo) dlo[(int64_t)r * ldd + c] = tf32_lo(v);
+        }
+    }
+    if (lane == 0) s_loss[warp] = row_loss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_loss[w];
+        partial[blockIdx.x] = t;
+        __threadfence();
+        s_last = atomicAdd(sync, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (warp == 0) {                                    // fixed order: lane-strided, then the shuffle tree
+        float t = 0.f;
+        for (int i = lane; i < (int)gridDim.x; i += 32) t += __ldcg(partial + i);
+        t = warp_sum(t);
+        if (lane == 0) {
+            out[0] = t * inv;        // 0 * inf = nan, as torch's mean over an empty selection
+            out[1] = inv;
+            *sync = 0u;
+        }
+    }
+}
+
 // -------------------------------------------------------------------- adam ----
 struct AdamTensor {
     float *p;
@@ -705,6 +781,26 @@ extern "C" int gist_masked_ce_bwd_f32(const float *logits, int64_t ld, int32_t n
         return GIST_ERR_BADARG;
     ce_bwd_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(logits, ld, n, C, labels, mask, lse, loss_out,
                                                                 grad_out, dlogits, ldd, fill_cols, dlogits_lo);
+    count_launch();
+    return last_error();
+}
+
+extern "C" size_t gist_masked_ce_fused_workspace_bytes(int32_t n) {
+    return (size_t)((n + 7) / 8 + 1) * sizeof(float);
+}
+
+extern "C" int gist_masked_ce_fused_f32(const float *logits, int64_t ld, int32_t n, int32_t C,
+                                        const int64_t *labels, const uint8_t *mask, float *dlogits,
+                                        int64_t ldd, int32_t fill_cols, float *dlogits_lo, float *loss_out,
+                                        void *workspace, size_t workspace_bytes, uint32_t *sync,
+                                        gist_stream_t stream) {
+    if (n <= 0 || C <= 0) return GIST_ERR_BADARG;
+    if (!logits || !labels || !dlogits || !loss_out || !workspace || !sync || ld < C || fill_cols < C ||
+        ldd < fill_cols || workspace_bytes < gist_masked_ce_fused_workspace_bytes(n))
+        return GIST_ERR_BADARG;
+    ce_fused_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(logits, ld, n, C, labels, mask, dlogits, ldd,
+                                                                  fill_cols, dlogits_lo, (float *)workspace, sync,
+                                                                  loss_out);
     count_launch();
     return last_error();
 }

@@ -30,7 +30,7 @@ import torch
 
 from . import ops
 from .modules import GCN as _SageGCN, SAGE_PRE0
-from .train import make_optimizer, masked_cross_entropy
+from .train import loss_and_backward, make_optimizer
 
 _KEYS = ('feat', 'label', 'train_mask')
 
@@ -129,10 +129,9 @@ class GraphedClusterTrainer:
     def _train(self, cluster, loss_out):
         self.opt.zero_grad(set_to_none=True)
         pred = self.model(cluster)          # (the dropout clock is ticked by the caller: auto_tick off)
-        loss = masked_cross_entropy(pred, cluster.ndata['label'], cluster.ndata['train_mask'])
-        loss.backward()
+        loss = loss_and_backward(pred, cluster.ndata['label'], cluster.ndata['train_mask'])
         self.opt.step()
-        loss_out.copy_(loss.detach())
+        loss_out.copy_(loss)
 
     def capture(self):
         """Warm up on a real batch, capture, then restore parameters / optimizer state so the

@@ -734,11 +734,17 @@ class _SageLinear(torch.autograd.Function):
         dh = dW = db = None
         need_dW, need_db = ctx.needs_input_grad[2], ctx.has_bias and ctx.needs_input_grad[3]
 
+        # first layer (no dh): the main stream has nothing left to do, so the bias gradient runs
+        # there, beside the dW GEMM, instead of behind it at the tail of the step
+        db_here = need_db and not ctx.needs_input_grad[1]
+
         def weight_grads():
             return (gemm(dy, z, a_mn=True, b_mn=True, A_lo=dy_lo, B_lo=z_lo) if need_dW else None,
-                    colsum(dy) if need_db else None)
-        if need_dW or need_db:      # forked first: the branch depends on dy only
+                    colsum(dy) if need_db and not db_here else None)
+        if need_dW or (need_db and not db_here):      # forked first: the branch depends on dy only
             dW, db = _weight_grad_branch(dy.device, weight_grads, (dy, dy_lo, z, z_lo))
+        if db_here:
+            db = colsum(dy)
         if ctx.needs_input_grad[1]:
             if ctx.drop is not None:
                 desc = dropout_state(dy.device).desc(ctx.drop[0], ctx.drop[1], step=ctx.step_saved)
@@ -929,6 +935,52 @@ def masked_cross_entropy(logits, labels, mask=None):
     kernels forward, one backward, no boolean-index gather (hence no host sync)."""
     require_cuda(logits, labels, mask)
     return _MaskedCrossEntropy.apply(logits, labels, mask)
+
+
+_CE_SYNC = {}
+
+
+def _ce_sync(device):
+    """Arrival counter of the fused CE kernel: one zeroed uint32 per stream (the kernel leaves it
+    zero; two launches in flight on different streams must not share it)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    t = _CE_SYNC.get(key)
+    if t is None:
+        t = _CE_SYNC[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return t
+
+
+@torch.no_grad()
+def masked_ce_loss_and_grad(logits, labels, mask=None):
+    """(loss, dlogits) of ``CrossEntropyLoss()(logits[mask], labels[mask])`` in ONE launch — the
+    trainers' replacement for ``loss = ...; loss.backward()`` (…distrib.py:413-415): call
+    ``logits.backward(dlogits)`` to run the rest of the backward pass.  dlogits is the gradient for
+    an upstream gradient of 1; its 3xTF32 low half is handed to the consuming linear backward."""
+    require_cuda(logits, labels, mask)
+    logits = _mat(logits.detach(), 'logits')
+    n, C = logits.shape
+    assert n > 0
+    assert labels.dtype == torch.int64 and labels.shape == (n,)
+    labels = labels.contiguous()
+    if mask is not None:
+        assert mask.dtype == torch.bool and mask.shape == (n,)
+        mask = mask.contiguous()
+    dev = logits.device
+    lib = _lib.load()
+    ldd = (C + 3) // 4 * 4            # padded rows: the gradient feeds the TMA-addressed GEMMs
+    buf = torch.empty((n, ldd), dtype=torch.float32, device=dev)
+    x3 = _MATMUL_PRECISION == '3xtf32'
+    buf_lo = torch.empty((n, ldd), dtype=torch.float32, device=dev) if x3 else None
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    wsb = lib.gist_masked_ce_fused_workspace_bytes(n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    check(lib.gist_masked_ce_fused_f32(ptr(logits), _ld(logits), n, C, ptr(labels), ptr(mask), ptr(buf), ldd, ldd,
+                                       ptr(buf_lo), ptr(out), ptr(ws), wsb, ptr(_ce_sync(dev)), stream_ptr(dev)),
+          'masked_ce_fused_f32')
+    dl = buf[:, :C]
+    if x3:
+        _lo_put(dl, buf_lo[:, :C])
+    return out[0], dl
 
 
 # --------------------------------------------------------------------------

@@ -14,6 +14,19 @@ def masked_cross_entropy(pred, labels, mask):
     return ops.masked_cross_entropy(pred, labels, mask.bool())
 
 
+def loss_and_backward(pred, labels, mask):
+    """``loss = CrossEntropyLoss()(pred[mask], labels[mask]); loss.backward()`` (…distrib.py:413-415)
+    with the loss and its gradient seed d loss / d pred produced by one kernel: the backward pass
+    starts from ``pred`` directly.  Returns the detached 0-d loss."""
+    if pred.shape[0] == 0:
+        loss = masked_cross_entropy(pred, labels, mask)
+        loss.backward()
+        return loss.detach()
+    loss, dpred = ops.masked_ce_loss_and_grad(pred, labels, mask.bool())
+    pred.backward(dpred)
+    return loss
+
+
 def make_optimizer(params, lr, weight_decay):
     """Adam as the reference builds it (…distrib.py:405-407: torch.optim.Adam(lr, weight_decay)),
     with the update of all tensors in one launch."""
@@ -25,10 +38,9 @@ def train_step(model, optimizer, cluster):
     Returns the loss as a 0-d device tensor (no sync)."""
     optimizer.zero_grad(set_to_none=True)
     pred = model(cluster)
-    loss = masked_cross_entropy(pred, cluster.ndata['label'], cluster.ndata['train_mask'])
-    loss.backward()
+    loss = loss_and_backward(pred, cluster.ndata['label'], cluster.ndata['train_mask'])
     optimizer.step()
-    return loss.detach()
+    return loss
 
 
 @torch.no_grad()

@@ -10,6 +10,7 @@ from . import ops
 from .gcn import GCN
 from .graph import GistGraph
 from .optim import Adam
+from .train import loss_and_backward
 from .train_ist import _flag, add_self_loops, evaluate
 
 
@@ -50,10 +51,9 @@ class GCNTrainer:
     def _step(self):
         self.optimizer.zero_grad(set_to_none=True)
         logits = self.model(self.features)
-        loss = ops.masked_cross_entropy(logits, self.labels, self.train_mask)
-        loss.backward()
+        loss = loss_and_backward(logits, self.labels, self.train_mask)     # train.py:106-108
         self.optimizer.step()
-        self._loss.copy_(loss.detach())
+        self._loss.copy_(loss)
 
 
 def main(args, data, device='cuda', log=print, eval_every=1, use_graph=False):

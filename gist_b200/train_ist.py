@@ -25,6 +25,7 @@ from . import ops
 from .gcn import GCN
 from .graph import GistGraph
 from .optim import Adam
+from .train import loss_and_backward
 
 
 def _flag(v):
@@ -188,10 +189,9 @@ class ISTGCNTrainer:
         opt.zero_grad(set_to_none=True)
         sub.train()
         logits = sub(self.model_inputs[s])
-        loss = ops.masked_cross_entropy(logits, self.labels, self.train_mask)
-        loss.backward()
+        loss = loss_and_backward(logits, self.labels, self.train_mask)     # train_ist.py:220-222
         opt.step()
-        self._loss[s].copy_(loss.detach())
+        self._loss[s].copy_(loss)
 
 
 def main(args, data, device='cuda', log=print, eval_every=1, use_graph=False):

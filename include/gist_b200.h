@@ -360,6 +360,19 @@ int gist_masked_ce_bwd_f32(const float *logits, int64_t ld, int32_t n, int32_t C
                            const float *grad_out, float *dlogits, int64_t ldd, int32_t fill_cols,
                            float *dlogits_lo, gist_stream_t stream);
 
+/* Loss and its gradient seed in ONE launch — what `loss = CrossEntropyLoss()(pred[mask], y[mask]);
+ * loss.backward()` (cluster_gcn_ist_distrib.py:413-415) puts at the head of the backward pass:
+ * loss_out[0] = mean masked-row loss, loss_out[1] = 1 / #masked rows, and
+ * dlogits[r,c] = mask_r * (softmax(logits[r])_c - [c == labels[r]]) / #masked rows (d loss / d logits
+ * for an upstream gradient of 1), padding columns zeroed, optional 3xTF32 low half as in
+ * gist_masked_ce_bwd_f32.  Requires n > 0.  workspace: gist_masked_ce_fused_workspace_bytes(n);
+ * sync: one zeroed uint32 the kernel leaves zero (never shared by two launches in flight). */
+size_t gist_masked_ce_fused_workspace_bytes(int32_t n);
+int gist_masked_ce_fused_f32(const float *logits, int64_t ld, int32_t n, int32_t C, const int64_t *labels,
+                             const uint8_t *mask, float *dlogits, int64_t ldd, int32_t fill_cols,
+                             float *dlogits_lo, float *loss_out, void *workspace, size_t workspace_bytes,
+                             uint32_t *sync, gist_stream_t stream);
+
 /* dx_lo (layer norm backward) / dlogits_lo (cross entropy backward): optional (NULL) 3xTF32 low
  * halves tf32(v - trunc_tf32(v)) of the gradient just written, in the same layout (dlogits_lo: same
  * leading dimension and padding as dlogits) — the nn.Linear backward that consumes the gradient

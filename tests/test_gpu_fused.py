@@ -79,6 +79,47 @@ def test_masked_cross_entropy(n, C, use_mask):
         assert (logits.grad[~mask] == 0).all()
 
 
+@pytest.mark.parametrize('mode', ['fp32', '3xtf32'])
+@pytest.mark.parametrize('n,C', [(2586, 41), (1000, 47), (17, 3), (5000, 7), (300, 1000), (1, 5)])
+@pytest.mark.parametrize('use_mask', [True, False])
+def test_masked_ce_loss_and_grad_one_launch(n, C, use_mask, mode):
+    """The trainers' fused loss + gradient seed (ops.masked_ce_loss_and_grad) against fp64 torch and
+    against the two-pass autograd op; repeated launches reuse the arrival counter (left at zero)."""
+    from gist_b200 import ops
+    torch.manual_seed(n + C)
+    logits = torch.randn(n, C, device='cuda') * 4
+    labels = torch.randint(0, C, (n,), device='cuda')
+    mask = (torch.rand(n, device='cuda') < 0.6) if use_mask else None
+    if use_mask:
+        mask[0] = True
+    old = ops.get_matmul_precision()
+    ops.set_matmul_precision(mode)
+    try:
+        for _ in range(3):
+            loss, dl = ops.masked_ce_loss_and_grad(logits, labels, mask)
+        lo = ops._lo_take(dl)
+        assert (lo is not None) == (mode == '3xtf32')
+    finally:
+        ops.set_matmul_precision(old)
+    l2 = logits.double().requires_grad_(True)
+    sel = mask if use_mask else torch.ones(n, dtype=torch.bool, device='cuda')
+    ref = F.cross_entropy(l2[sel], labels[sel])
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    assert dl.shape == (n, C) and _rel(dl, l2.grad) < 2e-6
+    if use_mask:
+        assert (dl[~mask] == 0).all()
+    l3 = logits.clone().requires_grad_(True)
+    ops.masked_cross_entropy(l3, labels, mask).backward()
+    assert torch.equal(dl, l3.grad)                    # same arithmetic as the two-pass kernels
+    if lo is not None:                                 # x = trunc_tf32(x) + lo up to tf32 rounding of lo
+        hi = (dl.view(torch.int32) & ~0x1fff).view(torch.float32)
+        assert ((dl - hi - lo).abs() <= 2.0 ** -10 * (dl - hi).abs() + 1e-45).all()
+    assert dl.stride(0) % 4 == 0 and dl.data_ptr() % 16 == 0       # TMA-addressable, padding zeroed
+    pad = torch.as_strided(dl, (n, dl.stride(0)), (dl.stride(0), 1))[:, C:]
+    assert (pad == 0).all()
+
+
 def test_adam_matches_torch():
     from gist_b200.optim import Adam
     torch.manual_seed(0)
