@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libgist_b200.so')
+# GIST_B200_LIB: an alternative build of the same library (A/B measurements of compile-time knobs)
+LIB_PATH = os.environ.get('GIST_B200_LIB') or os.path.join(_HERE, 'csrc', 'libgist_b200.so')
 
 _c_i32p = ctypes.c_void_p
 _P = ctypes.c_void_p
@@ -44,6 +45,7 @@ SIGNATURES = {
     'gist_gemm_3xtf32': (ctypes.c_int, [_P, _P, _I64, _I64, _I32, _P, _P, _I64, _I64, _I32, _P, _I64, _I32, _I32,
                                         _I32, _P, _U32, _P, _SZ, _P]),
     'gist_split_tf32_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P, _I64, _P]),
+    'gist_split_tf32_multi_f32': (ctypes.c_int, [_I32, _P, _P, _P, _P, _P, _P, _P]),
     'gist_gemm_plan': (ctypes.c_int, [_I32, _I32, _I32, _U32, _I32, _P, _P, _P]),
     'gist_gemm_tn_tf32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _U32, _P]),
     'gist_transpose_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P]),
@@ -75,6 +77,7 @@ SIGNATURES = {
 }
 
 SPMM_RELU, SPMM_NARROW, SPMM_WIDE = 1, 2, 4
+SPMM_BG_SHIFT = 8
 NORM_INV, NORM_RSQRT_CLAMP = 0, 1
 GEMM_RELU, GEMM_NO_SPLITK, GEMM_TILE_N64, GEMM_TILE_N128, GEMM_TILE_N256 = 1, 2, 4, 8, 16
 GEMM_K_MAJOR, GEMM_MN_MAJOR = 0, 1

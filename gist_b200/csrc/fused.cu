@@ -444,7 +444,18 @@ __global__ void __launch_bounds__(256) ce_fused_kernel(const float *__restrict__
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int cnt = 0;
     if (mask) {
-        for (int i = threadIdx.x; i < n; i += 256) cnt += mask[i] != 0;
+        // 32-bit words, all loads of a thread in flight together (a byte-per-iteration loop is a
+        // chain of L2 round trips: measured 11 us for 2.6 k rows)
+        const int head = min(n, (int)((4 - (reinterpret_cast<uintptr_t>(mask) & 3)) & 3));
+        const uint32_t *m4 = reinterpret_cast<const uint32_t *>(mask + head);
+        const int nw = (n - head) >> 2;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < nw; i += 256) {
+            const uint32_t w = __ldg(m4 + i);
+            cnt += ((w & 0xffu) != 0) + ((w & 0xff00u) != 0) + ((w & 0xff0000u) != 0) + ((w & 0xff000000u) != 0);
+        }
+        if ((int)threadIdx.x < head) cnt += mask[threadIdx.x] != 0;
+        for (int i = head + (nw << 2) + threadIdx.x; i < n; i += 256) cnt += mask[i] != 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0) s_cnt[warp] = cnt;

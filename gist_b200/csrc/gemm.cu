@@ -500,6 +500,42 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict
     }
 }
 
+// Several matrices in ONE launch (the weights of a model at the head of a training step: three
+// 2 us launches in a row are three launch latencies on the step's critical path).
+constexpr int kSplitMaxTensors = 16;
+struct SplitTensor {
+    const float *x;
+    float *lo;
+    int64_t ld_x, ld_lo;
+    int32_t rows, cols;
+    int32_t block0;     // first CTA of this tensor
+    int32_t vec4;
+};
+struct SplitArgs {
+    SplitTensor t[kSplitMaxTensors];
+    int32_t n_tensors;
+};
+
+__global__ void __launch_bounds__(256) split_tf32_multi_kernel(const __grid_constant__ SplitArgs a) {
+    int ti = 0;
+#pragma unroll 1
+    for (int k = 1; k < a.n_tensors; ++k)
+        if ((int)blockIdx.x >= a.t[k].block0) ti = k;
+    const SplitTensor &T = a.t[ti];
+    const int per_row = T.vec4 ? (T.cols + 3) >> 2 : T.cols;
+    const int64_t i = (int64_t)(blockIdx.x - T.block0) * 256 + threadIdx.x;
+    if (i >= (int64_t)T.rows * per_row) return;
+    const int r = (int)(i / per_row), c = (int)(i % per_row) * (T.vec4 ? 4 : 1);
+    if (T.vec4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(T.x + (int64_t)r * T.ld_x + c));
+        float4 l;
+        l.x = tf32_lo(v.x); l.y = tf32_lo(v.y); l.z = tf32_lo(v.z); l.w = tf32_lo(v.w);
+        *reinterpret_cast<float4 *>(T.lo + (int64_t)r * T.ld_lo + c) = l;
+    } else {
+        T.lo[(int64_t)r * T.ld_lo + c] = tf32_lo(__ldg(T.x + (int64_t)r * T.ld_x + c));
+    }
+}
+
 // ---------------------------------------------------------------- transpose ----
 __global__ void __launch_bounds__(256) transpose_kernel(const float *__restrict__ src, int64_t ld_src,
                                                         int rows, int cols, float *__restrict__ dst,
@@ -816,6 +852,33 @@ extern "C" int gist_split_tf32_f32(const float *x, int64_t ld_x, int32_t rows, i
     const unsigned grid = (unsigned)((items + 255) / 256);
     if (v4) split_tf32_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, ld_x, rows, cols, hi, ld_hi, lo, ld_lo);
     else split_tf32_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, ld_x, rows, cols, hi, ld_hi, lo, ld_lo);
+    count_launch();
+    return last_error();
+}
+
+extern "C" int gist_split_tf32_multi_f32(int32_t n_tensors, const float *const *x, const int64_t *ld_x,
+                                         const int32_t *rows, const int32_t *cols, float *const *lo,
+                                         const int64_t *ld_lo, gist_stream_t stream) {
+    if (n_tensors < 0 || n_tensors > kSplitMaxTensors) return GIST_ERR_BADARG;
+    if (n_tensors == 0) return GIST_OK;
+    if (!x || !ld_x || !rows || !cols || !lo || !ld_lo) return GIST_ERR_BADARG;
+    SplitArgs a;
+    a.n_tensors = 0;
+    int64_t blocks = 0;
+    for (int i = 0; i < n_tensors; ++i) {
+        if (rows[i] < 0 || cols[i] < 0) return GIST_ERR_BADARG;
+        if (rows[i] == 0 || cols[i] == 0) continue;
+        if (!x[i] || !lo[i] || ld_x[i] < cols[i] || ld_lo[i] < cols[i]) return GIST_ERR_BADARG;
+        SplitTensor &T = a.t[a.n_tensors++];
+        T.x = x[i]; T.lo = lo[i]; T.ld_x = ld_x[i]; T.ld_lo = ld_lo[i]; T.rows = rows[i]; T.cols = cols[i];
+        T.vec4 = aligned(x[i], 16) && aligned(lo[i], 16) && ld_x[i] % 4 == 0 && ld_lo[i] % 4 == 0;
+        T.block0 = (int32_t)blocks;
+        const int per_row = T.vec4 ? (cols[i] + 3) / 4 : cols[i];
+        blocks += ((int64_t)rows[i] * per_row + 255) / 256;
+        if (blocks > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
+    }
+    if (blocks == 0) return GIST_OK;
+    split_tf32_multi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
     count_launch();
     return last_error();
 }

@@ -37,6 +37,7 @@ struct SpmmParams {
     int32_t relu;
     int32_t row_blocks;
     int32_t heavy_deg;  // rows with more edges are split over the whole CTA (INT_MAX = never)
+    int32_t total_blocks;   // EX variants: (row block, chunk) items; the grid may be smaller (background mode)
     // EX variants only (gist_spmm_csr_ex_f32): dropout on the two outputs and their 3xTF32 halves
     float *y_lo;
     int32_t ld_y_lo;
@@ -88,14 +89,17 @@ __device__ __forceinline__ void gather_range(const SpmmParams &p, int eb, int ee
                                              float (&acc)[VPL][VEC]) {
     constexpr int UMAX = (VPL == 1) ? 8 : 4;
     constexpr int U = (LPR < UMAX) ? LPR : UMAX;  // independent gathers in flight per lane
+    // the column indices of block b+1 are requested before block b's gathers are issued, so the
+    // index load of every block but the first is hidden behind a block of feature gathers
+    int u_next = (eb + lg < ee) ? __ldg(p.col + eb + lg) : 0;
     for (int e0 = eb; e0 < ee; e0 += LPR) {
         const int my = e0 + lg;
-        int u_mine = 0;
+        const int u_mine = u_next;
         float s_mine = 0.f;
-        if (my < ee) {
-            u_mine = __ldg(p.col + my);
-            if constexpr (HAS_SS) s_mine = __ldg(p.src_scale + u_mine);
+        if constexpr (HAS_SS) {
+            if (my < ee) s_mine = __ldg(p.src_scale + u_mine);
         }
+        u_next = (my + LPR < ee) ? __ldg(p.col + my + LPR) : 0;
         const int cnt = min(LPR, ee - e0);
         float blk[VPL][VEC];
 #pragma unroll
@@ -241,18 +245,24 @@ spmm_csr_kernel(const SpmmParams p) {
     __shared__ int s_nheavy;
     __shared__ float s_part[COOP ? NGROUPS : 1][COOP ? CHUNK : 1];   // 256*VEC*VPL floats = 1..8 KB
 
+    static_assert(!EX || COOP, "the extended epilogue is launched with cooperative hub rows only");
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int grp = lane / LPR;
     const int lg = lane % LPR;
     const int gid = warp * GPW + grp;             // group index inside the CTA
-    const int chunk = blockIdx.x / p.row_blocks;
-    const int rb = blockIdx.x - chunk * p.row_blocks;
-    const int v = rb * NGROUPS + gid;
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
     const int lane0 = grp * LPR;
     constexpr bool coop = COOP;
     if constexpr (EX) record_drop_step(p);
+    // EX (training-step shapes): the grid may be smaller than the number of (row block, chunk)
+    // items — background mode caps the CTAs resident per SM so a concurrent high-priority branch
+    // always finds free slots — and each CTA then walks the items with a grid stride.
+    unsigned bid = blockIdx.x;
+    while (true) {
+    const int chunk = bid / p.row_blocks;
+    const int rb = bid - chunk * p.row_blocks;
+    const int v = rb * NGROUPS + gid;
 
     int c[VPL];
     bool cv[VPL];
@@ -317,6 +327,14 @@ spmm_csr_kernel(const SpmmParams p) {
         }
         __syncthreads();
     }
+    if constexpr (!EX) {
+        break;
+    } else {
+        bid += gridDim.x;
+        if (bid >= (unsigned)p.total_blocks) break;
+        __syncthreads();        // every thread has read s_nheavy / s_heavy of this item
+    }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -329,8 +347,14 @@ spmm_csr_kernel(const SpmmParams p) {
 // arrives last re-reads ALL partials and adds them in segment order — the sum does not depend on
 // which group happens to be last, so the result is deterministic without a second launch or float
 // atomics — then runs the epilogue and re-arms the counter.
+#ifndef SEG_BATCH
+#define SEG_BATCH 1    // warp items taken per queue fetch
+#endif
+#ifndef SEG_CTAS
+#define SEG_CTAS 3     // resident CTAs per SM of the segment kernel (register budget 64K / (256 * SEG_CTAS))
+#endif
 template <int VEC, int LPR, int VPL, bool HAS_SS, bool EX>
-__global__ void __launch_bounds__(256, 3) spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
+__global__ void __launch_bounds__(256, SEG_CTAS) spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
     constexpr int GPW = 32 / LPR;
     constexpr int CHUNK = LPR * VEC * VPL;
     const int lane = threadIdx.x & 31;
@@ -355,16 +379,29 @@ __global__ void __launch_bounds__(256, 3) spmm_seg_kernel(const __grid_constant_
     const unsigned n_warps = gridDim.x * 8u;
     uint32_t *head = p.seg_count;
     uint32_t *arrivals = p.seg_count + 1;
+    // Every warp's FIRST item is its own index — no fetch: at launch all W warps would otherwise
+    // queue on one address (same-address atomics are served one at a time by their L2 slice) —
+    // and the queue hands out items W, W + 1, ...  A fetch takes SEG_BATCH consecutive items
+    // (1: measured 4 -> 40 us, 16 -> 108 us vs 23 us; the tail of a batch outweighs the atomics).
+    const unsigned q_total = total > n_warps ? total - n_warps : 0u;                     // items behind the queue
+    const unsigned q_total_b = (q_total + SEG_BATCH - 1u) / SEG_BATCH * SEG_BATCH;
+    unsigned work = blockIdx.x * 8u + (threadIdx.x >> 5), work_end = work + 1u;
+    if (work >= total) work_end = work;                  // fewer items than warps: straight to the failing fetch
     while (true) {
-        unsigned work = 0;
-        if (lane == 0) work = atomicAdd(head, 1u);
-        work = __shfl_sync(0xffffffffu, work, 0);
-        if (work >= total) {
-            if (work == total + n_warps - 1u && lane == 0) *head = 0u;
-            break;
+        if (work == work_end) {
+            if (lane == 0) work = atomicAdd(head, (unsigned)SEG_BATCH);
+            work = __shfl_sync(0xffffffffu, work, 0);
+            if (work >= q_total) {
+                // W failing fetches follow the last successful one; the last of them re-arms the head
+                if (work == q_total_b + (n_warps - 1u) * SEG_BATCH && lane == 0) *head = 0u;
+                break;
+            }
+            work_end = min(work + SEG_BATCH, q_total) + n_warps;
+            work += n_warps;
         }
-        const int chunk = (int)work / wipc;
-        const int seg = ((int)work - chunk * wipc) * GPW + grp;
+        const unsigned item = work++;
+        const int chunk = (int)item / wipc;
+        const int seg = ((int)item - chunk * wipc) * GPW + grp;
         if (seg >= n_seg) continue;                        // whole group skips together
 
         int c[VPL];
@@ -408,24 +445,36 @@ __global__ void __launch_bounds__(256, 3) spmm_seg_kernel(const __grid_constant_
         for (int k = 0; k < VPL; ++k)
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[k][i] = 0.f;
-        for (int j = 0; j < nseg; ++j) {                   // fixed order: segment 0, 1, 2, ...
-            const float *part = p.seg_ws + (int64_t)(s0 + j) * p.ld_ws;
+        // fixed order: segment 0, 1, 2, ...; four partial rows are requested before the first is
+        // added (a hub row has tens of segments and this is the tail of the launch; a missing one
+        // contributes +0, which changes nothing)
+        for (int j = 0; j < nseg; j += 4) {
+            float t[4][VPL][VEC];
 #pragma unroll
-            for (int k = 0; k < VPL; ++k) {
-                if (!cv[k]) continue;
-                float t[VEC];
-                if constexpr (VEC == 4) {
-                    const float4 q = __ldcg(reinterpret_cast<const float4 *>(part + c[k]));   // L2: other SMs wrote it
-                    t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
-                } else if constexpr (VEC == 2) {
-                    const float2 q = __ldcg(reinterpret_cast<const float2 *>(part + c[k]));
-                    t[0] = q.x; t[1] = q.y;
-                } else {
-                    t[0] = __ldcg(part + c[k]);
+            for (int q = 0; q < 4; ++q) {
+                const float *part = p.seg_ws + (int64_t)(s0 + min(j + q, nseg - 1)) * p.ld_ws;
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) t[q][k][i] = 0.f;
+                    if (!cv[k] || j + q >= nseg) continue;
+                    if constexpr (VEC == 4) {
+                        const float4 w = __ldcg(reinterpret_cast<const float4 *>(part + c[k]));   // L2: other SMs wrote it
+                        t[q][k][0] = w.x; t[q][k][1] = w.y; t[q][k][2] = w.z; t[q][k][3] = w.w;
+                    } else if constexpr (VEC == 2) {
+                        const float2 w = __ldcg(reinterpret_cast<const float2 *>(part + c[k]));
+                        t[q][k][0] = w.x; t[q][k][1] = w.y;
+                    } else {
+                        t[q][k][0] = __ldcg(part + c[k]);
+                    }
                 }
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) acc[k][i] += t[i];
             }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int k = 0; k < VPL; ++k)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) acc[k][i] += t[q][k][i];
         }
         epilogue<VEC, VPL, EX>(p, v, c, cv, acc);
     }
@@ -440,8 +489,8 @@ static int launch_spmm_seg(const SpmmParams &p0, int64_t max_segments, cudaStrea
     const int64_t max_work = ceil_div64(max_segments, GPW) * ceil_div64(p.d, CHUNK);     // warp items
     if (max_work <= 0) return GIST_OK;
     if (max_work > 0x3fffffffLL) return GIST_ERR_UNSUPPORTED;
-    // resident CTAs only (3 per SM by the launch bounds); their warps pull from the device-side queue
-    int64_t grid = 3LL * kNumSMs;
+    // resident CTAs only (SEG_CTAS per SM by the launch bounds); their warps pull from the device-side queue
+    int64_t grid = (int64_t)SEG_CTAS * kNumSMs;
     if (grid > ceil_div64(max_work, 8)) grid = ceil_div64(max_work, 8);
     p.seg_blocks = 0;
     const bool ex = p.y_lo || p.self_lo || p.drop.p != 0.f;
@@ -483,7 +532,7 @@ __global__ void seg_fill_kernel(const int32_t *__restrict__ seg_ptr, int32_t n, 
 }
 
 template <int VEC, int LPR, int VPL>
-static int launch_spmm(const SpmmParams &p0, cudaStream_t stream) {
+static int launch_spmm(const SpmmParams &p0, cudaStream_t stream, int bg_ctas_per_sm = 0) {
     SpmmParams p = p0;
     constexpr int ROWS_PER_BLOCK = 8 * (32 / LPR);
     constexpr int CHUNK = LPR * VEC * VPL;
@@ -493,13 +542,16 @@ static int launch_spmm(const SpmmParams &p0, cudaStream_t stream) {
     if (grid <= 0) return GIST_OK;
     if (grid > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
     p.row_blocks = (int32_t)row_blocks;
+    p.total_blocks = (int32_t)grid;
     const bool coop = p.heavy_deg != 0x7fffffff;
     if (p.y_lo || p.self_lo || p.drop.p != 0.f) {
         // extended epilogue (dropout / 3xTF32 halves): the training-step shapes only — rows are
         // scarce there, so always the CTA-cooperative variant
         if (!coop) p.heavy_deg = 128;
-        if (p.src_scale) spmm_csr_kernel<VEC, LPR, VPL, true, true, true><<<(unsigned)grid, 256, 0, stream>>>(p);
-        else spmm_csr_kernel<VEC, LPR, VPL, false, true, true><<<(unsigned)grid, 256, 0, stream>>>(p);
+        int64_t g2 = grid;
+        if (bg_ctas_per_sm > 0 && g2 > (int64_t)bg_ctas_per_sm * kNumSMs) g2 = (int64_t)bg_ctas_per_sm * kNumSMs;
+        if (p.src_scale) spmm_csr_kernel<VEC, LPR, VPL, true, true, true><<<(unsigned)g2, 256, 0, stream>>>(p);
+        else spmm_csr_kernel<VEC, LPR, VPL, false, true, true><<<(unsigned)g2, 256, 0, stream>>>(p);
         count_launch();
         return last_error();
     }
@@ -517,10 +569,11 @@ static int launch_spmm(const SpmmParams &p0, cudaStream_t stream) {
 template <int VEC>
 static int dispatch_lanes(const SpmmParams &p, uint32_t flags, int32_t n_src, cudaStream_t stream) {
     const int lanes = (p.d + VEC - 1) / VEC;
-    if (lanes <= 4) return launch_spmm<VEC, 4, 1>(p, stream);
-    if (lanes <= 8) return launch_spmm<VEC, 8, 1>(p, stream);
-    if (lanes <= 16) return launch_spmm<VEC, 16, 1>(p, stream);
-    if (lanes <= 32) return launch_spmm<VEC, 32, 1>(p, stream);
+    const int bg = (int)((flags >> GIST_SPMM_BG_SHIFT) & 15u);
+    if (lanes <= 4) return launch_spmm<VEC, 4, 1>(p, stream, bg);
+    if (lanes <= 8) return launch_spmm<VEC, 8, 1>(p, stream, bg);
+    if (lanes <= 16) return launch_spmm<VEC, 16, 1>(p, stream, bg);
+    if (lanes <= 32) return launch_spmm<VEC, 32, 1>(p, stream, bg);
     bool wide;
     if (flags & GIST_SPMM_NARROW) wide = false;
     else if (flags & GIST_SPMM_WIDE) wide = true;
@@ -532,7 +585,7 @@ static int dispatch_lanes(const SpmmParams &p, uint32_t flags, int32_t n_src, cu
         const int64_t warps_wide = (int64_t)p.n_dst * ((lanes + 63) / 64);
         wide = lanes >= 64 && warps_wide >= 4LL * kNumSMs * 64 && src_bytes <= (64LL << 20);
     }
-    return wide ? launch_spmm<VEC, 32, 2>(p, stream) : launch_spmm<VEC, 32, 1>(p, stream);
+    return wide ? launch_spmm<VEC, 32, 2>(p, stream, bg) : launch_spmm<VEC, 32, 1>(p, stream, bg);
 }
 
 static bool vec_ok(int vec, const SpmmParams &p) {
@@ -596,6 +649,7 @@ extern "C" int gist_spmm_csr_ex_f32(const int32_t *rowptr, const int32_t *col, i
     p.addend = addend; p.ld_add = (int32_t)ld_addend; p.self_out = self_out; p.ld_self = (int32_t)ld_self;
     p.relu = (flags & GIST_SPMM_RELU) ? 1 : 0;
     p.row_blocks = 0;
+    p.total_blocks = 0;
     p.y_lo = p.self_lo = nullptr;
     p.ld_y_lo = p.ld_self_lo = p.col0_y = p.col0_self = 0;
     make_drop_params(nullptr, &p.drop);

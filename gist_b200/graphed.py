@@ -26,6 +26,8 @@ dispatch (cluster_gcn/sampler.py:92, cluster_gcn_ist_distrib.py:398-404).
 
 Callers: bench.py and the trainers; mirrors cluster_gcn_ist_distrib.py:398-417.
 """
+import os
+
 import torch
 
 from . import ops
@@ -33,6 +35,10 @@ from .modules import GCN as _SageGCN, SAGE_PRE0
 from .train import loss_and_backward, make_optimizer
 
 _KEYS = ('feat', 'label', 'train_mask')
+# resident CTAs per SM the next batch's layer-0 aggregation may take while the current batch trains
+# (0 = no cap); A/B switches for the measurements in profiles/
+PREP_CTAS_PER_SM = int(os.environ.get('GIST_PREP_CTAS', '0'))
+TRAIN_FIRST = os.environ.get('GIST_TRAIN_FIRST', '0') != '0'
 
 
 class GraphedClusterTrainer:
@@ -123,7 +129,7 @@ class GraphedClusterTrainer:
             # (row-per-warp kernel here: in the shadow of the training branch the balanced kernel's
             # resident-CTA grid only competes with it — measured 0.281 vs 0.299 ms/step)
             sg._cache[SAGE_PRE0] = self.model.layers[0].prepare_input(sg, sg.ndata['feat'], out=prev,
-                                                                     balanced=False)
+                                                                     balanced=False, background=PREP_CTAS_PER_SM)
         return sg
 
     def _train(self, cluster, loss_out):
@@ -140,8 +146,8 @@ class GraphedClusterTrainer:
         params = list(self.model.parameters())
         saved = [p.detach().clone() for p in params]
         self.model.train()
-        # the dropout clock (ops.DropoutState) is advanced by one node at the head of every
-        # captured step, BEFORE the build / train branches fork, so both read a stable value
+        # the dropout clock (ops.DropoutState) is advanced by one node per captured step, outside
+        # the region where the build / train branches run, so both read a stable value
         clock = ops.dropout_state(self.dev)
         auto_tick, clock.auto_tick = clock.auto_tick, False
         try:
@@ -159,7 +165,15 @@ class GraphedClusterTrainer:
         main = torch.cuda.current_stream(self.dev)
         self._upload(0)                                  # batch 0
         main.wait_event(self._ev_ids[0])
-        s = torch.cuda.Stream(device=self.dev)
+        # the training branch is captured on a high-priority stream and the preparation
+        # branch on a low-priority one: kernel nodes inherit the priority, so when both have
+        # CTAs pending (the d = 602 aggregation of the next batch floods the chip) the block
+        # scheduler serves the critical path first and the preparation fills the gaps.
+        # The warm-up runs on the SAME stream as the capture: per-stream state the kernels keep
+        # zeroed (queue heads, arrival counters) is then created here, eagerly, and not as fill
+        # nodes at the head of every replayed step.
+        lo_p, hi_p = torch.cuda.Stream.priority_range()
+        s = torch.cuda.Stream(device=self.dev, priority=hi_p) if self.pipeline else torch.cuda.Stream(device=self.dev)
         s.wait_stream(main)
         with torch.cuda.stream(s):
             for _ in range(3):
@@ -170,32 +184,40 @@ class GraphedClusterTrainer:
         self.graphs = []
         if self.pipeline:
             # prologue: batch 0 is built eagerly into buffer set 0; graph j trains on set j and
-            # builds the NEXT batch (ids staged in nids[j] before the replay) into set 1 - j
+            # builds the NEXT batch (ids staged in nids[j] before the replay) into set 1 - j.
+            # The dropout clock is advanced by the LAST node of every step (after the branches
+            # join), for the next one: both branches are then roots of the graph and start with
+            # the launch — with the tick as their common parent the training branch's first kernel
+            # started ~8 us late at every replay (cross-branch dependency resolution).
             clock.tick()
             self.clusters[0] = self._build(self.nids[0].clone())
+            clock.tick()                                 # the value step 0 runs with
             torch.cuda.synchronize(self.dev)
             # Each graph captures into its OWN memory pool.  Persistent state is created inside the
             # captures (buffer set 1, its segment schedule, counters, prepared layer-0 input); in a
             # shared pool the second capture would place such tensors on memory the first graph
             # still uses for its temporaries at every replay.
-            # the training branch is captured on a high-priority stream and the preparation
-            # branch on a low-priority one: kernel nodes inherit the priority, so when both have
-            # CTAs pending (the d = 602 aggregation of the next batch floods the chip) the block
-            # scheduler serves the critical path first and the preparation fills the gaps
-            lo_p, hi_p = torch.cuda.Stream.priority_range()
-            train_stream = torch.cuda.Stream(device=self.dev, priority=hi_p)
+            train_stream = s
             for j in (0, 1):
                 gph = torch.cuda.CUDAGraph()
                 side = torch.cuda.Stream(device=self.dev, priority=lo_p)
                 l0 = _lib.launch_count()
                 with torch.cuda.graph(gph, stream=train_stream):
                     cap_main = torch.cuda.current_stream(self.dev)
-                    clock.tick()
                     side.wait_stream(cap_main)
-                    with torch.cuda.stream(side):
-                        self.clusters[1 - j] = self._build(self.nids[j], out=self.clusters[1 - j])
+
+                    def prepare():
+                        with torch.cuda.stream(side):
+                            self.clusters[1 - j] = self._build(self.nids[j], out=self.clusters[1 - j])
+                    # the training branch's nodes are created first: a replay hands its nodes to
+                    # the GPU in creation order, a few microseconds apart at the head of the graph
+                    if not TRAIN_FIRST:
+                        prepare()
                     self._train(self.clusters[j], self.loss[j])
+                    if TRAIN_FIRST:
+                        prepare()
                     cap_main.wait_stream(side)
+                    clock.tick()
                 self.gist_launches_per_step = _lib.launch_count() - l0
                 self.graphs.append(gph)
         else:

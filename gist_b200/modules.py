@@ -236,11 +236,12 @@ class ISTSAGELayer(nn.Module):
     def _p_drop(self):
         return float(self.dropout.p) if (self.dropout and self.training) else 0.0
 
-    def prepare_input(self, g, h, out=None, balanced=True):
+    def prepare_input(self, g, h, out=None, balanced=True, background=0):
         """z = dropout([h ‖ (A h) / in_deg]) (+ its 3xTF32 low half) for this layer, outside
         autograd — the pipelined trainer runs it for the NEXT batch's input features while the
         current batch trains (they do not depend on the weights and need no gradient)."""
-        return ops.sage_prepare(g, h, self._p_drop(), self._drop_stream, out=out, balanced=balanced)
+        return ops.sage_prepare(g, h, self._p_drop(), self._drop_stream, out=out, balanced=balanced,
+                                background=background)
 
     def forward(self, g, h, pre=None):
         # pre: this layer's prepared input for (g, h) (prepare_input), if already computed
@@ -345,8 +346,16 @@ class GCN(nn.Module):
             st = ops.dropout_state(h.device)
             if st.auto_tick:
                 st.tick()                   # one dropout step per training forward
-        for i, layer in enumerate(self.layers):
-            h = layer(g, h, pre=pre0) if (i == 0 and pre0 is not None) else layer(g, h)
+        if (h.is_cuda and ops.get_matmul_precision() == '3xtf32'
+                and (torch.is_grad_enabled() or self.training)):
+            # every layer's weight low half in one launch at the head of the step, instead of one
+            # small launch in front of each layer's GEMM (consumed by ops._weight_lo)
+            ops.presplit_weights([layer.linear.weight for layer in self.layers])
+        try:
+            for i, layer in enumerate(self.layers):
+                h = layer(g, h, pre=pre0) if (i == 0 and pre0 is not None) else layer(g, h)
+        finally:
+            ops.clear_presplit()            # the low halves are valid for this forward only
         return h
 
 

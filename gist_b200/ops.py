@@ -94,7 +94,12 @@ class SegSchedule:
         dev = rowptr.device
         self.seg_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
         self.seg_row = torch.empty(self.max_segments, dtype=torch.int32, device=dev)
-        self._counters = {}
+        # work-queue head + arrival counters (zeroed once; the kernel leaves them zero).  The first
+        # stream that launches on this schedule owns the set allocated here; any other stream gets
+        # its own (see counters()).  Sized for the widest scheduled launch (d <= 384: 12 chunks).
+        self._counters = torch.zeros(1 + 12 * max(n, 1), dtype=torch.int32, device=dev)
+        self._owner = None
+        self._others = {}
         self.rebuild(rowptr)
 
     def rebuild(self, rowptr):
@@ -110,13 +115,21 @@ class SegSchedule:
         """Zeroed work-queue head + arrival counters for `chunks` feature chunks (the kernel leaves
         them zero).  One set PER STREAM: launches on one stream are ordered, but the same structure
         is aggregated concurrently from parallel streams / graph branches (the m sub-networks of
-        train_ist share the graph), and two running launches must never share a queue head."""
+        train_ist share the graph), and two running launches must never share a queue head.  The
+        owner stream's set exists from construction, so a schedule first used inside a CUDA-graph
+        capture adds no fill node to the captured step."""
         need = 1 + chunks * max(self.n, 1)
         dev = self.seg_ptr.device
         key = torch.cuda.current_stream(dev).cuda_stream
-        cnt = self._counters.get(key)
+        if self._owner is None:
+            self._owner = key
+        if key == self._owner:
+            if self._counters.numel() < need:
+                self._counters = torch.zeros(need, dtype=torch.int32, device=dev)
+            return self._counters
+        cnt = self._others.get(key)
         if cnt is None or cnt.numel() < need:
-            cnt = self._counters[key] = torch.zeros(need, dtype=torch.int32, device=dev)
+            cnt = self._others[key] = torch.zeros(need, dtype=torch.int32, device=dev)
         return cnt
 
 
@@ -268,17 +281,20 @@ def sage_concat(g, h):
     return _SageConcat.apply(g, h)
 
 
-def sage_concat_into(g, h, out, out_lo=None, drop=None, balanced=True):
+def sage_concat_into(g, h, out, out_lo=None, drop=None, balanced=True, background=0):
     """No-grad z = [h ‖ (A h) / in_deg] into a caller-owned [n, 2d] buffer; optionally with the
     layer's dropout applied as z is written (``drop``) and z's 3xTF32 low half (``out_lo``).
-    ``balanced``: use the segment-scheduled kernel when the graph has a schedule."""
+    ``balanced``: use the segment-scheduled kernel when the graph has a schedule.
+    ``background`` (1..15, row-per-group kernel with an extended epilogue only): at most that many
+    CTAs per SM (GIST_SPMM_BG_SHIFT), for a launch that runs beside a latency-critical branch."""
     h = _mat(h, 'h')
     n, d = h.shape
     assert out.shape == (n, 2 * d) and out.dtype == torch.float32 and out.stride(1) == 1
     spmm_raw(g.rowptr, g.col_buffer, n, n, h, out[:, d:], dst_scale=g.inv_in_degree(), self_out=out[:, :d],
              out_lo=out_lo[:, d:] if out_lo is not None else None,
              self_lo=out_lo[:, :d] if out_lo is not None else None,
-             drop=drop, drop_col0_out=d, drop_col0_self=0, schedule=g.seg_schedule() if balanced else None)
+             drop=drop, drop_col0_out=d, drop_col0_self=0, schedule=g.seg_schedule() if balanced else None,
+             flags=(int(background) & 15) << _lib.SPMM_BG_SHIFT)
     return out
 
 
@@ -296,7 +312,7 @@ class SagePre:
         self.z, self.z_lo, self.step_saved, self.dropped = z, z_lo, step_saved, dropped
 
 
-def sage_prepare(g, h, p_drop, stream_id, out=None, balanced=True):
+def sage_prepare(g, h, p_drop, stream_id, out=None, balanced=True, background=0):
     """Aggregation + concat (+ dropout, + 3xTF32 split) of a SAGE layer's input, no autograd.
     ``out``: a SagePre of the same shape to overwrite in place."""
     h = _mat(h, 'h')
@@ -308,7 +324,7 @@ def sage_prepare(g, h, p_drop, stream_id, out=None, balanced=True):
         saved = torch.empty(1, dtype=torch.int64, device=h.device) if p_drop else None   # K1 writes it
         out = SagePre(z, z_lo, saved, bool(p_drop))
     desc = dropout_state(h.device).desc(p_drop, stream_id, step_saved=out.step_saved) if p_drop else None
-    sage_concat_into(g, h, out.z, out.z_lo, desc, balanced=balanced)
+    sage_concat_into(g, h, out.z, out.z_lo, desc, balanced=balanced, background=background)
     return out
 
 
@@ -388,10 +404,25 @@ def _lo_take(t):
 
 
 def presplit_weights(params):
-    """Split every 2-D fp32 parameter once (3xTF32 mode) so the layers find W_lo ready."""
-    for p in params:
-        if p.dim() == 2 and p.is_cuda and _tma_ok(p.data):
-            _WEIGHT_LO[p.data_ptr()] = (p, split_tf32(p.data))
+    """3xTF32 low halves of every TMA-addressable 2-D fp32 tensor in ``params`` with ONE launch
+    (gist_split_tf32_multi_f32), left for the layers to pick up: each entry is consumed by the first
+    _weight_lo() of that tensor, so nothing outlives the forward pass that asked for it."""
+    _WEIGHT_LO.clear()
+    ws = [p.data if isinstance(p, torch.nn.Parameter) else p for p in params]
+    ws = [w for w in ws if w.dim() == 2 and w.numel() > 0 and _tma_ok(w)][:16]
+    if not ws:
+        return
+    n = len(ws)
+    los = [_padded_empty(w.shape[0], w.shape[1], w.device) for w in ws]
+    X, LO = (ctypes.c_void_p * n)(), (ctypes.c_void_p * n)()
+    LDX, LDL = (ctypes.c_int64 * n)(), (ctypes.c_int64 * n)()
+    R, C = (ctypes.c_int32 * n)(), (ctypes.c_int32 * n)()
+    for i, (w, lo) in enumerate(zip(ws, los)):
+        X[i], LO[i], LDX[i], LDL[i], R[i], C[i] = w.data_ptr(), lo.data_ptr(), _ld(w), _ld(lo), w.shape[0], w.shape[1]
+    check(_lib.load().gist_split_tf32_multi_f32(n, X, LDX, R, C, LO, LDL, stream_ptr(ws[0].device)),
+          'split_tf32_multi_f32')
+    for w, lo in zip(ws, los):
+        _WEIGHT_LO[w.data_ptr()] = (w, lo)
 
 
 def clear_presplit():
@@ -399,8 +430,8 @@ def clear_presplit():
 
 
 def _weight_lo(Wv):
-    e = _WEIGHT_LO.get(Wv.data_ptr())
-    if e is not None and e[1].shape == Wv.shape:
+    e = _WEIGHT_LO.pop(Wv.data_ptr(), None)
+    if e is not None and e[1].shape == Wv.shape and e[0].stride() == Wv.stride():
         return e[1]
     return split_tf32(Wv)
 

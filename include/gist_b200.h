@@ -62,6 +62,11 @@ typedef struct gist_dropout {
 #define GIST_SPMM_WIDE 4u        /* force 2 vectors / lane                        */
 #define GIST_SPMM_COOP_ON 8u     /* force CTA-cooperative hub rows (row split)    */
 #define GIST_SPMM_COOP_OFF 16u   /* never split rows (default: on iff n_dst<=32k) */
+/* bits 8..11: background mode for gist_spmm_csr_ex_f32's extended epilogue (0 = off): at most
+ * this many CTAs per SM are launched and walk the work with a grid stride, so a kernel that runs
+ * in the shadow of a latency-critical branch (the next batch's layer-0 aggregation beside the
+ * training step) never occupies every register file / warp slot of the chip. */
+#define GIST_SPMM_BG_SHIFT 8
 
 /* modes of gist_degree_norm_f32 */
 #define GIST_NORM_INV 0       /* 1/deg, deg==0 -> 0   (ISTSAGELayer.get_norm, cluster_gcn/modules.py:239-243) */
@@ -305,6 +310,12 @@ int gist_gemm_dropmask_f32(const float *A, const float *A_lo, int64_t lda, int64
  * (x with its 13 low mantissa bits cleared) for a [rows, cols] row-major matrix. */
 int gist_split_tf32_f32(const float *x, int64_t ld_x, int32_t rows, int32_t cols, float *hi, int64_t ld_hi,
                         float *lo, int64_t ld_lo, gist_stream_t stream);
+
+/* gist_split_tf32_f32 (lo only) for up to 16 matrices in one launch: the weights of every layer at
+ * the head of a training step (nn.Linear weights of cluster_gcn/modules.py:191-211). */
+int gist_split_tf32_multi_f32(int32_t n_tensors, const float *const *x, const int64_t *ld_x,
+                              const int32_t *rows, const int32_t *cols, float *const *lo,
+                              const int64_t *ld_lo, gist_stream_t stream);
 
 /* dst[c, r] = src[r, c] for a [rows, cols] row-major matrix (dst is [cols, rows]). */
 int gist_transpose_f32(const float *src, int64_t ld_src, int32_t rows, int32_t cols, float *dst,

@@ -87,6 +87,32 @@ def test_sage_prepare_matches_composed(d):
     assert torch.equal(pre0.z, z_plain) and not pre0.dropped and pre0.step_saved is None
 
 
+@pytest.mark.parametrize('background', [1, 2, 5])
+@pytest.mark.parametrize('n,nnz,d', [(700, 9000, 602), (5000, 200000, 256), (40, 300, 7)])
+def test_sage_prepare_background_mode_is_bit_identical(n, nnz, d, background):
+    """Background mode (GIST_SPMM_BG_SHIFT: a capped grid walking the work with a grid stride, used
+    for the next batch's layer-0 aggregation beside the training branch) computes exactly what the
+    one-CTA-per-item launch computes — including hub rows split over the CTA."""
+    from gist_b200 import GistGraph, ops
+    src, dst = random_graph(n, nnz, seed=n + d)
+    torch.manual_seed(d)
+    hub_src = torch.randint(0, n, (min(4 * n, 3000),), dtype=src.dtype)      # rows 0 and n-1: hub rows
+    src = torch.cat((src, hub_src, hub_src))
+    dst = torch.cat((dst, torch.zeros_like(hub_src), torch.full_like(hub_src, n - 1)))
+    g = GistGraph.from_edges(src, dst, n, device='cuda')
+    h = torch.randn(n, d, device='cuda')
+    ops.set_matmul_precision('3xtf32')
+    try:
+        ref = ops.sage_prepare(g, h, 0.3, 4, balanced=False)
+        got = ops.sage_prepare(g, h, 0.3, 4, balanced=False, background=background)
+        again = ops.sage_prepare(g, h, 0.3, 4, balanced=False, background=background, out=got)
+    finally:
+        ops.set_matmul_precision('fp32')
+    assert again is got
+    assert torch.equal(got.z, ref.z) and torch.equal(got.z_lo, ref.z_lo)
+    assert torch.equal(got.step_saved, ref.step_saved)
+
+
 @pytest.mark.parametrize('x3', [False, True])
 @pytest.mark.parametrize('shape', [(700, 512, 256), (300, 70, 100), (1000, 1204, 32)])
 def test_gemm_dropmask_matches_masked_gemm(shape, x3):

@@ -81,7 +81,7 @@ def test_masked_cross_entropy(n, C, use_mask):
 
 @pytest.mark.parametrize('mode', ['fp32', '3xtf32'])
 @pytest.mark.parametrize('n,C', [(2586, 41), (1000, 47), (17, 3), (5000, 7), (300, 1000), (1, 5)])
-@pytest.mark.parametrize('use_mask', [True, False])
+@pytest.mark.parametrize('use_mask', [True, False, 1, 3])      # 1, 3: mask at a byte offset (unaligned words)
 def test_masked_ce_loss_and_grad_one_launch(n, C, use_mask, mode):
     """The trainers' fused loss + gradient seed (ops.masked_ce_loss_and_grad) against fp64 torch and
     against the two-pass autograd op; repeated launches reuse the arrival counter (left at zero)."""
@@ -89,9 +89,11 @@ def test_masked_ce_loss_and_grad_one_launch(n, C, use_mask, mode):
     torch.manual_seed(n + C)
     logits = torch.randn(n, C, device='cuda') * 4
     labels = torch.randint(0, C, (n,), device='cuda')
-    mask = (torch.rand(n, device='cuda') < 0.6) if use_mask else None
+    mask = (torch.rand(n + 3, device='cuda') < 0.6)[int(use_mask) % 4 if use_mask is not True else 0:][:n] \
+        if use_mask else None
     if use_mask:
         mask[0] = True
+        assert mask.is_contiguous() and mask.data_ptr() % 4 == (0 if use_mask is True else use_mask)
     old = ops.get_matmul_precision()
     ops.set_matmul_precision(mode)
     try:
