@@ -314,6 +314,16 @@ def run_gist(a):
 
     steps_per_epoch = psize // a.batch_size
 
+    # Round-boundary warm-up on a throwaway wrapper: the first sync / re-dispatch of a process pays
+    # one-off costs (NCCL's first all-gather sets up its channels, the slice kernels' module loads)
+    # that otherwise land inside whichever timed region reaches step `iter_per_site` first.
+    _, w0 = fresh('epoch')
+    w0.inplace_dispatch = True
+    w0.sync_model()
+    w0.dispatch_model()
+    torch.cuda.synchronize()
+    del w0
+
     # ---- device-resident arm: node-id lists already in HBM, no loss readback -------
     it, w = fresh('epoch')
     LoopT = GraphLoop if a.mode == 'graph' else Loop
