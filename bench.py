@@ -394,7 +394,7 @@ def run_gist(a):
         traffic, traffic_src = tj['traffic_bytes_per_launch'], 'profiles/r1_spmm_step_traffic.json: ' + tj['source']
     achieved = alg_b / 1e9 / (spmm_ms / 1e3) if spmm_ms > 0 else 0.0
     roofline = {
-        'bound': 'hbm', 'kernel': 'spmm_csr_kernel (all %d launches/step, fwd + transpose)' % (len(prof) // max(prof_steps, 1)),
+        'bound': 'hbm', 'kernel': 'spmm_seg_kernel + spmm_csr_kernel (all %d SpMM launches/step, fwd + transpose)' % (len(prof) // max(prof_steps, 1)),
         'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4),
         'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
         'bytes_per_launch': round(alg_b / n_l), 'compulsory_bytes_per_launch': round(comp_b / n_l),
