@@ -355,6 +355,9 @@ def run_gist(a):
     ops.SPMM_PROFILE = []
     ops.GEMM_PROFILE = []
     ops.GAT_PROFILE = []
+    # every kernel alone on one stream: with the weight-gradient branch on its side stream the
+    # event pairs would time a launch together with whatever GEMM happens to run beside it
+    overlap, ops.OVERLAP_WEIGHT_GRADS = ops.OVERLAP_WEIGHT_GRADS, False
     step_evs = []
     torch.cuda.synchronize()
     for _ in range(prof_steps):
@@ -365,6 +368,7 @@ def run_gist(a):
         s1.record()
         step_evs.append((s0, s1))
         torch.cuda.synchronize()
+    ops.OVERLAP_WEIGHT_GRADS = overlap
     prof, ops.SPMM_PROFILE = ops.SPMM_PROFILE, None
     gprof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
     aprof, ops.GAT_PROFILE = ops.GAT_PROFILE, None
