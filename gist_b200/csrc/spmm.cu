@@ -89,6 +89,12 @@ __device__ __forceinline__ void gather_range(const SpmmParams &p, int eb, int ee
                                              float (&acc)[VPL][VEC]) {
     constexpr int UMAX = (VPL == 1) ? 8 : 4;
     constexpr int U = (LPR < UMAX) ? LPR : UMAX;  // independent gathers in flight per lane
+    // lanes past the end of the row (the last chunk's tail) gather column 0 instead of being
+    // predicated off: their sums are never stored (every store checks cv), and the gathers of the
+    // whole group stay free of per-lane predicates
+    int cs[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) cs[k] = cv[k] ? c[k] : 0;
     // the column indices of block b+1 are requested before block b's gathers are issued, so the
     // index load of every block but the first is hidden behind a block of feature gathers
     int u_next = (eb + lg < ee) ? __ldg(p.col + eb + lg) : 0;
@@ -109,19 +115,31 @@ __device__ __forceinline__ void gather_range(const SpmmParams &p, int eb, int ee
         for (int j = 0; j < cnt; j += U) {
             float x[U][VPL][VEC];
             float s[U];
+            if (j + U <= cnt) {
+                // full round (the common case): U unpredicated gathers, nothing to zero-fill
 #pragma unroll
-            for (int jj = 0; jj < U; ++jj) {
-                const int u = __shfl_sync(gmask, u_mine, lane0 + j + jj);
-                if constexpr (HAS_SS) s[jj] = __shfl_sync(gmask, s_mine, lane0 + j + jj);
-                const bool ok = (j + jj) < cnt;
-                const float *xr = p.X + (int64_t)u * p.ldx;
+                for (int jj = 0; jj < U; ++jj) {
+                    const int u = __shfl_sync(gmask, u_mine, lane0 + j + jj);
+                    if constexpr (HAS_SS) s[jj] = __shfl_sync(gmask, s_mine, lane0 + j + jj);
+                    const float *xr = p.X + (int64_t)u * p.ldx;
 #pragma unroll
-                for (int k = 0; k < VPL; ++k) {
-                    if (ok && cv[k]) {
-                        ld_vec<VEC>(x[jj][k], xr + c[k]);
-                    } else {
+                    for (int k = 0; k < VPL; ++k) ld_vec<VEC>(x[jj][k], xr + cs[k]);
+                }
+            } else {
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i) x[jj][k][i] = 0.f;
+                for (int jj = 0; jj < U; ++jj) {
+                    const int u = __shfl_sync(gmask, u_mine, lane0 + j + jj);
+                    if constexpr (HAS_SS) s[jj] = __shfl_sync(gmask, s_mine, lane0 + j + jj);
+                    const bool ok = (j + jj) < cnt;
+                    const float *xr = p.X + (int64_t)u * p.ldx;
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) {
+                        if (ok) {
+                            ld_vec<VEC>(x[jj][k], xr + cs[k]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) x[jj][k][i] = 0.f;
+                        }
                     }
                 }
             }
@@ -227,7 +245,7 @@ __device__ __forceinline__ void epilogue(const SpmmParams &p, int v, const int (
 // variants are gather-latency bound and live on occupancy (40 regs -> 6 CTAs = 48 warps).
 template <int VEC, int VPL, bool HAS_SS, bool COOP>
 constexpr int min_ctas() {
-    if (COOP) return 2;
+    if (COOP) return VEC * VPL <= 2 ? 4 : (VEC * VPL <= 4 ? 3 : 2);   // cluster batches: short rows live on warps in flight too
     if (VEC * VPL <= 2) return HAS_SS ? 4 : 6;
     if (VEC * VPL <= 4) return 4;
     return 3;
