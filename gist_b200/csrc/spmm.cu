@@ -83,7 +83,7 @@ __device__ __forceinline__ void st_vec(float *p, const float (&r)[VEC]) {
 // Two-level summation: every block of <= LPR edges is summed on its own and then added
 // to the running total, which keeps the fp32 rounding error of hub rows (10^4 edges)
 // ~sqrt(LPR) lower than one long chain, at the cost of VPL*VEC adds per block.
-template <int VEC, int LPR, int VPL, bool HAS_SS>
+template <int VEC, int LPR, int VPL, bool HAS_SS, bool PACK = true>
 __device__ __forceinline__ void gather_range(const SpmmParams &p, int eb, int ee, int lg, int lane0,
                                              unsigned gmask, const int (&c)[VPL], const bool (&cv)[VPL],
                                              float (&acc)[VPL][VEC]) {
@@ -146,12 +146,28 @@ __device__ __forceinline__ void gather_range(const SpmmParams &p, int eb, int ee
 #pragma unroll
             for (int jj = 0; jj < U; ++jj)
 #pragma unroll
-                for (int k = 0; k < VPL; ++k)
+                for (int k = 0; k < VPL; ++k) {
+                    if constexpr (VEC >= 2 && PACK) {
+                        // packed fp32x2 adds / fmas (sm_100): half the issue slots, each component
+                        // an ordinary IEEE round-to-nearest operation — bit-identical results
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        if constexpr (HAS_SS) blk[k][i] = fmaf(s[jj], x[jj][k][i], blk[k][i]);
-                        else blk[k][i] += x[jj][k][i];
+                        for (int i = 0; i < VEC; i += 2) {
+                            const float2 b = make_float2(blk[k][i], blk[k][i + 1]);
+                            const float2 v = make_float2(x[jj][k][i], x[jj][k][i + 1]);
+                            float2 r;
+                            if constexpr (HAS_SS) r = __ffma2_rn(make_float2(s[jj], s[jj]), v, b);
+                            else r = __fadd2_rn(b, v);
+                            blk[k][i] = r.x;
+                            blk[k][i + 1] = r.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) {
+                            if constexpr (HAS_SS) blk[k][i] = fmaf(s[jj], x[jj][k][i], blk[k][i]);
+                            else blk[k][i] += x[jj][k][i];
+                        }
                     }
+                }
         }
 #pragma unroll
         for (int k = 0; k < VPL; ++k)
@@ -272,6 +288,9 @@ spmm_csr_kernel(const SpmmParams p) {
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
     const int lane0 = grp * LPR;
     constexpr bool coop = COOP;
+    // packed adds need aligned register pairs: the 64-register large-graph VEC = 4 variant spills
+    // with them (12.5 vs 12.0 ms on the full Reddit-shape graph), every other variant gains
+    constexpr bool kPack = COOP || VEC != 4;
     if constexpr (EX) record_drop_step(p);
     // EX (training-step shapes): the grid may be smaller than the number of (row block, chunk)
     // items — background mode caps the CTAs resident per SM so a concurrent high-priority branch
@@ -305,7 +324,7 @@ spmm_csr_kernel(const SpmmParams p) {
         if (coop && re - rs > p.heavy_deg) {
             if (lg == 0) s_heavy[atomicAdd(&s_nheavy, 1)] = v;   // order irrelevant: rows are independent
         } else {
-            gather_range<VEC, LPR, VPL, HAS_SS>(p, rs, re, lg, lane0, gmask, c, cv, acc);
+            gather_range<VEC, LPR, VPL, HAS_SS, kPack>(p, rs, re, lg, lane0, gmask, c, cv, acc);
             epilogue<VEC, VPL, EX>(p, v, c, cv, acc);
         }
     }
@@ -325,7 +344,7 @@ spmm_csr_kernel(const SpmmParams p) {
         for (int k = 0; k < VPL; ++k)
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[k][i] = 0.f;
-        gather_range<VEC, LPR, VPL, HAS_SS>(p, eb, ee, lg, lane0, gmask, c, cv, acc);
+        gather_range<VEC, LPR, VPL, HAS_SS, kPack>(p, eb, ee, lg, lane0, gmask, c, cv, acc);
 #pragma unroll
         for (int k = 0; k < VPL; ++k)
 #pragma unroll
