@@ -83,7 +83,7 @@ __device__ __forceinline__ void st_vec(float *p, const float (&r)[VEC]) {
 // Two-level summation: every block of <= LPR edges is summed on its own and then added
 // to the running total, which keeps the fp32 rounding error of hub rows (10^4 edges)
 // ~sqrt(LPR) lower than one long chain, at the cost of VPL*VEC adds per block.
-template <int VEC, int LPR, int VPL, bool HAS_SS, bool PACK = true>
+template <int VEC, int LPR, int VPL, bool HAS_SS>
 __device__ __forceinline__ void gather_range(const SpmmParams &p, int eb, int ee, int lg, int lane0,
                                              unsigned gmask, const int (&c)[VPL], const bool (&cv)[VPL],
                                              float (&acc)[VPL][VEC]) {
@@ -92,18 +92,24 @@ __device__ __forceinline__ void gather_range(const SpmmParams &p, int eb, int ee
     // lanes past the end of the row (the last chunk's tail) gather column 0 instead of being
     // predicated off: their sums are never stored (every store checks cv), and the gathers of the
     // whole group stay free of per-lane predicates
-    int cs[VPL];
+    // One address = one IMAD.WIDE.U32: byte pointer of this lane's column(s) + u * (row pitch in
+    // bytes, < 2^32 — checked on the host); and the index of gather jj of a round always comes from
+    // lane jj of the group (the indices are rotated down by U after every round), so the shuffle's
+    // source lane is an immediate.  The kernels are instruction-issue bound: per gathered vector
+    // this is shuffle + address + load + packed adds.
+    const char *xb[VPL];
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) cs[k] = cv[k] ? c[k] : 0;
+    for (int k = 0; k < VPL; ++k) xb[k] = reinterpret_cast<const char *>(p.X + (cv[k] ? c[k] : 0));
+    const uint32_t pitch = (uint32_t)p.ldx * 4u;
     // the column indices of block b+1 are requested before block b's gathers are issued, so the
     // index load of every block but the first is hidden behind a block of feature gathers
     int u_next = (eb + lg < ee) ? __ldg(p.col + eb + lg) : 0;
     for (int e0 = eb; e0 < ee; e0 += LPR) {
         const int my = e0 + lg;
-        const int u_mine = u_next;
-        float s_mine = 0.f;
+        int u_rot = u_next;
+        float s_rot = 0.f;
         if constexpr (HAS_SS) {
-            if (my < ee) s_mine = __ldg(p.src_scale + u_mine);
+            if (my < ee) s_rot = __ldg(p.src_scale + u_rot);
         }
         u_next = (my + LPR < ee) ? __ldg(p.col + my + LPR) : 0;
         const int cnt = min(LPR, ee - e0);
@@ -119,23 +125,22 @@ __device__ __forceinline__ void gather_range(const SpmmParams &p, int eb, int ee
                 // full round (the common case): U unpredicated gathers, nothing to zero-fill
 #pragma unroll
                 for (int jj = 0; jj < U; ++jj) {
-                    const int u = __shfl_sync(gmask, u_mine, lane0 + j + jj);
-                    if constexpr (HAS_SS) s[jj] = __shfl_sync(gmask, s_mine, lane0 + j + jj);
-                    const float *xr = p.X + (int64_t)u * p.ldx;
+                    const uint32_t u = (uint32_t)__shfl_sync(gmask, u_rot, lane0 + jj);
+                    if constexpr (HAS_SS) s[jj] = __shfl_sync(gmask, s_rot, lane0 + jj);
 #pragma unroll
-                    for (int k = 0; k < VPL; ++k) ld_vec<VEC>(x[jj][k], xr + cs[k]);
+                    for (int k = 0; k < VPL; ++k)
+                        ld_vec<VEC>(x[jj][k], reinterpret_cast<const float *>(xb[k] + (uint64_t)u * pitch));
                 }
             } else {
 #pragma unroll
                 for (int jj = 0; jj < U; ++jj) {
-                    const int u = __shfl_sync(gmask, u_mine, lane0 + j + jj);
-                    if constexpr (HAS_SS) s[jj] = __shfl_sync(gmask, s_mine, lane0 + j + jj);
+                    const uint32_t u = (uint32_t)__shfl_sync(gmask, u_rot, lane0 + jj);
+                    if constexpr (HAS_SS) s[jj] = __shfl_sync(gmask, s_rot, lane0 + jj);
                     const bool ok = (j + jj) < cnt;
-                    const float *xr = p.X + (int64_t)u * p.ldx;
 #pragma unroll
                     for (int k = 0; k < VPL; ++k) {
                         if (ok) {
-                            ld_vec<VEC>(x[jj][k], xr + cs[k]);
+                            ld_vec<VEC>(x[jj][k], reinterpret_cast<const float *>(xb[k] + (uint64_t)u * pitch));
                         } else {
 #pragma unroll
                             for (int i = 0; i < VEC; ++i) x[jj][k][i] = 0.f;
@@ -143,11 +148,15 @@ __device__ __forceinline__ void gather_range(const SpmmParams &p, int eb, int ee
                     }
                 }
             }
+            if constexpr (U < LPR) {      // next round's indices move down to lanes 0..U-1 of the group
+                u_rot = __shfl_down_sync(gmask, u_rot, U, LPR);
+                if constexpr (HAS_SS) s_rot = __shfl_down_sync(gmask, s_rot, U, LPR);
+            }
 #pragma unroll
             for (int jj = 0; jj < U; ++jj)
 #pragma unroll
                 for (int k = 0; k < VPL; ++k) {
-                    if constexpr (VEC >= 2 && PACK) {
+                    if constexpr (VEC >= 2) {
                         // packed fp32x2 adds / fmas (sm_100): half the issue slots, each component
                         // an ordinary IEEE round-to-nearest operation — bit-identical results
 #pragma unroll
@@ -288,9 +297,6 @@ spmm_csr_kernel(const SpmmParams p) {
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
     const int lane0 = grp * LPR;
     constexpr bool coop = COOP;
-    // packed adds need aligned register pairs: the 64-register large-graph VEC = 4 variant spills
-    // with them (12.5 vs 12.0 ms on the full Reddit-shape graph), every other variant gains
-    constexpr bool kPack = COOP || VEC != 4;
     if constexpr (EX) record_drop_step(p);
     // EX (training-step shapes): the grid may be smaller than the number of (row block, chunk)
     // items — background mode caps the CTAs resident per SM so a concurrent high-priority branch
@@ -324,7 +330,7 @@ spmm_csr_kernel(const SpmmParams p) {
         if (coop && re - rs > p.heavy_deg) {
             if (lg == 0) s_heavy[atomicAdd(&s_nheavy, 1)] = v;   // order irrelevant: rows are independent
         } else {
-            gather_range<VEC, LPR, VPL, HAS_SS, kPack>(p, rs, re, lg, lane0, gmask, c, cv, acc);
+            gather_range<VEC, LPR, VPL, HAS_SS>(p, rs, re, lg, lane0, gmask, c, cv, acc);
             epilogue<VEC, VPL, EX>(p, v, c, cv, acc);
         }
     }
@@ -344,7 +350,7 @@ spmm_csr_kernel(const SpmmParams p) {
         for (int k = 0; k < VPL; ++k)
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[k][i] = 0.f;
-        gather_range<VEC, LPR, VPL, HAS_SS, kPack>(p, eb, ee, lg, lane0, gmask, c, cv, acc);
+        gather_range<VEC, LPR, VPL, HAS_SS>(p, eb, ee, lg, lane0, gmask, c, cv, acc);
 #pragma unroll
         for (int k = 0; k < VPL; ++k)
 #pragma unroll
@@ -673,7 +679,7 @@ extern "C" int gist_spmm_csr_ex_f32(const int32_t *rowptr, const int32_t *col, i
     if (n_dst == 0 || d == 0) return GIST_OK;
     if (!rowptr || !X || !Y) return GIST_ERR_BADARG;  // col may be NULL for an edgeless graph
     if (ldx < d || ldy < d) return GIST_ERR_BADARG;
-    if (ldx > 0x7fffffffLL || ldy > 0x7fffffffLL || ld_addend > 0x7fffffffLL || ld_self > 0x7fffffffLL)
+    if (ldx > 0x3fffffffLL || ldy > 0x7fffffffLL || ld_addend > 0x7fffffffLL || ld_self > 0x7fffffffLL)   // ldx * 4 fits 32 bits
         return GIST_ERR_UNSUPPORTED;
     if (addend && ld_addend < d) return GIST_ERR_BADARG;
     if (self_out && (ld_self < d || n_dst != n_src)) return GIST_ERR_BADARG;
