@@ -65,6 +65,29 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(_lib.launch_count(), int)
 
 
+def test_python_constants_match_the_header():
+    """The flag / enum values the ctypes host passes are the header's #defines, and the ctypes
+    argument lists have one entry per declared parameter."""
+    from gist_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'gist_b200.h')).read()
+    defs = {m.group(1): m.group(2) for m in re.finditer(r'#define\s+GIST_([A-Z0-9_]+)\s+\(?(-?\d+)u?\)?', header)}
+    for py, c in (('SPMM_RELU', 'SPMM_RELU'), ('SPMM_NARROW', 'SPMM_NARROW'), ('SPMM_WIDE', 'SPMM_WIDE'),
+                  ('SPMM_BG_SHIFT', 'SPMM_BG_SHIFT'), ('NORM_INV', 'NORM_INV'),
+                  ('NORM_RSQRT_CLAMP', 'NORM_RSQRT_CLAMP'), ('GEMM_RELU', 'GEMM_RELU'),
+                  ('GEMM_NO_SPLITK', 'GEMM_NO_SPLITK'), ('GEMM_TILE_N64', 'GEMM_TILE_N64'),
+                  ('GEMM_TILE_N128', 'GEMM_TILE_N128'), ('GEMM_TILE_N256', 'GEMM_TILE_N256'),
+                  ('GEMM_K_MAJOR', 'GEMM_K_MAJOR'), ('GEMM_MN_MAJOR', 'GEMM_MN_MAJOR'), ('ACT_RELU', 'ACT_RELU')):
+        assert getattr(_lib, py) == int(defs[c]), (py, defs[c])
+    # parameter counts: text between the parentheses of every prototype
+    flat = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        m = re.search(r'\b%s\s*\(([^)]*)\)\s*;' % name, flat)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ('', 'void') else params.count(',') + 1
+        assert n == len(argtypes), (name, n, len(argtypes))
+
+
 def test_compute_on_cpu_tensor_fails_loudly():
     from gist_b200 import GistGraph, ops
     from gist_b200._lib import GistLibraryError
