@@ -618,6 +618,12 @@ def run_reference(a):
     import scipy.sparse as sp
     from gist_b200 import synth          # synthetic-shape generator only (plain torch ops)
     from oracle import cpu_reference as R
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to every rank,
+    # and the other ranks have exited, so rank 0 takes the box's cores back
+    try:
+        torch.set_num_threads(max(len(os.sched_getaffinity(0)), 1))
+    except AttributeError:
+        torch.set_num_threads(max(os.cpu_count() or 1, 1))
     random.seed(a.seed)
     torch.manual_seed(a.seed)
     use_cuda = torch.cuda.is_available()
