@@ -9,6 +9,9 @@ reference trains from, read into the graph object the kernels use.
   ``dgl.data.load_data`` (cluster_gcn/utils.py:7, :110-ff): ``reddit_data.npz`` (feature, label,
   node_types 1/2/3 = train/val/test) and ``reddit_graph.npz`` / ``reddit_self_loop_graph.npz``
   (scipy ``save_npz``) [DGL-recall: file names and fields of DGL 0.5.x].
+* Cora / Citeseer / PubMed — the Planetoid ``ind.{name}.{x,y,tx,ty,allx,ally,graph,test.index}``
+  files behind ``dgl.data.load_data`` in gcn/train.py:33-41 and gcn/train_ist.py:64-92
+  (``load_citation``) [DGL-recall: CitationGraphDataset of DGL 0.5.x = Kipf & Welling's loader].
 * ``standardize_features`` — the StandardScaler step of get_data (…distrib.py:493-499).
 * ``load_data`` / ``get_data`` — the two reference entry points (utils.py:82-ff,
   cluster_gcn_ist_distrib.py:484-518) on top of them.
@@ -18,7 +21,9 @@ Everything here is host-side preprocessing, as in the reference; the result is a
 """
 import json
 import os
+import pickle
 from collections import namedtuple
+from types import SimpleNamespace
 
 import numpy as np
 import scipy.sparse as sp
@@ -133,6 +138,59 @@ def load_reddit(raw_dir, self_loop=False):
     return Dataset(num_classes=int(data['label'].max()) + 1, g=g)
 
 
+def load_citation(raw_dir, name):
+    """The citation datasets as DGL 0.5's ``CitationGraphDataset`` hands them to gcn/train.py:33-41
+    and gcn/train_ist.py:64-92: ``features`` (row-normalised, dense float32), ``labels`` (int64),
+    ``train_mask`` / ``val_mask`` / ``test_mask``, ``num_labels``, and the graph as the directed edge
+    list of ``nx.DiGraph(nx.from_dict_of_lists(graph))`` (``src`` / ``dst``; the trainers add the
+    self-loops themselves, train.py:66-68).  [DGL-recall]"""
+    def rd(suffix):
+        with open(os.path.join(raw_dir, 'ind.%s.%s' % (name, suffix)), 'rb') as f:
+            return pickle.load(f, encoding='latin1')
+    x, y, tx, ty, allx, ally, graph = (rd(sfx) for sfx in ('x', 'y', 'tx', 'ty', 'allx', 'ally', 'graph'))
+    with open(os.path.join(raw_dir, 'ind.%s.test.index' % name)) as f:
+        test_idx_reorder = np.array([int(line.strip()) for line in f if line.strip()], dtype=np.int64)
+    test_idx_range = np.sort(test_idx_reorder)
+    if name == 'citeseer':
+        # isolated test nodes are missing from tx / ty: zero rows at their positions
+        full = np.arange(test_idx_range.min(), test_idx_range.max() + 1)
+        tx_ext = sp.lil_matrix((len(full), x.shape[1]))
+        tx_ext[test_idx_range - test_idx_range.min(), :] = tx
+        tx = tx_ext
+        ty_ext = np.zeros((len(full), y.shape[1]))
+        ty_ext[test_idx_range - test_idx_range.min(), :] = ty
+        ty = ty_ext
+    features = sp.vstack((allx, tx)).tolil()
+    features[test_idx_reorder, :] = features[test_idx_range, :]
+    onehot = np.vstack((ally, ty))
+    onehot[test_idx_reorder, :] = onehot[test_idx_range, :]
+    labels = np.argmax(onehot, 1).astype(np.int64)
+    n = features.shape[0]
+    train_mask = np.zeros(n, dtype=bool)
+    val_mask = np.zeros(n, dtype=bool)
+    test_mask = np.zeros(n, dtype=bool)
+    train_mask[:len(y)] = True
+    val_mask[len(y):len(y) + 500] = True
+    test_mask[test_idx_range] = True
+    # _preprocess_features: rows scaled to sum 1, empty rows stay 0
+    features = sp.csr_matrix(features, dtype=np.float64)
+    rowsum = np.asarray(features.sum(1)).reshape(-1)
+    with np.errstate(divide='ignore'):
+        r_inv = np.power(rowsum, -1.0)
+    r_inv[np.isinf(r_inv)] = 0.0
+    features = np.asarray(sp.diags(r_inv).dot(features).todense()).astype(np.float32)
+    # nx.from_dict_of_lists -> undirected simple graph (a self-loop stays one edge); DiGraph: both directions
+    keys = np.fromiter(graph.keys(), dtype=np.int64, count=len(graph))
+    lens = np.fromiter((len(v) for v in graph.values()), dtype=np.int64, count=len(graph))
+    u = np.repeat(keys, lens)
+    v = np.fromiter((w for nb in graph.values() for w in nb), dtype=np.int64, count=int(lens.sum()))
+    a = sp.coo_matrix((np.ones(len(u), dtype=np.float32), (u, v)), shape=(n, n)).tocsr()
+    a = (a + a.transpose()).tocoo()
+    return SimpleNamespace(src=torch.from_numpy(a.row.astype(np.int64)), dst=torch.from_numpy(a.col.astype(np.int64)),
+                           features=features, labels=labels, train_mask=train_mask, val_mask=val_mask,
+                           test_mask=test_mask, num_labels=int(onehot.shape[1]), num_nodes=n)
+
+
 def load_data(args, raw_dir=None):
     """cluster_gcn/utils.py::load_data for the datasets of the hot path's configs."""
     name = args.dataset
@@ -140,7 +198,9 @@ def load_data(args, raw_dir=None):
         return load_amazon2m(raw_dir or './amazon2m_data/amazon2M')       # AmazonDataset(save_dir=…) default
     if name.startswith('reddit'):
         return load_reddit(raw_dir or os.path.expanduser('~/.dgl/reddit'), self_loop='self-loop' in name)
-    raise ValueError('gist_b200.datasets.load_data: unknown dataset %r (amazon2m, reddit, reddit-self-loop)' % name)
+    if name in ('cora', 'citeseer', 'pubmed'):                          # gcn/train.py:33-34
+        return load_citation(raw_dir or os.path.expanduser('~/.dgl/%s' % name), name)
+    raise ValueError('gist_b200.datasets.load_data: unknown dataset %r (amazon2m, reddit, reddit-self-loop, cora, citeseer, pubmed)' % name)
 
 
 def get_data(args, device, raw_dir=None):

@@ -70,3 +70,44 @@ def amazon_process(raw_path, name='amazon2M'):
                 labels=_labels.astype(np.int64), train_mask=sample_mask(train_nodes, _nodes),
                 val_mask=sample_mask(val_nodes, _nodes), test_mask=sample_mask(test_nodes, _nodes),
                 num_classes=num_classes)
+
+
+def citation_load(raw_path, name):
+    """Kipf & Welling's ``load_data`` as DGL 0.5's CitationGraphDataset runs it [DGL-recall], with
+    networkx building the graph exactly as gcn/train.py receives it (``data.graph``)."""
+    import pickle
+    import networkx as nx
+    objects = []
+    for suffix in ['x', 'y', 'tx', 'ty', 'allx', 'ally', 'graph']:
+        with open('{}/ind.{}.{}'.format(raw_path, name, suffix), 'rb') as f:
+            objects.append(pickle.load(f, encoding='latin1'))
+    x, y, tx, ty, allx, ally, graph = tuple(objects)
+    test_idx_reorder = [int(line.strip()) for line in open('{}/ind.{}.test.index'.format(raw_path, name))]
+    test_idx_range = np.sort(test_idx_reorder)
+    if name == 'citeseer':
+        test_idx_range_full = range(min(test_idx_reorder), max(test_idx_reorder) + 1)
+        tx_extended = sp.lil_matrix((len(test_idx_range_full), x.shape[1]))
+        tx_extended[test_idx_range - min(test_idx_range), :] = tx
+        tx = tx_extended
+        ty_extended = np.zeros((len(test_idx_range_full), y.shape[1]))
+        ty_extended[test_idx_range - min(test_idx_range), :] = ty
+        ty = ty_extended
+    features = sp.vstack((allx, tx)).tolil()
+    features[test_idx_reorder, :] = features[test_idx_range, :]
+    g = nx.DiGraph(nx.from_dict_of_lists(graph))
+    onehot_labels = np.vstack((ally, ty))
+    onehot_labels[test_idx_reorder, :] = onehot_labels[test_idx_range, :]
+    labels = np.argmax(onehot_labels, 1)
+    idx_test = test_idx_range.tolist()
+    idx_train = range(len(y))
+    idx_val = range(len(y), len(y) + 500)
+    n = labels.shape[0]
+    rowsum = np.asarray(features.sum(1))
+    with np.errstate(divide='ignore'):
+        r_inv = np.power(rowsum, -1.).flatten()
+    r_inv[np.isinf(r_inv)] = 0.
+    feats = np.asarray(sp.diags(r_inv).dot(features).todense())
+    e = np.array(list(g.edges()), dtype=np.int64).reshape(-1, 2)
+    return dict(src=e[:, 0], dst=e[:, 1], n=n, features=feats.astype(np.float32), labels=labels.astype(np.int64),
+                train_mask=sample_mask(idx_train, n), val_mask=sample_mask(idx_val, n),
+                test_mask=sample_mask(idx_test, n), num_labels=onehot_labels.shape[1])

@@ -116,3 +116,52 @@ def test_load_data_rejects_unknown_dataset():
     from gist_b200 import datasets
     with pytest.raises(ValueError):
         datasets.load_data(SimpleNamespace(dataset='ppi'))
+
+
+def _write_planetoid(d, name, n, n_lab, n_test, F, C, seed, gaps):
+    import pickle
+    from collections import defaultdict
+    rng = np.random.RandomState(seed)
+    n_all = n - n_test - gaps                       # allx rows; test ids live in [n_all, n)
+    feat = sp.random(n, F, density=0.2, random_state=rng, format='csr', dtype=np.float64)
+    feat.data[:] = rng.randint(1, 4, size=feat.nnz)
+    feat = feat.tolil()
+    feat[5, :] = 0                                   # an empty row: stays zero after normalisation
+    feat = feat.tocsr()
+    lab = rng.randint(0, C, size=n)
+    onehot = np.eye(C, dtype=np.int32)[lab]
+    test_ids = np.sort(rng.choice(np.arange(n_all, n), size=n_test, replace=False))    # gaps: citeseer's isolated nodes
+    graph = defaultdict(list)
+    for _ in range(4 * n):
+        u, v = int(rng.randint(n)), int(rng.randint(n))
+        graph[u].append(v)                           # asymmetric listings and duplicates on purpose
+        if rng.rand() < 0.5:
+            graph[v].append(u)
+    graph[7].append(7)                               # a self-loop
+    order = rng.permutation(n_test)
+    objs = {'x': feat[:n_lab], 'y': onehot[:n_lab], 'allx': feat[:n_all], 'ally': onehot[:n_all],
+            'tx': feat[test_ids], 'ty': onehot[test_ids], 'graph': graph}
+    for k, v in objs.items():
+        with open(os.path.join(d, 'ind.%s.%s' % (name, k)), 'wb') as f:
+            pickle.dump(v, f)
+    with open(os.path.join(d, 'ind.%s.test.index' % name), 'w') as f:
+        f.write('\n'.join(str(int(t)) for t in test_ids[order]) + '\n')
+
+
+@pytest.mark.parametrize('name,gaps', [('cora', 0), ('pubmed', 0), ('citeseer', 6)])
+def test_citation_loader_matches_restatement(tmp_path, name, gaps):
+    from gist_b200 import datasets
+    from oracle import datasets_oracle as O
+    d = str(tmp_path)
+    _write_planetoid(d, name, n=900, n_lab=60, n_test=150, F=40, C=6, seed=len(name), gaps=gaps)
+    ref = O.citation_load(d, name)
+    got = datasets.load_data(SimpleNamespace(dataset=name), raw_dir=d)
+    assert got.num_nodes == ref['n'] and got.num_labels == ref['num_labels']
+    assert np.array_equal(_canon(got.src.numpy(), got.dst.numpy(), ref['n']), _canon(ref['src'], ref['dst'], ref['n']))
+    for k in ('train_mask', 'val_mask', 'test_mask'):
+        assert np.array_equal(getattr(got, k), ref[k]), k
+    assert got.train_mask.sum() == 60 and got.val_mask.sum() == 500 and got.test_mask.sum() == 150
+    assert np.array_equal(got.labels, ref['labels'])
+    np.testing.assert_allclose(got.features, ref['features'], rtol=1e-6, atol=0)
+    rs = got.features.sum(1)
+    assert np.allclose(rs[rs > 0], 1.0, atol=1e-5) and got.features.dtype == np.float32
