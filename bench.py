@@ -558,8 +558,8 @@ def run_gist(a):
                             'sub-GCNs (one per GPU), iter_per_site %d' % (
                                 CONFIG_OF[a.shape], n_nodes, n_edges, in_feats, psize, a.batch_size, a.n_hidden,
                                 a.n_layers + 1, world, a.iter_per_site),
-                'model': ('GAT (cluster_gcn_ist_distrib_gat.py), %d heads, fused edge-softmax + weighted SpMM (K6)' % a.n_heads
-                          if a.model == 'gat' else 'GraphSAGE (cluster_gcn_ist_distrib.py)'),
+                'reference_caller': ('cluster_gcn_ist_distrib_gat.py (GAT, %d heads: fused edge-softmax + weighted SpMM, K6)' % a.n_heads
+                                     if a.model == 'gat' else 'cluster_gcn_ist_distrib.py (GraphSAGE aggregation path)'),
                 'steps_per_epoch': steps_per_epoch, 'num_subnet': world, 'scale': a.scale, 'mode': a.mode,
                 'pipeline': (a.mode == 'graph' and not a.no_pipeline),
                 'epoch_accounting': 'm ranks x one local pass = m epochs (reference: local_epochs = n_epochs // num_subnet)',
