@@ -39,6 +39,14 @@ CONFIG_OF = {'reddit': 'configs[2]: Cluster-GCN GraphSAGE on a Reddit-shaped',
              'pubmed': 'PubMed-shaped', 'cora': 'Cora-shaped'}
 
 
+def workload_string(a, n_nodes, n_edges, in_feats, psize, world):
+    """config.workload — ONE string for both arms (the driver compares them)."""
+    return ('%s synthetic graph (%d nodes, %d directed edges, %d feats, %d parts, batch %d parts), hidden %d, '
+            '%d layers, GIST m=%d sub-GCNs (one per GPU), iter_per_site %d' % (
+                CONFIG_OF[a.shape], n_nodes, n_edges, in_feats, psize, a.batch_size, a.n_hidden, a.n_layers + 1,
+                world, a.iter_per_site))
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -60,11 +68,23 @@ def parse():
     ap.add_argument('--dropout', type=float, default=0.2)
     ap.add_argument('--lr', type=float, default=1e-2)
     ap.add_argument('--weight-decay', type=float, default=5e-4)
-    ap.add_argument('--iter-per-site', type=int, default=100)
+    ap.add_argument('--iter-per-site', type=int, default=None,
+                    help='local steps between GIST syncs; default min(100, max(1, steps // 2)) so that EVERY '
+                         'timed region holds at least one sync_model() + dispatch_model() round boundary')
+    ap.add_argument('--first-epoch-rule', action='store_true',
+                    help='apply the reference\'s "no re-dispatch during epoch 0" rule (…distrib.py:401) from the '
+                         'first benchmarked step; default: steady state (rounds as in epochs >= 1: sync + dispatch)')
+    ap.add_argument('--base-init', default=None, choices=['cpu', 'device'],
+                    help='where rank 0 draws the full model\'s initial values; default cpu (reference-identical) '
+                         'below hidden 8192, device above')
+    ap.add_argument('--soak-s', type=float, default=1.0,
+                    help='seconds of extra, untimed steps of the same loop run under the clock sampler after the '
+                         'timed region (a 5 ms timed region cannot hold a 50 ms nvidia-smi sample)')
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--cpu-steps', type=int, default=6, help='CPU-baseline sample size (steps)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-eval-spmm', action='store_true')
+    ap.add_argument('--no-timeline', action='store_true', help='skip the CUPTI timeline of the replayed step')
     ap.add_argument('--matmul', default='3xtf32', choices=['fp32', 'tf32', '3xtf32'],
                     help='nn.Linear contractions: the tcgen05 kernel (K4) in fp32-accurate 3xTF32 mode '
                          '(default; meets the 1e-5 parity tolerance), single-pass TF32 (~1e-3), or cuBLAS '
@@ -111,7 +131,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                       '--format=csv,noheader,nounits', '-lms', '50'],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -120,7 +140,7 @@ class ClockSampler:
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         if self.p is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.08)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -157,6 +177,93 @@ def spmm_bytes(nnz, n_dst, n_src, d, scaled):
     return alg, comp
 
 
+def replay_timeline(loop, steps, record):
+    """Run `steps` more steps of `loop` (all ranks, so round boundaries stay collective-safe); on the
+    recording rank under torch.profiler (CUPTI).  Returns per-kernel-class busy time per step, its
+    share of the step's wall time and of all kernel time, and kernel launches per step."""
+    import torch
+    if not record:
+        for _ in range(steps):
+            loop.next_step()
+        torch.cuda.synchronize()
+        return None
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(steps):
+                loop.next_step()
+            torch.cuda.synchronize()
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA
+               and 'memcpy' not in e.name.lower() and 'memset' not in e.name.lower()]
+    except Exception as ex:          # profiling is diagnostic: never fail the bench on it
+        return {'error': repr(ex)[:200], 'classes': {}}
+    if not evs:
+        return None
+    t0 = min(e.time_range.start for e in evs)
+    t1 = max(e.time_range.end for e in evs)
+    wall = (t1 - t0) / steps
+
+    def klass(name):
+        n = name.lower()
+        if 'spmm' in n:
+            return 'spmm'
+        if 'gemm_tf32' in n or 'splitk' in n:
+            return 'gemm'
+        if 'batch_' in n or 'gather_' in n or 'scan_' in n or 'seg_' in n:
+            return 'batch_build'
+        if 'gat_' in n:
+            return 'gat'
+        return 'other'
+    cls = {}
+    for e in evs:
+        c = cls.setdefault(klass(e.name), [0, 0.0])
+        c[0] += 1
+        c[1] += e.time_range.end - e.time_range.start
+    total = sum(c[1] for c in cls.values())
+    return {'steps': steps, 'wall_us_per_step': round(wall, 2), 'kernels_per_step': round(len(evs) / steps, 1),
+            'kernel_busy_us_per_step': round(total / steps, 2),
+            'classes': {k: {'launches_per_step': round(c[0] / steps, 1), 'busy_us_per_step': round(c[1] / steps, 2),
+                            'share_of_wall': round(c[1] / steps / wall, 4), 'share_of_kernel_time': round(c[1] / total, 4)}
+                        for k, c in sorted(cls.items())},
+            'note': 'branches of the graph overlap, so shares of wall can sum to more than 1; measured under the '
+                    'profiler (shares only, not bench values)'}
+
+
+def sync_summary(prof, world, timed_ms, steps):
+    """GIST round boundaries inside the timed region: CUDA-event pairs recorded by
+    DistributedGNNWrapper (sync = pack -> ONE all-gather -> local scatter; dispatch = local gathers)."""
+    by = {}
+    for r in prof:
+        e = by.setdefault(r['what'], {'n': 0, 'ms': 0.0, 'rec': r})
+        e['n'] += 1
+        e['ms'] += r['ev0'].elapsed_time(r['ev1'])
+    if 'sync_all_gather' not in by:
+        return {'rounds_in_timed_region': 0}
+    rounds = by['sync_all_gather']['n']
+    mean = lambda k: (by[k]['ms'] / by[k]['n']) if k in by else 0.0     # noqa: E731
+    ag = by['sync_all_gather']['rec']
+    ag_ms = mean('sync_all_gather')
+    sync_ms = mean('sync_pack') + ag_ms + mean('sync_scatter')
+    out = {
+        'rounds_in_timed_region': rounds, 'dispatches_in_timed_region': by.get('dispatch', {'n': 0})['n'],
+        'ms': round(sync_ms, 4), 'pack_ms': round(mean('sync_pack'), 4), 'all_gather_ms': round(ag_ms, 4),
+        'scatter_ms': round(mean('sync_scatter'), 4), 'dispatch_ms': round(mean('dispatch'), 4),
+        'bytes_per_rank': ag['bytes_sent'], 'bytes_received_per_rank': ag['bytes_received'],
+        'share_of_timed_region': round((by['sync_all_gather']['ms'] + by.get('sync_pack', {'ms': 0})['ms'] +
+                                        by.get('sync_scatter', {'ms': 0})['ms'] + by.get('dispatch', {'ms': 0})['ms'])
+                                       / max(timed_ms, 1e-9), 4),
+        'what': 'per round: pack this rank\'s trained slices -> one NCCL all_gather_into_tensor -> K5 scatter of '
+                'all m slices into the local full-model replica; dispatch = K5 gathers with the next partition '
+                '(no communication).  Event pairs on the training stream, rank 0.',
+    }
+    if world > 1 and ag_ms > 0:
+        out['GBps'] = round(ag['bytes_received'] / 1e9 / (ag_ms / 1e3), 2)
+        out['nvlink_line_rate_GBps'] = 900.0
+        out['frac_of_line_rate'] = round(out['GBps'] / 900.0, 4)
+        out['GBps_note'] = 'bytes received per rank / all-gather time (ingress per GPU; NVLink 5: 900 GB/s per direction)'
+    return out
+
+
 # ------------------------------------------------------------------ gist arm --
 def run_gist(a):
     import torch
@@ -175,6 +282,10 @@ def run_gist(a):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     assert a.warmup >= 3, 'timing rules: warm-up >= 3 steps'
+    if a.iter_per_site is None:
+        a.iter_per_site = min(100, max(1, a.steps // 2))
+    if a.base_init is None:
+        a.base_init = 'device' if a.n_hidden >= 8192 else 'cpu'
     ops.set_matmul_precision(a.matmul)
     assert a.n_hidden % world == 0
 
@@ -201,7 +312,7 @@ def run_gist(a):
         random.seed(a.seed)
         torch.manual_seed(a.seed)
         it = gb.ClusterIter('', g, psize, a.batch_size, train_nid, use_pp=False, h2d=h2d)
-        w = Wrapper(wargs, g, in_feats, n_classes, dev)
+        w = Wrapper(wargs, g, in_feats, n_classes, dev, **({} if a.model == 'gat' else {'base_init': a.base_init}))
         w.ini_sync_dispatch_model()
         return it, w
 
@@ -222,7 +333,7 @@ def run_gist(a):
 
         def next_step(self):
             if self.total_iter % a.iter_per_site == 0 and self.total_iter > 0:
-                e = self.total_iter // len(self.it)
+                e = self.total_iter // len(self.it) + (0 if a.first_epoch_rule else 1)
                 if e > 0:                                   # …distrib.py:401
                     if world > 1:
                         dist.barrier()
@@ -268,7 +379,7 @@ def run_gist(a):
                 self.iter = iter(self.it)
                 cluster = next(self.iter)
             if self.total_iter % a.iter_per_site == 0:
-                if self.e > 0:                            # …distrib.py:401 (never re-dispatched in epoch 0)
+                if self.e + (0 if a.first_epoch_rule else 1) > 0 and self.total_iter > 0:   # …distrib.py:401
                     if world > 1:
                         dist.barrier()
                     self.w.dispatch_model()
@@ -328,19 +439,39 @@ def run_gist(a):
     it, w = fresh('epoch')
     LoopT = GraphLoop if a.mode == 'graph' else Loop
     loop = LoopT(it, w, readback=False)
-    for _ in range(a.warmup):
-        loop.next_step()
+    # clocks are sampled from the warm-up, through the timed region, to the end of an untimed soak of
+    # the SAME loop (>= --soak-s seconds): the timed region alone (steps x ~0.25 ms) is shorter than
+    # one nvidia-smi sampling period
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(a.warmup):
+        loop.next_step()
     if a.ncu == 'steps':
         torch.cuda.profiler.start()
+    if hasattr(w, 'profile'):
+        w.profile = []
     ms, launches = timed(loop, a.steps)
+    sync_prof = getattr(w, 'profile', None)
+    if hasattr(w, 'profile'):
+        w.profile = None
     if a.ncu == 'steps':
         torch.cuda.profiler.stop()
-    clocks = sampler.stop() if rank == 0 else None
     value = world * a.steps / steps_per_epoch / (ms / 1e3)
     final_loss = float(loop.loss_acc) / max(a.steps + a.warmup, 1)
+    soak_steps = 0
+    if a.soak_s > 0 and not a.ncu:
+        soak_steps = int(a.soak_s * 1e3 / max(ms / a.steps, 1e-3)) + 1     # same count on every rank (ms is the max over ranks)
+        for i in range(soak_steps):
+            loop.next_step()
+            if i % 64 == 63:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks['window'] = ('warm-up + timed region + %d untimed soak steps of the same loop (%.2f s)'
+                            % (soak_steps, soak_steps * ms / a.steps / 1e3))
+    sync = sync_summary(sync_prof, world, ms, a.steps) if sync_prof is not None else None
 
     # ---- instrumented pass: per-launch SpMM durations with CUDA events --------------
     # Eager steps on the same workload, each preceded by a device-side sleep long enough for
@@ -453,6 +584,20 @@ def run_gist(a):
                     'tensor core actually executes' % big['passes'],
         }
 
+    # ---- kernel shares of the REPLAYED step (CUPTI timeline of a few more steps of the same loop) ----
+    # roofline.share_of_step above divides eager single-stream kernel time by the overlapped graph
+    # step; the replayed graph runs three branches concurrently, so the honest figures are each
+    # kernel class's busy time over the step's wall time, from the timeline of the replay itself.
+    timeline = None
+    if a.mode == 'graph' and not a.no_timeline and not a.ncu:
+        timeline = replay_timeline(loop, 8, rank == 0)
+        if timeline is not None:
+            roofline['share_of_step'] = timeline['classes'].get('spmm', {}).get('share_of_wall', roofline['share_of_step'])
+            roofline['share_of_step_source'] = 'CUPTI timeline of the replayed graph: SpMM busy time / step wall time'
+            if roofline_gemm is not None and 'gemm' in timeline['classes']:
+                roofline_gemm['share_of_step'] = timeline['classes']['gemm']['share_of_wall']
+                roofline_gemm['share_of_step_source'] = roofline['share_of_step_source'].replace('SpMM', 'GEMM')
+
     # ---- end-to-end arm: node ids from pinned host memory + loss readback every step --
     it2, w2 = fresh('step')
     loop2 = LoopT(it2, w2, readback=True)
@@ -548,21 +693,26 @@ def run_gist(a):
         line = {
             'metric': metric_name(a.shape, a.model), 'value': round(value, 4), 'unit': 'epochs/s', 'n_gpus': world,
             'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': round(ms / a.steps, 4),
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'per_rank_steps_per_s': round(a.steps / (ms / 1e3), 1),
+            'epochs_per_s_one_pass_by_all_ranks': round(value / world, 4),
             'dtype': {'fp32': 'f32', '3xtf32': 'f32 (GEMMs: 3xTF32 split-operand tensor-core products, fp32-accurate)',
                       'tf32': 'f32 (aggregation, norms, loss, Adam) + tf32 tensor-core GEMM inputs'}[a.matmul],
             'data': 'synthetic',
             'config': {
-                'workload': '%s synthetic graph (%d nodes, %d '
-                            'directed edges, %d feats, %d parts, batch %d parts), hidden %d, %d layers, GIST m=%d '
-                            'sub-GCNs (one per GPU), iter_per_site %d' % (
-                                CONFIG_OF[a.shape], n_nodes, n_edges, in_feats, psize, a.batch_size, a.n_hidden,
-                                a.n_layers + 1, world, a.iter_per_site),
+                'workload': workload_string(a, n_nodes, n_edges, in_feats, psize, world),
                 'reference_caller': ('cluster_gcn_ist_distrib_gat.py (GAT, %d heads: fused edge-softmax + weighted SpMM, K6)' % a.n_heads
                                      if a.model == 'gat' else 'cluster_gcn_ist_distrib.py (GraphSAGE aggregation path)'),
                 'steps_per_epoch': steps_per_epoch, 'num_subnet': world, 'scale': a.scale, 'mode': a.mode,
                 'pipeline': (a.mode == 'graph' and not a.no_pipeline),
-                'epoch_accounting': 'm ranks x one local pass = m epochs (reference: local_epochs = n_epochs // num_subnet)',
+                'epoch_accounting': 'value: GIST accounting — m ranks x one local pass = m epochs (reference: '
+                                    'local_epochs = n_epochs // num_subnet, …distrib.py:385); '
+                                    'epochs_per_s_one_pass_by_all_ranks = value / m is SURVEY 8(d)\'s literal '
+                                    'definition (one pass executed concurrently by all m ranks = 1 epoch)',
+                'scaling_note': 'a FIXED model (hidden %d) and a fixed epoch budget are split m = N ways: every rank '
+                                'trains a hidden/m-wide sub-GCN over the full batch sequence for n_epochs/m local '
+                                'epochs, so the job is fixed and per-GPU work shrinks with N (strong scaling of the '
+                                'GIST job; neither per-GPU work nor per-GPU model is constant)' % a.n_hidden,
                 'l2': 'inputs larger than L2: every step gathers a different ~%d-node batch from the %.0f MB '
                       'training feature matrix' % (loop.nodes // max(loop.total_iter, 1),
                                                    4.0 * it.g.number_of_nodes() * in_feats / 1e6),
@@ -573,6 +723,7 @@ def run_gist(a):
                 'loss_after': round(final_loss, 4),
             },
             'roofline': roofline, 'roofline_gemm': roofline_gemm, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
+            'sync': sync, 'replay_timeline': timeline,
             'clocks': clocks, 'roofline_fullgraph': full, 'evaluate': ev,
             'setup_s': round(time.time() - t_setup, 1),
         }
@@ -614,6 +765,8 @@ def run_reference(a):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if rank != 0:
         return
+    if a.iter_per_site is None:
+        a.iter_per_site = min(100, max(1, a.steps // 2))
     import torch
     import scipy.sparse as sp
     from gist_b200 import synth          # synthetic-shape generator only (plain torch ops)
@@ -654,8 +807,10 @@ def run_reference(a):
 
     def batch_ids(i):
         return np.concatenate(par_li[i * a.batch_size:(i + 1) * a.batch_size]).astype(np.int64)
-    k = min(a.steps, 40)                       # bounded sample: the CPU step is ~100 ms
-    wu = min(max(a.warmup, 1), 3)
+    # bounded sample: the CPU step is ~50-100 ms (Reddit shape), ~2 s at the ultra-wide widths
+    cap = 400 if a.n_hidden < 2048 else 12
+    k = min(a.steps, cap)
+    wu = min(max(a.warmup, 1), cap)
     batches = [batch_ids(i % steps_per_epoch) for i in range(k + wu)]
     sec = R.time_steps(tr, batches, warmup=wu)
     # N sub-GCNs time-share the same host cores: N local passes take N x as long
@@ -663,12 +818,13 @@ def run_reference(a):
     line = {
         'impl': 'reference', 'metric': metric_name(a.shape), 'value': round(value, 5), 'unit': 'epochs/s', 'n_gpus': world,
         'steps': k, 'warmup': wu, 'ms_per_step': round(sec * 1e3, 3), 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': '%s synthetic graph (%d nodes, %d directed edges, %d feats, '
-                               '%d parts, batch %d), hidden %d/%d, %d layers — CPU port of the reference step '
-                               '(DGL 0.5.3 not installable)' % (CONFIG_OF[a.shape], n_nodes, n_edges, in_feats, psize,
-                                                                  a.batch_size,
-                                                                  a.n_hidden, world, a.n_layers + 1),
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'epoch_accounting': 'same as the gist arm (GIST accounting): the m = N sub-GCNs (hidden/m wide) time-share this '
+                            'host, so their m local passes — m epochs — take m x one pass: value = m / (m x pass time) '
+                            '= 1 / pass time of ONE hidden/m-wide sub-GCN',
+        'config': {'workload': workload_string(a, n_nodes, n_edges, in_feats, psize, world),
+                   'reference_note': 'CPU port of the reference step (oracle/cpu_reference.py; DGL 0.5.3 is not installable): '
+                                     'one hidden/m-wide sub-GCN on all host threads, no sync (single process)',
                    'steps_per_epoch': steps_per_epoch, 'scale': a.scale},
         'cpu_baseline': {'value': round(value, 5), 'unit': 'epochs/s', 'cores': torch.get_num_threads(),
                          'host_cpus': os.cpu_count(), 'kind': 'port',

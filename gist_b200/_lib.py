@@ -46,6 +46,8 @@ SIGNATURES = {
                                         _I32, _P, _U32, _P, _SZ, _P]),
     'gist_split_tf32_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P, _I64, _P]),
     'gist_split_tf32_multi_f32': (ctypes.c_int, [_I32, _P, _P, _P, _P, _P, _P, _P]),
+    'gist_gemm_set_trace': (ctypes.c_int, [_P, _I32]),
+    'gist_gemm_trace_slots': (ctypes.c_int, []),
     'gist_gemm_plan': (ctypes.c_int, [_I32, _I32, _I32, _U32, _I32, _P, _P, _P]),
     'gist_gemm_tn_tf32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _U32, _P]),
     'gist_transpose_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P]),

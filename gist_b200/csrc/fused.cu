@@ -363,10 +363,10 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(const float *__restrict__ 
     for (int c = lane; c < C; c += 32) mx = fmaxf(mx, __ldg(xr + c));
     mx = warp_max(mx);
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += __expf(__ldg(xr + c) - mx);
+    for (int c = lane; c < C; c += 32) s += expf(__ldg(xr + c) - mx);
     s = warp_sum(s);
     if (lane == 0) {
-        const float l = mx + __logf(s);
+        const float l = mx + logf(s);
         lse[r] = l;
         const bool m = mask ? (mask[r] != 0) : true;
         const int64_t y = labels[r];
@@ -375,14 +375,19 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(const float *__restrict__ 
 }
 
 // Single CTA: loss = sum(row_loss) / count(mask); out[0] = loss, out[1] = 1 / count.
+// A row counts iff it is masked in AND its label is a class index: rows labelled outside [0, C)
+// (torch's ignore_index = -100 included) are excluded from the mean's denominator and get a zero
+// gradient, as CrossEntropyLoss's ignore_index rows do.
 __global__ void __launch_bounds__(1024) ce_reduce_kernel(const float *__restrict__ row_loss,
-                                                         const uint8_t *__restrict__ mask, int n,
+                                                         const uint8_t *__restrict__ mask,
+                                                         const int64_t *__restrict__ labels, int C, int n,
                                                          float *__restrict__ out) {
     __shared__ float s_l[32], s_c[32];
     float l = 0.f, c = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         l += row_loss[i];
-        c += mask ? (mask[i] != 0 ? 1.f : 0.f) : 1.f;
+        const bool ok = (mask ? mask[i] != 0 : true) && (uint64_t)labels[i] < (uint64_t)C;
+        c += ok ? 1.f : 0.f;
     }
     l = warp_sum(l);
     c = warp_sum(c);
@@ -415,13 +420,13 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float *__restrict__ l
     if (r >= n) return;
     const float *xr = logits + (int64_t)r * ld;
     float *dr = dlogits + (int64_t)r * ldd;
-    const bool m = mask ? (mask[r] != 0) : true;
+    const int64_t y = labels[r];
+    const bool m = (mask ? (mask[r] != 0) : true) && (uint64_t)y < (uint64_t)C;
     const float scale = m ? __ldg(gout) * __ldg(loss_out + 1) : 0.f;
     const float l = lse[r];
-    const int64_t y = labels[r];
     for (int c = lane; c < ldd_fill; c += 32) {     // columns [C, ldd_fill) are row padding: zeroed
         float v = 0.f;
-        if (c < C && m) v = (__expf(__ldg(xr + c) - l) - (c == y ? 1.f : 0.f)) * scale;
+        if (c < C && m) v = (expf(__ldg(xr + c) - l) - (c == y ? 1.f : 0.f)) * scale;
         dr[c] = v;
         if (dlo) dlo[(int64_t)r * ldd + c] = tf32_lo(v);       // same layout as dlogits
     }
@@ -442,30 +447,21 @@ __global__ void __launch_bounds__(256) ce_fused_kernel(const float *__restrict__
     __shared__ float s_loss[8];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // rows that count: masked in AND labelled with a class index (see ce_reduce_kernel).  All loads of
+    // a thread are independent (unrolled), so the loop is a couple of L2 round trips, not a chain.
     int cnt = 0;
-    if (mask) {
-        // 32-bit words, all loads of a thread in flight together (a byte-per-iteration loop is a
-        // chain of L2 round trips: measured 11 us for 2.6 k rows)
-        const int head = min(n, (int)((4 - (reinterpret_cast<uintptr_t>(mask) & 3)) & 3));
-        const uint32_t *m4 = reinterpret_cast<const uint32_t *>(mask + head);
-        const int nw = (n - head) >> 2;
 #pragma unroll 4
-        for (int i = threadIdx.x; i < nw; i += 256) {
-            const uint32_t w = __ldg(m4 + i);
-            cnt += ((w & 0xffu) != 0) + ((w & 0xff00u) != 0) + ((w & 0xff0000u) != 0) + ((w & 0xff000000u) != 0);
-        }
-        if ((int)threadIdx.x < head) cnt += mask[threadIdx.x] != 0;
-        for (int i = head + (nw << 2) + threadIdx.x; i < n; i += 256) cnt += mask[i] != 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) s_cnt[warp] = cnt;
-        __syncthreads();
-        cnt = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) cnt += s_cnt[w];
-    } else {
-        cnt = n;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const bool ok = (mask ? __ldg(mask + i) != 0 : true) && (uint64_t)__ldg(labels + i) < (uint64_t)C;
+        cnt += ok ? 1 : 0;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    cnt = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) cnt += s_cnt[w];
     const float inv = 1.f / (float)cnt;         // cnt == 0: inf, and no row is masked in
     const int r = blockIdx.x * 8 + warp;
     float row_loss = 0.f;
@@ -475,16 +471,16 @@ __global__ void __launch_bounds__(256) ce_fused_kernel(const float *__restrict__
         for (int c = lane; c < C; c += 32) mx = fmaxf(mx, __ldg(xr + c));
         mx = warp_max(mx);
         float se = 0.f;
-        for (int c = lane; c < C; c += 32) se += __expf(__ldg(xr + c) - mx);
+        for (int c = lane; c < C; c += 32) se += expf(__ldg(xr + c) - mx);
         se = warp_sum(se);
-        const float l = mx + __logf(se);
-        const bool m = mask ? (mask[r] != 0) : true;
+        const float l = mx + logf(se);
         const int64_t y = labels[r];
-        if (m && y >= 0 && y < C) row_loss = l - __ldg(xr + y);
+        const bool m = (mask ? (mask[r] != 0) : true) && (uint64_t)y < (uint64_t)C;
+        if (m) row_loss = l - __ldg(xr + y);
         float *dr = dlogits + (int64_t)r * ldd;
         for (int c = lane; c < ldd_fill; c += 32) {     // columns [C, ldd_fill) are row padding: zeroed
             float v = 0.f;
-            if (c < C && m) v = (__expf(__ldg(xr + c) - l) - (c == y ? 1.f : 0.f)) * inv;
+            if (c < C && m) v = (expf(__ldg(xr + c) - l) - (c == y ? 1.f : 0.f)) * inv;
             dr[c] = v;
             if (dlo) dlo[(int64_t)r * ldd + c] = tf32_lo(v);
         }
@@ -776,7 +772,7 @@ extern "C" int gist_masked_ce_fwd_f32(const float *logits, int64_t ld, int32_t n
         ce_rows_kernel<<<(n + 7) / 8, 256, 0, s>>>(logits, ld, n, C, labels, mask, lse, row_loss);
         count_launch();
     }
-    ce_reduce_kernel<<<1, 1024, 0, s>>>(row_loss, mask, n, loss_out);
+    ce_reduce_kernel<<<1, 1024, 0, s>>>(row_loss, mask, labels, C, n, loss_out);
     count_launch();
     return last_error();
 }

@@ -156,7 +156,23 @@ struct GemmParams {
     int32_t vec4;       // output rows and bias are 16-byte aligned: float4 epilogue stores
     int32_t kc;         // NT == 3: K blocks chained into one TMEM accumulator before it is drained
     DropParams drop;    // p != 0: C[r, c] *= dropout multiplier of (r, c) (the dz = dy W contraction)
+    long long *trace;   // diagnostic (gist_gemm_set_trace): kTraceSlots clock stamps per CTA, or NULL
 };
+
+// Phase stamps of a CTA's FIRST work unit (tools/gemm_trace.py): SM clock at  0 entry, 1 set-up done,
+// 2 first TMA issued, 3 first stage landed, 4 last MMA committed, 5 accumulator seen by the epilogue,
+// 6 epilogue stores done, 7 exit;  8 / 9 = %globaltimer (ns) at entry / exit;  10 = SM id.
+constexpr int kTraceSlots = 12;
+__device__ __forceinline__ void trace_stamp(const GemmParams &p, int slot) {
+    if (p.trace) p.trace[(size_t)blockIdx.x * kTraceSlots + slot] = clock64();
+}
+__device__ __forceinline__ void trace_wall(const GemmParams &p, int slot) {
+    if (p.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[(size_t)blockIdx.x * kTraceSlots + slot] = (long long)t;
+    }
+}
 
 template <int BN, int NT>
 struct GemmCfg {
@@ -192,6 +208,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int n_work = p.tiles_m * p.tiles_n * p.splits;
 
     if (threadIdx.x == 0) {
+        trace_stamp(p, 0);
+        trace_wall(p, 8);
+        if (p.trace) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            p.trace[(size_t)blockIdx.x * kTraceSlots + 10] = smid;
+        }
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
@@ -213,6 +236,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_base_slot;
+    if (threadIdx.x == 0) trace_stamp(p, 1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -254,6 +278,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             tma_load_2d(mb, &full[s], b, kb * kBK, n0);
                         }
                     }
+                    if (w == (int)blockIdx.x && kb == kb0) trace_stamp(p, 2);
                     if (++s == kStages) { s = 0; ph ^= 1; }
                 }
             }
@@ -282,6 +307,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int kb = kc0; kb < kc1; ++kb) {
                         mbar_wait(&full[s], ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (w == (int)blockIdx.x && kb == kb0) trace_stamp(p, 3);
                         const uint32_t a_addr = smem_u32(sA + (size_t)s * kBM * kBK);
                         const uint32_t b_addr = smem_u32(sB + (size_t)s * BN * kBK);
                         auto a_desc = [](uint32_t addr, int k) {
@@ -310,6 +336,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (++s == kStages) { s = 0; ph ^= 1; }
                     }
                     umma_commit(&tmem_full[acc]);        // this chunk's accumulator is complete
+                    if (w == (int)blockIdx.x && kc1 == kb1) trace_stamp(p, 4);
                     acc ^= 1;
                     if (acc == 0) acc_ph ^= 1;
                 }
@@ -384,6 +411,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int kc0 = kb0; kc0 < kb1; kc0 += p.kc) {
                     mbar_wait(&tmem_full[acc], acc_ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (warp == 2 && lane == 0 && w == (int)blockIdx.x && kc0 + p.kc >= kb1) trace_stamp(p, 5);
 #pragma unroll
                     for (int c = 0; c < BN; c += 32) {
                         if (c < ncols) {
@@ -411,6 +439,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             } else {
                 mbar_wait(&tmem_full[acc], acc_ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (warp == 2 && lane == 0 && w == (int)blockIdx.x) trace_stamp(p, 5);
 #pragma unroll 1
                 for (int c = 0; c < ncols; c += 32) {
                     float v[32];
@@ -423,10 +452,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 acc ^= 1;
                 if (acc == 0) acc_ph ^= 1;
             }
+            if (warp == 2 && lane == 0 && w == (int)blockIdx.x) trace_stamp(p, 6);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) {
+        trace_stamp(p, 7);
+        trace_wall(p, 9);
+    }
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d),
                      "r"((uint32_t)Cfg::kTmemCols)
@@ -603,6 +637,10 @@ static int sm_count() {
     return n;
 }
 
+// diagnostic trace buffer (gist_gemm_set_trace); NULL in production
+static long long *g_gemm_trace = nullptr;
+static int g_gemm_trace_ctas = 0;
+
 struct GemmMaps {
     CUtensorMap a, b, al, bl;     // al / bl = the x_lo operands (NT == 3); copies of a / b otherwise
 };
@@ -729,6 +767,14 @@ extern "C" int gist_gemm_plan(int32_t M, int32_t N, int32_t K, uint32_t flags, i
     return GIST_OK;
 }
 
+extern "C" int gist_gemm_set_trace(void *buffer, int32_t max_ctas) {
+    g_gemm_trace = reinterpret_cast<long long *>(buffer);
+    g_gemm_trace_ctas = buffer ? max_ctas : 0;
+    return GIST_OK;
+}
+
+extern "C" int gist_gemm_trace_slots(void) { return kTraceSlots; }
+
 extern "C" size_t gist_gemm_3xtf32_workspace_bytes(int32_t M, int32_t N, int32_t K, uint32_t flags) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     return plan_gemm(M, N, K, flags, true).ws_bytes;
@@ -776,6 +822,7 @@ static int gemm_impl(const float *A, const float *A_lo, int64_t lda, int64_t lda
     p.drop = dp;
     p.kc = (int)((flags >> 8) & 0xFFu);
     if (p.kc == 0) p.kc = 4;          // 128 K elements = 48 chained MMAs per accumulator
+    p.trace = (g_gemm_trace && g_gemm_trace_ctas >= sm_count()) ? g_gemm_trace : nullptr;
     if (pl.splits > 1) {
         p.C = reinterpret_cast<float *>(workspace); p.ldc = pl.ldp; p.bias = nullptr; p.vec4 = 1;
     } else {

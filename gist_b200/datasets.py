@@ -41,8 +41,12 @@ def _key(k, is_digit):
 def standardize_features(feats, train_rows):
     """sklearn.preprocessing.StandardScaler fitted on the training rows and applied to all rows
     (AmazonDataset.py:87-90; cluster_gcn_ist_distrib.py:493-499): population variance, a
-    zero-variance column is left unscaled.  float64 moments, float32 result, like sklearn on
-    float32 input."""
+    zero-variance column is left unscaled.  Moments are accumulated in float64; the transform
+    mirrors sklearn's arithmetic on float32 input: ``X -= mean_.astype(float32)`` then
+    ``X /= scale_.astype(float32)`` in place on the float32 copy (sklearn >= 1.x casts the moments
+    to the data type first; the reference pins only ``scikit-learn>=0.20.0``, and releases that
+    subtract the float64 moments directly differ from this by at most 1 ulp).  Bit-identical to
+    the installed StandardScaler — pinned by tests/test_datasets.py against the real sklearn."""
     feats = np.asarray(feats)
     tr = feats[train_rows].astype(np.float64)
     mean = tr.mean(axis=0)
@@ -51,8 +55,10 @@ def standardize_features(feats, train_rows):
     # sklearn's _handle_zeros_in_scale: (near-)constant columns get scale 1
     eps = 10 * np.finfo(scale.dtype).eps
     scale[scale < eps] = 1.0
-    out = (feats.astype(np.float64) - mean) / scale
-    return out.astype(np.float32)
+    out = feats.astype(np.float32, copy=True)
+    out -= mean.astype(np.float32)
+    out /= scale.astype(np.float32)
+    return out
 
 
 def load_amazon2m(raw_dir, name='amazon2M', standardize=True):

@@ -36,6 +36,10 @@ class CapturedStep:
         saved_p = [p.detach().clone() for p in self.params]
         had_state = self._opt_state()
         saved_s = [t.clone() for t in had_state]
+        # the warm-up steps and the capture run nn.Dropout: put the device generator back afterwards,
+        # so a captured run consumes the same random stream as the eager one (train_ist re-captures
+        # at every lr change)
+        rng = torch.cuda.get_rng_state(self.dev)
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(main)
         with torch.cuda.stream(s):
@@ -57,6 +61,7 @@ class CapturedStep:
             for t, q in zip(had_state, saved_s):    # state that existed before: back to what it was
                 t.copy_(q)
         torch.cuda.synchronize(self.dev)
+        torch.cuda.set_rng_state(rng, self.dev)
 
     def replay(self):
         self.graph.replay()

@@ -70,6 +70,10 @@ class GraphedClusterTrainer:
         self._dev_tab = ([torch.empty((steps, self.n_pad), dtype=torch.int64, device=self.dev) for _ in range(2)]
                          if h2d == 'epoch' else None)
         self._tab = 1
+        # last asynchronous reader of each pinned table (the whole-table upload, or the latest row
+        # copy): the host must not refill a table before that copy has executed — step() never
+        # blocks the host, so it can run several epochs ahead of the GPU when epochs are short
+        self._tab_read = [None, None]
         # two copy streams: uploads must never queue behind a loss readback, which waits for the
         # running graph to finish (one shared stream delayed the ids of batch k+1 — and with them
         # graph k+1 — until graph k had completed and its loss had been copied out)
@@ -89,12 +93,23 @@ class GraphedClusterTrainer:
         """Fill the other id table with the (re)shuffled epoch; h2d='epoch' uploads it whole."""
         self._tab ^= 1
         host = self._host_tab[self._tab]
+        if self._tab_read[self._tab] is not None:
+            self._tab_read[self._tab].synchronize()      # its previous contents have been consumed
         self.it.padded_epoch_ids(self.n_pad, out=host.numpy())
         if self.h2d == 'epoch':
             with torch.cuda.stream(self._copy):
                 self._dev_tab[self._tab].copy_(host, non_blocking=True)
+                self._mark_table_read()
             self.h2d_bytes += host.numel() * 8
         self.i = 0
+
+    def _mark_table_read(self):
+        """Record, on the copy stream, that every copy issued so far from the current pinned table
+        has been enqueued (event reused per table: only the latest record matters)."""
+        ev = self._tab_read[self._tab]
+        if ev is None:
+            ev = self._tab_read[self._tab] = torch.cuda.Event()
+        ev.record(self._copy)
 
     def _next_row(self):
         if self.i >= len(self.it):
@@ -112,6 +127,8 @@ class GraphedClusterTrainer:
                 self._copy.wait_event(after)
             self.nids[j].copy_(row, non_blocking=True)
             self._ev_ids[j].record(self._copy)
+            if self.h2d == 'step':
+                self._mark_table_read()                  # the row lives in pinned host memory
         if self.h2d == 'step':
             self.h2d_bytes += self.n_pad * 8
 

@@ -50,8 +50,17 @@ class DistributedGNNWrapper(torch.nn.Module):
 
     args needs: rank, num_subnet, n_hidden, n_layers, dropout, use_layernorm."""
 
-    def __init__(self, args, g, in_feats, n_classes, device, slice_ops=None):
+    def __init__(self, args, g, in_feats, n_classes, device, slice_ops=None, base_init='cpu'):
+        """base_init: 'cpu' (default) builds the full model on the host and moves it, exactly as the
+        reference does (…distrib.py:81-83: same seed -> bit-identical initial parameters);
+        'device' draws rank 0's initial values with the device generator instead (same
+        distributions) — for the ultra-wide configurations, where the host-side uniform_() of an
+        8.6 GB layer dominates set-up.  Replicas on ranks > 0 never draw values: they are
+        allocated on the device and filled by the broadcast from rank 0."""
         super().__init__()
+        assert base_init in ('cpu', 'device')
+        # set to a list to record CUDA-event timestamps of every sync / dispatch (bench.py)
+        self.profile = None
         # (gather, scatter_) executors for the 2-D slices; the product path is the CUDA
         # K5 kernels.  Tests of the host-side plan / pack / all-gather logic on CPU
         # (gloo) inject a checker here; nothing in the package does.
@@ -67,24 +76,27 @@ class DistributedGNNWrapper(torch.nn.Module):
         self.device = device
         mk_base = lambda: GCN(in_feats, args.n_hidden, n_classes, args.n_layers, F.relu,  # noqa: E731
                               args.dropout, args.use_layernorm, False, False, 1, True)
-        if args.rank == 0:
+        if args.rank == 0 and base_init == 'cpu':
             self.base_model = mk_base().to(device)
+        elif args.rank == 0:
+            with torch.device(device):
+                self.base_model = mk_base()
         else:
-            # replica: built without disturbing this rank's RNG stream (the reference
-            # builds nothing here), filled from rank 0 below
-            with torch.random.fork_rng(devices=[]):
-                self.base_model = mk_base().to(device)
+            # replica: allocated on the device without drawing anything from this rank's RNG
+            # streams (the reference builds nothing here); filled from rank 0 below
+            with torch.device('meta'):
+                self.base_model = mk_base()
+            self.base_model = self.base_model.to_empty(device=device)
         self.sub_model = GCN(in_feats, args.n_hidden, n_classes, args.n_layers, F.relu,
                              args.dropout, args.use_layernorm, False, True, args.num_subnet,
                              True).to(device)
         self.current_partition = None
         if _dist_ready() and args.num_subnet > 1:
-            flat = torch.cat([p.data.reshape(-1) for p in self.base_model.parameters()])
-            dist.broadcast(flat, src=0)
-            off = 0
-            for p in self.base_model.parameters():
-                p.data.copy_(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
+            for p in self.base_model.parameters():      # in place, tensor by tensor: no packed 8.6 GB copy
+                dist.broadcast(p.data, src=0)
+        elif args.rank != 0:
+            raise RuntimeError('rank %d of a %d-way GIST job needs an initialised process group '
+                               '(the full-model replica is filled from rank 0)' % (args.rank, args.num_subnet))
 
     # ---------------------------------------------------------- partition --
     def sample_partitions(self):
@@ -131,9 +143,23 @@ class DistributedGNNWrapper(torch.nn.Module):
         self.current_partition = parts
 
     def dispatch_model(self):
+        ev = self._stamp()
         parts = self._to_dev(self.sample_partitions())
         self._dispatch_local(parts)
         self.current_partition = parts
+        self._stamp(ev, 'dispatch')
+
+    # ------------------------------------------------------------- timing --
+    def _stamp(self, ev=None, what=None, **extra):
+        """Event pair around a round-boundary operation on the current stream (profile mode only)."""
+        if self.profile is None or not torch.cuda.is_available():
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        if ev is None:
+            return e
+        self.profile.append(dict(what=what, ev0=ev, ev1=e, **extra))
+        return e
 
     # ---------------------------------------------------------------- sync --
     def _pack(self):
@@ -145,7 +171,9 @@ class DistributedGNNWrapper(torch.nn.Module):
         parts = self.current_partition
         L = len(parts)
         with torch.no_grad():
+            ev = self._stamp()
             flat = self._pack()
+            ev = self._stamp(ev, 'sync_pack', bytes=flat.numel() * 4) or ev
             if _dist_ready() and m > 1:
                 out = torch.empty(m * flat.numel(), dtype=flat.dtype, device=flat.device)
                 dist.all_gather_into_tensor(out, flat)       # ONE collective for all slices
@@ -153,7 +181,10 @@ class DistributedGNNWrapper(torch.nn.Module):
             else:
                 assert m == 1, 'num_subnet > 1 needs an initialised process group'
                 gathered = flat.unsqueeze(0)
+            ev = self._stamp(ev, 'sync_all_gather', bytes_sent=flat.numel() * 4,
+                             bytes_received=(m - 1) * flat.numel() * 4) or ev
             self._merge(gathered, parts)
+            self._stamp(ev, 'sync_scatter', bytes=m * flat.numel() * 4)
             # the reference all-reduces the last bias IN PLACE on every rank's sub-model
             if self.inplace_dispatch:
                 self.sub_model.layers[L].linear.bias.data.copy_(self.base_model.layers[L].linear.bias.data)

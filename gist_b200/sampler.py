@@ -169,11 +169,18 @@ class ClusterIter(object):
                 if self._pinned is None or self._pinned[0].shape[0] < n_b:
                     self._pinned = [torch.empty(max(n_b * 2, 1024), dtype=torch.int64).pin_memory()
                                     for _ in range(4)]
+                    self._pin_ev = [None] * 4
                     self._pin_slot = 0
-                buf = self._pinned[self._pin_slot]
-                self._pin_slot = (self._pin_slot + 1) % len(self._pinned)
+                slot = self._pin_slot
+                buf = self._pinned[slot]
+                self._pin_slot = (slot + 1) % len(self._pinned)
+                if self._pin_ev[slot] is not None:
+                    self._pin_ev[slot].synchronize()     # the copy issued from this slot 4 steps ago has run
                 buf[:n_b].copy_(torch.from_numpy(ids))
                 nids = buf[:n_b].to(self.g.device, non_blocking=True)
+                if self._pin_ev[slot] is None:
+                    self._pin_ev[slot] = torch.cuda.Event()
+                self._pin_ev[slot].record()
                 self.h2d_bytes += n_b * 8
             result = self.g.subgraph(nids, col_capacity=cap)
             self.n += 1

@@ -272,6 +272,13 @@ int gist_gemm_tf32(const float *A, int64_t lda, int32_t a_layout, const float *B
 int gist_gemm_plan(int32_t M, int32_t N, int32_t K, uint32_t flags, int32_t three_pass, int32_t *tile_n,
                    int32_t *splits, int32_t *kblocks_per_split);
 
+/* Diagnostic: per-CTA phase stamps of every following GEMM launch (tools/gemm_trace.py).  `buffer`
+ * = device memory for max_ctas * gist_gemm_trace_slots() int64 (max_ctas >= the SM count), or NULL to
+ * switch tracing off (the default; production launches carry a NULL pointer and skip the stamps).
+ * Not thread-safe: a process-wide switch for profiling sessions. */
+int gist_gemm_set_trace(void *buffer, int32_t max_ctas);
+int gist_gemm_trace_slots(void);
+
 /* Both operands K-major, no workspace (never splits K). */
 int gist_gemm_tn_tf32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
                       int32_t M, int32_t N, int32_t K, const float *bias, uint32_t flags,

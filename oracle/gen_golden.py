@@ -420,12 +420,101 @@ def gen_gat(out):
     out['mh_out'] = h.detach().numpy()
 
 
+def gen_graphsage(out):
+    """cluster_gcn/modules.py:100-189 — GraphSAGELayer (affine LayerNorm, optional bias, use_pp) and the
+    GraphSAGE container; plus BaselineGCN (:316-349) with gradients."""
+    import dgl
+    import modules
+    # single layers: (bias, use_pp, use_lynorm, train-mode?) — dropout 0 so train mode is deterministic
+    lcases = [dict(bias=True, pp=False, ln=True, train=False, act=True, seed=11),
+              dict(bias=False, pp=False, ln=True, train=True, act=True, seed=12),
+              dict(bias=True, pp=True, ln=True, train=True, act=True, seed=13),      # use_pp: no aggregation
+              dict(bias=True, pp=True, ln=False, train=False, act=False, seed=14)]    # use_pp in eval aggregates
+    for ci, c in enumerate(lcases):
+        src, dst = small_graph(48, 380, c['seed'], loops=False)
+        g = dgl.DGLGraph((src, dst), num_nodes=48)
+        torch.manual_seed(c['seed'])
+        fin, fout = 6, 9
+        layer = modules.GraphSAGELayer(fin, fout, F.relu if c['act'] else None, 0.0, bias=c['bias'],
+                                       use_pp=c['pp'], use_lynorm=c['ln'])
+        if c['ln']:
+            with torch.no_grad():
+                layer.lynorm.weight.uniform_(0.5, 1.5)
+                layer.lynorm.bias.uniform_(-0.3, 0.3)
+        layer.train(c['train'])
+        skip_agg = c['pp'] and c['train']
+        x = torch.randn(48, 2 * fin if skip_agg else fin, requires_grad=True)
+        y = layer(g, x)
+        wy = torch.randn(48, fout)
+        (y * wy).sum().backward()
+        p = 'gl%d_' % ci
+        out[p + 'src'], out[p + 'dst'] = src, dst
+        out[p + 'cfg'] = np.array([fin, fout, int(c['bias']), int(c['pp']), int(c['ln']), int(c['train']), int(c['act'])])
+        out[p + 'x'], out[p + 'wy'], out[p + 'out'] = x.detach().numpy(), wy.numpy(), y.detach().numpy()
+        out[p + 'dx'] = x.grad.numpy().copy()
+        for k, v in sd_np(layer).items():
+            out[p + 'param.' + k] = v
+        for k, v in layer.named_parameters():
+            out[p + 'grad.' + k] = v.grad.numpy().copy()
+    # GraphSAGE containers
+    for ci, c in enumerate([dict(n=70, nnz=700, fin=10, hid=12, ncls=4, L=2, pp=False, seed=21),
+                            dict(n=56, nnz=500, fin=8, hid=8, ncls=3, L=1, pp=False, seed=22)]):
+        src, dst = small_graph(c['n'], c['nnz'], c['seed'], loops=False)
+        g = dgl.DGLGraph((src, dst), num_nodes=c['n'])
+        torch.manual_seed(c['seed'])
+        x = torch.randn(c['n'], c['fin'])
+        y = torch.randint(0, c['ncls'], (c['n'],))
+        g.ndata['feat'] = x
+        model = modules.GraphSAGE(c['fin'], c['hid'], c['ncls'], c['L'], F.relu, 0.4, c['pp'])
+        with torch.no_grad():
+            for l in model.layers[:-1]:
+                l.lynorm.weight.uniform_(0.5, 1.5)
+                l.lynorm.bias.uniform_(-0.3, 0.3)
+        model.eval()
+        logits = model(g)
+        F.cross_entropy(logits, y).backward()
+        p = 'gs%d_' % ci
+        out[p + 'src'], out[p + 'dst'], out[p + 'n'] = src, dst, np.int64(c['n'])
+        out[p + 'x'], out[p + 'y'] = x.numpy(), y.numpy()
+        out[p + 'cfg'] = np.array([c['fin'], c['hid'], c['ncls'], c['L'], int(c['pp'])])
+        out[p + 'logits'] = logits.detach().numpy()
+        for k, v in sd_np(model).items():
+            out[p + 'param.' + k] = v
+        for k, v in model.named_parameters():
+            out[p + 'grad.' + k] = v.grad.numpy().copy()
+    # BaselineGCN forward + CE gradients, with and without the whole-tensor layer norm
+    for ci, c in enumerate([dict(n=50, nnz=400, fin=9, hid=12, ncls=4, L=2, ln=True, seed=31),
+                            dict(n=44, nnz=300, fin=20, hid=6, ncls=3, L=1, ln=False, seed=32)]):
+        src, dst = small_graph(c['n'], c['nnz'], c['seed'], loops=True)
+        g = dgl.DGLGraph((src, dst), num_nodes=c['n'])
+        torch.manual_seed(c['seed'])
+        x = torch.randn(c['n'], c['fin'])
+        y = torch.randint(0, c['ncls'], (c['n'],))
+        g.ndata['feat'] = x
+        model = modules.BaselineGCN(c['fin'], c['hid'], c['ncls'], c['L'], F.relu, 0.5, c['ln'])
+        with torch.no_grad():
+            for l in model.layers:
+                l.bias.uniform_(-0.3, 0.3)
+        model.eval()
+        logits = model(g)
+        F.cross_entropy(logits, y).backward()
+        p = 'bg%d_' % ci
+        out[p + 'src'], out[p + 'dst'], out[p + 'n'] = src, dst, np.int64(c['n'])
+        out[p + 'x'], out[p + 'y'] = x.numpy(), y.numpy()
+        out[p + 'cfg'] = np.array([c['fin'], c['hid'], c['ncls'], c['L'], int(c['ln'])])
+        out[p + 'logits'] = logits.detach().numpy()
+        for k, v in sd_np(model).items():
+            out[p + 'param.' + k] = v
+        for k, v in model.named_parameters():
+            out[p + 'grad.' + k] = v.grad.numpy().copy()
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     bind_reference('cluster_gcn')
-    which = sys.argv[1:] or ['sage', 'graphconv', 'partition', 'cluster_iter', 'wrapper', 'train_ist', 'train_ist_data', 'gat']
+    which = sys.argv[1:] or ['sage', 'graphconv', 'partition', 'cluster_iter', 'wrapper', 'train_ist', 'train_ist_data', 'gat', 'graphsage']
     gens = dict(sage=gen_sage, graphconv=gen_graphconv, partition=gen_partition,
-                cluster_iter=gen_cluster_iter, wrapper=gen_wrapper, train_ist=gen_train_ist, train_ist_data=gen_train_ist_data, gat=gen_gat)
+                cluster_iter=gen_cluster_iter, wrapper=gen_wrapper, train_ist=gen_train_ist, train_ist_data=gen_train_ist_data, gat=gen_gat, graphsage=gen_graphsage)
     for name in which:
         out = {}
         gens[name](out)

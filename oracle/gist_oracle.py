@@ -98,6 +98,37 @@ def sage_gcn_forward(g, feat, params, use_layernorm, activation=F.relu, dropout_
     return h
 
 
+def graphsage_layer(g, h, weight, bias, ln_weight=None, ln_bias=None, use_lynorm=True, activation=None,
+                    aggregate=True, dropout_mask=None):
+    """GraphSAGELayer.forward (modules.py:131-148): as ISTSAGELayer but the layer norm is AFFINE
+    (nn.LayerNorm(out, elementwise_affine=True), :125), the bias is optional (:112) and with
+    ``use_pp`` in training mode the aggregation + concat are skipped (``aggregate=False``, :133):
+    the input is then already [h ‖ ah] wide."""
+    if aggregate:
+        norm = sage_norm(g, h.dtype)
+        h = torch.cat((h, copy_src_sum(g, h) * norm), dim=1)
+    if dropout_mask is not None:
+        h = h * dropout_mask
+    y = F.linear(h, weight, bias)
+    if use_lynorm:
+        y = F.layer_norm(y, (y.shape[-1],), ln_weight, ln_bias, 1e-5)
+    if activation is not None:
+        y = activation(y)
+    return y
+
+
+def graphsage_forward(g, feat, params, activation=F.relu):
+    """GraphSAGE.forward (modules.py:161-189), eval mode / use_pp False: every layer but the last has
+    the affine layer norm + activation, the last has neither.
+    params = [(W, b, ln_weight | None, ln_bias | None)]."""
+    h = feat
+    L = len(params)
+    for l, (w, b, lw, lb) in enumerate(params):
+        last = l == L - 1
+        h = graphsage_layer(g, h, w, b, lw, lb, not last, None if last else activation)
+    return h
+
+
 def graph_conv(g, feat, weight, bias, activation=None, norm='both'):
     """DGL 0.5.x GraphConv.forward (App. A): src-norm on the input, W first iff
     in > out (strict), dst-norm, bias, activation.  weight is [in, out]."""

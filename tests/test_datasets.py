@@ -82,7 +82,9 @@ def test_standardize_features_is_sklearn_standard_scaler():
     x[:, 4] = -1.0
     mask = rng.rand(500) < 0.6
     sc = sklearn.preprocessing.StandardScaler().fit(x[mask])         # …distrib.py:493-499
-    np.testing.assert_allclose(datasets.standardize_features(x, mask), sc.transform(x), rtol=2e-5, atol=2e-5)
+    got, ref = datasets.standardize_features(x, mask), sc.transform(x)
+    np.testing.assert_allclose(got, ref, rtol=2e-6, atol=2e-6)
+    assert np.array_equal(got, ref)          # same float32 arithmetic as the installed sklearn, bit for bit
 
 
 @pytest.mark.parametrize('self_loop', [False, True])

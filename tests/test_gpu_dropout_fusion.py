@@ -72,7 +72,7 @@ def test_sage_prepare_matches_composed(d):
     try:
         pre = ops.sage_prepare(g, h, 0.3, 9)
     finally:
-        ops.set_matmul_precision('fp32')
+        ops.set_matmul_precision(ops.DEFAULT_MATMUL_PRECISION)
     z_plain = ops.sage_concat(g, h)
     m = _mask(n, 2 * d, 0.3, 9, step=pre.step_saved)
     assert torch.equal(pre.z, z_plain * m)
@@ -83,7 +83,7 @@ def test_sage_prepare_matches_composed(d):
     try:
         pre0 = ops.sage_prepare(g, h, 0.0, 9)
     finally:
-        ops.set_matmul_precision('fp32')
+        ops.set_matmul_precision(ops.DEFAULT_MATMUL_PRECISION)
     assert torch.equal(pre0.z, z_plain) and not pre0.dropped and pre0.step_saved is None
 
 
@@ -107,7 +107,7 @@ def test_sage_prepare_background_mode_is_bit_identical(n, nnz, d, background):
         got = ops.sage_prepare(g, h, 0.3, 4, balanced=False, background=background)
         again = ops.sage_prepare(g, h, 0.3, 4, balanced=False, background=background, out=got)
     finally:
-        ops.set_matmul_precision('fp32')
+        ops.set_matmul_precision(ops.DEFAULT_MATMUL_PRECISION)
     assert again is got
     assert torch.equal(got.z, ref.z) and torch.equal(got.z_lo, ref.z_lo)
     assert torch.equal(got.step_saved, ref.step_saved)
@@ -160,7 +160,7 @@ def test_sage_linear_forward_backward(precision, tol, p, hub):
         y = ops.sage_linear(g, h, W, b, p, 4)
         (y * wy).sum().backward()
     finally:
-        ops.set_matmul_precision('fp32')
+        ops.set_matmul_precision(ops.DEFAULT_MATMUL_PRECISION)
     m = _mask(n, 2 * d, p, 4).double() if p else 1.0
     h2, W2, b2 = (t.detach().double().requires_grad_(True) for t in (h, W, b))
     rp, col = g.rowptr.long(), g.col.long()
@@ -191,7 +191,7 @@ def test_ist_sage_layer_train_mode_3xtf32_vs_oracle():
     try:
         out = layer(g, x.cuda())
     finally:
-        ops.set_matmul_precision('fp32')
+        ops.set_matmul_precision(ops.DEFAULT_MATMUL_PRECISION)
     mask = _mask(n, 2 * fin, 0.5, layer._drop_stream).cpu().double()
     ref = O.ist_sage_layer(og, x.double(), layer.linear.weight.detach().double().cpu(),
                            layer.linear.bias.detach().double().cpu(), True, F.relu, mask)
@@ -220,4 +220,4 @@ def test_backward_low_halves_match_split():
         assert lo is not None and torch.equal(lo, ops.split_tf32(dl))
         assert ops._lo_take(dl) is None                     # consumed
     finally:
-        ops.set_matmul_precision('fp32')
+        ops.set_matmul_precision(ops.DEFAULT_MATMUL_PRECISION)

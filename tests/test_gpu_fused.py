@@ -122,6 +122,36 @@ def test_masked_ce_loss_and_grad_one_launch(n, C, use_mask, mode):
     assert (pad == 0).all()
 
 
+@pytest.mark.parametrize('use_mask', [True, False])
+def test_cross_entropy_ignores_rows_with_out_of_range_labels(use_mask):
+    """torch.nn.CrossEntropyLoss (…distrib.py:383) excludes ignore_index = -100 rows from the mean's
+    denominator and gives them a zero gradient.  Both CE paths treat every label outside [0, C) that
+    way (the one-launch kernel and the two-pass autograd op)."""
+    from gist_b200 import ops
+    torch.manual_seed(5)
+    n, C = 1500, 41
+    logits = torch.randn(n, C, device='cuda') * 3
+    labels = torch.randint(0, C, (n,), device='cuda')
+    ign = torch.rand(n, device='cuda') < 0.2
+    labels[ign] = -100
+    mask = (torch.rand(n, device='cuda') < 0.7) if use_mask else None
+    sel = mask if use_mask else torch.ones(n, dtype=torch.bool, device='cuda')
+    l2 = logits.double().requires_grad_(True)
+    ref = F.cross_entropy(l2[sel], labels[sel], ignore_index=-100)
+    ref.backward()
+    loss, dl = ops.masked_ce_loss_and_grad(logits, labels, mask)
+    assert abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    assert _rel(dl, l2.grad) < 2e-6 and (dl[ign] == 0).all()
+    l3 = logits.clone().requires_grad_(True)
+    loss3 = ops.masked_cross_entropy(l3, labels, mask)
+    loss3.backward()
+    assert abs(loss3.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    assert torch.equal(dl, l3.grad)
+    labels[~ign] = C + 3                       # other invalid labels: same treatment, nothing counts
+    loss, dl = ops.masked_ce_loss_and_grad(logits, labels, mask)
+    assert torch.isnan(loss) and (dl == 0).all()
+
+
 def test_adam_matches_torch():
     from gist_b200.optim import Adam
     torch.manual_seed(0)

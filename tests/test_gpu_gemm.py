@@ -134,7 +134,7 @@ def _check_linear(n, fin, fout):
         y = ops.linear(z, W, b)
         (y * wy).sum().backward()
     finally:
-        ops.set_matmul_precision('fp32')
+        ops.set_matmul_precision(ops.DEFAULT_MATMUL_PRECISION)
     z2, W2, b2 = (t.detach().double().requires_grad_(True) for t in (z, W, b))
     y2 = torch.nn.functional.linear(z2, W2, b2)
     (y2 * wy.double()).sum().backward()
@@ -227,7 +227,7 @@ def test_linear_3xtf32_autograd():
             y = ops.linear(z, W, b)
             (y * wy).sum().backward()
         finally:
-            ops.set_matmul_precision('fp32')
+            ops.set_matmul_precision(ops.DEFAULT_MATMUL_PRECISION)
         z2, W2, b2 = (t.detach().double().requires_grad_(True) for t in (z, W, b))
         y2 = torch.nn.functional.linear(z2, W2, b2)
         (y2 * wy.double()).sum().backward()

@@ -31,7 +31,7 @@ def matmul_precision(request):
     from gist_b200 import ops
     ops.set_matmul_precision(request.param)
     yield request.param
-    ops.set_matmul_precision('fp32')
+    ops.set_matmul_precision(ops.DEFAULT_MATMUL_PRECISION)
 
 
 @pytest.mark.parametrize('cfg', [(602, 256, 41, 2, True), (100, 64, 47, 3, True), (50, 32, 5, 1, False)])
@@ -208,7 +208,7 @@ def test_weight_grad_branch_is_safe_when_the_side_stream_lags():
                 assert torch.equal(a, b)
     finally:
         ops.OVERLAP_WEIGHT_GRADS = True
-        ops.set_matmul_precision('fp32')
+        ops.set_matmul_precision(ops.DEFAULT_MATMUL_PRECISION)
 
 
 @pytest.mark.parametrize('cfg', [(602, 256, 41, 2, True), (100, 64, 47, 3, True), (50, 64, 5, 1, False)])
@@ -247,3 +247,177 @@ def test_evaluate_masks_one_pass_equals_two_evaluate_calls():
     assert both[0] == evaluate(model, g, labels, val)
     assert both[1] == evaluate(model, g, labels, test)
     assert both[2] == -1 == evaluate(model, g, labels, empty)
+
+
+# ---------------------------------------------------------------------------------------------
+# GraphSAGELayer / GraphSAGE / BaselineGCN (cluster_gcn/modules.py:100-189, 316-349): golden vectors
+# recorded from the reference's own classes (oracle/gen_golden.py:gen_graphsage) and larger random
+# cases against the oracle restatement.
+# ---------------------------------------------------------------------------------------------
+import os
+
+import numpy as np
+
+_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _gold(name):
+    return np.load(os.path.join(_GOLD, name + '.npz'))
+
+
+def _T(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def _load_state(module, G, prefix):
+    sd = {k: _T(G[prefix + k]) for k in module.state_dict().keys()}
+    module.load_state_dict(sd)
+
+
+@pytest.mark.parametrize('ci', [0, 1, 2, 3])
+def test_graphsage_layer_vs_reference_golden(ci, matmul_precision):
+    from gist_b200 import GistGraph, GraphSAGELayer
+    G = _gold('graphsage')
+    p = 'gl%d_' % ci
+    fin, fout, has_bias, pp, ln, train, act = (int(v) for v in G[p + 'cfg'])
+    g = GistGraph.from_edges(_T(G[p + 'src']), _T(G[p + 'dst']), 48, device='cuda')
+    layer = GraphSAGELayer(fin, fout, F.relu if act else None, 0.0, bias=bool(has_bias), use_pp=bool(pp),
+                           use_lynorm=bool(ln))
+    _load_state(layer, G, p + 'param.')
+    layer = layer.cuda().train(bool(train))
+    x = _T(G[p + 'x']).cuda().requires_grad_(True)
+    y = layer(g, x)
+    (y * _T(G[p + 'wy']).cuda()).sum().backward()
+    assert_close(y, _T(G[p + 'out']), rtol=1e-5, what='GraphSAGELayer out')
+    assert_close(x.grad, _T(G[p + 'dx']), rtol=2e-5, what='dx')
+    for k, v in layer.named_parameters():
+        assert_close(v.grad, _T(G[p + 'grad.' + k]), rtol=2e-5, what='grad ' + k)
+
+
+@pytest.mark.parametrize('ci', [0, 1])
+def test_graphsage_container_vs_reference_golden(ci, matmul_precision):
+    from gist_b200 import GistGraph, GraphSAGE
+    G = _gold('graphsage')
+    p = 'gs%d_' % ci
+    fin, hid, ncls, L, pp = (int(v) for v in G[p + 'cfg'])
+    n = int(G[p + 'n'])
+    g = GistGraph.from_edges(_T(G[p + 'src']), _T(G[p + 'dst']), n, device='cuda')
+    model = GraphSAGE(fin, hid, ncls, L, F.relu, 0.4, bool(pp))
+    _load_state(model, G, p + 'param.')
+    model = model.cuda().eval()
+    g.ndata['feat'] = _T(G[p + 'x']).cuda()
+    logits = model(g)
+    F.cross_entropy(logits, _T(G[p + 'y']).cuda()).backward()
+    assert_close(logits, _T(G[p + 'logits']), rtol=1e-5, what='GraphSAGE logits')
+    for k, v in model.named_parameters():
+        assert_close(v.grad, _T(G[p + 'grad.' + k]), rtol=2e-5, what='grad ' + k)
+    assert list(model.state_dict().keys())[:4] == ['layers.0.linear.weight', 'layers.0.linear.bias',
+                                                   'layers.0.lynorm.weight', 'layers.0.lynorm.bias']
+
+
+@pytest.mark.parametrize('cfg', [(602, 128, 41, 2), (100, 64, 47, 1)])
+def test_graphsage_container_vs_oracle(cfg, matmul_precision):
+    from gist_b200 import GraphSAGE
+    fin, hid, ncls, L = cfg
+    n = 900
+    g, og = _graphs(n, 14000, seed=20 + L, loops=False)
+    torch.manual_seed(3)
+    model = GraphSAGE(fin, hid, ncls, L, F.relu, 0.3, False).cuda().eval()
+    with torch.no_grad():
+        for l in model.layers[:-1]:
+            l.lynorm.weight.uniform_(0.5, 1.5)
+            l.lynorm.bias.uniform_(-0.3, 0.3)
+    x = torch.randn(n, fin)
+    y = torch.randint(0, ncls, (n,))
+    g.ndata['feat'] = x.cuda()
+    params = []
+    for i, l in enumerate(model.layers):
+        t = [l.linear.weight, l.linear.bias] + ([l.lynorm.weight, l.lynorm.bias] if i < L else [None, None])
+        params.append(tuple(v.detach().double().cpu().requires_grad_(True) if v is not None else None for v in t))
+    ref = O.graphsage_forward(og, x.double(), params)
+    F.cross_entropy(ref, y).backward()
+    out = model(g)
+    F.cross_entropy(out, y.cuda()).backward()
+    assert_close(out, ref, rtol=2e-5, what='GraphSAGE logits')
+    for l, tup in zip(model.layers, params):
+        assert_close(l.linear.weight.grad, tup[0].grad, rtol=5e-5, what='dW')
+        assert_close(l.linear.bias.grad, tup[1].grad, rtol=5e-5, what='db')
+        if tup[2] is not None:
+            assert_close(l.lynorm.weight.grad, tup[2].grad, rtol=5e-5, what='d ln.weight')
+            assert_close(l.lynorm.bias.grad, tup[3].grad, rtol=5e-5, what='d ln.bias')
+
+
+def test_graphsage_layer_use_pp_train_skips_aggregation():
+    """use_pp=True in training mode: the layer consumes pre-aggregated [h ‖ ah] input and must not
+    aggregate again (modules.py:133); in eval mode it aggregates."""
+    from gist_b200 import GraphSAGELayer
+    n, fin, fout = 300, 10, 6
+    g, og = _graphs(n, 3000, seed=5, loops=False)
+    torch.manual_seed(0)
+    layer = GraphSAGELayer(fin, fout, None, 0.0, use_pp=True, use_lynorm=False).cuda()
+    W, b = layer.linear.weight.detach().double().cpu(), layer.linear.bias.detach().double().cpu()
+    x2 = torch.randn(n, 2 * fin)
+    layer.train()
+    assert_close(layer(g, x2.cuda()), F.linear(x2.double(), W, b), rtol=1e-5, what='use_pp train')
+    layer.eval()
+    x = torch.randn(n, fin)
+    ref = O.graphsage_layer(og, x.double(), W, b, use_lynorm=False)
+    assert_close(layer(g, x.cuda()), ref, rtol=1e-5, what='use_pp eval')
+
+
+def test_baseline_gcn_vs_reference_golden_forward(matmul_precision):
+    """graphconv.npz:base_* — the reference's BaselineGCN logits (recorded in round 1, until now only
+    used to check the oracle)."""
+    from gist_b200 import BaselineGCN, GistGraph
+    G = _gold('graphconv')
+    g = GistGraph.from_edges(_T(G['base_src']), _T(G['base_dst']), 50, device='cuda')
+    model = BaselineGCN(9, 12, 4, 2, F.relu, 0.5, True)
+    _load_state(model, G, 'base_param.')
+    model = model.cuda().eval()
+    g.ndata['feat'] = _T(G['base_x']).cuda()
+    assert_close(model(g), _T(G['base_logits']), rtol=1e-5, what='BaselineGCN logits')
+
+
+@pytest.mark.parametrize('ci', [0, 1])
+def test_baseline_gcn_vs_reference_golden_with_grads(ci, matmul_precision):
+    from gist_b200 import BaselineGCN, GistGraph
+    G = _gold('graphsage')
+    p = 'bg%d_' % ci
+    fin, hid, ncls, L, ln = (int(v) for v in G[p + 'cfg'])
+    n = int(G[p + 'n'])
+    g = GistGraph.from_edges(_T(G[p + 'src']), _T(G[p + 'dst']), n, device='cuda')
+    model = BaselineGCN(fin, hid, ncls, L, F.relu, 0.5, bool(ln))
+    _load_state(model, G, p + 'param.')
+    model = model.cuda().eval()
+    g.ndata['feat'] = _T(G[p + 'x']).cuda()
+    logits = model(g)
+    F.cross_entropy(logits, _T(G[p + 'y']).cuda()).backward()
+    assert_close(logits, _T(G[p + 'logits']), rtol=1e-5, what='BaselineGCN logits')
+    for k, v in model.named_parameters():
+        assert_close(v.grad, _T(G[p + 'grad.' + k]), rtol=2e-5, what='grad ' + k)
+
+
+@pytest.mark.parametrize('cfg', [(602, 128, 41, 2, True), (64, 96, 7, 1, False)])
+def test_baseline_gcn_vs_oracle(cfg, matmul_precision):
+    from gist_b200 import BaselineGCN
+    fin, hid, ncls, L, ln = cfg
+    n = 1000
+    g, og = _graphs(n, 16000, seed=30 + L)
+    torch.manual_seed(4)
+    model = BaselineGCN(fin, hid, ncls, L, F.relu, 0.5, ln).cuda().eval()
+    with torch.no_grad():
+        for l in model.layers:
+            l.bias.uniform_(-0.3, 0.3)
+    x = torch.randn(n, fin)
+    y = torch.randint(0, ncls, (n,))
+    g.ndata['feat'] = x.cuda()
+    params = [(l.weight.detach().double().cpu().requires_grad_(True),
+               l.bias.detach().double().cpu().requires_grad_(True)) for l in model.layers]
+    ref = O.graphconv_gcn_forward(og, x.double(), params, ln)
+    F.cross_entropy(ref, y).backward()
+    out = model(g)
+    F.cross_entropy(out, y.cuda()).backward()
+    assert_close(out, ref, rtol=2e-5, what='BaselineGCN logits')
+    for l, (w, b) in zip(model.layers, params):
+        assert_close(l.weight.grad, w.grad, rtol=5e-5, what='dW')
+        assert_close(l.bias.grad, b.grad, rtol=5e-5, what='db')

@@ -78,6 +78,73 @@ def test_baseline_gcn():
     close(O.graphconv_gcn_forward(g, T(G['base_x']), params, True), G['base_logits'])
 
 
+@pytest.mark.parametrize('ci', [0, 1, 2, 3])
+def test_graphsage_layer(ci):
+    """GraphSAGELayer of the reference (affine LN, optional bias, use_pp) -> oracle restatement."""
+    G = load('graphsage')
+    p = 'gl%d_' % ci
+    fin, fout, has_bias, pp, ln, train, act = (int(v) for v in G[p + 'cfg'])
+    g = O.OGraph(G[p + 'src'], G[p + 'dst'], 48)
+    w = T(G[p + 'param.linear.weight']).requires_grad_(True)
+    b = T(G[p + 'param.linear.bias']).requires_grad_(True) if has_bias else None
+    lw = T(G[p + 'param.lynorm.weight']).requires_grad_(True) if ln else None
+    lb = T(G[p + 'param.lynorm.bias']).requires_grad_(True) if ln else None
+    x = T(G[p + 'x']).requires_grad_(True)
+    y = O.graphsage_layer(g, x, w, b, lw, lb, bool(ln), F.relu if act else None, aggregate=not (pp and train))
+    close(y.detach(), G[p + 'out'])
+    (y * T(G[p + 'wy'])).sum().backward()
+    close(x.grad, G[p + 'dx'], 1e-4)
+    close(w.grad, G[p + 'grad.linear.weight'], 1e-4)
+    if has_bias:
+        close(b.grad, G[p + 'grad.linear.bias'], 1e-4)
+    if ln:
+        close(lw.grad, G[p + 'grad.lynorm.weight'], 1e-4)
+        close(lb.grad, G[p + 'grad.lynorm.bias'], 1e-4)
+
+
+def graphsage_params(G, p, L, grad=True):
+    out = []
+    for l in range(L + 1):
+        pre = p + 'param.layers.%d.' % l
+        t = [T(G[pre + 'linear.weight']), T(G[pre + 'linear.bias']),
+             T(G[pre + 'lynorm.weight']) if l < L else None, T(G[pre + 'lynorm.bias']) if l < L else None]
+        out.append(tuple(v.requires_grad_(True) if (v is not None and grad) else v for v in t))
+    return out
+
+
+@pytest.mark.parametrize('ci', [0, 1])
+def test_graphsage_container(ci):
+    G = load('graphsage')
+    p = 'gs%d_' % ci
+    fin, hid, ncls, L, pp = (int(v) for v in G[p + 'cfg'])
+    g = O.OGraph(G[p + 'src'], G[p + 'dst'], int(G[p + 'n']))
+    params = graphsage_params(G, p, L)
+    logits = O.graphsage_forward(g, T(G[p + 'x']), params)
+    close(logits.detach(), G[p + 'logits'])
+    F.cross_entropy(logits, T(G[p + 'y'])).backward()
+    names = ('linear.weight', 'linear.bias', 'lynorm.weight', 'lynorm.bias')
+    for l, tup in enumerate(params):
+        for nm, t in zip(names, tup):
+            if t is not None:
+                close(t.grad, G[p + 'grad.layers.%d.%s' % (l, nm)], 1e-4)
+
+
+@pytest.mark.parametrize('ci', [0, 1])
+def test_baseline_gcn_with_grads(ci):
+    G = load('graphsage')
+    p = 'bg%d_' % ci
+    fin, hid, ncls, L, ln = (int(v) for v in G[p + 'cfg'])
+    g = O.OGraph(G[p + 'src'], G[p + 'dst'], int(G[p + 'n']))
+    params = [(T(G[p + 'param.layers.%d.weight' % l]).requires_grad_(True),
+               T(G[p + 'param.layers.%d.bias' % l]).requires_grad_(True)) for l in range(L + 1)]
+    logits = O.graphconv_gcn_forward(g, T(G[p + 'x']), params, bool(ln))
+    close(logits.detach(), G[p + 'logits'])
+    F.cross_entropy(logits, T(G[p + 'y'])).backward()
+    for l, (w, b) in enumerate(params):
+        close(w.grad, G[p + 'grad.layers.%d.weight' % l], 1e-4)
+        close(b.grad, G[p + 'grad.layers.%d.bias' % l], 1e-4)
+
+
 def test_create_partition_bit_exact():
     G = load('partition')
     for t, (seed, m, size) in enumerate(G['cp_triples']):
