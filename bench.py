@@ -621,27 +621,34 @@ def run_gist(a):
         full = {}
         n = g.number_of_nodes()
         for d in (in_feats, a.n_hidden):
-            x = torch.randn(n, d, device=dev)
-            y = torch.empty(n, d, device=dev)
+            # operands laid out as the product lays feature matrices out in HBM (ops.pad_rows): rows
+            # padded to a multiple of 4 floats, so d = 602 is gathered with 128-bit loads
+            x = ops._padded_empty(n, d, dev).normal_()
+            y = ops._padded_empty(n, d, dev)
             best = {}
-            for name, fl in (('auto', 0), ('narrow', _lib.SPMM_NARROW), ('wide', _lib.SPMM_WIDE)):
+            variants = [('auto', 0, x, y), ('lanes8', 2 << _lib.SPMM_LANES_SHIFT, x, y),
+                        ('lanes16', 3 << _lib.SPMM_LANES_SHIFT, x, y), ('lanes32', 4 << _lib.SPMM_LANES_SHIFT, x, y)]
+            if d % 4:      # round 1's layout: contiguous rows, 64-bit gathers
+                variants.append(('unpadded_rows', 0, x.contiguous(), torch.empty(n, d, device=dev)))
+            for name, fl, xx, yy in variants:
                 for _ in range(2):
-                    ops.spmm_raw(g.rowptr, g.col_buffer, n, n, x, y, dst_scale=g.inv_in_degree(), flags=fl)
+                    ops.spmm_raw(g.rowptr, g.col_buffer, n, n, xx, yy, dst_scale=g.inv_in_degree(), flags=fl)
                 torch.cuda.synchronize()
                 ts = []
                 if a.ncu == 'fullgraph' and name == 'auto':
                     torch.cuda.profiler.start()
-                    ops.spmm_raw(g.rowptr, g.col_buffer, n, n, x, y, dst_scale=g.inv_in_degree(), flags=fl)
+                    ops.spmm_raw(g.rowptr, g.col_buffer, n, n, xx, yy, dst_scale=g.inv_in_degree(), flags=fl)
                     torch.cuda.synchronize()
                     torch.cuda.profiler.stop()
                 for _ in range(5):
                     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     f0.record()
-                    ops.spmm_raw(g.rowptr, g.col_buffer, n, n, x, y, dst_scale=g.inv_in_degree(), flags=fl)
+                    ops.spmm_raw(g.rowptr, g.col_buffer, n, n, xx, yy, dst_scale=g.inv_in_degree(), flags=fl)
                     f1.record()
                     torch.cuda.synchronize()
                     ts.append(f0.elapsed_time(f1))
                 best[name] = float(np.mean(ts))
+            del variants
             ab, cb = spmm_bytes(n_edges, n, n, d, True)
             t = best['auto']
             full['d%d' % d] = {'ms': round(t, 3), 'achieved': round(ab / 1e9 / (t / 1e3), 1), 'peak': peak,

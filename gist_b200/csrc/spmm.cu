@@ -217,6 +217,37 @@ __device__ __forceinline__ void drop_store(const SpmmParams &p, int64_t step, in
     }
 }
 
+// Ragged tail (d % VEC != 0, e.g. d = 602 gathered with 128-bit loads from rows padded to 604
+// floats): the last active lane of a row owns fewer than VEC valid columns.  Its GATHERS still read
+// a whole vector (in bounds: every leading dimension is a multiple of VEC and >= d), its epilogue
+// touches the valid columns only, one by one — pad columns are never written.
+template <int VPL, bool EX>
+__device__ __noinline__ void epilogue_tail(const SpmmParams &p, int v, int c0, int nvalid, const float *acc, float t,
+                                           int64_t step) {
+    for (int i = 0; i < nvalid; ++i) {
+        const int c = c0 + i;
+        float r[1] = {acc[i] * t};
+        if (p.addend) r[0] += __ldg(p.addend + (int64_t)v * p.ld_add + c);
+        if (p.bias) r[0] += __ldg(p.bias + c);
+        if (p.relu) r[0] = fmaxf(r[0], 0.f);
+        if constexpr (EX) {
+            drop_store<1>(p, step, v, p.col0_y + c, r, p.Y + (int64_t)v * p.ldy + c,
+                          p.y_lo ? p.y_lo + (int64_t)v * p.ld_y_lo + c : nullptr);
+        } else {
+            p.Y[(int64_t)v * p.ldy + c] = r[0];
+        }
+        if (p.self_out) {
+            float sx[1] = {__ldg(p.X + (int64_t)v * p.ldx + c)};
+            if constexpr (EX) {
+                drop_store<1>(p, step, v, p.col0_self + c, sx, p.self_out + (int64_t)v * p.ld_self + c,
+                              p.self_lo ? p.self_lo + (int64_t)v * p.ld_self_lo + c : nullptr);
+            } else {
+                p.self_out[(int64_t)v * p.ld_self + c] = sx[0];
+            }
+        }
+    }
+}
+
 template <int VEC, int VPL, bool EX>
 __device__ __forceinline__ void epilogue(const SpmmParams &p, int v, const int (&c)[VPL],
                                          const bool (&cv)[VPL], const float (&acc)[VPL][VEC]) {
@@ -228,6 +259,12 @@ __device__ __forceinline__ void epilogue(const SpmmParams &p, int v, const int (
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
         if (!cv[k]) continue;
+        if constexpr (VEC > 1) {
+            if (c[k] + VEC > p.d) {          // ragged tail of the row
+                epilogue_tail<VPL, EX>(p, v, c[k], p.d - c[k], acc[k], t, step);
+                continue;
+            }
+        }
         float r[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) r[i] = acc[k][i] * t;
@@ -609,10 +646,33 @@ static int launch_spmm(const SpmmParams &p0, cudaStream_t stream, int bg_ctas_pe
     return last_error();
 }
 
+// L2 the gathered column slab should fit in with room for the index / output streams.  B200's 126 MB
+// L2 is two 63 MB partitions and a line gathered by SMs of both dies occupies both, so the budget
+// for a slab every SM reads is well under one partition.
+constexpr int64_t kSlabBudgetBytes = 36LL << 20;
+
 template <int VEC>
 static int dispatch_lanes(const SpmmParams &p, uint32_t flags, int32_t n_src, cudaStream_t stream) {
     const int lanes = (p.d + VEC - 1) / VEC;
     const int bg = (int)((flags >> GIST_SPMM_BG_SHIFT) & 15u);
+    int force = (int)((flags >> GIST_SPMM_LANES_SHIFT) & 7u);       // 1..4 -> 4, 8, 16, 32 lanes per row
+    if (force == 0 && lanes > 8 && !(flags & (GIST_SPMM_NARROW | GIST_SPMM_WIDE))) {
+        // Large gathered operand (the full-graph SpMM of evaluate()): the chunk index is the slow grid
+        // dimension, so the chip sweeps one column slab of X at a time; pick the lane-group width
+        // whose slab (n_src x lanes x VEC floats) stays L2-resident while it is swept.
+        const int64_t x_bytes = (int64_t)n_src * p.d * 4;
+        if (x_bytes > (96LL << 20)) {
+            if ((int64_t)n_src * 32 * VEC * 4 <= kSlabBudgetBytes || lanes > 32) force = 0;   // widest fits, or nothing does
+            if ((int64_t)n_src * 32 * VEC * 4 > kSlabBudgetBytes) {
+                if ((int64_t)n_src * 16 * VEC * 4 <= kSlabBudgetBytes) force = 3;
+                else if ((int64_t)n_src * 8 * VEC * 4 <= kSlabBudgetBytes) force = 2;
+            }
+        }
+    }
+    if (force == 1) return launch_spmm<VEC, 4, 1>(p, stream, bg);
+    if (force == 2) return launch_spmm<VEC, 8, 1>(p, stream, bg);
+    if (force == 3) return launch_spmm<VEC, 16, 1>(p, stream, bg);
+    if (force == 4) return launch_spmm<VEC, 32, 1>(p, stream, bg);
     if (lanes <= 4) return launch_spmm<VEC, 4, 1>(p, stream, bg);
     if (lanes <= 8) return launch_spmm<VEC, 8, 1>(p, stream, bg);
     if (lanes <= 16) return launch_spmm<VEC, 16, 1>(p, stream, bg);
@@ -632,8 +692,10 @@ static int dispatch_lanes(const SpmmParams &p, uint32_t flags, int32_t n_src, cu
 }
 
 static bool vec_ok(int vec, const SpmmParams &p) {
+    // d itself may be ragged (d % vec != 0): the row's last vector is gathered whole — in bounds,
+    // because every leading dimension below is a multiple of vec and >= d — and its epilogue is
+    // scalar (epilogue_tail).  What vector accesses need is alignment of every base and pitch.
     const size_t a = 4u * vec;
-    if (p.d % vec) return false;
     if (!aligned(p.X, a) || p.ldx % vec) return false;
     if (!aligned(p.Y, a) || p.ldy % vec) return false;
     if (p.bias && !aligned(p.bias, a)) return false;

@@ -37,7 +37,9 @@ class NodeFrame(dict):
         if val.shape[0] != self._n:
             raise GistError('Expect number of features to match number of nodes. Got %d and %d instead.'
                             % (val.shape[0], self._n))
-        super().__setitem__(key, val)
+        # device feature matrices live in HBM with 16-byte-aligned rows (ops.pad_rows): same values,
+        # same shape, padded leading dimension — 128-bit gathers and direct TMA addressing
+        super().__setitem__(key, ops.pad_rows(val))
 
 
 class GistGraph:

@@ -155,20 +155,60 @@ def exclusive_scan(x):
     return out
 
 
+def _row_pitch(t):
+    """(bytes per row, row pitch in bytes) of a tensor whose rows are contiguous runs of elements
+    (any trailing shape; a 2-D matrix may carry a padded leading dimension), else None."""
+    if t.dim() == 2 and (t.shape[1] <= 1 or t.stride(1) == 1) and (t.shape[0] <= 1 or t.stride(0) >= t.shape[1]):
+        return t.shape[1] * t.element_size(), (t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)) * t.element_size()
+    if t.is_contiguous():
+        rb = t.element_size()
+        for s in t.shape[1:]:
+            rb *= s
+        return rb, rb
+    return None
+
+
+def pad_rows(t):
+    """HBM layout of feature matrices: a 2-D fp32 matrix whose width is not a multiple of 4 floats
+    (Reddit's 602 input features) is re-laid with a leading dimension rounded up to 4 floats and a
+    16-byte-aligned base, and returned as the [n, d] view of that buffer (pad columns zero).  Rows
+    are then 16-byte aligned: the SpMM gathers them with 128-bit loads and TMA addresses the matrix
+    directly.  Anything else is returned unchanged."""
+    if not (torch.is_tensor(t) and t.is_cuda and t.dim() == 2 and t.dtype == torch.float32):
+        return t
+    n, d = t.shape
+    if d < 8 or (d % 4 == 0 and t.is_contiguous()) or _tma_ok(t):
+        return t
+    buf = torch.zeros((n, (d + 3) // 4 * 4), dtype=torch.float32, device=t.device)
+    v = buf[:, :d]
+    v.copy_(t)
+    return v
+
+
 def gather_rows(src, idx, out=None):
-    """src[idx] along dim 0 for any dtype / trailing shape (ndata row-gather)."""
+    """src[idx] along dim 0 for any dtype / trailing shape (ndata row-gather).  A 2-D fp32 source
+    with padded rows (pad_rows) yields a result with padded rows."""
     require_cuda(src, idx, out)
     assert idx.dtype == torch.int64 and idx.dim() == 1
-    src = src.contiguous()
+    rp = _row_pitch(src)
+    if rp is None:
+        src = src.contiguous()
+        rp = _row_pitch(src)
+    row_bytes, src_pitch = rp
     n = idx.shape[0]
     if out is None:
-        out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
-    assert out.shape == (n,) + tuple(src.shape[1:]) and out.dtype == src.dtype and out.is_contiguous()
-    row_bytes = src.element_size()
-    for s in src.shape[1:]:
-        row_bytes *= s
-    check(_lib.load().gist_gather_rows(ptr(src), row_bytes, ptr(idx.contiguous()), n, ptr(out),
-                                       row_bytes, row_bytes, stream_ptr(src.device)), 'gather_rows')
+        if src.dim() == 2 and src.dtype == torch.float32 and src.shape[1] >= 8 and src.shape[1] % 4:
+            out = torch.zeros((n, (src.shape[1] + 3) // 4 * 4), dtype=src.dtype, device=src.device)[:, :src.shape[1]]
+        else:
+            out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    assert out.shape == (n,) + tuple(src.shape[1:]) and out.dtype == src.dtype
+    op = _row_pitch(out)
+    assert op is not None and op[0] == row_bytes, 'gather_rows: output rows must be contiguous runs'
+    if row_bytes % 16 and src_pitch % 16 == 0 and op[1] % 16 == 0:
+        # padded rows on both sides: move whole 16-byte vectors, pad columns included
+        row_bytes = min((row_bytes + 15) // 16 * 16, src_pitch, op[1])
+    check(_lib.load().gist_gather_rows(ptr(src), src_pitch, ptr(idx.contiguous()), n, ptr(out),
+                                       op[1], row_bytes, stream_ptr(src.device)), 'gather_rows')
     return out
 
 

@@ -67,6 +67,11 @@ typedef struct gist_dropout {
  * in the shadow of a latency-critical branch (the next batch's layer-0 aggregation beside the
  * training step) never occupies every register file / warp slot of the chip. */
 #define GIST_SPMM_BG_SHIFT 8
+/* bits 12..14: force the lane-group width of the row-per-group kernel (0 = chosen from d and, for
+ * operands larger than L2, from the L2 slab budget): 1, 2, 3, 4 -> 4, 8, 16, 32 lanes per row, i.e.
+ * feature chunks of lanes x vector-width floats.  Tuning / measurement switch. */
+#define GIST_SPMM_LANES_SHIFT 12
+#define GIST_SPMM_LANES(code) ((uint32_t)(code) << GIST_SPMM_LANES_SHIFT)
 
 /* modes of gist_degree_norm_f32 */
 #define GIST_NORM_INV 0       /* 1/deg, deg==0 -> 0   (ISTSAGELayer.get_norm, cluster_gcn/modules.py:239-243) */

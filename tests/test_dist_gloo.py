@@ -15,15 +15,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, 'tests', 'golden')
 
 
-def _worker(rank, m, port, ci, q):
+def _worker(rank, m, port, ci, q, backend='gloo'):
     try:
-        _worker_body(rank, m, port, ci, q)
+        _worker_body(rank, m, port, ci, q, backend)
     except Exception as e:      # surface the failure instead of hanging the parent
         import traceback
         q.put((rank, ['EXC ' + traceback.format_exc()]))
 
 
-def _worker_body(rank, m, port, ci, q):
+def _worker_body(rank, m, port, ci, q, backend='gloo'):
+    """backend 'gloo': CPU tensors, injected slice checker.  backend 'nccl' (tests/test_gpu_dist_nccl.py):
+    one GPU per rank, the real K5 slice kernels and the NCCL all-gather."""
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from gist_b200.ist import DistributedGNNWrapper
@@ -34,14 +36,23 @@ def _worker_body(rank, m, port, ci, q):
     torch.manual_seed(seed)
     np.random.seed(seed)
     random.seed(seed)
-    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=m)
+    if backend == 'nccl':
+        torch.cuda.set_device(rank)
+        dev = torch.device('cuda', rank)
+        dist.init_process_group('nccl', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=m,
+                                device_id=dev)
+        slice_ops = None
+    else:
+        dev = torch.device('cpu')
+        dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=m)
+        slice_ops = cpu_slice_ops()
     args = SimpleNamespace(rank=rank, num_subnet=m, n_hidden=hid, n_layers=L, dropout=0.0, use_layernorm=True)
-    w = DistributedGNNWrapper(args, None, fin, ncls, torch.device('cpu'), slice_ops=cpu_slice_ops())
+    w = DistributedGNNWrapper(args, None, fin, ncls, dev, slice_ops=slice_ops)
     errs = []
 
     def eq(name, got, exact=True):
         ref = G[p + name]
-        got = got.detach().numpy()
+        got = got.detach().cpu().numpy()
         ok = np.array_equal(got, ref) if exact else np.allclose(got, ref, rtol=1e-6, atol=1e-7)
         if not ok:
             errs.append(name)
