@@ -94,7 +94,7 @@ def parse():
     ap.add_argument('--no-pipeline', action='store_true',
                     help='graph mode: build batch k inside step k instead of overlapping the build of batch '
                          'k+1 with the training of batch k')
-    ap.add_argument('--ncu', default='', choices=['', 'steps', 'fullgraph'],
+    ap.add_argument('--ncu', default='', choices=['', 'steps', 'fullgraph', 'fullgraph-all'],
                     help='bracket that region with cudaProfilerStart/Stop (ncu --profile-from-start off)')
     return ap.parse_args()
 
@@ -635,7 +635,7 @@ def run_gist(a):
                     ops.spmm_raw(g.rowptr, g.col_buffer, n, n, xx, yy, dst_scale=g.inv_in_degree(), flags=fl)
                 torch.cuda.synchronize()
                 ts = []
-                if a.ncu == 'fullgraph' and name == 'auto':
+                if (a.ncu == 'fullgraph' and name == 'auto') or a.ncu == 'fullgraph-all':
                     torch.cuda.profiler.start()
                     ops.spmm_raw(g.rowptr, g.col_buffer, n, n, xx, yy, dst_scale=g.inv_in_degree(), flags=fl)
                     torch.cuda.synchronize()

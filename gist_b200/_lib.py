@@ -79,6 +79,7 @@ SIGNATURES = {
 }
 
 SPMM_RELU, SPMM_NARROW, SPMM_WIDE = 1, 2, 4
+SPMM_SLAB_OFF = 32
 SPMM_BG_SHIFT = 8
 SPMM_LANES_SHIFT = 12      # flags |= code << 12: 1, 2, 3, 4 -> 4, 8, 16, 32 lanes per row
 NORM_INV, NORM_RSQRT_CLAMP = 0, 1

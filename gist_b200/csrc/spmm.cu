@@ -22,6 +22,7 @@ struct SpmmParams {
     const int32_t *rowptr;
     const int32_t *col;
     int32_t n_dst;
+    int32_t n_src;
     const float *X;
     int32_t ldx;        // leading dimensions fit 32 bits (checked on the host): the row
     int32_t d;          // address is one IMAD.WIDE instead of a 64-bit multiply
@@ -221,29 +222,25 @@ __device__ __forceinline__ void drop_store(const SpmmParams &p, int64_t step, in
 // floats): the last active lane of a row owns fewer than VEC valid columns.  Its GATHERS still read
 // a whole vector (in bounds: every leading dimension is a multiple of VEC and >= d), its epilogue
 // touches the valid columns only, one by one — pad columns are never written.
-template <int VPL, bool EX>
-__device__ __noinline__ void epilogue_tail(const SpmmParams &p, int v, int c0, int nvalid, const float *acc, float t,
-                                           int64_t step) {
-    for (int i = 0; i < nvalid; ++i) {
-        const int c = c0 + i;
-        float r[1] = {acc[i] * t};
-        if (p.addend) r[0] += __ldg(p.addend + (int64_t)v * p.ld_add + c);
-        if (p.bias) r[0] += __ldg(p.bias + c);
-        if (p.relu) r[0] = fmaxf(r[0], 0.f);
+template <bool EX>
+__device__ __forceinline__ void epilogue_tail_elem(const SpmmParams &p, int v, int c, float a, float t, int64_t step) {
+    float r[1] = {a * t};
+    if (p.addend) r[0] += __ldg(p.addend + (int64_t)v * p.ld_add + c);
+    if (p.bias) r[0] += __ldg(p.bias + c);
+    if (p.relu) r[0] = fmaxf(r[0], 0.f);
+    if constexpr (EX) {
+        drop_store<1>(p, step, v, p.col0_y + c, r, p.Y + (int64_t)v * p.ldy + c,
+                      p.y_lo ? p.y_lo + (int64_t)v * p.ld_y_lo + c : nullptr);
+    } else {
+        p.Y[(int64_t)v * p.ldy + c] = r[0];
+    }
+    if (p.self_out) {
+        float sx[1] = {__ldg(p.X + (int64_t)v * p.ldx + c)};
         if constexpr (EX) {
-            drop_store<1>(p, step, v, p.col0_y + c, r, p.Y + (int64_t)v * p.ldy + c,
-                          p.y_lo ? p.y_lo + (int64_t)v * p.ld_y_lo + c : nullptr);
+            drop_store<1>(p, step, v, p.col0_self + c, sx, p.self_out + (int64_t)v * p.ld_self + c,
+                          p.self_lo ? p.self_lo + (int64_t)v * p.ld_self_lo + c : nullptr);
         } else {
-            p.Y[(int64_t)v * p.ldy + c] = r[0];
-        }
-        if (p.self_out) {
-            float sx[1] = {__ldg(p.X + (int64_t)v * p.ldx + c)};
-            if constexpr (EX) {
-                drop_store<1>(p, step, v, p.col0_self + c, sx, p.self_out + (int64_t)v * p.ld_self + c,
-                              p.self_lo ? p.self_lo + (int64_t)v * p.ld_self_lo + c : nullptr);
-            } else {
-                p.self_out[(int64_t)v * p.ld_self + c] = sx[0];
-            }
+            p.self_out[(int64_t)v * p.ld_self + c] = sx[0];
         }
     }
 }
@@ -260,8 +257,10 @@ __device__ __forceinline__ void epilogue(const SpmmParams &p, int v, const int (
     for (int k = 0; k < VPL; ++k) {
         if (!cv[k]) continue;
         if constexpr (VEC > 1) {
-            if (c[k] + VEC > p.d) {          // ragged tail of the row
-                epilogue_tail<VPL, EX>(p, v, c[k], p.d - c[k], acc[k], t, step);
+            if (c[k] + VEC > p.d) {          // ragged tail of the row: valid columns only, one by one
+#pragma unroll
+                for (int i = 0; i < VEC - 1; ++i)
+                    if (c[k] + i < p.d) epilogue_tail_elem<EX>(p, v, c[k] + i, acc[k][i], t, step);
                 continue;
             }
         }
@@ -560,6 +559,215 @@ __global__ void __launch_bounds__(256, SEG_CTAS) spmm_seg_kernel(const __grid_co
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Slab variant for cluster batches: the gathered operand of a batch (<= ~3 k rows) is small enough
+// that a COLUMN SLAB of it — SW floats of every source row — fits in one SM's shared memory.  A CTA
+// (1024 threads) stages its slab once (coalesced 128-bit loads, src_scale folded in) and gathers every
+// edge from shared memory instead of L2: 128 B/clk per SM against the ~50 B/clk an SM gets from L2 under
+// load, and the L2 traffic of a launch drops from 4*nnz*d bytes to (CTAs per slab) x the operand.
+// Grid = slabs x P parts; part p of a slab owns a contiguous range of the batch's segments (the schedule
+// of spmm_seg_kernel: rows cut into <= seg_len edges), i.e. a contiguous range of the column-index
+// array.  The CTA walks its range in tiles: per tile, all threads resolve the segments' metadata in
+// parallel (two dependent L2 round trips for the whole tile instead of a chain per segment) and copy the
+// tile's column indices into shared memory as 16-bit values (n_src < 65536); the gather loop itself then
+// touches shared memory only.  A group of SW/4 lanes owns one (segment, slab): per edge one broadcast
+// LDS.U16 (index) and one LDS.128 (data) per lane.  Rows of several segments are combined as in
+// spmm_seg_kernel (partials to the workspace, last arriver adds them in segment order): deterministic,
+// no float atomics, and independent of P.
+constexpr int kSlabThreads = 1024;
+constexpr int kSlabIdxCap = 16384;      // edges per tile (32 KB of 16-bit indices)
+constexpr int kSlabSegCap = 768;        // segments per tile
+struct SlabMeta {
+    int v, eb, len, s0;                 // row, first edge (absolute), edges, first segment of the row
+};
+
+template <int SW, int OV, bool EX>
+__global__ void __launch_bounds__(kSlabThreads, 1) spmm_slab_kernel(const __grid_constant__ SpmmParams p) {
+    constexpr int LPR = SW / 4;                 // lanes per (segment, slab) group, one float4 each
+    constexpr int NGROUPS = kSlabThreads / LPR;
+    extern __shared__ float4 slab[];            // [n_src][LPR] | meta[kSlabSegCap] | nsegs[kSlabSegCap] | idx[kSlabIdxCap]
+    SlabMeta *meta = reinterpret_cast<SlabMeta *>(slab + (size_t)p.n_src * LPR);
+    int *nsegs = reinterpret_cast<int *>(meta + kSlabSegCap);
+    uint16_t *idx = reinterpret_cast<uint16_t *>(nsegs + kSlabSegCap);
+    __shared__ int s_te;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int lg = lane % LPR;
+    const int gid = tid / LPR;
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((lane / LPR) * LPR));
+    const int lane0 = (lane / LPR) * LPR;
+    const int P = p.seg_blocks;
+    const int slab_id = blockIdx.x / P;
+    const int part = blockIdx.x - slab_id * P;
+    const int c0 = slab_id * SW;
+    if constexpr (EX) record_drop_step(p);
+
+    const int n_seg = __ldg(p.seg_ptr + p.n_dst);
+    const int s_begin = (int)((int64_t)n_seg * part / P);
+    const int s_end = (int)((int64_t)n_seg * (part + 1) / P);
+
+    // stage the slab.  Columns past d hold zeros (their sums are never stored).
+    {
+        const int nvec = p.n_src * LPR;
+        const float *xb = p.X + c0;
+#pragma unroll 4
+        for (int i = tid; i < nvec; i += kSlabThreads) {
+            const int row = i / LPR, q = i - row * LPR;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + 4 * q < p.d) v = __ldg(reinterpret_cast<const float4 *>(xb + (int64_t)row * p.ldx + 4 * q));
+            if (p.src_scale) {
+                const float sc = __ldg(p.src_scale + row);
+                v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+            }
+            slab[i] = v;
+        }
+    }
+
+    int c[1];
+    bool cv[1];
+    c[0] = c0 + 4 * lg;
+    cv[0] = c[0] < p.d;
+    // the outputs may be less aligned than the staged operand (z = [h | agg] with an odd half width):
+    // OV = 4 / 2 / 1 floats per store
+    auto finish = [&](int v, const float (&a)[1][4]) {
+        if constexpr (OV == 4) {
+            epilogue<4, 1, EX>(p, v, c, cv, a);
+        } else {
+            constexpr int NV = 4 / OV;
+            int c2[NV];
+            bool cv2[NV];
+            float a2[NV][OV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                c2[k] = c[0] + k * OV;
+                cv2[k] = c2[k] < p.d;
+#pragma unroll
+                for (int i = 0; i < OV; ++i) a2[k][i] = a[0][k * OV + i];
+            }
+            epilogue<OV, NV, EX>(p, v, c2, cv2, a2);
+        }
+    };
+    uint32_t *arrivals = p.seg_count + 1;
+
+    for (int ts = s_begin; ts < s_end;) {
+        // ---- tile metadata: every thread resolves segments of [ts, ts + kSlabSegCap) in parallel
+        const int tcap = min(s_end - ts, kSlabSegCap);
+        if (tid == 0) s_te = ts + tcap;
+        for (int i = tid; i < tcap; i += kSlabThreads) {
+            const int seg = ts + i;
+            const int v = __ldg(p.seg_row + seg);
+            const int s0 = __ldg(p.seg_ptr + v);
+            const int s1 = __ldg(p.seg_ptr + v + 1);
+            const int rs = __ldg(p.rowptr + v), re = __ldg(p.rowptr + v + 1);
+            const int eb = min(re, rs + (seg - s0) * p.seg_len);
+            const int ee = min(re, eb + p.seg_len);
+            SlabMeta m;
+            m.v = v; m.eb = eb; m.len = ee - eb; m.s0 = s0;
+            meta[i] = m;
+            nsegs[i] = s1 - s0;
+        }
+        __syncthreads();                                   // (also: the slab is staged, first time round)
+        const int E0 = meta[0].eb;
+        // segments are contiguous in the index array: the tile ends before the first one that does not
+        // fit the index buffer (a single segment always fits: seg_len <= kSlabIdxCap)
+        for (int i = tid; i < tcap; i += kSlabThreads)
+            if (meta[i].eb - E0 + meta[i].len > kSlabIdxCap) atomicMin(&s_te, ts + i);
+        __syncthreads();
+        const int te = s_te;
+        const int nt = te - ts;
+        const int n_edges = meta[nt - 1].eb - E0 + meta[nt - 1].len;
+        for (int e = tid; e < n_edges; e += kSlabThreads) idx[e] = (uint16_t)__ldg(p.col + E0 + e);
+        __syncthreads();
+
+        // ---- gather: shared memory only
+        for (int i = gid; i < nt; i += NGROUPS) {
+            const SlabMeta m = meta[i];
+            const uint16_t *ix = idx + (m.eb - E0);
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            int e = 0;
+            for (; e + 4 <= m.len; e += 4) {               // four independent loads in flight, added in edge order
+                const float4 x0 = slab[(int)ix[e] * LPR + lg];
+                const float4 x1 = slab[(int)ix[e + 1] * LPR + lg];
+                const float4 x2 = slab[(int)ix[e + 2] * LPR + lg];
+                const float4 x3 = slab[(int)ix[e + 3] * LPR + lg];
+                a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
+                a0.x += x1.x; a0.y += x1.y; a0.z += x1.z; a0.w += x1.w;
+                a0.x += x2.x; a0.y += x2.y; a0.z += x2.z; a0.w += x2.w;
+                a0.x += x3.x; a0.y += x3.y; a0.z += x3.z; a0.w += x3.w;
+            }
+            for (; e < m.len; ++e) {
+                const float4 x0 = slab[(int)ix[e] * LPR + lg];
+                a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
+            }
+            float acc[1][4] = {{a0.x, a0.y, a0.z, a0.w}};
+            const int v = m.v;
+            const int nseg = nsegs[i];
+            if (nseg == 1) {
+                finish(v, acc);
+                continue;
+            }
+            const int seg = ts + i;
+            float *mine = p.seg_ws + (int64_t)seg * p.ld_ws;
+            if (cv[0]) st_vec<4>(mine + c[0], acc[0]);
+            __threadfence();                               // partials visible before the arrival
+            __syncwarp(gmask);
+            unsigned prev = 0;
+            uint32_t *cnt_p = arrivals + (int64_t)slab_id * p.n_dst + v;
+            if (lg == 0) prev = atomicAdd(cnt_p, 1u);
+            prev = __shfl_sync(gmask, prev, lane0);
+            if (prev != (unsigned)(nseg - 1)) continue;
+            __threadfence();
+            if (lg == 0) *cnt_p = 0u;                      // re-armed for the next launch
+            acc[0][0] = acc[0][1] = acc[0][2] = acc[0][3] = 0.f;
+            for (int j = 0; j < nseg; j += 4) {            // fixed order: segment 0, 1, 2, ...
+                float4 t[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    t[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cv[0] && j + q < nseg)
+                        t[q] = __ldcg(reinterpret_cast<const float4 *>(p.seg_ws + (int64_t)(m.s0 + j + q) * p.ld_ws + c[0]));
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    acc[0][0] += t[q].x; acc[0][1] += t[q].y; acc[0][2] += t[q].z; acc[0][3] += t[q].w;
+                }
+            }
+            finish(v, acc);
+        }
+        ts = te;
+        if (ts < s_end) __syncthreads();                   // meta / idx are rewritten by the next tile
+    }
+}
+
+constexpr size_t kSlabExtraSmem = kSlabSegCap * (sizeof(SlabMeta) + sizeof(int)) + kSlabIdxCap * sizeof(uint16_t);
+constexpr size_t kSlabSmemBudget = 224 * 1024 - kSlabExtraSmem;     // bytes left for the slab itself
+
+template <int SW, int OV>
+static int launch_spmm_slab(const SpmmParams &p0, int bg, cudaStream_t stream) {
+    SpmmParams p = p0;
+    const int n_slabs = (p.d + SW - 1) / SW;
+    int P = bg > 0 ? 1 : kNumSMs / n_slabs;       // background: one CTA per slab leaves the rest of the chip free
+    if (P < 1) P = 1;
+    p.seg_blocks = P;
+    const size_t smem = (size_t)p.n_src * SW * sizeof(float) + kSlabExtraSmem;
+    const bool ex = p.y_lo || p.self_lo || p.drop.p != 0.f;
+    static bool configured[2] = {false, false};
+    if (!configured[ex ? 1 : 0]) {
+        cudaError_t e = ex ? cudaFuncSetAttribute(spmm_slab_kernel<SW, OV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  224 * 1024)
+                           : cudaFuncSetAttribute(spmm_slab_kernel<SW, OV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  224 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured[ex ? 1 : 0] = true;
+    }
+    const unsigned grid = (unsigned)(n_slabs * P);
+    if (ex) spmm_slab_kernel<SW, OV, true><<<grid, kSlabThreads, smem, stream>>>(p);
+    else spmm_slab_kernel<SW, OV, false><<<grid, kSlabThreads, smem, stream>>>(p);
+    count_launch();
+    return last_error();
+}
+
 template <int VEC, int LPR, int VPL>
 static int launch_spmm_seg(const SpmmParams &p0, int64_t max_segments, cudaStream_t stream) {
     SpmmParams p = p0;
@@ -646,29 +854,11 @@ static int launch_spmm(const SpmmParams &p0, cudaStream_t stream, int bg_ctas_pe
     return last_error();
 }
 
-// L2 the gathered column slab should fit in with room for the index / output streams.  B200's 126 MB
-// L2 is two 63 MB partitions and a line gathered by SMs of both dies occupies both, so the budget
-// for a slab every SM reads is well under one partition.
-constexpr int64_t kSlabBudgetBytes = 36LL << 20;
-
 template <int VEC>
 static int dispatch_lanes(const SpmmParams &p, uint32_t flags, int32_t n_src, cudaStream_t stream) {
     const int lanes = (p.d + VEC - 1) / VEC;
     const int bg = (int)((flags >> GIST_SPMM_BG_SHIFT) & 15u);
     int force = (int)((flags >> GIST_SPMM_LANES_SHIFT) & 7u);       // 1..4 -> 4, 8, 16, 32 lanes per row
-    if (force == 0 && lanes > 8 && !(flags & (GIST_SPMM_NARROW | GIST_SPMM_WIDE))) {
-        // Large gathered operand (the full-graph SpMM of evaluate()): the chunk index is the slow grid
-        // dimension, so the chip sweeps one column slab of X at a time; pick the lane-group width
-        // whose slab (n_src x lanes x VEC floats) stays L2-resident while it is swept.
-        const int64_t x_bytes = (int64_t)n_src * p.d * 4;
-        if (x_bytes > (96LL << 20)) {
-            if ((int64_t)n_src * 32 * VEC * 4 <= kSlabBudgetBytes || lanes > 32) force = 0;   // widest fits, or nothing does
-            if ((int64_t)n_src * 32 * VEC * 4 > kSlabBudgetBytes) {
-                if ((int64_t)n_src * 16 * VEC * 4 <= kSlabBudgetBytes) force = 3;
-                else if ((int64_t)n_src * 8 * VEC * 4 <= kSlabBudgetBytes) force = 2;
-            }
-        }
-    }
     if (force == 1) return launch_spmm<VEC, 4, 1>(p, stream, bg);
     if (force == 2) return launch_spmm<VEC, 8, 1>(p, stream, bg);
     if (force == 3) return launch_spmm<VEC, 16, 1>(p, stream, bg);
@@ -689,6 +879,18 @@ static int dispatch_lanes(const SpmmParams &p, uint32_t flags, int32_t n_src, cu
         wide = lanes >= 64 && warps_wide >= 4LL * kNumSMs * 64 && src_bytes <= (64LL << 20);
     }
     return wide ? launch_spmm<VEC, 32, 2>(p, stream, bg) : launch_spmm<VEC, 32, 1>(p, stream, bg);
+}
+
+// alignment of everything the epilogue touches (outputs, addend, bias, low halves)
+static bool vec_ok_out(int vec, const SpmmParams &p) {
+    const size_t a = 4u * vec;
+    if (!aligned(p.Y, a) || p.ldy % vec) return false;
+    if (p.bias && !aligned(p.bias, a)) return false;
+    if (p.addend && (!aligned(p.addend, a) || p.ld_add % vec)) return false;
+    if (p.self_out && (!aligned(p.self_out, a) || p.ld_self % vec || !aligned(p.X, a) || p.ldx % vec)) return false;
+    if (p.y_lo && (!aligned(p.y_lo, a) || p.ld_y_lo % vec)) return false;
+    if (p.self_lo && (!aligned(p.self_lo, a) || p.ld_self_lo % vec)) return false;
+    return true;
 }
 
 static bool vec_ok(int vec, const SpmmParams &p) {
@@ -748,7 +950,7 @@ extern "C" int gist_spmm_csr_ex_f32(const int32_t *rowptr, const int32_t *col, i
     if (!aligned(rowptr, 4) || !aligned(col, 4) || !aligned(X, 4) || !aligned(Y, 4))
         return GIST_ERR_ALIGN;
     SpmmParams p;
-    p.rowptr = rowptr; p.col = col; p.n_dst = n_dst;
+    p.rowptr = rowptr; p.col = col; p.n_dst = n_dst; p.n_src = n_src;
     p.X = X; p.ldx = (int32_t)ldx; p.d = d; p.Y = Y; p.ldy = (int32_t)ldy;
     p.src_scale = src_scale; p.dst_scale = dst_scale; p.bias = bias;
     p.addend = addend; p.ld_add = (int32_t)ld_addend; p.self_out = self_out; p.ld_self = (int32_t)ld_self;
@@ -781,6 +983,16 @@ extern "C" int gist_spmm_csr_ex_f32(const int32_t *rowptr, const int32_t *col, i
         p.seg_count = sch->counters; p.seg_ws = sch->workspace; p.ld_ws = (int32_t)sch->ld_workspace;
         p.heavy_deg = 0x7fffffff;
         cudaStream_t s2 = (cudaStream_t)stream;
+        // slab kernel: the whole batch's column slab in shared memory (needs 128-bit alignment everywhere
+        // and n_src small enough); 16-float slabs, 8-float ones for batches up to twice as large
+        if (!(flags & GIST_SPMM_SLAB_OFF) && aligned(p.X, 16) && p.ldx % 4 == 0 && n_src > 0 && n_src < 65536 &&
+            sch->seg_len <= 64 && (size_t)n_src * 8 * sizeof(float) <= kSlabSmemBudget) {
+            const int bg = (int)((flags >> GIST_SPMM_BG_SHIFT) & 15u);
+            const bool wide = (size_t)n_src * 16 * sizeof(float) <= kSlabSmemBudget;
+            if (vec_ok_out(4, p)) return wide ? launch_spmm_slab<16, 4>(p, bg, s2) : launch_spmm_slab<8, 4>(p, bg, s2);
+            if (vec_ok_out(2, p)) return wide ? launch_spmm_slab<16, 2>(p, bg, s2) : launch_spmm_slab<8, 2>(p, bg, s2);
+            return wide ? launch_spmm_slab<16, 1>(p, bg, s2) : launch_spmm_slab<8, 1>(p, bg, s2);
+        }
         if (vec_ok(4, p)) return dispatch_lanes_seg<4>(p, sch->max_segments, s2);
         if (vec_ok(2, p)) return dispatch_lanes_seg<2>(p, sch->max_segments, s2);
         return dispatch_lanes_seg<1>(p, sch->max_segments, s2);

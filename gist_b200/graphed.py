@@ -39,6 +39,7 @@ _KEYS = ('feat', 'label', 'train_mask')
 # (0 = no cap); A/B switches for the measurements in profiles/
 PREP_CTAS_PER_SM = int(os.environ.get('GIST_PREP_CTAS', '0'))
 TRAIN_FIRST = os.environ.get('GIST_TRAIN_FIRST', '0') != '0'
+PREP_BALANCED = os.environ.get('GIST_PREP_BALANCED', '0') != '0'
 
 
 class GraphedClusterTrainer:
@@ -143,10 +144,13 @@ class GraphedClusterTrainer:
             # so it belongs to the batch-preparation branch (what the reference's use_pp idea is
             # after, but computed per batch on the batch subgraph: identical arithmetic), together
             # with that layer's dropout and 3xTF32 split, which K1 applies as it writes z
-            # (row-per-warp kernel here: in the shadow of the training branch the balanced kernel's
-            # resident-CTA grid only competes with it — measured 0.281 vs 0.299 ms/step)
+            # (row-per-warp kernel here: in the shadow of the training branch the scheduled kernels'
+            # resident-CTA grids only compete with it — measured 0.281 vs 0.299 ms/step for the segment
+            # kernel in round 1, 0.315 vs 0.340 for the shared-memory slab kernel in background mode in
+            # round 2; GIST_PREP_BALANCED=1 opts in for A/B runs)
             sg._cache[SAGE_PRE0] = self.model.layers[0].prepare_input(sg, sg.ndata['feat'], out=prev,
-                                                                     balanced=False, background=PREP_CTAS_PER_SM)
+                                                                     balanced=PREP_BALANCED,
+                                                                     background=PREP_CTAS_PER_SM or (1 if PREP_BALANCED else 0))
         return sg
 
     def _train(self, cluster, loss_out):

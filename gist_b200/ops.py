@@ -5,6 +5,7 @@ Every function here enqueues hand-written sm_100a kernels from
 non-CUDA inputs raise ``GistLibraryError``.
 """
 import ctypes
+import os
 
 import torch
 
@@ -50,21 +51,21 @@ def spmm_raw(rowptr, col, n_dst, n_src, X, out, *, src_scale=None, dst_scale=Non
     assert out.shape[0] == n_dst and out.shape[1] == d and X.shape[0] == n_src
     assert out.stride(1) == 1 or d == 1
     lib = _lib.load()
-    f = flags | (_lib.SPMM_RELU if relu else 0)
+    f = flags | (_lib.SPMM_RELU if relu else 0) | (0 if SLAB_ENABLED else _lib.SPMM_SLAB_OFF)
     prof = SPMM_PROFILE
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     ex = None
-    if schedule is not None and d > 384:
-        schedule = None         # wide rows: per-segment overheads outweigh the balance (measured d = 602)
+    if schedule is not None and d > 384 and not (SLAB_ENABLED and not (flags & _lib.SPMM_SLAB_OFF) and _slab_ok(X, n_src)):
+        schedule = None         # wide rows on the L2-gather segment kernel: per-segment overheads outweigh the balance (measured d = 602)
     if out_lo is not None or self_lo is not None or drop is not None or schedule is not None:
         sch = None
         if schedule is not None:
             assert schedule.n == n_dst
             ld_ws = (d + 3) // 4 * 4
             ws = torch.empty((schedule.max_segments, ld_ws), dtype=torch.float32, device=X.device)
-            cnt = schedule.counters(max(1, (d + 31) // 32))
+            cnt = schedule.counters(max(1, (d + 7) // 8))       # one arrival counter per (feature chunk, row); 8-float chunks are the narrowest
             sch = _lib.SpmmSchedule(ptr(schedule.seg_ptr), ptr(schedule.seg_row), schedule.seg_len,
                                     schedule.max_segments, ptr(cnt), ptr(ws), ld_ws)
         ex = _lib.SpmmEx(ptr(out_lo), _ld(out_lo) if out_lo is not None else 0,
@@ -85,6 +86,20 @@ def spmm_raw(rowptr, col, n_dst, n_src, X, out, *, src_scale=None, dst_scale=Non
     return out
 
 
+SLAB_SMEM_BYTES = 224 * 1024 - (768 * 20 + 16384 * 2)      # csrc/spmm.cu kSlabSmemBudget
+# Shared-memory slab kernel (spmm_slab_kernel): OFF by default.  Measured on the Reddit-shape step
+# (profiles/README.md, round 2): 24.5 us per d = 256 launch against 20.1 us for the L2-gather segment
+# kernel in isolation, and 30-48 us inside the replayed step, where a 1024-thread / 200 KB CTA has to
+# wait for a whole SM to drain from the preparation branch's kernels.  GIST_SPMM_SLAB=1 opts in.
+SLAB_ENABLED = os.environ.get('GIST_SPMM_SLAB', '0') != '0'
+
+
+def _slab_ok(X, n_src):
+    """The scheduled launch will stage column slabs of X in shared memory (spmm_slab_kernel): X rows
+    16-byte aligned and an 8-float slab of all n_src rows within the shared-memory budget."""
+    return (X.data_ptr() % 16 == 0 and _ld(X) % 4 == 0 and 0 < n_src * 32 <= SLAB_SMEM_BYTES and n_src < 65536)
+
+
 class SegSchedule:
     """Segment schedule of one CSR (gist_spmm_schedule_t minus the per-launch workspace)."""
 
@@ -96,8 +111,9 @@ class SegSchedule:
         self.seg_row = torch.empty(self.max_segments, dtype=torch.int32, device=dev)
         # work-queue head + arrival counters (zeroed once; the kernel leaves them zero).  The first
         # stream that launches on this schedule owns the set allocated here; any other stream gets
-        # its own (see counters()).  Sized for the widest scheduled launch (d <= 384: 12 chunks).
-        self._counters = torch.zeros(1 + 12 * max(n, 1), dtype=torch.int32, device=dev)
+        # its own (see counters()).  Sized for the widest scheduled launch of a Reddit-shape batch
+        # (d = 602 in 8-float chunks: 76).
+        self._counters = torch.zeros(1 + 76 * max(n, 1), dtype=torch.int32, device=dev)
         self._owner = None
         self._others = {}
         self.rebuild(rowptr)

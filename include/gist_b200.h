@@ -62,6 +62,7 @@ typedef struct gist_dropout {
 #define GIST_SPMM_WIDE 4u        /* force 2 vectors / lane                        */
 #define GIST_SPMM_COOP_ON 8u     /* force CTA-cooperative hub rows (row split)    */
 #define GIST_SPMM_COOP_OFF 16u   /* never split rows (default: on iff n_dst<=32k) */
+#define GIST_SPMM_SLAB_OFF 32u   /* scheduled launches: never stage column slabs in shared memory (A/B switch) */
 /* bits 8..11: background mode for gist_spmm_csr_ex_f32's extended epilogue (0 = off): at most
  * this many CTAs per SM are launched and walk the work with a grid stride, so a kernel that runs
  * in the shadow of a latency-critical branch (the next batch's layer-0 aggregation beside the
@@ -130,8 +131,9 @@ int gist_spmm_csr_f32(const int32_t *rowptr, const int32_t *col, int32_t n_dst, 
  * batch; shared by the forward and — for a symmetric pattern — the transpose launches).
  *   seg_ptr[n+1]  first segment of each row (seg_ptr[n] = number of segments, read on the device)
  *   seg_row[max_segments]  row of each segment;  max_segments >= n + nnz / seg_len (host bound)
- *   counters[1 + chunks * n]  uint32, ZERO on entry, left zero on exit (chunks <= ceil(d / 4)):
- *                  [0] head of the launch's work queue, then one arrival counter per (chunk, row)
+ *   counters[1 + chunks * n]  uint32, ZERO on entry, left zero on exit; chunks = ceil(d / 8) covers
+ *                  every kernel variant: [0] head of the launch's work queue, then one arrival
+ *                  counter per (feature chunk, row)
  *   workspace[max_segments][ld_workspace >= d, % 4 == 0]  fp32 scratch, no initialisation needed
  * Two launches that share `counters` / `workspace` must not run concurrently. */
 typedef struct gist_spmm_schedule {

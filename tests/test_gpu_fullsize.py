@@ -84,5 +84,5 @@ def test_real_bench_batch_end_to_end_vs_oracle(reddit):
     F.cross_entropy(ref, y.cpu()).backward()
     assert_close(out, ref, rtol=1e-5, what='bench batch logits')
     for l, (w, b) in zip(model.layers, params):
-        assert_close(l.linear.weight.grad, w.grad, rtol=2e-5, what='dW')
-        assert_close(l.linear.bias.grad, b.grad, rtol=2e-5, what='db')
+        assert_close(l.linear.weight.grad, w.grad, rtol=1e-5, what='dW')
+        assert_close(l.linear.bias.grad, b.grad, rtol=1e-5, what='db')

@@ -50,17 +50,17 @@ def test_sage_gcn_forward_backward(cfg, matmul_precision):
     F.cross_entropy(ref, y).backward()
     out = model(g)
     F.cross_entropy(out, y.cuda()).backward()
-    assert_close(out, ref, rtol=5e-5, what='logits')
+    assert_close(out, ref, rtol=1e-5, what='logits')          # north_star: 1e-5 relative
     for l, (w, b) in zip(model.layers, params):
-        assert_close(l.linear.weight.grad, w.grad, rtol=1e-4, what='dW')
-        assert_close(l.linear.bias.grad, b.grad, rtol=1e-4, what='db')
+        assert_close(l.linear.weight.grad, w.grad, rtol=1e-5, what='dW')
+        assert_close(l.linear.bias.grad, b.grad, rtol=1e-5, what='db')
 
 
 def test_ist_sage_layer_train_mode_injected_dropout():
     """Train-mode parity with the SAME dropout mask: torch's Philox stream cannot be
     reproduced on the CPU, so the mask is captured from the CUDA run and injected
     into the oracle."""
-    from gist_b200 import ISTSAGELayer
+    from gist_b200 import ISTSAGELayer, ops
     n, fin, fout = 500, 64, 32
     g, og = _graphs(n, 6000, seed=4, loops=False)
     torch.manual_seed(0)
@@ -68,12 +68,18 @@ def test_ist_sage_layer_train_mode_injected_dropout():
     masks = []
     layer.dropout.register_forward_hook(lambda m, i, o: masks.append((o / i[0]).nan_to_num(0.0)))
     x = torch.randn(n, fin)
-    out = layer(g, x.cuda())
+    # the nn.Dropout module itself only runs in the cuBLAS cross-check mode; on the default tensor-core
+    # path dropout is fused into K1 / K4 and is covered, mask for mask, by tests/test_gpu_dropout_fusion.py
+    ops.set_matmul_precision('fp32')
+    try:
+        out = layer(g, x.cuda())
+    finally:
+        ops.set_matmul_precision(ops.DEFAULT_MATMUL_PRECISION)
     mask = masks[0].cpu().double()
     # entries where the input was exactly 0 give 0/0 -> 0 in the mask; harmless (z*mask = 0)
     ref = O.ist_sage_layer(og, x.double(), layer.linear.weight.detach().double().cpu(),
                            layer.linear.bias.detach().double().cpu(), True, F.relu, mask)
-    assert_close(out, ref, rtol=5e-5, what='train-mode layer')
+    assert_close(out, ref, rtol=1e-5, what='train-mode layer')
 
 
 @pytest.mark.parametrize('dims', [(1433, 16), (32, 32), (16, 7), (8, 24)])
@@ -98,10 +104,10 @@ def test_graph_conv(dims, act):
     xg = x.cuda().requires_grad_(True)
     out = conv(g, xg)
     (out * wy.float().cuda()).sum().backward()
-    assert_close(out, ref, rtol=5e-5, what='GraphConv fwd')
-    assert_close(xg.grad, x64.grad, rtol=1e-4, what='dX')
-    assert_close(conv.weight.grad, w64.grad, rtol=1e-4, what='dW')
-    assert_close(conv.bias.grad, b64.grad, rtol=1e-4, what='db')
+    assert_close(out, ref, rtol=1e-5, what='GraphConv fwd')
+    assert_close(xg.grad, x64.grad, rtol=1e-5, what='dX')
+    assert_close(conv.weight.grad, w64.grad, rtol=1e-5, what='dW')
+    assert_close(conv.bias.grad, b64.grad, rtol=1e-5, what='db')
 
 
 def test_graph_conv_zero_in_degree_raises():
@@ -126,7 +132,7 @@ def test_graphconv_gcn_container(split):
     params = [(l.weight.detach().double().cpu(), l.bias.detach().double().cpu()) for l in model.layers]
     ref = O.graphconv_gcn_forward(og, x.double(), params, True)
     out = model(x.cuda())
-    assert_close(out, ref, rtol=5e-5, what='GCN(GraphConv) logits')
+    assert_close(out, ref, rtol=1e-5, what='GCN(GraphConv) logits')
     assert list(model.state_dict().keys())[:2] == ['layers.0.weight', 'layers.0.bias']
 
 
@@ -228,8 +234,8 @@ def test_sage_gcn_inference_project_first_vs_oracle(cfg, matmul_precision):
     with torch.no_grad():
         fast = model(g)
     slow = model(g)                         # grad enabled: aggregate-first path
-    assert_close(fast, ref, rtol=5e-5, what='project-first logits')
-    assert_close(fast, slow, rtol=5e-5, what='project-first vs aggregate-first')
+    assert_close(fast, ref, rtol=1e-5, what='project-first logits')
+    assert_close(fast, slow, rtol=1e-5, what='project-first vs aggregate-first')
 
 
 def test_evaluate_masks_one_pass_equals_two_evaluate_calls():
@@ -289,9 +295,9 @@ def test_graphsage_layer_vs_reference_golden(ci, matmul_precision):
     y = layer(g, x)
     (y * _T(G[p + 'wy']).cuda()).sum().backward()
     assert_close(y, _T(G[p + 'out']), rtol=1e-5, what='GraphSAGELayer out')
-    assert_close(x.grad, _T(G[p + 'dx']), rtol=2e-5, what='dx')
+    assert_close(x.grad, _T(G[p + 'dx']), rtol=1e-5, what='dx')
     for k, v in layer.named_parameters():
-        assert_close(v.grad, _T(G[p + 'grad.' + k]), rtol=2e-5, what='grad ' + k)
+        assert_close(v.grad, _T(G[p + 'grad.' + k]), rtol=1e-5, what='grad ' + k)
 
 
 @pytest.mark.parametrize('ci', [0, 1])
@@ -310,7 +316,7 @@ def test_graphsage_container_vs_reference_golden(ci, matmul_precision):
     F.cross_entropy(logits, _T(G[p + 'y']).cuda()).backward()
     assert_close(logits, _T(G[p + 'logits']), rtol=1e-5, what='GraphSAGE logits')
     for k, v in model.named_parameters():
-        assert_close(v.grad, _T(G[p + 'grad.' + k]), rtol=2e-5, what='grad ' + k)
+        assert_close(v.grad, _T(G[p + 'grad.' + k]), rtol=1e-5, what='grad ' + k)
     assert list(model.state_dict().keys())[:4] == ['layers.0.linear.weight', 'layers.0.linear.bias',
                                                    'layers.0.lynorm.weight', 'layers.0.lynorm.bias']
 
@@ -338,13 +344,13 @@ def test_graphsage_container_vs_oracle(cfg, matmul_precision):
     F.cross_entropy(ref, y).backward()
     out = model(g)
     F.cross_entropy(out, y.cuda()).backward()
-    assert_close(out, ref, rtol=2e-5, what='GraphSAGE logits')
+    assert_close(out, ref, rtol=1e-5, what='GraphSAGE logits')
     for l, tup in zip(model.layers, params):
-        assert_close(l.linear.weight.grad, tup[0].grad, rtol=5e-5, what='dW')
-        assert_close(l.linear.bias.grad, tup[1].grad, rtol=5e-5, what='db')
+        assert_close(l.linear.weight.grad, tup[0].grad, rtol=1e-5, what='dW')
+        assert_close(l.linear.bias.grad, tup[1].grad, rtol=1e-5, what='db')
         if tup[2] is not None:
-            assert_close(l.lynorm.weight.grad, tup[2].grad, rtol=5e-5, what='d ln.weight')
-            assert_close(l.lynorm.bias.grad, tup[3].grad, rtol=5e-5, what='d ln.bias')
+            assert_close(l.lynorm.weight.grad, tup[2].grad, rtol=1e-5, what='d ln.weight')
+            assert_close(l.lynorm.bias.grad, tup[3].grad, rtol=1e-5, what='d ln.bias')
 
 
 def test_graphsage_layer_use_pp_train_skips_aggregation():
@@ -394,7 +400,7 @@ def test_baseline_gcn_vs_reference_golden_with_grads(ci, matmul_precision):
     F.cross_entropy(logits, _T(G[p + 'y']).cuda()).backward()
     assert_close(logits, _T(G[p + 'logits']), rtol=1e-5, what='BaselineGCN logits')
     for k, v in model.named_parameters():
-        assert_close(v.grad, _T(G[p + 'grad.' + k]), rtol=2e-5, what='grad ' + k)
+        assert_close(v.grad, _T(G[p + 'grad.' + k]), rtol=1e-5, what='grad ' + k)
 
 
 @pytest.mark.parametrize('cfg', [(602, 128, 41, 2, True), (64, 96, 7, 1, False)])
@@ -417,7 +423,7 @@ def test_baseline_gcn_vs_oracle(cfg, matmul_precision):
     F.cross_entropy(ref, y).backward()
     out = model(g)
     F.cross_entropy(out, y.cuda()).backward()
-    assert_close(out, ref, rtol=2e-5, what='BaselineGCN logits')
+    assert_close(out, ref, rtol=1e-5, what='BaselineGCN logits')
     for l, (w, b) in zip(model.layers, params):
-        assert_close(l.weight.grad, w.grad, rtol=5e-5, what='dW')
-        assert_close(l.bias.grad, b.grad, rtol=5e-5, what='db')
+        assert_close(l.weight.grad, w.grad, rtol=1e-5, what='dW')
+        assert_close(l.bias.grad, b.grad, rtol=1e-5, what='db')

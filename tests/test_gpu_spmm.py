@@ -165,11 +165,16 @@ def test_full_size_linearity_and_degree_identity():
 # ------------------------------------------------------------ segment-balanced K1/K2 ----
 @pytest.mark.parametrize('d', [1, 7, 32, 100, 256, 602])
 @pytest.mark.parametrize('has_scale', [False, True])
-def test_segment_balanced_matches_oracle_and_is_deterministic(d, has_scale):
-    """The segment-scheduled kernel (cluster batches) on a power-law graph: hub rows span dozens
-    of segments finished by whichever group arrives last, yet the result is run-to-run identical
-    and within tolerance of the fp64 oracle; arrival counters are left zero."""
-    from gist_b200 import ops
+@pytest.mark.parametrize('slab', [True, False])
+def test_segment_balanced_matches_oracle_and_is_deterministic(d, has_scale, slab, monkeypatch):
+    """The scheduled kernels (cluster batches) on a power-law graph: hub rows span dozens of segments
+    finished by whichever group arrives last, yet the result is run-to-run identical and within
+    tolerance of the fp64 oracle; arrival counters are left zero.  slab=True lets the launch stage
+    column slabs of X in shared memory where the layout allows it (here: X rows 16-byte aligned,
+    outputs at odd offsets -> scalar stores), slab=False forces the L2-gather segment kernel."""
+    from gist_b200 import _lib, ops
+    fl = 0 if slab else _lib.SPMM_SLAB_OFF
+    monkeypatch.setattr(ops, 'SLAB_ENABLED', True)          # the slab kernel is opt-in (ops.SLAB_ENABLED)
     n = 3000
     src, dst = powerlaw_graph(n, 40, seed=7)
     g = _gist(src, dst, n)
@@ -195,7 +200,7 @@ def test_segment_balanced_matches_oracle_and_is_deterministic(d, has_scale):
     for _ in range(3):
         out = torch.full((n, 2 * d + 1), float('nan'), device='cuda')
         ops.spmm_raw(g.rowptr, g.col_buffer, n, n, x.cuda(), out[:, d:2 * d], src_scale=cu(s), dst_scale=cu(t),
-                     bias=bias.cuda(), addend=addend.cuda(), self_out=out[:, :d], relu=True, schedule=sch)
+                     bias=bias.cuda(), addend=addend.cuda(), self_out=out[:, :d], relu=True, schedule=sch, flags=fl)
         outs.append(out)
     assert_close(outs[0][:, d:2 * d], ref, what='segment-balanced')
     assert torch.equal(outs[0][:, :d].cpu(), x)
@@ -207,6 +212,53 @@ def test_segment_balanced_matches_oracle_and_is_deterministic(d, has_scale):
     ops.spmm_raw(g.rowptr, g.col_buffer, n, n, x.cuda(), plain, src_scale=cu(s), dst_scale=cu(t),
                  bias=bias.cuda(), addend=addend.cuda(), relu=True)
     assert_close(outs[0][:, d:2 * d], plain, what='vs row-per-group kernel')
+
+
+@pytest.mark.parametrize('d', [16, 30, 32, 41, 256, 602])
+@pytest.mark.parametrize('mode', ['fwd', 'transpose', 'background'])
+def test_slab_kernel_on_the_training_layouts(d, mode, monkeypatch):
+    """spmm_slab_kernel on the buffer layouts of the training step: X with 16-byte-aligned (padded)
+    rows, z = [h | agg] in ONE padded buffer (the aggregate half is 16-, 8- or 4-byte aligned depending
+    on d), dst_scale = 1/deg, self copy; 'transpose' = the backward launch (src_scale, addend, no self
+    copy); 'background' = one CTA per slab.  Against the fp64 oracle, bit-identical across repeats and
+    across the foreground / background grids (the summation order does not depend on the grid)."""
+    from gist_b200 import ops
+    monkeypatch.setattr(ops, 'SLAB_ENABLED', True)
+    n = 2600
+    src, dst = powerlaw_graph(n, 40, seed=11)
+    src, dst = torch.cat([src, dst]), torch.cat([dst, src])           # symmetric, like the bench graphs
+    g = _gist(src, dst, n)
+    og = ograph(src, dst, n)
+    sch = g.seg_schedule()
+    torch.manual_seed(d)
+    x = ops.pad_rows(torch.randn(n, d, device='cuda'))
+    assert x.data_ptr() % 16 == 0 and x.stride(0) % 4 == 0
+    inv = g.inv_in_degree()
+    norm = O.sage_norm(og, torch.float64)
+    if mode == 'transpose':
+        add = ops._padded_empty(n, d, 'cuda').normal_()
+        ref = O.copy_src_sum(og, x.double().cpu() * norm) + add.double().cpu()      # symmetric: A^T = A
+        outs = []
+        for _ in range(2):
+            y = torch.empty(n, d, device='cuda')
+            ops.spmm_raw(g.rowptr, g.col_buffer, n, n, x, y, src_scale=inv, addend=add, schedule=sch)
+            outs.append(y)
+        assert_close(outs[0], ref, what='slab transpose')
+        assert torch.equal(outs[0], outs[1])
+        return
+    ref = O.copy_src_sum(og, x.double().cpu()) * norm
+    outs = []
+    for bg in ((0, 0, 1) if mode == 'background' else (0, 0)):
+        z = ops._padded_empty(n, 2 * d, 'cuda')
+        z.fill_(float('nan'))
+        ops.spmm_raw(g.rowptr, g.col_buffer, n, n, x, z[:, d:], dst_scale=inv, self_out=z[:, :d], schedule=sch,
+                     flags=bg << 8)
+        outs.append(z)
+    assert_close(outs[0][:, d:], ref, what='slab forward')
+    assert torch.equal(outs[0][:, :d], x)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    assert (sch.counters(1) == 0).all()
 
 
 def test_segment_schedule_edge_cases():
