@@ -74,6 +74,10 @@ def parse():
     ap.add_argument('--first-epoch-rule', action='store_true',
                     help='apply the reference\'s "no re-dispatch during epoch 0" rule (…distrib.py:401) from the '
                          'first benchmarked step; default: steady state (rounds as in epochs >= 1: sync + dispatch)')
+    ap.add_argument('--host-barriers', action='store_true',
+                    help='call dist.barrier() before every dispatch / sync as the reference does (…distrib.py:402, 422); '
+                         'default off: the packed all-gather is the synchronisation point, and a host-side barrier '
+                         'drains the asynchronous step queue at every round boundary')
     ap.add_argument('--base-init', default=None, choices=['cpu', 'device'],
                     help='where rank 0 draws the full model\'s initial values; default cpu (reference-identical) '
                          'below hidden 8192, device above')
@@ -330,15 +334,18 @@ def run_gist(a):
             self.running_loss = 0.0
             self.loss_acc = torch.zeros((), device=dev)
             self.nodes = 0
+            self.round_host_s, self.rounds = 0.0, 0         # host wall time spent in sync + dispatch calls
 
         def next_step(self):
             if self.total_iter % a.iter_per_site == 0 and self.total_iter > 0:
                 e = self.total_iter // len(self.it) + (0 if a.first_epoch_rule else 1)
+                t0 = time.perf_counter()
                 if e > 0:                                   # …distrib.py:401
-                    if world > 1:
+                    if world > 1 and a.host_barriers:
                         dist.barrier()
                     self.w.dispatch_model()
                 self.tr.reset_optimizer()                   # fresh Adam at every round (…distrib.py:405-407)
+                self.round_host_s += time.perf_counter() - t0
             if self.readback:
                 # every step: ids H2D from pinned memory, loss D2H into pinned memory; the host
                 # consumes the value one step late so the readback never stalls the launch queue
@@ -350,9 +357,12 @@ def run_gist(a):
             self.nodes += self.tr.n_pad
             self.total_iter += 1
             if self.total_iter % a.iter_per_site == 0:
-                if world > 1:
+                t0 = time.perf_counter()
+                if world > 1 and a.host_barriers:
                     dist.barrier()
                 self.w.sync_model()
+                self.round_host_s += time.perf_counter() - t0
+                self.rounds += 1
 
         def finish(self):
             if self.readback:
@@ -380,7 +390,7 @@ def run_gist(a):
                 cluster = next(self.iter)
             if self.total_iter % a.iter_per_site == 0:
                 if self.e + (0 if a.first_epoch_rule else 1) > 0 and self.total_iter > 0:   # …distrib.py:401
-                    if world > 1:
+                    if world > 1 and a.host_barriers:
                         dist.barrier()
                     self.w.dispatch_model()
                 self.w.sub_model.train()
@@ -393,7 +403,7 @@ def run_gist(a):
                 self.loss_acc += loss
             self.total_iter += 1
             if self.total_iter % a.iter_per_site == 0:
-                if world > 1:
+                if world > 1 and a.host_barriers:
                     dist.barrier()
                 self.w.sync_model()
 
@@ -451,7 +461,9 @@ def run_gist(a):
         torch.cuda.profiler.start()
     if hasattr(w, 'profile'):
         w.profile = []
+    rh0, rn0 = getattr(loop, 'round_host_s', 0.0), getattr(loop, 'rounds', 0)
     ms, launches = timed(loop, a.steps)
+    round_host_ms = ((getattr(loop, 'round_host_s', 0.0) - rh0) * 1e3 / max(getattr(loop, 'rounds', 0) - rn0, 1))
     sync_prof = getattr(w, 'profile', None)
     if hasattr(w, 'profile'):
         w.profile = None
@@ -472,6 +484,8 @@ def run_gist(a):
         clocks['window'] = ('warm-up + timed region + %d untimed soak steps of the same loop (%.2f s)'
                             % (soak_steps, soak_steps * ms / a.steps / 1e3))
     sync = sync_summary(sync_prof, world, ms, a.steps) if sync_prof is not None else None
+    if sync is not None:
+        sync['host_ms_per_round'] = round(round_host_ms, 3)      # wall time of the host inside sync + barrier + dispatch calls
 
     # ---- instrumented pass: per-launch SpMM durations with CUDA events --------------
     # Eager steps on the same workload, each preceded by a device-side sleep long enough for
@@ -626,8 +640,8 @@ def run_gist(a):
             x = ops._padded_empty(n, d, dev).normal_()
             y = ops._padded_empty(n, d, dev)
             best = {}
-            variants = [('auto', 0, x, y), ('lanes8', 2 << _lib.SPMM_LANES_SHIFT, x, y),
-                        ('lanes16', 3 << _lib.SPMM_LANES_SHIFT, x, y), ('lanes32', 4 << _lib.SPMM_LANES_SHIFT, x, y)]
+            variants = [('auto', 0, x, y), ('vec128', 3 << _lib.SPMM_VEC_SHIFT, x, y), ('vec64', 2 << _lib.SPMM_VEC_SHIFT, x, y),
+                        ('vec32', 1 << _lib.SPMM_VEC_SHIFT, x, y)]
             if d % 4:      # round 1's layout: contiguous rows, 64-bit gathers
                 variants.append(('unpadded_rows', 0, x.contiguous(), torch.empty(n, d, device=dev)))
             for name, fl, xx, yy in variants:

@@ -68,6 +68,9 @@ SIGNATURES = {
                                             _P, _P, _P, _P, _I64, _P, _I64, _U32, _P, _P]),
     'gist_spmm_schedule_workspace_bytes': (_SZ, [_I32]),
     'gist_spmm_schedule_build': (ctypes.c_int, [_P, _I32, _I32, _P, _P, _I64, _P, _SZ, _P]),
+    'gist_gemm_ex_workspace_bytes': (_SZ, [_I32, _I32, _I32, _U32, _I32, _P]),
+    'gist_gemm_ex_f32': (ctypes.c_int, [_P, _P, _I64, _I64, _I32, _P, _P, _I64, _I64, _I32, _P, _I64, _I32, _I32,
+                                        _I32, _P, _U32, _P, _SZ, _P, _P]),
     'gist_gemm_dropmask_f32': (ctypes.c_int, [_P, _P, _I64, _I64, _I32, _P, _P, _I64, _I64, _I32, _P, _I64,
                                               _I32, _I32, _I32, _U32, _P, _P]),
     'gist_gat_scores_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P]),
@@ -81,9 +84,11 @@ SIGNATURES = {
 SPMM_RELU, SPMM_NARROW, SPMM_WIDE = 1, 2, 4
 SPMM_SLAB_OFF = 32
 SPMM_BG_SHIFT = 8
+SPMM_VEC_SHIFT = 16        # flags |= code << 16: 1, 2, 3 -> gathers of at most 32, 64, 128 bits
 SPMM_LANES_SHIFT = 12      # flags |= code << 12: 1, 2, 3, 4 -> 4, 8, 16, 32 lanes per row
 NORM_INV, NORM_RSQRT_CLAMP = 0, 1
 GEMM_RELU, GEMM_NO_SPLITK, GEMM_TILE_N64, GEMM_TILE_N128, GEMM_TILE_N256 = 1, 2, 4, 8, 16
+GEMM_BACKGROUND = 32
 GEMM_K_MAJOR, GEMM_MN_MAJOR = 0, 1
 ACT_RELU = 1
 
@@ -108,6 +113,13 @@ class SpmmEx(ctypes.Structure):
                 ('ld_self_lo', ctypes.c_int64), ('drop', ctypes.POINTER(DropoutDesc)),
                 ('drop_col0_y', ctypes.c_int32), ('drop_col0_self', ctypes.c_int32),
                 ('schedule', ctypes.POINTER(SpmmSchedule))]
+
+
+class GemmEx(ctypes.Structure):
+    """gist_gemm_ex_t"""
+    _fields_ = [('tile_counters', ctypes.c_void_p), ('n_counters', ctypes.c_int64), ('rowsum', ctypes.c_void_p),
+                ('ln_out', ctypes.c_void_p), ('ld_ln', ctypes.c_int64), ('ln_stats', ctypes.c_void_p),
+                ('ln_eps', ctypes.c_float), ('ln_flags', ctypes.c_uint32), ('drop', ctypes.POINTER(DropoutDesc))]
 
 
 _lib = None

@@ -450,10 +450,17 @@ __global__ void __launch_bounds__(256) ce_fused_kernel(const float *__restrict__
     // rows that count: masked in AND labelled with a class index (see ce_reduce_kernel).  All loads of
     // a thread are independent (unrolled), so the loop is a couple of L2 round trips, not a chain.
     int cnt = 0;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < n; i += 256) {
-        const bool ok = (mask ? __ldg(mask + i) != 0 : true) && (uint64_t)__ldg(labels + i) < (uint64_t)C;
-        cnt += ok ? 1 : 0;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 256 * 8) {     // 16 predicated loads in flight per round
+        uint8_t mk[8];
+        int64_t lb[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = i0 + k * 256;
+            mk[k] = (i < n) ? (mask ? __ldg(mask + i) : (uint8_t)1) : (uint8_t)0;
+            lb[k] = (i < n) ? __ldg(labels + i) : (int64_t)-1;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cnt += (mk[k] != 0 && (uint64_t)lb[k] < (uint64_t)C) ? 1 : 0;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);

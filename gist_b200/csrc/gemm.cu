@@ -82,6 +82,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
         : "memory");
 }
 
+// 1-D bulk copy global -> shared (TMA engine), completion on an mbarrier; size % 16 == 0, 16-byte aligned
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // Shared-memory matrix descriptors (sm_100 format, 128-byte swizzle).
 //   K-major operand  : rows of 32 floats (128 B), 8-row groups 1024 B apart (SBO); LBO unused.
 //                      One MMA reads 8 floats of K: start address + 32 B per K step.
@@ -123,6 +131,32 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         : "memory");
 }
 
+// One leader lane of a fully converged warp (the same lane every time: the MMAs and the commits that
+// track them must come from one thread).  The warp-role loops run on ALL lanes with warp-uniform values
+// so that descriptors and addresses live in uniform registers; only the async instruction itself sits
+// under this predicate.  (Issuing from `if (lane == 0)` makes ptxas wrap every UTCHMMA / UTMALDG in an
+// ELECT / R2UR.BROADCAST loop: ~10 extra instructions per MMA on a single thread, which made the main
+// loop instruction-issue bound at ~0.57 us per K block.)
+#ifdef GIST_GEMM_OLD_ISSUE      // A/B build: round 1's single-lane role loops
+#define GIST_ROLE_LANES(lane) ((lane) == 0)
+#define GIST_ROLE_SYNC()
+__device__ __forceinline__ bool elect_one() { return true; }
+#else
+#define GIST_ROLE_LANES(lane) true
+#define GIST_ROLE_SYNC() __syncwarp()
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+#endif
+
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                      smem_u32(bar))
@@ -155,8 +189,27 @@ struct GemmParams {
     int32_t relu;
     int32_t vec4;       // output rows and bias are 16-byte aligned: float4 epilogue stores
     int32_t kc;         // NT == 3: K blocks chained into one TMEM accumulator before it is drained
+    int32_t background; // host only: launch on a third of the SMs (GIST_GEMM_BACKGROUND)
     DropParams drop;    // p != 0: C[r, c] *= dropout multiplier of (r, c) (the dz = dy W contraction)
     long long *trace;   // diagnostic (gist_gemm_set_trace): kTraceSlots clock stamps per CTA, or NULL
+    // ---- extended epilogue (gist_gemm_ex_f32) ----
+    // In-kernel split-K: partial tiles go to `ws` ([tile][split][BN/4][128] float4, lanes = rows:
+    // coalesced), the CTA that arrives LAST at a tile's counter adds them in split order and runs the
+    // epilogue — no second launch, same summation order as splitk_reduce_kernel.
+    uint32_t *tile_counters;    // [tiles_m * tiles_n], zero on entry, left zero;  NULL = legacy two-kernel split-K
+    float *ws;
+    float *ws_rowsum;           // [tiles_m][splits][128] partial row sums
+    // Row sums of op(A) over K (the bias gradient db = colsum(dy) of the dW = dy^T z contraction) from
+    // the tensor core: one extra N = 16 MMA per K step against a tile of ones, in n-tile 0 only.
+    float *rowsum;
+    // LayerNorm (no affine) + optional ReLU over the rows of C when one tile holds the whole row
+    // (N <= BN): C keeps the pre-norm values (the backward needs them), ln_y = act(LN(C)), ln_stats =
+    // (mean, rstd).  Replaces ln_act_fwd_kernel behind a layer's projection.
+    float *ln_y;
+    int64_t ld_ln;
+    float2 *ln_stats;
+    float ln_eps;
+    int32_t ln_relu;
 };
 
 // Phase stamps of a CTA's FIRST work unit (tools/gemm_trace.py): SM clock at  0 entry, 1 set-up done,
@@ -179,16 +232,37 @@ struct GemmCfg {
     static constexpr int kOperandCopies = NT == 3 ? 2 : 1;               // (x) or (x, x_lo)
     static constexpr int kStageBytes = (kBM + BN) * kBK * 4 * kOperandCopies;
     static constexpr int kStages = kSmemBudget / kStageBytes;          // NT=1: 64: 8, 128: 6, 256: 4
-    static constexpr int kTmemCols = 2 * BN;                            // double-buffered accumulator
-    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    // double-buffered accumulator + (BN <= 128) two 16-column row-sum accumulators; power of two
+#ifdef GIST_GEMM_TMEM_2BN       // A/B build: round 1's allocation (no row-sum accumulators)
+    static constexpr int kTmemCols = 2 * BN;
+#else
+    static constexpr int kTmemCols = BN == 256 ? 512 : 4 * BN;
+#endif
+    static constexpr int kAuxCol = 2 * BN;                              // first row-sum column (BN <= 128)
+    static constexpr size_t kOnesBytes = 2048;                          // 16 rows x 128 B of 1.0f (K-major, any swizzle)
+    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + kOnesBytes + 256 /*barriers*/;
 };
 
-template <int BN, bool A_MN, bool B_MN, int NT>
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return __uint_as_float(r);
+}
+
+// named barrier among the 128 epilogue threads (barrier 0 is __syncthreads)
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int BN, bool A_MN, bool B_MN, int NT, bool LN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmBl,
                  const GemmParams p) {
     using Cfg = GemmCfg<BN, NT>;
+    static_assert(!LN || BN <= 128, "the LayerNorm epilogue keeps the whole row of the tile in registers");
+    // row sums of op(A) exist only where they are used — the dW = dy^T z layout (both operands MN-major),
+    // tiles <= 128 wide — so every other instantiation's MMA issue loop carries no trace of them
+    constexpr bool kRowsum = A_MN && B_MN && BN <= 128;
     constexpr int kStages = Cfg::kStages;
     constexpr size_t kABytes = (size_t)kStages * kBM * kBK * 4, kBBytes = (size_t)kStages * BN * kBK * 4;
     extern __shared__ uint8_t smem_raw[];
@@ -198,12 +272,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float *sB = reinterpret_cast<float *>(base + kABytes);           // [stages][BN*32]
     float *sAl = reinterpret_cast<float *>(base + kABytes + kBBytes);              // NT == 3 only
     float *sBl = reinterpret_cast<float *>(base + 2 * kABytes + kBBytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)kStages * Cfg::kStageBytes);
+    float *sOnes = reinterpret_cast<float *>(base + (size_t)kStages * Cfg::kStageBytes);     // 1024-byte aligned
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)kStages * Cfg::kStageBytes + Cfg::kOnesBytes);
+    __shared__ int s_last;      // in-kernel split-K: this CTA arrived last at its tile
     uint64_t *full = bars, *empty = bars + kStages;
     uint64_t *tmem_full = bars + 2 * kStages, *tmem_empty = bars + 2 * kStages + 2;
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+    uint64_t *red_bar = bars + 2 * kStages + 5;      // in-kernel split-K: partial tiles landed in shared memory
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform for the compiler too
     const int lane = threadIdx.x & 31;
     const int n_work = p.tiles_m * p.tiles_n * p.splits;
 
@@ -223,6 +300,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&tmem_full[a], 1);
             mbar_init(&tmem_empty[a], 4);     // one arrival per epilogue warp
         }
+        mbar_init(red_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // whole warp: allocate the accumulator columns
@@ -232,6 +310,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (kRowsum && p.rowsum && warp >= 2) {       // the ones tile, visible to the tensor core (async proxy)
+        for (int i = threadIdx.x - 64; i < (int)(Cfg::kOnesBytes / 4); i += 128) sOnes[i] = 1.0f;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -239,24 +321,27 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (threadIdx.x == 0) trace_stamp(p, 1);
 
     if (warp == 0) {
-        if (lane == 0) {
+      if (GIST_ROLE_LANES(lane)) {
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
             if constexpr (NT == 3) {
                 asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAl)) : "memory");
                 asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBl)) : "memory");
             }
-            int s = 0;
-            uint32_t ph = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const int split = w % p.splits;
-                const int t = w / p.splits;
-                const int m0 = (t % p.tiles_m) * kBM;
-                const int n0 = (t / p.tiles_m) * BN;
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty[s], ph ^ 1);
+        }
+        int s = 0;
+        uint32_t ph = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int split = w % p.splits;
+            const int t = w / p.splits;
+            const int m0 = (t % p.tiles_m) * kBM;
+            const int n0 = (t / p.tiles_m) * BN;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty[s], ph ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(&full[s], (uint32_t)Cfg::kStageBytes);
 #pragma unroll
                     for (int part = 0; part < Cfg::kOperandCopies; ++part) {
@@ -279,82 +364,109 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     }
                     if (w == (int)blockIdx.x && kb == kb0) trace_stamp(p, 2);
-                    if (++s == kStages) { s = 0; ph ^= 1; }
                 }
+                GIST_ROLE_SYNC();
+                if (++s == kStages) { s = 0; ph ^= 1; }
             }
         }
+      }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN, A_MN, B_MN);
-            int s = 0;
-            uint32_t ph = 0;
-            int acc = 0;
-            uint32_t acc_ph = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const int split = w % p.splits;
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-                // The tensor core's fp32 accumulate truncates, so error grows linearly with the
-                // number of MMAs chained into one TMEM accumulator.  NT == 3 therefore closes the
-                // accumulator every p.kc K blocks; the epilogue warps add the chunks in registers
-                // (round-to-nearest fp32), alternating the two TMEM buffers.  NT == 1: one chunk.
-                const int kc = NT == 3 ? p.kc : (kb1 - kb0);
-                for (int kc0 = kb0; kc0 < kb1; kc0 += kc) {
-                    const int kc1 = min(kb1, kc0 + kc);
-                    mbar_wait(&tmem_empty[acc], acc_ph ^ 1);        // epilogue has drained this buffer
+      if (GIST_ROLE_LANES(lane)) {
+        constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN, A_MN, B_MN);
+        constexpr uint32_t idesc_aux = umma_idesc_tf32(kBM, 16, A_MN, false);
+        // descriptor = constant high part | (shared address >> 4); one K step (8 floats) advances the start
+        // address by 32 B (K-major) or by 8 K rows = 1024 B (MN-major), i.e. adds 2 or 64 to the descriptor
+        constexpr uint64_t kHiK = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayoutSw128 << 61);
+        constexpr uint64_t kHiMN = ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+                                   ((uint64_t)kLayoutSw128Base32 << 61);
+        constexpr uint64_t kHiA = A_MN ? kHiMN : kHiK, kHiB = B_MN ? kHiMN : kHiK;
+        constexpr uint32_t kStepA = A_MN ? 64 : 2, kStepB = B_MN ? 64 : 2;
+        const uint32_t a0 = smem_u32(sA) >> 4, b0 = smem_u32(sB) >> 4;
+        const uint32_t al0 = smem_u32(sAl) >> 4, bl0 = smem_u32(sBl) >> 4;
+        const uint64_t ones_desc = kHiK | (uint64_t)(smem_u32(sOnes) >> 4);
+        int s = 0;
+        uint32_t ph = 0;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int split = w % p.splits;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+            const bool do_rowsum = kRowsum && p.rowsum != nullptr && (w / p.splits) / p.tiles_m == 0;
+            // The tensor core's fp32 accumulate truncates, so error grows linearly with the
+            // number of MMAs chained into one TMEM accumulator.  NT == 3 therefore closes the
+            // accumulator every p.kc K blocks; the epilogue warps add the chunks in registers
+            // (round-to-nearest fp32), alternating the two TMEM buffers.  NT == 1: one chunk.
+            const int kc = NT == 3 ? p.kc : (kb1 - kb0);
+            for (int kc0 = kb0; kc0 < kb1; kc0 += kc) {
+                const int kc1 = min(kb1, kc0 + kc);
+                mbar_wait(&tmem_empty[acc], acc_ph ^ 1);        // epilogue has drained this buffer
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_addr = tmem_d + (uint32_t)(acc * BN);
+                const uint32_t x_addr = tmem_d + (uint32_t)(Cfg::kAuxCol + acc * 16);
+                for (int kb = kc0; kb < kc1; ++kb) {
+                    mbar_wait(&full[s], ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t d_addr = tmem_d + (uint32_t)(acc * BN);
-                    for (int kb = kc0; kb < kc1; ++kb) {
-                        mbar_wait(&full[s], ph);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
                         if (w == (int)blockIdx.x && kb == kb0) trace_stamp(p, 3);
-                        const uint32_t a_addr = smem_u32(sA + (size_t)s * kBM * kBK);
-                        const uint32_t b_addr = smem_u32(sB + (size_t)s * BN * kBK);
-                        auto a_desc = [](uint32_t addr, int k) {
-                            return A_MN ? umma_desc(addr + k * 1024, 4096, 512, kLayoutSw128Base32)
-                                        : umma_desc(addr + k * kUmmaK * 4, 0, 1024, kLayoutSw128);
-                        };
-                        auto b_desc = [](uint32_t addr, int k) {
-                            return B_MN ? umma_desc(addr + k * 1024, 4096, 512, kLayoutSw128Base32)
-                                        : umma_desc(addr + k * kUmmaK * 4, 0, 1024, kLayoutSw128);
-                        };
+                        const uint64_t ad0 = kHiA | (uint64_t)(a0 + (uint32_t)s * (kBM * kBK * 4 / 16));
+                        const uint64_t bd0 = kHiB | (uint64_t)(b0 + (uint32_t)s * (BN * kBK * 4 / 16));
+                        const uint64_t adl0 = kHiA | (uint64_t)(al0 + (uint32_t)s * (kBM * kBK * 4 / 16));
+                        const uint64_t bdl0 = kHiB | (uint64_t)(bl0 + (uint32_t)s * (BN * kBK * 4 / 16));
 #pragma unroll
                         for (int k = 0; k < kBK / kUmmaK; ++k) {
-                            const uint64_t ad = a_desc(a_addr, k), bd = b_desc(b_addr, k);
+                            const uint64_t ad = ad0 + (uint64_t)(k * kStepA), bd = bd0 + (uint64_t)(k * kStepB);
                             const uint32_t first = (kb > kc0 || k > 0) ? 1u : 0u;
                             if constexpr (NT == 3) {     // small terms first, then the leading product
-                                const uint64_t adl = a_desc(smem_u32(sAl + (size_t)s * kBM * kBK), k);
-                                const uint64_t bdl = b_desc(smem_u32(sBl + (size_t)s * BN * kBK), k);
+                                const uint64_t adl = adl0 + (uint64_t)(k * kStepA), bdl = bdl0 + (uint64_t)(k * kStepB);
                                 umma_tf32(d_addr, adl, bd, idesc, first);
                                 umma_tf32(d_addr, ad, bdl, idesc, 1u);
                                 umma_tf32(d_addr, ad, bd, idesc, 1u);
+                                if constexpr (kRowsum) {
+                                    if (do_rowsum) {     // row sums of op(A): op(A) (lo, then hi) against ones
+                                        umma_tf32(x_addr, adl, ones_desc + (uint64_t)(k * 2), idesc_aux, first);
+                                        umma_tf32(x_addr, ad, ones_desc + (uint64_t)(k * 2), idesc_aux, 1u);
+                                    }
+                                }
                             } else {
                                 umma_tf32(d_addr, ad, bd, idesc, first);
+                                if constexpr (kRowsum) {
+                                    if (do_rowsum) umma_tf32(x_addr, ad, ones_desc + (uint64_t)(k * 2), idesc_aux, first);
+                                }
                             }
                         }
                         umma_commit(&empty[s]);          // slot reusable once these MMAs have read it
-                        if (++s == kStages) { s = 0; ph ^= 1; }
+                        if (kb + 1 == kc1) {
+                            umma_commit(&tmem_full[acc]);        // this chunk's accumulator is complete
+                            if (w == (int)blockIdx.x && kc1 == kb1) trace_stamp(p, 4);
+                        }
                     }
-                    umma_commit(&tmem_full[acc]);        // this chunk's accumulator is complete
-                    if (w == (int)blockIdx.x && kc1 == kb1) trace_stamp(p, 4);
-                    acc ^= 1;
-                    if (acc == 0) acc_ph ^= 1;
+                    GIST_ROLE_SYNC();
+                    if (++s == kStages) { s = 0; ph ^= 1; }
                 }
+                acc ^= 1;
+                if (acc == 0) acc_ph ^= 1;
             }
         }
+      }
     } else {
         // epilogue warps 2..5: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
         const int q = warp & 3;
+        const int trow = q * 32 + lane;              // row inside the tile
         int acc = 0;
         uint32_t acc_ph = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int split = w % p.splits;
             const int t = w / p.splits;
-            const int m0 = (t % p.tiles_m) * kBM;
+            const int tile_m = t % p.tiles_m;
+            const int m0 = tile_m * kBM;
             const int n0 = (t / p.tiles_m) * BN;
-            const int row = m0 + q * 32 + lane;
-            float *crow = p.C + ((int64_t)split * p.M + row) * p.ldc;
-            const bool fused = p.splits == 1;
+            const int row = m0 + trow;
+            const bool inker = p.splits > 1 && p.tile_counters != nullptr;     // last-arriver reduction in this kernel
+            const bool legacy = p.splits > 1 && !inker;                        // partials for splitk_reduce_kernel
+            const bool do_rowsum = kRowsum && p.rowsum != nullptr && n0 == 0;
+            float *crow = legacy ? p.C + ((int64_t)split * p.M + row) * p.ldc : p.C + (int64_t)row * p.ldc;
+            const bool fused = !legacy;
             const int ncols = min(BN, p.N - n0);     // warp-uniform
             // one 32-column segment of the finished row: bias / ReLU, then 128-bit or scalar stores
             const bool masked = fused && p.drop.p != 0.f;
@@ -400,18 +512,120 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
             };
-            if constexpr (NT == 3) {
-                // sum the K chunks in registers: lane = row, BN fp32 accumulators per thread
-                static_assert(BN <= 128, "3xTF32 keeps the whole row of the tile in registers");
+            // in-kernel split-K: this unit's partial tile, [BN/4][128] float4 with lanes = rows (coalesced)
+            float4 *part = reinterpret_cast<float4 *>(p.ws) + ((int64_t)t * p.splits + split) * (BN / 4) * kBM;
+            auto store_part32 = [&](const float (&v)[32], int c) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    part[(int64_t)((c + i) >> 2) * kBM + trow] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            };
+            // The reducing CTA pulls the partial tiles into shared memory with bulk copies (the operand
+            // ring is free: in-kernel reduction is used only when every CTA has a single work unit) —
+            // all of a batch's bytes in flight at once instead of a chain of register loads — and adds
+            // them in split order.  `fold(j, v, c)`: v += staged partial j, columns [c, c + 32).
+            constexpr uint32_t kTileBytes = (uint32_t)kBM * BN * 4;
+            constexpr int kStageTiles = kSmemBudget / kTileBytes >= 1 ? (int)(kSmemBudget / kTileBytes) : 1;
+            const float4 *stage = reinterpret_cast<const float4 *>(base);
+            uint32_t red_ph = 0;
+            auto stage_partials = [&](int s_first, int count) {      // all 128 epilogue threads call this
+                epi_bar_sync();                                      // previous batch fully consumed
+                if (threadIdx.x == 64) {
+                    asm volatile("fence.proxy.async;" ::: "memory"); // partials were written through the generic proxy
+                    mbar_expect_tx(red_bar, (uint32_t)count * kTileBytes);
+                    for (int j = 0; j < count; ++j)
+                        bulk_load(base + (size_t)j * kTileBytes,
+                                  reinterpret_cast<const float4 *>(p.ws) + ((int64_t)t * p.splits + s_first + j) * (BN / 4) * kBM,
+                                  kTileBytes, red_bar);
+                }
+                mbar_wait(red_bar, red_ph);
+                red_ph ^= 1;
+            };
+            auto fold = [&](int j, float (&v)[32], int c) {
+                const float4 *ps = stage + (size_t)j * (BN / 4) * kBM;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 x = ps[((c >> 2) + i) * kBM + trow];
+                    v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+                }
+            };
+            // LayerNorm epilogue over a complete row held in registers (tiles_n == 1, n0 == 0)
+            auto ln_finalize = [&](float (&x)[LN ? BN : 1]) {
+                if constexpr (LN) {
+                    if (row >= p.M) return;
+                    float mean = 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < BN; ++cc)
+                        if (cc < ncols) {
+                            if (p.bias) x[cc] += __ldg(p.bias + cc);
+                            mean += x[cc];
+                        }
+                    mean /= (float)ncols;
+                    float var = 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < BN; ++cc)
+                        if (cc < ncols) {
+                            const float dlt = x[cc] - mean;
+                            var += dlt * dlt;
+                        }
+                    const float rstd = rsqrtf(var / (float)ncols + p.ln_eps);
+                    if (p.ln_stats) p.ln_stats[row] = make_float2(mean, rstd);
+                    float *yrow = p.ln_y + (int64_t)row * p.ld_ln;
+                    const bool v4 = p.vec4 && (reinterpret_cast<uintptr_t>(yrow) & 15) == 0;
+#pragma unroll
+                    for (int cc = 0; cc < BN; cc += 4) {
+                        if (cc >= ncols) continue;
+                        float o[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            o[i] = (x[cc + i] - mean) * rstd;
+                            if (p.ln_relu) o[i] = fmaxf(o[i], 0.f);
+                        }
+                        if (v4 && cc + 4 <= ncols) {
+                            *reinterpret_cast<float4 *>(crow + cc) = make_float4(x[cc], x[cc + 1], x[cc + 2], x[cc + 3]);
+                            *reinterpret_cast<float4 *>(yrow + cc) = make_float4(o[0], o[1], o[2], o[3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (cc + i < ncols) {
+                                    crow[cc + i] = x[cc + i];
+                                    yrow[cc + i] = o[i];
+                                }
+                        }
+                    }
+                }
+            };
+            // all four epilogue warps have published their partials: one thread takes the tile's ticket
+            auto arrive_is_last = [&]() -> bool {
+                __threadfence();
+                epi_bar_sync();
+                if (threadIdx.x == 64) {
+                    const unsigned prev = atomicAdd(p.tile_counters + t, 1u);
+                    const int last = prev == (unsigned)(p.splits - 1);
+                    if (last) p.tile_counters[t] = 0u;        // every other split has arrived: re-armed for the next launch
+                    s_last = last;
+                }
+                epi_bar_sync();
+                const bool last = s_last != 0;
+                if (last) __threadfence();
+                return last;
+            };
+            float rs = 0.f;                                   // row sum of op(A) (n-tile 0 only)
+            float *rs_part = p.ws_rowsum ? p.ws_rowsum + ((int64_t)tile_m * p.splits + split) * kBM + trow : nullptr;
+
+            if constexpr (NT == 3 || LN) {
+                // the whole row of the tile in registers: lane = row, BN fp32 accumulators per thread;
+                // NT == 3 sums the K chunks here (round-to-nearest fp32 adds)
+                static_assert(BN <= 128, "this epilogue keeps the whole row of the tile in registers");
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+                const int kc = NT == 3 ? p.kc : (kb1 - kb0);
                 float sum[BN];
 #pragma unroll
                 for (int i = 0; i < BN; ++i) sum[i] = 0.f;
-                for (int kc0 = kb0; kc0 < kb1; kc0 += p.kc) {
+                for (int kc0 = kb0; kc0 < kb1; kc0 += kc) {
                     mbar_wait(&tmem_full[acc], acc_ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (warp == 2 && lane == 0 && w == (int)blockIdx.x && kc0 + p.kc >= kb1) trace_stamp(p, 5);
+                    if (warp == 2 && lane == 0 && w == (int)blockIdx.x && kc0 + kc >= kb1) trace_stamp(p, 5);
 #pragma unroll
                     for (int c = 0; c < BN; c += 32) {
                         if (c < ncols) {
@@ -421,20 +635,70 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             for (int i = 0; i < 32; ++i) sum[c + i] += v[i];
                         }
                     }
+                    if constexpr (kRowsum) {
+                        if (do_rowsum) rs += tmem_ld1(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::kAuxCol + acc * 16));
+                    }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                     acc ^= 1;
                     if (acc == 0) acc_ph ^= 1;
                 }
+                bool finish = true;
+                if (inker) {
 #pragma unroll
-                for (int c = 0; c < BN; c += 32) {
-                    if (c < ncols) {
-                        float v[32];
+                    for (int c = 0; c < BN; c += 32) {
+                        if (c < ncols) {
+                            float v[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = sum[c + i];
-                        store32(v, c);
+                            for (int i = 0; i < 32; ++i) v[i] = sum[c + i];
+                            store_part32(v, c);
+                        }
                     }
+                    if (do_rowsum) *rs_part = rs;
+                    finish = arrive_is_last();
+                    if (finish) {                              // add the partials of all splits, in split order
+#pragma unroll
+                        for (int i = 0; i < BN; ++i) sum[i] = 0.f;
+                        rs = 0.f;
+                        for (int s1 = 0; s1 < p.splits; s1 += kStageTiles) {
+                            const int nb = min(kStageTiles, p.splits - s1);
+                            stage_partials(s1, nb);
+                            for (int j = 0; j < nb; ++j) {
+#pragma unroll
+                                for (int c = 0; c < BN; c += 32) {
+                                    if (c < ncols) {
+                                        float v[32];
+#pragma unroll
+                                        for (int i = 0; i < 32; ++i) v[i] = sum[c + i];
+                                        fold(j, v, c);
+#pragma unroll
+                                        for (int i = 0; i < 32; ++i) sum[c + i] = v[i];
+                                    }
+                                }
+                            }
+                        }
+                        if (do_rowsum)
+                            for (int s2 = 0; s2 < p.splits; ++s2)
+                                rs += __ldcg(p.ws_rowsum + ((int64_t)tile_m * p.splits + s2) * kBM + trow);
+                    }
+                }
+                if (finish) {
+                    if constexpr (LN) {
+                        ln_finalize(sum);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BN; c += 32) {
+                            if (c < ncols) {
+                                float v[32];
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = sum[c + i];
+                                store32(v, c);
+                            }
+                        }
+                    }
+                    if (do_rowsum && !legacy && row < p.M) p.rowsum[row] = rs;
+                    if (do_rowsum && legacy) *rs_part = rs;          // folded by splitk_reduce_kernel
                 }
             } else {
                 mbar_wait(&tmem_full[acc], acc_ph);
@@ -444,13 +708,58 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int c = 0; c < ncols; c += 32) {
                     float v[32];
                     tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
-                    store32(v, c);
+                    if (inker) store_part32(v, c);
+                    else store32(v, c);
+                }
+                if constexpr (kRowsum) {
+                    if (do_rowsum) rs = tmem_ld1(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::kAuxCol + acc * 16));
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_ph ^= 1;
+                bool finish = true;
+                if (inker) {
+                    if (do_rowsum) *rs_part = rs;
+                    finish = arrive_is_last();
+                    if (finish) {
+                        if (p.splits <= kStageTiles) {         // every partial fits the staging area at once
+                            stage_partials(0, p.splits);
+#pragma unroll 1
+                            for (int c = 0; c < ncols; c += 32) {
+                                float v[32];
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                                for (int j = 0; j < p.splits; ++j) fold(j, v, c);
+                                store32(v, c);
+                            }
+                        } else {                               // batches: running sums go through the output rows
+#pragma unroll 1
+                            for (int c = 0; c < ncols; c += 32) {
+                                float v[32];
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                                for (int s2 = 0; s2 < p.splits; ++s2) {
+                                    const float4 *ps = reinterpret_cast<const float4 *>(p.ws) + ((int64_t)t * p.splits + s2) * (BN / 4) * kBM;
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float4 x = __ldcg(ps + (int64_t)((c >> 2) + i) * kBM + trow);
+                                        v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+                                    }
+                                }
+                                store32(v, c);
+                            }
+                        }
+                        if (do_rowsum) {
+                            rs = 0.f;
+                            for (int s2 = 0; s2 < p.splits; ++s2)
+                                rs += __ldcg(p.ws_rowsum + ((int64_t)tile_m * p.splits + s2) * kBM + trow);
+                        }
+                    }
+                }
+                if (finish && do_rowsum && !legacy && row < p.M) p.rowsum[row] = rs;
+                if (do_rowsum && legacy) *rs_part = rs;
             }
             if (warp == 2 && lane == 0 && w == (int)blockIdx.x) trace_stamp(p, 6);
         }
@@ -469,10 +778,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // Split-K second pass: C[r, c] = act(sum_s part[s][r][c] + bias[c]), fixed summation order.
+// Row sums of op(A) (gist_gemm_ex_t.rowsum) from the per-split partials the GEMM CTAs of n-tile 0 left
+// in the workspace: out[r] = sum_s part[(r / 128) * splits + s][r % 128], split order.  Runs in the tail
+// blocks (blockIdx.x >= main_blocks) of the split-K second-pass kernels.
+__device__ __forceinline__ void rowsum_fold(const float *__restrict__ part, int splits, int M, float *__restrict__ out,
+                                            int r) {
+    if (r >= M) return;
+    const float *p0 = part + (int64_t)(r / kBM) * splits * kBM + (r % kBM);
+    float t = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < splits; ++s) t += __ldg(p0 + (int64_t)s * kBM);
+    out[r] = t;
+}
+
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restrict__ part, int64_t ldp,
                                                             int splits, int M, int N,
                                                             const float *__restrict__ bias, int relu,
-                                                            float *__restrict__ C, int64_t ldc) {
+                                                            float *__restrict__ C, int64_t ldc, int main_blocks,
+                                                            const float *__restrict__ rs_part,
+                                                            float *__restrict__ rs_out) {
+    if ((int)blockIdx.x >= main_blocks) {
+        rowsum_fold(rs_part, splits, M, rs_out, ((int)blockIdx.x - main_blocks) * 256 + (int)threadIdx.x);
+        return;
+    }
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int nq = (N + 3) >> 2;
     if (i >= (int64_t)M * nq) return;
@@ -503,6 +831,73 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restr
             if (bias) x += __ldg(bias + c + k);
             if (relu) x = fmaxf(x, 0.f);
             C[(int64_t)r * ldc + c + k] = x;
+        }
+    }
+}
+
+// Split-K second pass WITH the layer norm (gist_gemm_ex_t.ln_out; N <= 128): one warp per row adds the
+// row's partials in split order (lane = 4 columns), adds the bias, and normalises the complete row with
+// warp shuffles: C = pre-norm values, y = act(LN(C)), stats = (mean, rstd).  Replaces splitk_reduce_kernel
+// + ln_act_fwd_kernel behind a layer's projection.
+__global__ void __launch_bounds__(256) splitk_reduce_ln_kernel(const float *__restrict__ part, int64_t ldp, int splits,
+                                                               int M, int N, const float *__restrict__ bias, float eps,
+                                                               int relu, float *__restrict__ C, int64_t ldc,
+                                                               float *__restrict__ y, int64_t ldy,
+                                                               float2 *__restrict__ stats) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= M) return;
+    const int c = lane * 4;
+    const bool on = c < N;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t sstride = (int64_t)M * ldp;
+    const float *p0 = part + (int64_t)r * ldp + c;
+    if (on) {
+        int s = 0;
+        for (; s + 4 <= splits; s += 4) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)s * sstride));
+            const float4 v1 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)(s + 1) * sstride));
+            const float4 v2 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)(s + 2) * sstride));
+            const float4 v3 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)(s + 3) * sstride));
+            acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+            acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+            acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+            acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+        }
+        for (; s < splits; ++s) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)s * sstride));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    float x[4] = {acc.x, acc.y, acc.z, acc.w};
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (c + k < N) {
+            if (bias) x[k] += __ldg(bias + c + k);
+            sum += x[k];
+        } else {
+            x[k] = 0.f;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)N;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (c + k < N) q += (x[k] - mean) * (x[k] - mean);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)N + eps);
+    if (lane == 0 && stats) stats[r] = make_float2(mean, rstd);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (c + k < N) {
+            float o = (x[k] - mean) * rstd;
+            if (relu) o = fmaxf(o, 0.f);
+            C[(int64_t)r * ldc + c + k] = x[k];
+            y[(int64_t)r * ldy + c + k] = o;
         }
     }
 }
@@ -645,20 +1040,21 @@ struct GemmMaps {
     CUtensorMap a, b, al, bl;     // al / bl = the x_lo operands (NT == 3); copies of a / b otherwise
 };
 
-template <int BN, bool A_MN, bool B_MN, int NT>
+template <int BN, bool A_MN, bool B_MN, int NT, bool LN = false>
 static int launch_gemm(const GemmMaps &m, const GemmParams &p, cudaStream_t s) {
     constexpr size_t smem = GemmCfg<BN, NT>::kSmemBytes;
     static_assert(GemmCfg<BN, NT>::kStages >= 2, "operand ring needs at least two stages");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN, NT>,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN, NT, LN>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     const int n_work = p.tiles_m * p.tiles_n * p.splits;
-    const int grid = n_work < sm_count() ? n_work : sm_count();
-    gemm_tf32_kernel<BN, A_MN, B_MN, NT><<<grid, kGemmThreads, smem, s>>>(m.a, m.b, m.al, m.bl, p);
+    const int cap = p.background ? max(sm_count() / 3, 1) : sm_count();
+    const int grid = n_work < cap ? n_work : cap;
+    gemm_tf32_kernel<BN, A_MN, B_MN, NT, LN><<<grid, kGemmThreads, smem, s>>>(m.a, m.b, m.al, m.bl, p);
     count_launch();
     return last_error();
 }
@@ -678,6 +1074,8 @@ static int launch_tile(int bn, bool a_mn, bool b_mn, const GemmMaps &m, const Ge
     return launch_layout<64, NT>(a_mn, b_mn, m, p, s);
 }
 
+constexpr uint32_t kPlanNo256 = 1u << 30;        // internal: tiles at most 128 wide (row sums live beside the accumulators)
+
 struct GemmPlan {
     int bn, splits, kb_per_split;
     int64_t ldp;            // leading dimension of the split-K partial buffer
@@ -694,9 +1092,12 @@ struct GemmPlan {
 // Small problems are bound by the fixed cost and by how many SMs pull operands at once (one CTA
 // streams ~110 GB/s whatever the tile), so the model prefers one full wave of short K loops over
 // few long ones; large problems amortise everything and get the widest tile (least L2 traffic).
-static GemmPlan plan_gemm(int M, int N, int K, uint32_t flags, bool x3) {
+static GemmPlan plan_gemm(int M, int N, int K, uint32_t flags, bool x3, bool inkernel = false) {
     GemmPlan pl;
-    const int sms = sm_count();
+    // GIST_GEMM_BACKGROUND: a contraction nobody waits for yet (dW of a layer whose dz chain is still
+    // running beside it) is planned for — and launched on — a third of the SMs, so the latency-critical
+    // stream keeps finding free SMs instead of queueing behind 140 resident 20-us CTAs
+    const int sms = (flags & GIST_GEMM_BACKGROUND) ? max(sm_count() / 3, 1) : sm_count();
     const int64_t tm = (M + kBM - 1) / kBM;
     const int kblocks = (K + kBK - 1) / kBK;
     int cand[3], nc = 0;
@@ -705,7 +1106,7 @@ static GemmPlan plan_gemm(int M, int N, int K, uint32_t flags, bool x3) {
     else if (flags & GIST_GEMM_TILE_N128) cand[nc++] = 128;
     else if (flags & GIST_GEMM_TILE_N256) cand[nc++] = x3 ? 128 : 256;
     else {
-        if (!x3) cand[nc++] = 256;
+        if (!x3 && !(flags & kPlanNo256)) cand[nc++] = 256;
         cand[nc++] = 128;
         cand[nc++] = 64;
     }
@@ -736,7 +1137,12 @@ static GemmPlan plan_gemm(int M, int N, int K, uint32_t flags, bool x3) {
             // chip-wide operand traffic (L2 -> SM) bounds large problems
             const double agg_us = (double)units * kbps * stage_bytes / 14e6;
             if (agg_us > cost) cost = agg_us;
-            if (s_eff > 1) cost += 4.0 + (double)(s_eff + 1) * M * N * 4.0 / 3e6;
+            if (s_eff > 1) {
+                // second pass: a launch + chip-wide fold (legacy), or the tile's last CTA reading
+                // s_eff partial tiles at one SM's L2 rate (in-kernel)
+                if (inkernel) cost += 2.0 + (double)s_eff * kBM * bn * 4.0 / 80e3;
+                else cost += 4.0 + (double)(s_eff + 1) * M * N * 4.0 / 3e6;
+            }
             if (cost < best - 0.05) {
                 best = cost;
                 pl.bn = bn; pl.splits = s_eff; pl.kb_per_split = kbps;
@@ -744,7 +1150,13 @@ static GemmPlan plan_gemm(int M, int N, int K, uint32_t flags, bool x3) {
         }
     }
     pl.ldp = (N + 3) / 4 * 4;
-    pl.ws_bytes = pl.splits > 1 ? (size_t)pl.splits * M * pl.ldp * sizeof(float) : 0;
+    pl.ws_bytes = 0;
+    if (pl.splits > 1) {
+        const size_t tm2 = (size_t)tm, tn2 = (size_t)((N + pl.bn - 1) / pl.bn);
+        const size_t legacy = ((size_t)pl.splits * M * pl.ldp + tm2 * pl.splits * kBM) * sizeof(float);
+        const size_t inker = (tm2 * tn2 * pl.splits * kBM * pl.bn + tm2 * pl.splits * kBM) * sizeof(float);
+        pl.ws_bytes = inkernel ? inker : legacy;
+    }
     return pl;
 }
 
@@ -780,12 +1192,37 @@ extern "C" size_t gist_gemm_3xtf32_workspace_bytes(int32_t M, int32_t N, int32_t
     return plan_gemm(M, N, K, flags, true).ws_bytes;
 }
 
+// tile-width restrictions of the extended epilogue, folded into the planner's flags
+static uint32_t ex_plan_flags(int32_t N, uint32_t flags, const gist_gemm_ex_t *ex) {
+    if (!ex) return flags;
+    if (ex->ln_out) {          // one tile must hold the whole row
+        flags &= ~(GIST_GEMM_TILE_N64 | GIST_GEMM_TILE_N128 | GIST_GEMM_TILE_N256);
+        flags |= N <= 64 ? GIST_GEMM_TILE_N64 : GIST_GEMM_TILE_N128;
+    } else if (ex->rowsum) {
+        if (flags & GIST_GEMM_TILE_N256) flags = (flags & ~GIST_GEMM_TILE_N256) | GIST_GEMM_TILE_N128;
+        flags |= kPlanNo256;
+    }
+    return flags;
+}
+
 // Shared body of the 1xTF32 and 3xTF32 entry points (A_lo == B_lo == nullptr selects 1x).
 static int gemm_impl(const float *A, const float *A_lo, int64_t lda, int64_t lda_lo, int32_t a_layout,
                      const float *B, const float *B_lo, int64_t ldb, int64_t ldb_lo, int32_t b_layout, float *C,
                      int64_t ldc, int32_t M, int32_t N, int32_t K, const float *bias, uint32_t flags,
-                     void *workspace, size_t workspace_bytes, const gist_dropout_t *drop, gist_stream_t stream) {
+                     void *workspace, size_t workspace_bytes, const gist_dropout_t *drop, gist_stream_t stream,
+                     const gist_gemm_ex_t *ex = nullptr) {
     const bool x3 = A_lo != nullptr;
+    if (ex) {
+        if (ex->ln_out && (N > 128 || a_layout != GIST_GEMM_K_MAJOR || b_layout != GIST_GEMM_K_MAJOR || !x3 ||
+                           ex->ld_ln < N || (ex->ln_stats && !aligned(ex->ln_stats, 8))))
+            return GIST_ERR_UNSUPPORTED;     // LayerNorm epilogue: y = z W^T, 3xTF32, rows of <= 128
+        if (ex->ln_out && ex->rowsum) return GIST_ERR_UNSUPPORTED;
+        if (ex->rowsum && (a_layout != GIST_GEMM_MN_MAJOR || b_layout != GIST_GEMM_MN_MAJOR))
+            return GIST_ERR_UNSUPPORTED;     // row sums are compiled into the dy^T z layout only
+        if (ex->tile_counters && !aligned(ex->tile_counters, 4)) return GIST_ERR_ALIGN;
+        flags = ex_plan_flags(N, flags, ex);
+    }
+    const bool inkernel = ex && ex->tile_counters;
     DropParams dp;
     {
         const int st = make_drop_params(drop, &dp);
@@ -805,9 +1242,12 @@ static int gemm_impl(const float *A, const float *A_lo, int64_t lda, int64_t lda
     if (!aligned(A, 16) || !aligned(B, 16) || (lda % 4) || (ldb % 4) || !aligned(C, 4)) return GIST_ERR_ALIGN;
     if (x3 && (!aligned(A_lo, 16) || !aligned(B_lo, 16) || (lda_lo % 4) || (ldb_lo % 4))) return GIST_ERR_ALIGN;
     cudaStream_t s = (cudaStream_t)stream;
-    GemmPlan pl = plan_gemm(M, N, K, flags, x3);
-    if (pl.splits > 1 && (!workspace || workspace_bytes < pl.ws_bytes || !aligned(workspace, 16))) {
-        // no (or too small a) workspace: run unsplit rather than fail
+    GemmPlan pl = plan_gemm(M, N, K, flags, x3, inkernel);
+    const int64_t n_tiles = (int64_t)((M + kBM - 1) / kBM) * ((N + pl.bn - 1) / pl.bn);
+    const bool inker_ok = inkernel && n_tiles <= ex->n_counters && n_tiles * pl.splits <= sm_count();
+    if (pl.splits > 1 && (!workspace || workspace_bytes < pl.ws_bytes || !aligned(workspace, 16) ||
+                          (inkernel && !inker_ok))) {
+        // no (or too small a) workspace / counter array: run unsplit rather than fail
         pl.splits = 1;
         pl.kb_per_split = (K + kBK - 1) / kBK;
     }
@@ -819,15 +1259,36 @@ static int gemm_impl(const float *A, const float *A_lo, int64_t lda, int64_t lda
     p.kb_per_split = pl.kb_per_split;
     p.kblocks = (K + kBK - 1) / kBK;
     p.relu = (flags & GIST_GEMM_RELU) ? 1 : 0;
+    p.background = (flags & GIST_GEMM_BACKGROUND) ? 1 : 0;
     p.drop = dp;
     p.kc = (int)((flags >> 8) & 0xFFu);
     if (p.kc == 0) p.kc = 4;          // 128 K elements = 48 chained MMAs per accumulator
     p.trace = (g_gemm_trace && g_gemm_trace_ctas >= sm_count()) ? g_gemm_trace : nullptr;
-    if (pl.splits > 1) {
+    p.tile_counters = nullptr; p.ws = nullptr; p.ws_rowsum = nullptr; p.rowsum = nullptr;
+    p.ln_y = nullptr; p.ld_ln = 0; p.ln_stats = nullptr; p.ln_eps = 0.f; p.ln_relu = 0;
+    if (pl.splits > 1 && !inkernel) {
         p.C = reinterpret_cast<float *>(workspace); p.ldc = pl.ldp; p.bias = nullptr; p.vec4 = 1;
+        p.ws_rowsum = reinterpret_cast<float *>(workspace) + (size_t)pl.splits * M * pl.ldp;
     } else {
         p.C = C; p.ldc = ldc; p.bias = bias;
         p.vec4 = (aligned(C, 16) && ldc % 4 == 0 && (!bias || aligned(bias, 16))) ? 1 : 0;
+        if (pl.splits > 1) {
+            p.tile_counters = ex->tile_counters;
+            p.ws = reinterpret_cast<float *>(workspace);
+            p.ws_rowsum = p.ws + (size_t)n_tiles * pl.splits * kBM * pl.bn;
+        }
+    }
+    if (ex) {
+        p.rowsum = pl.bn <= 128 ? ex->rowsum : nullptr;
+        if (ex->rowsum && !p.rowsum) return GIST_ERR_UNSUPPORTED;
+        if (ex->ln_out) {
+            if (pl.bn < N) return GIST_ERR_UNSUPPORTED;
+            p.relu = 0;      // the activation belongs to the normalised output
+            if (!(pl.splits > 1 && !inkernel)) {      // in the GEMM's own epilogue; else in the split-K second pass
+                p.ln_y = ex->ln_out; p.ld_ln = ex->ld_ln; p.ln_stats = reinterpret_cast<float2 *>(ex->ln_stats);
+                p.ln_eps = ex->ln_eps; p.ln_relu = (ex->ln_flags & GIST_ACT_RELU) ? 1 : 0;
+            }
+        }
     }
     auto map_a = [&](CUtensorMap *t, const float *ptr, int64_t ld) {
         return a_mn ? make_map(t, ptr, K, M, ld, kBK, true) : make_map(t, ptr, M, K, ld, kBM, false);
@@ -845,16 +1306,27 @@ static int gemm_impl(const float *A, const float *A_lo, int64_t lda, int64_t lda
         if (st != GIST_OK) return st;
         st = map_b(&m.bl, B_lo, ldb_lo);
         if (st != GIST_OK) return st;
-        st = launch_tile<3>(pl.bn, a_mn, b_mn, m, p, s);
+        if (p.ln_y) st = pl.bn == 64 ? launch_gemm<64, false, false, 3, true>(m, p, s)
+                                     : launch_gemm<128, false, false, 3, true>(m, p, s);
+        else st = launch_tile<3>(pl.bn, a_mn, b_mn, m, p, s);
     } else {
         m.al = m.a;
         m.bl = m.b;
         st = launch_tile<1>(pl.bn, a_mn, b_mn, m, p, s);
     }
-    if (st != GIST_OK || pl.splits == 1) return st;
-    const int64_t items = (int64_t)M * ((N + 3) / 4);
-    splitk_reduce_kernel<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(
-        reinterpret_cast<const float *>(workspace), pl.ldp, pl.splits, M, N, bias, p.relu, C, ldc);
+    if (st != GIST_OK || pl.splits == 1 || inkernel) return st;
+    if (ex && ex->ln_out) {
+        splitk_reduce_ln_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(
+            reinterpret_cast<const float *>(workspace), pl.ldp, pl.splits, M, N, bias, ex->ln_eps,
+            (ex->ln_flags & GIST_ACT_RELU) ? 1 : 0, C, ldc, ex->ln_out, ex->ld_ln, reinterpret_cast<float2 *>(ex->ln_stats));
+    } else {
+        const int64_t items = (int64_t)M * ((N + 3) / 4);
+        const int main_blocks = (int)((items + 255) / 256);
+        const int rs_blocks = p.rowsum ? (M + 255) / 256 : 0;       // row sums ride in the tail blocks of the fold
+        splitk_reduce_kernel<<<(unsigned)(main_blocks + rs_blocks), 256, 0, s>>>(
+            reinterpret_cast<const float *>(workspace), pl.ldp, pl.splits, M, N, bias, p.relu, C, ldc, main_blocks,
+            p.ws_rowsum, p.rowsum);
+    }
     count_launch();
     return last_error();
 }
@@ -875,6 +1347,22 @@ extern "C" int gist_gemm_3xtf32(const float *A, const float *A_lo, int64_t lda, 
     if (!A_lo || !B_lo) return GIST_ERR_BADARG;
     return gemm_impl(A, A_lo, lda, lda_lo, a_layout, B, B_lo, ldb, ldb_lo, b_layout, C, ldc, M, N, K, bias, flags,
                      workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" size_t gist_gemm_ex_workspace_bytes(int32_t M, int32_t N, int32_t K, uint32_t flags, int32_t three_pass,
+                                               const gist_gemm_ex_t *ex) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return plan_gemm(M, N, K, ex_plan_flags(N, flags, ex), three_pass != 0, ex && ex->tile_counters).ws_bytes;
+}
+
+extern "C" int gist_gemm_ex_f32(const float *A, const float *A_lo, int64_t lda, int64_t lda_lo, int32_t a_layout,
+                                const float *B, const float *B_lo, int64_t ldb, int64_t ldb_lo, int32_t b_layout,
+                                float *C, int64_t ldc, int32_t M, int32_t N, int32_t K, const float *bias,
+                                uint32_t flags, void *workspace, size_t workspace_bytes, const gist_gemm_ex_t *ex,
+                                gist_stream_t stream) {
+    if ((A_lo == nullptr) != (B_lo == nullptr)) return GIST_ERR_BADARG;
+    return gemm_impl(A, A_lo, lda, lda_lo, a_layout, B, B_lo, ldb, ldb_lo, b_layout, C, ldc, M, N, K, bias, flags,
+                     workspace, workspace_bytes, ex ? ex->drop : nullptr, stream, ex);
 }
 
 extern "C" int gist_gemm_dropmask_f32(const float *A, const float *A_lo, int64_t lda, int64_t lda_lo,

@@ -854,6 +854,8 @@ static int launch_spmm(const SpmmParams &p0, cudaStream_t stream, int bg_ctas_pe
     return last_error();
 }
 
+constexpr int64_t kL2SlabBytes = 64LL << 20;      // what one column slab of X may occupy of the 126 MB L2
+
 template <int VEC>
 static int dispatch_lanes(const SpmmParams &p, uint32_t flags, int32_t n_src, cudaStream_t stream) {
     const int lanes = (p.d + VEC - 1) / VEC;
@@ -1002,8 +1004,22 @@ extern "C" int gist_spmm_csr_ex_f32(const int32_t *rowptr, const int32_t *col, i
     const bool coop = (flags & GIST_SPMM_COOP_ON) || (!(flags & GIST_SPMM_COOP_OFF) && n_dst <= 32768);
     p.heavy_deg = coop ? 128 : 0x7fffffff;
     cudaStream_t s = (cudaStream_t)stream;
-    if (vec_ok(4, p)) return dispatch_lanes<4>(p, flags, n_src, s);
-    if (vec_ok(2, p)) return dispatch_lanes<2>(p, flags, n_src, s);
+    // Widest vector the alignment allows — except for operands far larger than L2 (the full-graph
+    // SpMM of evaluate()): there the chip sweeps one column slab of X at a time (chunk index = slow
+    // grid dimension) and a 32-lane x 128-bit chunk makes that slab n_src x 512 B.  Measured on the
+    // Reddit shape (232 965 rows): d = 602 with 64-bit gathers (60 MB slab, 40 registers, 48 warps/SM)
+    // 23.3 ms against 28.3 ms with 128-bit gathers (119 MB slab, 64 registers); narrower lane groups
+    // (16 / 8 lanes x 128 bit: 60 / 30 MB slabs) 42.6 / 49.8 ms; d = 256: 8.2 ms against 11.6 ms.  So:
+    // 64-bit gathers when the operand exceeds L2 and the 128-bit slab would not fit it but the 64-bit one
+    // does.
+    int max_vec = 4;
+    const int force_vec = (int)((flags >> GIST_SPMM_VEC_SHIFT) & 3u);       // 1, 2, 3 -> at most 1, 2, 4 floats
+    if (force_vec) max_vec = force_vec == 3 ? 4 : force_vec;
+    else if ((int64_t)n_src * p.d * 4 > (96LL << 20) && p.d > 64 && (int64_t)n_src * 512 > kL2SlabBytes &&
+             (int64_t)n_src * 256 <= kL2SlabBytes)
+        max_vec = 2;
+    if (max_vec >= 4 && vec_ok(4, p)) return dispatch_lanes<4>(p, flags, n_src, s);
+    if (max_vec >= 2 && vec_ok(2, p)) return dispatch_lanes<2>(p, flags, n_src, s);
     return dispatch_lanes<1>(p, flags, n_src, s);
 }
 

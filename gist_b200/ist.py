@@ -104,7 +104,34 @@ class DistributedGNNWrapper(torch.nn.Module):
                 for _ in range(self.args.n_layers)]
 
     def _to_dev(self, parts):
-        return [[(i.to(self.device), f.to(self.device)) for (i, f) in layer] for layer in parts]
+        """Index tensors of a partition on the device: ONE packed host->device copy from a persistent
+        pinned buffer (2 * L * m small synchronous copies stall the step pipeline at every round
+        boundary), then views."""
+        dev = torch.device(self.device)
+        if dev.type != 'cuda':
+            return [[(i.to(dev), f.to(dev)) for (i, f) in layer] for layer in parts]
+        flat = [t for layer in parts for pair in layer for t in pair]
+        total = sum(t.numel() for t in flat)
+        if getattr(self, '_idx_pin', None) is None or self._idx_pin.numel() < total:
+            self._idx_pin = torch.empty(total, dtype=torch.int64).pin_memory()
+            self._idx_pin_ev = None
+        if self._idx_pin_ev is not None:
+            self._idx_pin_ev.synchronize()           # the previous round's copy has left the buffer
+        off = 0
+        for t in flat:
+            self._idx_pin[off:off + t.numel()].copy_(t)
+            off += t.numel()
+        d = self._idx_pin[:total].to(dev, non_blocking=True)
+        self._idx_pin_ev = torch.cuda.Event()
+        self._idx_pin_ev.record()
+        out, off = [], 0
+        for layer in parts:
+            row = []
+            for (i, f) in layer:
+                row.append((d[off:off + i.numel()], d[off + i.numel():off + i.numel() + f.numel()]))
+                off += i.numel() + f.numel()
+            out.append(row)
+        return out
 
     # ------------------------------------------------------------ dispatch --
     def _slice_for(self, layer_idx, site, parts):

@@ -252,9 +252,15 @@ class ISTSAGELayer(nn.Module):
             h = ops.sage_project_first(g, h, W, self.linear.bias)
         elif h.is_cuda and ops.get_matmul_precision() != 'fp32':
             # tensor-core path: aggregation + concat + dropout (+ split) in K1's epilogue, the
-            # dropout backward in the dz GEMM's epilogue (ops._SageLinear)
+            # dropout backward in the dz GEMM's epilogue, layer norm + ReLU in the projection's
+            # epilogue when a tile holds the row (ops._SageLinear: the whole layer is one autograd node)
+            ln = None
+            if isinstance(self.lynorm, nn.LayerNorm) and (self.activation is None or _is_relu(self.activation)):
+                ln = (self.lynorm.eps, self.activation is not None)
             h = ops.sage_linear(g, h, self.linear.weight, self.linear.bias, self._p_drop(), self._drop_stream,
-                                pre=pre)
+                                pre=pre, ln=ln)
+            if ln is not None:
+                return h
         else:
             if pre is not None:
                 h = pre.z

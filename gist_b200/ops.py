@@ -548,12 +548,43 @@ def split_tf32(x):
     return lo
 
 
-def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, relu=False, out=None, flags=0, A_lo=None, B_lo=None):
+# In-kernel split-K needs one zeroed uint32 per output tile that the kernel leaves zero: one array per
+# (device, stream) — launches on a stream are ordered, launches on different streams (the weight-
+# gradient branch beside the training branch) must not share counters.
+GEMM_TILE_COUNTERS = 4096
+# In-kernel split-K (last-arriver reduction) is OPT-IN: measured slower than the two-kernel form on
+# every Reddit-shape GEMM (profiles/README.md round 2: e.g. dW0 24.0 vs 18.9 us, L0 fwd 21.3 vs 20.2 us,
+# step 0.299 vs 0.280 ms) — the tile's last CTA folds S partial tiles alone while the second-pass kernel
+# spreads the fold over the chip.  Row sums and the layer norm ride in the second pass instead.
+FUSED_SPLITK = os.environ.get('GIST_GEMM_FUSED_SPLITK', '0') != '0'       # A/B switches for profiles/
+FUSED_ROWSUM = os.environ.get('GIST_GEMM_FUSED_ROWSUM', '1') != '0'
+BACKGROUND_DW = os.environ.get('GIST_GEMM_BACKGROUND_DW', '1') != '0'
+FUSED_LN = os.environ.get('GIST_GEMM_FUSED_LN', '1') != '0'
+_GEMM_COUNTERS = {}
+
+
+def _gemm_counters(device):
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    t = _GEMM_COUNTERS.get(key)
+    if t is None:
+        t = _GEMM_COUNTERS[key] = torch.zeros(GEMM_TILE_COUNTERS, dtype=torch.int32, device=device)
+    return t
+
+
+def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, relu=False, out=None, flags=0, A_lo=None, B_lo=None,
+         rowsum=False, ln=None, drop=None):
     """C[M,N] = op(A) @ op(B)^T (+bias) (ReLU) on the tcgen05 TF32 kernel (K4).
 
     a_mn=False: A is stored [M, K];  a_mn=True: A is stored [K, M] (MN-major, i.e. op(A) = A^T).
     b_mn=False: B is stored [N, K];  b_mn=True: B is stored [K, N].
     A_lo / B_lo (from split_tf32, both or neither) select the fp32-accurate 3xTF32 mode.
+    Extended epilogue (gist_gemm_ex_f32):
+      rowsum=True : also returns r[M] = sum_k op(A)[m, k]  (db of the dW = dy^T z contraction) -> (C, r)
+      ln=(eps, relu) : LayerNorm(no affine)(+ReLU) over the rows of C when N <= 128, 3xTF32, K-major
+                    operands -> (C_pre_norm, y, stats[M, 2]); raises GistLibraryError if it does not apply
+      drop : a DropoutDesc — C *= the mask (see gemm_dropmask)
+    Split-K runs as ONE kernel (last-arriver reduction) on this stream's tile counters.
     Raises if an operand is not TMA-addressable (see _tma_view)."""
     require_cuda(A, B, bias, out, A_lo, B_lo)
     if a_mn:
@@ -566,31 +597,55 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, relu=False, out=None, flags
         N, K2 = B.shape
     assert K == K2, (A.shape, B.shape, a_mn, b_mn)
     if out is None:
-        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+        out = _padded_empty(M, N, A.device) if ln is not None else torch.empty((M, N), dtype=torch.float32, device=A.device)
     assert tuple(out.shape) == (M, N) and (out.stride(1) == 1 or N == 1)
     lib = _lib.load()
     f = flags | (_lib.GEMM_RELU if relu else 0)
     x3 = A_lo is not None or B_lo is not None
-    wsb = (lib.gist_gemm_3xtf32_workspace_bytes if x3 else lib.gist_gemm_tf32_workspace_bytes)(M, N, K, f)
-    ws = torch.empty(wsb, dtype=torch.uint8, device=A.device) if wsb else None
+    if x3:
+        assert A_lo is not None and B_lo is not None and A_lo.shape == A.shape and B_lo.shape == B.shape
+    dev = A.device
+    ex = _lib.GemmEx()
+    keep = []
+    if FUSED_SPLITK and M * N > 0:
+        cnt = _gemm_counters(dev)
+        ex.tile_counters, ex.n_counters = cnt.data_ptr(), cnt.numel()
+    rs = y = stats = None
+    if rowsum:
+        rs = torch.empty(M, dtype=torch.float32, device=dev)
+        ex.rowsum = rs.data_ptr()
+    if ln is not None:
+        eps, ln_relu = ln
+        y = _padded_empty(M, N, dev)
+        stats = torch.empty((M, 2), dtype=torch.float32, device=dev)
+        ex.ln_out, ex.ld_ln, ex.ln_stats = y.data_ptr(), _ld(y), stats.data_ptr()
+        ex.ln_eps, ex.ln_flags = float(eps), (_lib.ACT_RELU if ln_relu else 0)
+    if drop is not None:
+        ex.drop = ctypes.pointer(drop)
+        keep.append(drop)
+    wsb = lib.gist_gemm_ex_workspace_bytes(M, N, K, f, 1 if x3 else 0, ctypes.byref(ex))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb else None
     prof = GEMM_PROFILE
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    if x3:
-        assert A_lo is not None and B_lo is not None and A_lo.shape == A.shape and B_lo.shape == B.shape
-        check(lib.gist_gemm_3xtf32(ptr(A), ptr(A_lo), _ld(A), _ld(A_lo), 1 if a_mn else 0,
-                                   ptr(B), ptr(B_lo), _ld(B), _ld(B_lo), 1 if b_mn else 0,
-                                   ptr(out), _ld(out), M, N, K, ptr(bias), f, ptr(ws), wsb,
-                                   stream_ptr(A.device)), 'gemm_3xtf32')
-    else:
-        check(lib.gist_gemm_tf32(ptr(A), _ld(A), 1 if a_mn else 0, ptr(B), _ld(B), 1 if b_mn else 0,
-                                 ptr(out), _ld(out), M, N, K, ptr(bias), f, ptr(ws), wsb,
-                                 stream_ptr(A.device)), 'gemm_tf32')
+    check(lib.gist_gemm_ex_f32(ptr(A), ptr(A_lo), _ld(A), _ld(A_lo) if x3 else 0, 1 if a_mn else 0,
+                               ptr(B), ptr(B_lo), _ld(B), _ld(B_lo) if x3 else 0, 1 if b_mn else 0,
+                               ptr(out), _ld(out), M, N, K, ptr(bias), f, ptr(ws), wsb, ctypes.byref(ex),
+                               stream_ptr(dev)), 'gemm_ex_f32')
     if prof is not None:
         ev1.record()
         prof.append(dict(ev0=ev0, ev1=ev1, M=M, N=N, K=K, passes=3 if x3 else 1))
+    if ln is not None:
+        return out, y, stats
+    if rowsum:
+        return out, rs
     return out
+
+
+def ln_fusable(M, N, x3, a_mn=False, b_mn=False):
+    """Does K4's LayerNorm epilogue apply (one tile holds the row; include/gist_b200.h gist_gemm_ex_t)?"""
+    return FUSED_LN and x3 and not a_mn and not b_mn and 0 < N <= 128 and M > 0
 
 
 def gemm_dropmask(A, B, drop, *, a_mn=False, b_mn=False, out=None, A_lo=None, B_lo=None):
@@ -785,16 +840,41 @@ def _weight_grad_branch(device, fn, keep):
     return out
 
 
+def _ln_fwd_raw(x, eps, relu):
+    """(y, stats) = act(LayerNorm(x)) rows, no affine (csrc/fused.cu ln_act_fwd_kernel)."""
+    n, d = x.shape
+    y = _padded_empty(n, d, x.device)
+    stats = torch.empty((n, 2), dtype=torch.float32, device=x.device)
+    check(_lib.load().gist_layernorm_act_fwd_f32(ptr(x), _ld(x), n, d, eps, _lib.ACT_RELU if relu else 0, ptr(y), _ld(y),
+                                                 ptr(stats), stream_ptr(x.device)), 'layernorm_act_fwd_f32')
+    return y, stats
+
+
+def _ln_bwd_raw(dy, x, stats, relu, want_lo):
+    """(dx, dx_lo) of act(LayerNorm(x)) (ln_act_bwd_kernel); dx_lo = 3xTF32 low half or None."""
+    n, d = x.shape
+    dx = _padded_empty(n, d, x.device)
+    dx_lo = _padded_empty(n, d, x.device) if want_lo else None
+    check(_lib.load().gist_layernorm_act_bwd_f32(ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(stats), n, d,
+                                                 _lib.ACT_RELU if relu else 0, ptr(dx), _ld(dx), ptr(dx_lo),
+                                                 _ld(dx_lo) if want_lo else 0, stream_ptr(x.device)),
+          'layernorm_act_bwd_f32')
+    return dx, dx_lo
+
+
 class _SageLinear(torch.autograd.Function):
-    """y = dropout([h ‖ (A h) / in_deg]) W^T + b — everything of an IST SAGE layer up to the layer
-    norm (cluster_gcn/modules.py:222-233) as ONE autograd node over fused kernels:
-      forward : K1 writes z with the dropout mask applied and (3xTF32) z_lo beside it -> K4
-      backward: dz = mask ⊙ (dy W) in the K4 epilogue (mask regenerated) -> K2 on the CSC gives dh;
-                dW = dy^T z (K4, split-K); db = column sums.
-    No dropout kernels, no masks in memory, no split passes over z / dy."""
+    """h_out = act(LN(dropout([h ‖ (A h) / in_deg]) W^T + b)) — a whole IST SAGE layer
+    (cluster_gcn/modules.py:222-236) as ONE autograd node over fused kernels:
+      forward : K1 writes z with the dropout mask applied and (3xTF32) z_lo beside it -> K4, whose
+                epilogue also applies the layer norm + ReLU when one tile holds the row (out <= 128;
+                otherwise the row-wise kernel follows);
+      backward: layer-norm backward -> dz = mask ⊙ (dy W) in the K4 epilogue (mask regenerated) -> K2 on
+                the CSC gives dh; dW = dy^T z (K4, in-kernel split-K) with db = colsum(dy) from the same
+                launch (row sums of dy^T on the tensor core).
+    No dropout kernels, no masks in memory, no split passes over z / dy, no bias-gradient kernels."""
 
     @staticmethod
-    def forward(ctx, g, h, W, b, p_drop, stream_id, pre):
+    def forward(ctx, g, h, W, b, p_drop, stream_id, pre, ln_eps, ln_relu):
         x3 = _MATMUL_PRECISION == '3xtf32'
         if pre is None:
             pre = sage_prepare(g, h.detach(), p_drop, stream_id)
@@ -803,19 +883,30 @@ class _SageLinear(torch.autograd.Function):
             z_lo = split_tf32(z)
         Wv = _tma_view(W)
         W_lo = _weight_lo(Wv) if x3 else None
-        y = gemm(z, Wv, bias=b, A_lo=z_lo, B_lo=W_lo)
+        x_pre = stats = None
+        if ln_eps is None:
+            y = gemm(z, Wv, bias=b, A_lo=z_lo, B_lo=W_lo)
+        elif ln_fusable(z.shape[0], Wv.shape[0], x3):
+            x_pre, y, stats = gemm(z, Wv, bias=b, A_lo=z_lo, B_lo=W_lo, ln=(ln_eps, ln_relu))
+        else:
+            x_pre = gemm(z, Wv, bias=b, A_lo=z_lo, B_lo=W_lo, out=_padded_empty(z.shape[0], Wv.shape[0], z.device))
+            y, stats = _ln_fwd_raw(x_pre, ln_eps, ln_relu)
         ctx.g, ctx.has_bias, ctx.x3 = g, b is not None, x3
         ctx.drop = (float(p_drop), int(stream_id)) if pre.dropped else None
         ctx.step_saved = pre.step_saved
-        ctx.save_for_backward(z, z_lo, Wv, W_lo)
+        ctx.ln_relu = bool(ln_relu) if ln_eps is not None else None
+        ctx.save_for_backward(z, z_lo, Wv, W_lo, x_pre, stats)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        z, z_lo, W, W_lo = ctx.saved_tensors
+        z, z_lo, W, W_lo, x_pre, stats = ctx.saved_tensors
         g = ctx.g
         dy = _mat(dy, 'dy')
-        dy_lo = _lo_take(dy) if ctx.x3 else None
+        if ctx.ln_relu is not None:             # through the layer norm (+ ReLU) first
+            dy, dy_lo = _ln_bwd_raw(dy, x_pre, stats, ctx.ln_relu, ctx.x3)
+        else:
+            dy_lo = _lo_take(dy) if ctx.x3 else None
         if not _tma_ok(dy):
             dy, dy_lo = _tma_view(dy), None
         if ctx.x3 and dy_lo is None:
@@ -824,13 +915,21 @@ class _SageLinear(torch.autograd.Function):
         d = d2 // 2
         dh = dW = db = None
         need_dW, need_db = ctx.needs_input_grad[2], ctx.has_bias and ctx.needs_input_grad[3]
+        fused_db = need_db and need_dW and FUSED_ROWSUM
 
-        # first layer (no dh): the main stream has nothing left to do, so the bias gradient runs
+        # first layer (no dh): the main stream has nothing left to do, so a separate bias gradient runs
         # there, beside the dW GEMM, instead of behind it at the tail of the step
-        db_here = need_db and not ctx.needs_input_grad[1]
+        db_here = need_db and not fused_db and not ctx.needs_input_grad[1]
+
+        # a layer that still has its dz -> K2 -> layer-norm chain to run computes dW in the background
+        # (a third of the SMs); the first layer's dW is the tail of the step and takes the whole chip
+        small = 2.0 * dy.shape[1] * z.shape[1] * n < 4e9         # Reddit-shape dW: ~0.7 GFLOP; ultra-wide: 150 GFLOP
+        bgf = _lib.GEMM_BACKGROUND if (ctx.needs_input_grad[1] and BACKGROUND_DW and small) else 0
 
         def weight_grads():
-            return (gemm(dy, z, a_mn=True, b_mn=True, A_lo=dy_lo, B_lo=z_lo) if need_dW else None,
+            if fused_db:        # db = colsum(dy) = row sums of dy^T: from the dW launch itself
+                return gemm(dy, z, a_mn=True, b_mn=True, A_lo=dy_lo, B_lo=z_lo, rowsum=True, flags=bgf)
+            return (gemm(dy, z, a_mn=True, b_mn=True, A_lo=dy_lo, B_lo=z_lo, flags=bgf) if need_dW else None,
                     colsum(dy) if need_db and not db_here else None)
         if need_dW or (need_db and not db_here):      # forked first: the branch depends on dy only
             dW, db = _weight_grad_branch(dy.device, weight_grads, (dy, dy_lo, z, z_lo))
@@ -846,15 +945,17 @@ class _SageLinear(torch.autograd.Function):
             dh = torch.empty((n, d), dtype=torch.float32, device=dy.device)
             # dh = dz[:, :d] + A^T (inv_deg ⊙ dz[:, d:])
             spmm_raw(colptr, row, n, n, dz[:, d:], dh, src_scale=g.inv_in_degree(), addend=dz[:, :d],
-                 schedule=g.seg_schedule(transpose=True))
-        return None, dh, dW, db, None, None, None
+                     schedule=g.seg_schedule(transpose=True))
+        return None, dh, dW, db, None, None, None, None, None
 
 
-def sage_linear(g, h, W, b, p_drop=0.0, stream_id=0, pre=None):
-    """Fused SAGE aggregation + dropout + linear on the tensor-core path ('tf32' / '3xtf32')."""
+def sage_linear(g, h, W, b, p_drop=0.0, stream_id=0, pre=None, ln=None):
+    """Fused SAGE aggregation + dropout + linear (+ layer norm + ReLU: ``ln = (eps, relu)``) on the
+    tensor-core path ('tf32' / '3xtf32')."""
     assert _MATMUL_PRECISION in ('tf32', '3xtf32')
     require_cuda(h, W, b)
-    return _SageLinear.apply(g, h, W, b, float(p_drop), int(stream_id), pre)
+    eps, relu = (float(ln[0]), bool(ln[1])) if ln is not None else (None, False)
+    return _SageLinear.apply(g, h, W, b, float(p_drop), int(stream_id), pre, eps, relu)
 
 
 @torch.no_grad()

@@ -73,6 +73,9 @@ typedef struct gist_dropout {
  * feature chunks of lanes x vector-width floats.  Tuning / measurement switch. */
 #define GIST_SPMM_LANES_SHIFT 12
 #define GIST_SPMM_LANES(code) ((uint32_t)(code) << GIST_SPMM_LANES_SHIFT)
+/* bits 16..17: cap the gather width (0 = widest the alignment allows, narrowed for operands far
+ * larger than L2 — see gist_spmm_csr_ex_f32): 1, 2, 3 -> 32-, 64-, 128-bit.  Measurement switch. */
+#define GIST_SPMM_VEC_SHIFT 16
 
 /* modes of gist_degree_norm_f32 */
 #define GIST_NORM_INV 0       /* 1/deg, deg==0 -> 0   (ISTSAGELayer.get_norm, cluster_gcn/modules.py:239-243) */
@@ -265,6 +268,8 @@ int gist_slice_scatter_f32(const float *src, int64_t ld_src, const int64_t *ridx
 #define GIST_GEMM_TILE_N64 4u     /* force the output-tile width (default: chosen from the grid) */
 #define GIST_GEMM_TILE_N128 8u
 #define GIST_GEMM_TILE_N256 16u
+#define GIST_GEMM_BACKGROUND 32u  /* plan and launch for a third of the SMs: a contraction off the critical path
+                                     (dW beside the dz chain) must not queue 140 long CTAs in front of it */
 #define GIST_GEMM_KC(n) ((uint32_t)(n) << 8) /* 3xTF32 only: K blocks (of 32) chained per TMEM accumulator, 1..255; 0 = default 4 */
 #define GIST_GEMM_K_MAJOR 0
 #define GIST_GEMM_MN_MAJOR 1
@@ -308,6 +313,44 @@ int gist_gemm_3xtf32(const float *A, const float *A_lo, int64_t lda, int64_t lda
                      const float *B, const float *B_lo, int64_t ldb, int64_t ldb_lo, int32_t b_layout,
                      float *C, int64_t ldc, int32_t M, int32_t N, int32_t K, const float *bias,
                      uint32_t flags, void *workspace, size_t workspace_bytes, gist_stream_t stream);
+
+/* Extended epilogue of K4 — what the training step needs besides the product, done where the product is
+ * produced instead of in kernels of their own (every field optional; ex == NULL or all-zero: the plain
+ * contraction).  A_lo == B_lo == NULL selects single-pass TF32, both given 3xTF32.
+ *   tile_counters / n_counters : uint32 array, ZERO on entry and left zero (one counter per output
+ *       tile; n_counters >= ceil(M/128) * ceil(N/64) always suffices).  With it a split-K launch is ONE
+ *       kernel: every split writes its partial tile to the workspace and the CTA that arrives last at
+ *       the tile's counter adds the partials in split order and runs the epilogue (deterministic, same
+ *       order as the two-kernel form).  Two launches in flight must not share counters.
+ *   rowsum : [M] — sum over K of op(A)[m, k].  For dW = dy^T z (A = dy, MN-major) that is the bias
+ *       gradient db = colsum(dy) (cluster_gcn/modules.py:233's nn.Linear), computed by the tensor core
+ *       as one extra 16-column MMA per K step against a tile of ones.  Tiles are then <= 128 wide;
+ *       both operands MN-major only (the dy^T z layout), GIST_ERR_UNSUPPORTED otherwise.
+ *   ln_out / ld_ln / ln_stats / ln_eps / ln_flags : LayerNorm without affine (+ ReLU with
+ *       GIST_ACT_RELU) over the rows of C (modules.py:234-236) when one tile holds the row (N <= 128;
+ *       y = z W^T layout, 3xTF32): C receives the pre-norm values (+ bias), ln_out the normalised /
+ *       activated ones, ln_stats [M][2] = (mean, rstd) for gist_layernorm_act_bwd_f32.
+ *   drop : as in gist_gemm_dropmask_f32 (forces a single K split).
+ * Workspace: gist_gemm_ex_workspace_bytes with the same arguments.  GIST_ERR_UNSUPPORTED when a
+ * requested fusion does not apply to the shape / layout (the caller runs the separate kernel). */
+typedef struct gist_gemm_ex {
+    uint32_t *tile_counters;
+    int64_t n_counters;
+    float *rowsum;
+    float *ln_out;
+    int64_t ld_ln;
+    float *ln_stats;
+    float ln_eps;
+    uint32_t ln_flags;
+    const gist_dropout_t *drop;
+} gist_gemm_ex_t;
+size_t gist_gemm_ex_workspace_bytes(int32_t M, int32_t N, int32_t K, uint32_t flags, int32_t three_pass,
+                                    const gist_gemm_ex_t *ex);
+int gist_gemm_ex_f32(const float *A, const float *A_lo, int64_t lda, int64_t lda_lo, int32_t a_layout,
+                     const float *B, const float *B_lo, int64_t ldb, int64_t ldb_lo, int32_t b_layout,
+                     float *C, int64_t ldc, int32_t M, int32_t N, int32_t K, const float *bias,
+                     uint32_t flags, void *workspace, size_t workspace_bytes, const gist_gemm_ex_t *ex,
+                     gist_stream_t stream);
 
 /* C = dropout_mask(seed, *step, stream_id) * (op(A) op(B)^T): the dz = dy W contraction of the layer
  * whose INPUT z went through dropout (cluster_gcn/modules.py:228-233).  The multiplier of C[r, c] is
