@@ -241,30 +241,37 @@ def sync_summary(prof, world, timed_ms, steps):
         e = by.setdefault(r['what'], {'n': 0, 'ms': 0.0, 'rec': r})
         e['n'] += 1
         e['ms'] += r['ev0'].elapsed_time(r['ev1'])
-    if 'sync_all_gather' not in by:
+    key = 'sync_peer_merge' if 'sync_peer_merge' in by else 'sync_all_gather'
+    if key not in by:
         return {'rounds_in_timed_region': 0}
-    rounds = by['sync_all_gather']['n']
+    peer = key == 'sync_peer_merge'
+    rounds = by[key]['n']
     mean = lambda k: (by[k]['ms'] / by[k]['n']) if k in by else 0.0     # noqa: E731
-    ag = by['sync_all_gather']['rec']
-    ag_ms = mean('sync_all_gather')
+    ag = by[key]['rec']
+    ag_ms = mean(key)
     sync_ms = mean('sync_pack') + ag_ms + mean('sync_scatter')
     out = {
+        'mode': 'peer memory: one kernel reads every site\'s packed slices over NVLink and scatters them into the '
+                'local replica (no collective, no staging buffer)' if peer else
+                'NCCL: one all_gather_into_tensor of the packed slices, then one local scatter launch',
         'rounds_in_timed_region': rounds, 'dispatches_in_timed_region': by.get('dispatch', {'n': 0})['n'],
-        'ms': round(sync_ms, 4), 'pack_ms': round(mean('sync_pack'), 4), 'all_gather_ms': round(ag_ms, 4),
+        'ms': round(sync_ms, 4), 'pack_ms': round(mean('sync_pack'), 4),
+        ('peer_merge_ms' if peer else 'all_gather_ms'): round(ag_ms, 4),
         'scatter_ms': round(mean('sync_scatter'), 4), 'dispatch_ms': round(mean('dispatch'), 4),
         'bytes_per_rank': ag['bytes_sent'], 'bytes_received_per_rank': ag['bytes_received'],
-        'share_of_timed_region': round((by['sync_all_gather']['ms'] + by.get('sync_pack', {'ms': 0})['ms'] +
-                                        by.get('sync_scatter', {'ms': 0})['ms'] + by.get('dispatch', {'ms': 0})['ms'])
+        'share_of_timed_region': round(sum(by.get(k, {'ms': 0})['ms'] for k in
+                                           ('sync_pack', 'sync_all_gather', 'sync_peer_merge', 'sync_scatter', 'dispatch'))
                                        / max(timed_ms, 1e-9), 4),
-        'what': 'per round: pack this rank\'s trained slices -> one NCCL all_gather_into_tensor -> K5 scatter of '
-                'all m slices into the local full-model replica; dispatch = K5 gathers with the next partition '
-                '(no communication).  Event pairs on the training stream, rank 0.',
+        'what': 'per round: pack this rank\'s trained slices, exchange + merge them into the local full-model '
+                'replica, dispatch = one K5 multi-gather launch with the next partition (no communication).  '
+                'Event pairs on the training stream, rank 0.',
     }
     if world > 1 and ag_ms > 0:
         out['GBps'] = round(ag['bytes_received'] / 1e9 / (ag_ms / 1e3), 2)
         out['nvlink_line_rate_GBps'] = 900.0
         out['frac_of_line_rate'] = round(out['GBps'] / 900.0, 4)
-        out['GBps_note'] = 'bytes received per rank / all-gather time (ingress per GPU; NVLink 5: 900 GB/s per direction)'
+        out['GBps_note'] = ('bytes received per rank / %s time (ingress per GPU; NVLink 5: 900 GB/s per direction)'
+                            % ('merge-kernel (two device barriers included)' if peer else 'all-gather'))
     return out
 
 

@@ -38,6 +38,7 @@ SIGNATURES = {
     'gist_gather_rows': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _P]),
     'gist_slice_gather_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
     'gist_slice_scatter_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
+    'gist_slice_multi_f32': (ctypes.c_int, [_I32, _I32, _P, _P]),
     'gist_gemm_tf32_workspace_bytes': (_SZ, [_I32, _I32, _I32, _U32]),
     'gist_gemm_tf32': (ctypes.c_int, [_P, _I64, _I32, _P, _I64, _I32, _P, _I64, _I32, _I32, _I32, _P, _U32,
                                       _P, _SZ, _P]),
@@ -113,6 +114,12 @@ class SpmmEx(ctypes.Structure):
                 ('ld_self_lo', ctypes.c_int64), ('drop', ctypes.POINTER(DropoutDesc)),
                 ('drop_col0_y', ctypes.c_int32), ('drop_col0_self', ctypes.c_int32),
                 ('schedule', ctypes.POINTER(SpmmSchedule))]
+
+
+class SliceJob(ctypes.Structure):
+    """gist_slice_job_t"""
+    _fields_ = [('src', ctypes.c_void_p), ('ld_src', ctypes.c_int64), ('ridx', ctypes.c_void_p), ('n_rows', ctypes.c_int64),
+                ('cidx', ctypes.c_void_p), ('n_cols', ctypes.c_int64), ('dst', ctypes.c_void_p), ('ld_dst', ctypes.c_int64)]
 
 
 class GemmEx(ctypes.Structure):

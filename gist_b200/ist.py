@@ -17,6 +17,7 @@ copy in cluster_gcn_ist_ultra_wide.py).  What changed is the data movement:
 The partition is never communicated in either design: every rank draws it from
 the same Python ``random`` stream (same seed, same call order).
 """
+import os
 import random
 
 import torch
@@ -65,6 +66,8 @@ class DistributedGNNWrapper(torch.nn.Module):
         # K5 kernels.  Tests of the host-side plan / pack / all-gather logic on CPU
         # (gloo) inject a checker here; nothing in the package does.
         self._gather, self._scatter_ = slice_ops or (ops.slice_gather, ops.slice_scatter_)
+        self._cuda_slices = slice_ops is None       # product path: all slices of a round in ONE launch (ops.slice_multi)
+        self._symm = None                           # peer-memory sync state (see _peer_buffers)
         # True: dispatch writes the slices INTO the sub-model's existing parameter storage
         # (same values; keeps addresses stable for CUDA-graph replay) instead of rebinding
         # `.data` to fresh tensors as the reference does.
@@ -147,6 +150,29 @@ class DistributedGNNWrapper(torch.nn.Module):
         site = self.args.rank
         L = len(parts)
         with torch.no_grad():
+            if self._cuda_slices:
+                # product path: every slice of the round in one launch (K5 multi-gather)
+                jobs = []
+                for l in range(L + 1):
+                    ridx, cidx = self._slice_for(l, site, parts)
+                    base = self.base_model.layers[l].linear
+                    sub = self.sub_model.layers[l].linear
+                    wr = ridx.shape[0] if ridx is not None else base.weight.shape[0]
+                    wc = cidx.shape[0] if cidx is not None else base.weight.shape[1]
+                    if not (self.inplace_dispatch and tuple(sub.weight.shape) == (wr, wc)):
+                        sub.weight.data = torch.empty((wr, wc), dtype=torch.float32, device=base.weight.device)
+                    jobs.append((base.weight.data, ridx, cidx, sub.weight.data))
+                    if l == L:
+                        if self.inplace_dispatch:
+                            sub.bias.data.copy_(base.bias.data)
+                        else:
+                            sub.bias.data = base.bias.data.clone()      # shared, full (…distrib.py:217-219)
+                    else:
+                        if not (self.inplace_dispatch and tuple(sub.bias.shape) == (wr,)):
+                            sub.bias.data = torch.empty(wr, dtype=torch.float32, device=base.bias.device)
+                        jobs.append((base.bias.data, None, ridx, sub.bias.data))
+                ops.slice_multi(jobs, scatter=False)
+                return
             for l in range(L + 1):
                 ridx, cidx = self._slice_for(l, site, parts)
                 base = self.base_model.layers[l].linear
@@ -189,9 +215,43 @@ class DistributedGNNWrapper(torch.nn.Module):
         return e
 
     # ---------------------------------------------------------------- sync --
-    def _pack(self):
-        return torch.cat([t.data.reshape(-1) for lyr in self.sub_model.layers
-                          for t in (lyr.linear.weight, lyr.linear.bias)])
+    def _pack(self, out=None):
+        ts = [t.data.reshape(-1) for lyr in self.sub_model.layers for t in (lyr.linear.weight, lyr.linear.bias)]
+        return torch.cat(ts, out=out) if out is not None else torch.cat(ts)
+
+    def _peer_buffers(self, numel):
+        """Peer-memory sync — EXPERIMENTAL, opt-in with GIST_SYNC=peer (default: the NCCL all-gather path).
+        Every rank packs its trained slices into a SYMMETRIC buffer (torch.distributed._symmetric_memory)
+        that all ranks of the node map over NVLink; the merge kernel then reads each site's slices straight
+        from that site's HBM while it scatters them into the local replica — all-gather + scatter as ONE
+        kernel, no gathered staging buffer.  Status (round 2, 2 x B200): bit-exact against the reference
+        golden (tests/test_gpu_dist_nccl.py, sync_mode='peer') and 0.27 ms per Reddit-shape round, but the
+        ultra-wide configuration (139 MB per rank) did not complete in 25 minutes on the one attempt made,
+        so it is not the default.  Returns (handle, [one flat view per rank]) or None (-> all-gather)."""
+        m = self.args.num_subnet
+        if (m <= 1 or not _dist_ready() or not self._cuda_slices or torch.device(self.device).type != 'cuda'
+                or os.environ.get('GIST_SYNC', 'allgather') != 'peer'):
+            return None
+        if self._symm is not None and self._symm[0] == numel:
+            return self._symm[1], self._symm[2]
+        if self._symm is False:
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            if hasattr(symm_mem, 'enable_symm_mem_for_group'):
+                try:
+                    symm_mem.enable_symm_mem_for_group(dist.group.WORLD.group_name)
+                except Exception:
+                    pass
+            buf = symm_mem.empty(numel, dtype=torch.float32, device=self.device)
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            views = [buf if r == self.args.rank else hdl.get_buffer(r, (numel,), torch.float32) for r in range(m)]
+            self._symm = (numel, hdl, views)
+            return hdl, views
+        except Exception as ex:          # no NVLink peer mapping on this box: stay on the collective
+            self._symm = False
+            self._symm_error = repr(ex)[:300]
+            return None
 
     def sync_model(self):
         m = self.args.num_subnet
@@ -199,19 +259,30 @@ class DistributedGNNWrapper(torch.nn.Module):
         L = len(parts)
         with torch.no_grad():
             ev = self._stamp()
-            flat = self._pack()
-            ev = self._stamp(ev, 'sync_pack', bytes=flat.numel() * 4) or ev
-            if _dist_ready() and m > 1:
-                out = torch.empty(m * flat.numel(), dtype=flat.dtype, device=flat.device)
-                dist.all_gather_into_tensor(out, flat)       # ONE collective for all slices
-                gathered = out.view(m, flat.numel())
+            numel = sum(t.numel() for lyr in self.sub_model.layers for t in (lyr.linear.weight, lyr.linear.bias))
+            peer = self._peer_buffers(numel)
+            if peer is not None:
+                hdl, views = peer
+                self._pack(out=views[self.args.rank])
+                ev = self._stamp(ev, 'sync_pack', bytes=numel * 4) or ev
+                hdl.barrier(channel=0)                       # every site's slices are in its buffer
+                self._merge(views, parts)                    # reads peers over NVLink, scatters locally
+                hdl.barrier(channel=1)                       # nobody re-packs while a peer still reads
+                self._stamp(ev, 'sync_peer_merge', bytes_sent=numel * 4, bytes_received=(m - 1) * numel * 4)
             else:
-                assert m == 1, 'num_subnet > 1 needs an initialised process group'
-                gathered = flat.unsqueeze(0)
-            ev = self._stamp(ev, 'sync_all_gather', bytes_sent=flat.numel() * 4,
-                             bytes_received=(m - 1) * flat.numel() * 4) or ev
-            self._merge(gathered, parts)
-            self._stamp(ev, 'sync_scatter', bytes=m * flat.numel() * 4)
+                flat = self._pack()
+                ev = self._stamp(ev, 'sync_pack', bytes=flat.numel() * 4) or ev
+                if _dist_ready() and m > 1:
+                    out = torch.empty(m * flat.numel(), dtype=flat.dtype, device=flat.device)
+                    dist.all_gather_into_tensor(out, flat)       # ONE collective for all slices
+                    gathered = out.view(m, flat.numel())
+                else:
+                    assert m == 1, 'num_subnet > 1 needs an initialised process group'
+                    gathered = flat.unsqueeze(0)
+                ev = self._stamp(ev, 'sync_all_gather', bytes_sent=flat.numel() * 4,
+                                 bytes_received=(m - 1) * flat.numel() * 4) or ev
+                self._merge(gathered, parts)
+                self._stamp(ev, 'sync_scatter', bytes=m * flat.numel() * 4)
             # the reference all-reduces the last bias IN PLACE on every rank's sub-model
             if self.inplace_dispatch:
                 self.sub_model.layers[L].linear.bias.data.copy_(self.base_model.layers[L].linear.bias.data)
@@ -219,12 +290,14 @@ class DistributedGNNWrapper(torch.nn.Module):
                 self.sub_model.layers[L].linear.bias.data = self.base_model.layers[L].linear.bias.data.clone()
 
     def _merge(self, gathered, parts):
-        """Scatter every site's packed slices into the local full-model replica."""
-        m = gathered.shape[0]
+        """Scatter every site's packed slices into the local full-model replica.  ``gathered``: [m, numel]
+        tensor or a list of m flat views (peer buffers)."""
+        m = len(gathered)
         L = len(parts)
         shapes = [(tuple(lyr.linear.weight.shape), tuple(lyr.linear.bias.shape))
                   for lyr in self.sub_model.layers]
         last_bias = None
+        jobs = []
         for site in range(m):
             off = 0
             row = gathered[site]
@@ -234,9 +307,16 @@ class DistributedGNNWrapper(torch.nn.Module):
                 b = row[off:off + bn]; off += bn
                 ridx, cidx = self._slice_for(l, site, parts)
                 base = self.base_model.layers[l].linear
-                self._scatter_(base.weight.data, w, ridx, cidx)
+                if self._cuda_slices:
+                    jobs.append((w, ridx, cidx, base.weight.data))
+                else:
+                    self._scatter_(base.weight.data, w, ridx, cidx)
                 if l == L:
                     last_bias = b.clone() if last_bias is None else last_bias + b   # rank order
+                elif self._cuda_slices:
+                    jobs.append((b, None, ridx, base.bias.data))
                 else:
                     self._scatter_(base.bias.data, b, None, ridx)
+        if jobs:
+            ops.slice_multi(jobs, scatter=True)          # all sites x all tensors: one launch
         self.base_model.layers[L].linear.bias.data = last_bias / m

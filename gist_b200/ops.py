@@ -260,6 +260,34 @@ def slice_scatter_(dst, src, ridx=None, cidx=None):
     return dst
 
 
+def slice_multi(jobs, scatter):
+    """Many slice gathers / scatters in ONE launch (gist_slice_multi_f32).
+    jobs: list of (src, ridx, cidx, dst): gather  dst[r, c] = src[ridx[r], cidx[c]]
+                                          scatter dst[ridx[r], cidx[c]] = src[r, c]   (None = identity)
+    1-D tensors are rows.  `src` of a scatter may alias another rank's memory (peer-mapped buffer)."""
+    if not jobs:
+        return
+    arr = (_lib.SliceJob * len(jobs))()
+    dev = None
+    for k, (src, ridx, cidx, dst) in enumerate(jobs):
+        require_cuda(src, ridx, cidx, dst)
+        s2 = src.unsqueeze(0) if src.dim() == 1 else src
+        d2 = dst.unsqueeze(0) if dst.dim() == 1 else dst
+        assert s2.dtype == torch.float32 and d2.dtype == torch.float32
+        assert (s2.shape[1] <= 1 or s2.stride(1) == 1) and (d2.shape[1] <= 1 or d2.stride(1) == 1)
+        dense = s2 if scatter else d2            # the side indexed densely: [n_rows, n_cols]
+        nr, nc = dense.shape
+        other = d2 if scatter else s2
+        assert nr == (ridx.shape[0] if ridx is not None else other.shape[0]), (nr, other.shape)
+        assert nc == (cidx.shape[0] if cidx is not None else other.shape[1]), (nc, other.shape)
+        for ix in (ridx, cidx):
+            assert ix is None or (ix.dtype == torch.int64 and ix.is_contiguous())
+        arr[k] = _lib.SliceJob(s2.data_ptr(), _ld(s2), ridx.data_ptr() if ridx is not None else None, nr,
+                               cidx.data_ptr() if cidx is not None else None, nc, d2.data_ptr(), _ld(d2))
+        dev = dst.device
+    check(_lib.load().gist_slice_multi_f32(1 if scatter else 0, len(jobs), arr, stream_ptr(dev)), 'slice_multi_f32')
+
+
 # --------------------------------------------------------------------------
 # autograd
 # --------------------------------------------------------------------------

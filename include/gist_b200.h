@@ -240,6 +240,25 @@ int gist_slice_scatter_f32(const float *src, int64_t ld_src, const int64_t *ridx
                            const int64_t *cidx, int64_t n_cols, float *dst, int64_t ld_dst,
                            gist_stream_t stream);
 
+/* Several slice gathers (scatter == 0) or scatters (scatter != 0) in ONE launch: a GIST round boundary
+ * moves 2 (L + 1) tensors per site (cluster_gcn_ist_distrib.py:100-195, 285-367), and with eight sites
+ * the issue time of 48 small launches is what the step pipeline waits for.  `jobs` is a HOST array;
+ * pointers inside are device pointers.  A source may be peer memory (an NVLink-mapped buffer of another
+ * rank): the merge then reads every site's packed slices straight from that site's HBM while
+ * scattering into the local replica — the all-gather and the scatter as one kernel. */
+typedef struct gist_slice_job {
+    const float *src;
+    int64_t ld_src;
+    const int64_t *ridx;   /* NULL = identity */
+    int64_t n_rows;
+    const int64_t *cidx;   /* NULL = identity */
+    int64_t n_cols;
+    float *dst;
+    int64_t ld_dst;
+} gist_slice_job_t;
+int gist_slice_multi_f32(int32_t scatter, int32_t n_jobs, const gist_slice_job_t *jobs, gist_stream_t stream);
+
+
 /* ------------------------------------------------------------------------
  * K4  tensor-core GEMM (tcgen05 / TMEM, TF32 inputs, fp32 accumulate).
  *

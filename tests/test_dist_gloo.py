@@ -15,8 +15,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, 'tests', 'golden')
 
 
-def _worker(rank, m, port, ci, q, backend='gloo'):
+def _worker(rank, m, port, ci, q, backend='gloo', sync_mode=None):
     try:
+        if sync_mode is not None:
+            os.environ['GIST_SYNC'] = sync_mode          # 'peer' (NVLink peer memory) | 'allgather' (NCCL)
         _worker_body(rank, m, port, ci, q, backend)
     except Exception as e:      # surface the failure instead of hanging the parent
         import traceback
@@ -73,6 +75,8 @@ def _worker_body(rank, m, port, ci, q, backend='gloo'):
             lyr.linear.bias.data = lyr.linear.bias.data - 0.125 * (rank + 1)
     dist.barrier()
     w.sync_model()
+    if backend == 'nccl' and os.environ.get('GIST_SYNC') == 'peer' and not w._symm:
+        errs.append('peer-memory path was requested but not used: %s' % getattr(w, '_symm_error', '?'))
     eq('r%d_lastbias_after_sync' % rank, w.sub_model.layers[-1].linear.bias, exact=False)
     for l, lyr in enumerate(w.base_model.layers):        # EVERY rank's replica == reference rank 0
         eq('r0_base1.layers.%d.linear.weight' % l, lyr.linear.weight)
