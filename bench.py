@@ -571,7 +571,8 @@ def run_gist(a):
             if key not in nnz_cache:
                 nnz_cache[key] = int(r['rowptr'][r['n']].item())
             nnz = nnz_cache[key]
-            gb_ += 4.0 * nnz * r['D'] + 4.0 * nnz + 4.0 * nnz + 4.0 * r['n'] * r['D'] + 4.0 * (r['n'] + 1) + 8.0 * r['n']
+            hh = r.get('heads', 1)       # a batched launch aggregates all heads: per-head bytes x heads
+            gb_ += hh * (4.0 * nnz * r['D'] + 4.0 * nnz + 4.0 * nnz + 4.0 * r['n'] * r['D'] + 4.0 * (r['n'] + 1) + 8.0 * r['n'])
             gms += r['ev0'].elapsed_time(r['ev1'])
         roofline = {'bound': 'hbm', 'kernel': 'gat_aggregate_kernel (K6 forward, %d launches/step)' % (len(aprof) // max(prof_steps, 1)),
                     'achieved': round(gb_ / 1e9 / (gms / 1e3), 1), 'peak': peak, 'unit': 'GB/s',

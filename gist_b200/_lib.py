@@ -69,6 +69,12 @@ SIGNATURES = {
                                             _P, _P, _P, _P, _I64, _P, _I64, _U32, _P, _P]),
     'gist_spmm_schedule_workspace_bytes': (_SZ, [_I32]),
     'gist_spmm_schedule_build': (ctypes.c_int, [_P, _I32, _I32, _P, _P, _I64, _P, _SZ, _P]),
+    'gist_gemm_has_inkernel_splitk': (ctypes.c_int, []),
+    'gist_gat_scores_heads_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P, _P]),
+    'gist_gat_aggregate_heads_f32': (ctypes.c_int, [_P, _P, _I32, _P, _I64, _I32, _I32, _P, _F32, _P, _I64, _P, _P]),
+    'gist_gat_backward_heads_workspace_bytes': (_SZ, [_I32, _I32, _I32]),
+    'gist_gat_backward_heads_f32': (ctypes.c_int, [_P, _P, _P, _P, _I32, _P, _I64, _I32, _I32, _P, _P, _P, _F32, _P, _I64,
+                                                   _P, _I64, _P, _I64, _P, _P, _SZ, _P]),
     'gist_gemm_ex_workspace_bytes': (_SZ, [_I32, _I32, _I32, _U32, _I32, _P]),
     'gist_gemm_ex_f32': (ctypes.c_int, [_P, _P, _I64, _I64, _I32, _P, _P, _I64, _I64, _I32, _P, _I64, _I32, _I32,
                                         _I32, _P, _U32, _P, _SZ, _P, _P]),

@@ -82,6 +82,10 @@ __device__ __forceinline__ float dot_slots(const float (&a)[SLOTS][VEC], const f
 __global__ void __launch_bounds__(256) gat_scores_kernel(const float *__restrict__ z, int64_t ldz, int n, int D,
                                                          const float *__restrict__ attn,
                                                          float2 *__restrict__ s) {
+    // blockIdx.y = attention head: head h owns columns [h D, (h + 1) D) of z and its own attn / score rows
+    z += (int64_t)blockIdx.y * D;
+    attn += (int64_t)blockIdx.y * 2 * D;
+    s += (int64_t)blockIdx.y * n;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= n) return;
@@ -105,6 +109,10 @@ __global__ void __launch_bounds__(256) gat_fwd_kernel(const int32_t *__restrict_
                                                       const float2 *__restrict__ s, float slope,
                                                       float *__restrict__ out, int64_t ldo,
                                                       float *__restrict__ lse) {
+    z += (int64_t)blockIdx.y * D;        // all heads of a layer in one launch: head = blockIdx.y
+    s += (int64_t)blockIdx.y * n;
+    out += (int64_t)blockIdx.y * D;
+    lse += (int64_t)blockIdx.y * n;
     const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (v >= n) return;
@@ -168,6 +176,13 @@ __global__ void __launch_bounds__(256) gat_bwd_dst_kernel(const int32_t *__restr
                                                           const float *__restrict__ out, int64_t ldo,
                                                           float slope, float *__restrict__ cvec,
                                                           float *__restrict__ der) {
+    z += (int64_t)blockIdx.y * D;
+    g += (int64_t)blockIdx.y * D;
+    out += (int64_t)blockIdx.y * D;
+    s += (int64_t)blockIdx.y * n;
+    lse += (int64_t)blockIdx.y * n;
+    cvec += (int64_t)blockIdx.y * n;
+    der += (int64_t)blockIdx.y * n;
     const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (v >= n) return;
@@ -227,6 +242,15 @@ __global__ void __launch_bounds__(256) gat_bwd_src_kernel(const int32_t *__restr
                                                           const float *__restrict__ attn, float slope,
                                                           float *__restrict__ dz, int64_t lddz,
                                                           float *__restrict__ del) {
+    z += (int64_t)blockIdx.y * D;
+    g += (int64_t)blockIdx.y * D;
+    dz += (int64_t)blockIdx.y * D;
+    attn += (int64_t)blockIdx.y * 2 * D;
+    s += (int64_t)blockIdx.y * n;
+    lse += (int64_t)blockIdx.y * n;
+    cvec += (int64_t)blockIdx.y * n;
+    der += (int64_t)blockIdx.y * n;
+    del += (int64_t)blockIdx.y * n;
     const int u = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (u >= n) return;
@@ -297,6 +321,10 @@ __global__ void __launch_bounds__(256) gat_dattn_partial_kernel(const float *__r
                                                                 const float *__restrict__ der, int rows_per,
                                                                 float *__restrict__ part) {
     __shared__ float sl[8][33], sr[8][33];
+    z += (int64_t)blockIdx.z * D;            // head = blockIdx.z
+    del += (int64_t)blockIdx.z * n;
+    der += (int64_t)blockIdx.z * n;
+    part += (int64_t)blockIdx.z * gridDim.y * 2 * D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
     const int r0 = blockIdx.y * rows_per;
@@ -323,6 +351,8 @@ __global__ void __launch_bounds__(256) gat_dattn_partial_kernel(const float *__r
 
 __global__ void __launch_bounds__(256) gat_dattn_final_kernel(const float *__restrict__ part, int nparts, int D2,
                                                               float *__restrict__ out) {
+    part += (int64_t)blockIdx.y * nparts * D2;   // head = blockIdx.y
+    out += (int64_t)blockIdx.y * D2;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= D2) return;
     float t = 0.f;
@@ -377,14 +407,43 @@ static bool gat_pick(int D, bool v4, GatVec *o) {
 
 using namespace gist;
 
+// All H heads of a MultiHeadGATLayer in ONE launch per kernel (cluster_gcn/modules.py:67-76 loops over the
+// heads): head h owns columns [h D, (h + 1) D) of z / out / dout / dz (one [n, H D] buffer each, the
+// projection of all heads being one GEMM) and row h of attn [H, 2D], scores [H, n, 2], lse [H, n],
+// dattn [H, 2D].  The grid's y dimension is the head.  H = 1 is the single-head API below.
+extern "C" int gist_gat_scores_heads_f32(const float *z, int64_t ldz, int32_t n, int32_t D, int32_t heads,
+                                         const float *attn, float *scores, gist_stream_t stream) {
+    if (n < 0 || D <= 0 || heads <= 0 || heads > 65535) return GIST_ERR_BADARG;
+    if (n == 0) return GIST_OK;
+    if (!z || !attn || !scores || ldz < (int64_t)D * heads) return GIST_ERR_BADARG;
+    if (!aligned(scores, 8)) return GIST_ERR_ALIGN;
+    dim3 grid((unsigned)((n + 7) / 8), (unsigned)heads);
+    gat_scores_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, ldz, n, D, attn, reinterpret_cast<float2 *>(scores));
+    count_launch();
+    return last_error();
+}
+
 extern "C" int gist_gat_scores_f32(const float *z, int64_t ldz, int32_t n, int32_t D, const float *attn,
                                    float *scores, gist_stream_t stream) {
-    if (n < 0 || D <= 0) return GIST_ERR_BADARG;
+    return gist_gat_scores_heads_f32(z, ldz, n, D, 1, attn, scores, stream);
+}
+
+extern "C" int gist_gat_aggregate_heads_f32(const int32_t *rowptr, const int32_t *col, int32_t n, const float *z,
+                                            int64_t ldz, int32_t D, int32_t heads, const float *scores,
+                                            float negative_slope, float *out, int64_t ldo, float *lse,
+                                            gist_stream_t stream) {
+    if (n < 0 || D <= 0 || heads <= 0 || heads > 65535) return GIST_ERR_BADARG;
     if (n == 0) return GIST_OK;
-    if (!z || !attn || !scores || ldz < D) return GIST_ERR_BADARG;
+    if (!rowptr || !z || !scores || !out || !lse || ldz < (int64_t)D * heads || ldo < (int64_t)D * heads)
+        return GIST_ERR_BADARG;
     if (!aligned(scores, 8)) return GIST_ERR_ALIGN;
-    gat_scores_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(z, ldz, n, D, attn,
-                                                                    reinterpret_cast<float2 *>(scores));
+    const bool v4 = D % 4 == 0 && ldz % 4 == 0 && ldo % 4 == 0 && aligned(z, 16) && aligned(out, 16);
+    GatVec gv;
+    if (!gat_pick(D, v4, &gv)) return GIST_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid((unsigned)((n + 7) / 8), (unsigned)heads);
+    const float2 *sc = reinterpret_cast<const float2 *>(scores);
+    GAT_DISPATCH(gat_fwd_kernel, gv, rowptr, col, n, z, ldz, D, sc, negative_slope, out, ldo, lse);
     count_launch();
     return last_error();
 }
@@ -392,25 +451,58 @@ extern "C" int gist_gat_scores_f32(const float *z, int64_t ldz, int32_t n, int32
 extern "C" int gist_gat_aggregate_f32(const int32_t *rowptr, const int32_t *col, int32_t n, const float *z,
                                       int64_t ldz, int32_t D, const float *scores, float negative_slope,
                                       float *out, int64_t ldo, float *lse, gist_stream_t stream) {
-    if (n < 0 || D <= 0) return GIST_ERR_BADARG;
-    if (n == 0) return GIST_OK;
-    if (!rowptr || !z || !scores || !out || !lse || ldz < D || ldo < D) return GIST_ERR_BADARG;
-    if (!aligned(scores, 8)) return GIST_ERR_ALIGN;
-    const bool v4 = D % 4 == 0 && ldz % 4 == 0 && ldo % 4 == 0 && aligned(z, 16) && aligned(out, 16);
-    GatVec gv;
-    if (!gat_pick(D, v4, &gv)) return GIST_ERR_UNSUPPORTED;
-    cudaStream_t s = (cudaStream_t)stream;
-    const unsigned grid = (unsigned)((n + 7) / 8);
-    const float2 *sc = reinterpret_cast<const float2 *>(scores);
-    GAT_DISPATCH(gat_fwd_kernel, gv, rowptr, col, n, z, ldz, D, sc, negative_slope, out, ldo, lse);
-    count_launch();
-    return last_error();
+    return gist_gat_aggregate_heads_f32(rowptr, col, n, z, ldz, D, 1, scores, negative_slope, out, ldo, lse, stream);
+}
+
+extern "C" size_t gist_gat_backward_heads_workspace_bytes(int32_t n, int32_t D, int32_t heads) {
+    if (n <= 0 || D <= 0 || heads <= 0) return 0;
+    // per head: c[n], der[n], del[n], dattn partials [parts][2D]
+    return (size_t)heads * ((size_t)3 * n + (size_t)dattn_parts(n, D) * 2 * D) * sizeof(float);
 }
 
 extern "C" size_t gist_gat_backward_workspace_bytes(int32_t n, int32_t D) {
-    if (n <= 0 || D <= 0) return 0;
-    // c[n], der[n], del[n], dattn partials [parts][2D]
-    return ((size_t)3 * n + (size_t)dattn_parts(n, D) * 2 * D) * sizeof(float);
+    return gist_gat_backward_heads_workspace_bytes(n, D, 1);
+}
+
+extern "C" int gist_gat_backward_heads_f32(const int32_t *rowptr, const int32_t *col, const int32_t *colptr,
+                                           const int32_t *row, int32_t n, const float *z, int64_t ldz, int32_t D,
+                                           int32_t heads, const float *scores, const float *lse, const float *attn,
+                                           float negative_slope, const float *out, int64_t ldo, const float *dout,
+                                           int64_t lddo, float *dz, int64_t lddz, float *dattn, void *workspace,
+                                           size_t workspace_bytes, gist_stream_t stream) {
+    if (n < 0 || D <= 0 || heads <= 0 || heads > 65535) return GIST_ERR_BADARG;
+    if (!dattn) return GIST_ERR_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        cudaError_t e = cudaMemsetAsync(dattn, 0, (size_t)heads * 2 * D * sizeof(float), s);
+        return e == cudaSuccess ? GIST_OK : (int)e;
+    }
+    if (!rowptr || !colptr || !z || !scores || !lse || !attn || !out || !dout || !dz) return GIST_ERR_BADARG;
+    const int64_t W = (int64_t)D * heads;
+    if (ldz < W || ldo < W || lddo < W || lddz < W) return GIST_ERR_BADARG;
+    if (!workspace || workspace_bytes < gist_gat_backward_heads_workspace_bytes(n, D, heads)) return GIST_ERR_WORKSPACE;
+    if (!aligned(scores, 8) || !aligned(workspace, 4)) return GIST_ERR_ALIGN;
+    const bool v4 = D % 4 == 0 && ldz % 4 == 0 && ldo % 4 == 0 && lddo % 4 == 0 && lddz % 4 == 0 &&
+                    aligned(z, 16) && aligned(out, 16) && aligned(dout, 16) && aligned(dz, 16) &&
+                    aligned(attn, 16);
+    GatVec gv;
+    if (!gat_pick(D, v4, &gv)) return GIST_ERR_UNSUPPORTED;
+    float *cvec = reinterpret_cast<float *>(workspace);
+    float *der = cvec + (size_t)heads * n, *del = der + (size_t)heads * n, *part = del + (size_t)heads * n;
+    dim3 grid((unsigned)((n + 7) / 8), (unsigned)heads);
+    const float2 *sc = reinterpret_cast<const float2 *>(scores);
+    GAT_DISPATCH(gat_bwd_dst_kernel, gv, rowptr, col, n, z, ldz, D, sc, lse, dout, lddo, out, ldo,
+                 negative_slope, cvec, der);
+    GAT_DISPATCH(gat_bwd_src_kernel, gv, colptr, row, n, z, ldz, D, sc, lse, cvec, der, dout, lddo, attn,
+                 negative_slope, dz, lddz, del);
+    const int by = dattn_parts(n, D);
+    const int rows_per = (n + by - 1) / by;
+    dim3 g2((D + 31) / 32, by, (unsigned)heads);
+    gat_dattn_partial_kernel<<<g2, 256, 0, s>>>(z, ldz, n, D, del, der, rows_per, part);
+    dim3 g3((2 * D + 255) / 256, (unsigned)heads);
+    gat_dattn_final_kernel<<<g3, 256, 0, s>>>(part, by, 2 * D, dattn);
+    count_launch(4);
+    return last_error();
 }
 
 extern "C" int gist_gat_backward_f32(const int32_t *rowptr, const int32_t *col, const int32_t *colptr,
@@ -419,35 +511,6 @@ extern "C" int gist_gat_backward_f32(const int32_t *rowptr, const int32_t *col, 
                                      float negative_slope, const float *out, int64_t ldo, const float *dout,
                                      int64_t lddo, float *dz, int64_t lddz, float *dattn, void *workspace,
                                      size_t workspace_bytes, gist_stream_t stream) {
-    if (n < 0 || D <= 0) return GIST_ERR_BADARG;
-    if (!dattn) return GIST_ERR_BADARG;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (n == 0) {
-        cudaError_t e = cudaMemsetAsync(dattn, 0, (size_t)2 * D * sizeof(float), s);
-        return e == cudaSuccess ? GIST_OK : (int)e;
-    }
-    if (!rowptr || !colptr || !z || !scores || !lse || !attn || !out || !dout || !dz) return GIST_ERR_BADARG;
-    if (ldz < D || ldo < D || lddo < D || lddz < D) return GIST_ERR_BADARG;
-    if (!workspace || workspace_bytes < gist_gat_backward_workspace_bytes(n, D)) return GIST_ERR_WORKSPACE;
-    if (!aligned(scores, 8) || !aligned(workspace, 4)) return GIST_ERR_ALIGN;
-    const bool v4 = D % 4 == 0 && ldz % 4 == 0 && ldo % 4 == 0 && lddo % 4 == 0 && lddz % 4 == 0 &&
-                    aligned(z, 16) && aligned(out, 16) && aligned(dout, 16) && aligned(dz, 16) &&
-                    aligned(attn, 16);
-    GatVec gv;
-    if (!gat_pick(D, v4, &gv)) return GIST_ERR_UNSUPPORTED;
-    float *cvec = reinterpret_cast<float *>(workspace);
-    float *der = cvec + n, *del = der + n, *part = del + n;
-    const unsigned grid = (unsigned)((n + 7) / 8);
-    const float2 *sc = reinterpret_cast<const float2 *>(scores);
-    GAT_DISPATCH(gat_bwd_dst_kernel, gv, rowptr, col, n, z, ldz, D, sc, lse, dout, lddo, out, ldo,
-                 negative_slope, cvec, der);
-    GAT_DISPATCH(gat_bwd_src_kernel, gv, colptr, row, n, z, ldz, D, sc, lse, cvec, der, dout, lddo, attn,
-                 negative_slope, dz, lddz, del);
-    const int by = dattn_parts(n, D);
-    const int rows_per = (n + by - 1) / by;
-    dim3 g2((D + 31) / 32, by);
-    gat_dattn_partial_kernel<<<g2, 256, 0, s>>>(z, ldz, n, D, del, der, rows_per, part);
-    gat_dattn_final_kernel<<<(2 * D + 255) / 256, 256, 0, s>>>(part, by, 2 * D, dattn);
-    count_launch(4);
-    return last_error();
+    return gist_gat_backward_heads_f32(rowptr, col, colptr, row, n, z, ldz, D, 1, scores, lse, attn, negative_slope,
+                                       out, ldo, dout, lddo, dz, lddz, dattn, workspace, workspace_bytes, stream);
 }

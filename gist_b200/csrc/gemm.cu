@@ -29,7 +29,6 @@
 // recover ~2^-20 relative accuracy per product with fp32 accumulation in TMEM, which keeps the
 // layer outputs and gradients within the 1e-5 parity tolerance of the reference's fp32 sgemm.
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -191,7 +190,6 @@ struct GemmParams {
     int32_t vec4;       // output rows and bias are 16-byte aligned: float4 epilogue stores
     int32_t kc;         // NT == 3: K blocks chained into one TMEM accumulator before it is drained
     int32_t background; // host only: launch on a third of the SMs (GIST_GEMM_BACKGROUND)
-    int32_t single_unit;// every CTA has one work unit: the epilogue may stage through the idle operand ring
     DropParams drop;    // p != 0: C[r, c] *= dropout multiplier of (r, c) (the dz = dy W contraction)
     long long *trace;   // diagnostic (gist_gemm_set_trace): kTraceSlots clock stamps per CTA, or NULL
     // ---- extended epilogue (gist_gemm_ex_f32) ----
@@ -464,7 +462,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int m0 = tile_m * kBM;
             const int n0 = (t / p.tiles_m) * BN;
             const int row = m0 + trow;
+            // In-kernel split-K (last-arriver fold) is compiled in only with -DGIST_GEMM_INKERNEL_SPLITK: it
+            // measured slower than the two-kernel form on every shape of the training step, and merely
+            // carrying its code in the epilogue cost the replayed Reddit-shape step 4.7 % (0.2621 vs 0.2499
+            // ms; the epilogue of a one-tile CTA runs once, cold, and is as long as its code).
+#ifdef GIST_GEMM_INKERNEL_SPLITK
             const bool inker = p.splits > 1 && p.tile_counters != nullptr;     // last-arriver reduction in this kernel
+#else
+            constexpr bool inker = false;
+#endif
             const bool legacy = p.splits > 1 && !inker;                        // partials for splitk_reduce_kernel
             const bool do_rowsum = kRowsum && p.rowsum != nullptr && n0 == 0;
             float *crow = legacy ? p.C + ((int64_t)split * p.M + row) * p.ldc : p.C + (int64_t)row * p.ldc;
@@ -474,42 +480,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool masked = fused && p.drop.p != 0.f;
             const int64_t dstep = masked ? drop_step(p.drop) : 0;
             auto store32 = [&](const float (&v)[32], int c) {
-                if (p.single_unit && !inker) {       // (the in-kernel split-K fold stages partial tiles in the ring)
-                    // Every CTA of this launch has ONE work unit, so the operand ring is idle once the last
-                    // accumulator is complete: transpose the warp's 32 x 32 block through it and write whole
-                    // 128-byte row segments.  (lane = row straight from TMEM means 32 rows x 16 B per store
-                    // instruction: 32 LSU wavefronts each — ~4 us of exposed epilogue on a 128 x 128 tile.)
-                    float *stg = reinterpret_cast<float *>(base) + q * (32 * 33);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float r = v[i];
-                        if (fused) {
-                            if (p.bias && c + i < ncols) r += __ldg(p.bias + n0 + c + i);
-                            if (p.relu) r = fmaxf(r, 0.f);
-                        }
-                        stg[lane * 33 + i] = r;
-                    }
-                    if (masked && row < p.M) {       // one Philox call per aligned group of 4 columns
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const uint4 rnd = drop_rand4(p.drop, dstep, (uint32_t)row, (uint32_t)(n0 + c + i) >> 2);
-                            stg[lane * 33 + i] = rnd.x >= p.drop.thresh ? stg[lane * 33 + i] * p.drop.scale : 0.f;
-                            stg[lane * 33 + i + 1] = rnd.y >= p.drop.thresh ? stg[lane * 33 + i + 1] * p.drop.scale : 0.f;
-                            stg[lane * 33 + i + 2] = rnd.z >= p.drop.thresh ? stg[lane * 33 + i + 2] * p.drop.scale : 0.f;
-                            stg[lane * 33 + i + 3] = rnd.w >= p.drop.thresh ? stg[lane * 33 + i + 3] * p.drop.scale : 0.f;
-                        }
-                    }
-                    __syncwarp();
-                    if (c + lane < ncols) {
-                        float *col0 = (legacy ? p.C + (int64_t)split * p.M * p.ldc : p.C) + n0 + c + lane;
-                        const int rbase = m0 + q * 32;
-#pragma unroll 8
-                        for (int rr = 0; rr < 32; ++rr)
-                            if (rbase + rr < p.M) col0[(int64_t)(rbase + rr) * p.ldc] = stg[rr * 33 + lane];
-                    }
-                    __syncwarp();
-                    return;
-                }
                 if (row >= p.M) return;
                 float *out = crow + n0 + c;
                 if (p.vec4 && c + 32 <= ncols) {             // 16-byte aligned 128-byte segment
@@ -1092,9 +1062,7 @@ static int launch_gemm(const GemmMaps &m, const GemmParams &p, cudaStream_t s) {
     const int n_work = p.tiles_m * p.tiles_n * p.splits;
     const int cap = p.background ? max(sm_count() / 3, 1) : sm_count();
     const int grid = n_work < cap ? n_work : cap;
-    GemmParams p2 = p;
-    p2.single_unit = (n_work <= grid && !getenv("GIST_GEMM_NO_STAGED_EPILOGUE")) ? 1 : 0;
-    gemm_tf32_kernel<BN, A_MN, B_MN, NT, LN><<<grid, kGemmThreads, smem, s>>>(m.a, m.b, m.al, m.bl, p2);
+    gemm_tf32_kernel<BN, A_MN, B_MN, NT, LN><<<grid, kGemmThreads, smem, s>>>(m.a, m.b, m.al, m.bl, p);
     count_launch();
     return last_error();
 }
@@ -1262,7 +1230,11 @@ static int gemm_impl(const float *A, const float *A_lo, int64_t lda, int64_t lda
         if (ex->tile_counters && !aligned(ex->tile_counters, 4)) return GIST_ERR_ALIGN;
         flags = ex_plan_flags(N, flags, ex);
     }
+#ifdef GIST_GEMM_INKERNEL_SPLITK
     const bool inkernel = ex && ex->tile_counters;
+#else
+    const bool inkernel = false;
+#endif
     DropParams dp;
     {
         const int st = make_drop_params(drop, &dp);
@@ -1389,10 +1361,19 @@ extern "C" int gist_gemm_3xtf32(const float *A, const float *A_lo, int64_t lda, 
                      workspace, workspace_bytes, nullptr, stream);
 }
 
+extern "C" int gist_gemm_has_inkernel_splitk(void) {
+#ifdef GIST_GEMM_INKERNEL_SPLITK
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 extern "C" size_t gist_gemm_ex_workspace_bytes(int32_t M, int32_t N, int32_t K, uint32_t flags, int32_t three_pass,
                                                const gist_gemm_ex_t *ex) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    return plan_gemm(M, N, K, ex_plan_flags(N, flags, ex), three_pass != 0, ex && ex->tile_counters).ws_bytes;
+    const bool inkernel = gist_gemm_has_inkernel_splitk() && ex && ex->tile_counters;
+    return plan_gemm(M, N, K, ex_plan_flags(N, flags, ex), three_pass != 0, inkernel).ws_bytes;
 }
 
 extern "C" int gist_gemm_ex_f32(const float *A, const float *A_lo, int64_t lda, int64_t lda_lo, int32_t a_layout,

@@ -273,7 +273,9 @@ class DistributedGNNWrapper(torch.nn.Module):
                 flat = self._pack()
                 ev = self._stamp(ev, 'sync_pack', bytes=flat.numel() * 4) or ev
                 if _dist_ready() and m > 1:
-                    out = torch.empty(m * flat.numel(), dtype=flat.dtype, device=flat.device)
+                    out = getattr(self, '_gather_buf', None)     # persistent: a round must not pay a cudaMalloc
+                    if out is None or out.numel() != m * flat.numel() or out.device != flat.device:
+                        out = self._gather_buf = torch.empty(m * flat.numel(), dtype=flat.dtype, device=flat.device)
                     dist.all_gather_into_tensor(out, flat)       # ONE collective for all slices
                     gathered = out.view(m, flat.numel())
                 else:

@@ -8,6 +8,7 @@ aggregation, degree normalisation, concat, bias and ReLU run in the sm_100a
 kernels of ``csrc/``; nothing here falls back to a CPU or library SpMM.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -109,6 +110,9 @@ class GATLayer(nn.Module):
 
 
 PARALLEL_HEADS = True
+# all heads of a layer as ONE projection GEMM + one K6 launch per kernel (heads = grid dimension) instead of
+# a GEMM + three K6 launches per head on per-head streams (GIST_GAT_BATCH_HEADS=0: round 1's form)
+BATCH_HEADS = os.environ.get('GIST_GAT_BATCH_HEADS', '1') != '0'
 _HEAD_STREAMS = {}
 
 
@@ -134,7 +138,23 @@ class MultiHeadGATLayer(nn.Module):
         for _ in range(num_heads):
             self.heads.append(GATLayer(in_dim, out_dim))
 
+    def _batched(self, g, h):
+        """The heads' fc weights stacked into one [H*D, in] projection, their attention vectors into
+        [H, 2D]; autograd splits the gradients back to the per-head parameters."""
+        H = len(self.heads)
+        W_all = torch.cat([hd.fc.weight for hd in self.heads], dim=0)
+        attn_all = torch.stack([hd.attn_fc.weight.reshape(-1) for hd in self.heads])
+        z_all = ops.linear(h, W_all, None)
+        out_all = ops.gat_aggregate_heads(g, z_all, attn_all, H, 0.01)
+        if self.reduce == 'scalar':
+            return torch.mean(out_all)
+        D = out_all.shape[1] // H
+        return out_all.reshape(out_all.shape[0], H, D).mean(dim=1)
+
     def forward(self, g, h):
+        if (h.is_cuda and len(self.heads) > 1 and BATCH_HEADS
+                and len({tuple(hd.fc.weight.shape) for hd in self.heads}) == 1):
+            return self._batched(g, h)
         if h.is_cuda and len(self.heads) > 1 and PARALLEL_HEADS:
             # the heads share only read-only inputs (graph, h): one stream per head, so their
             # projection GEMMs and row-per-warp attention kernels (tail-bound on a cluster batch's hub

@@ -587,6 +587,7 @@ GEMM_TILE_COUNTERS = 4096
 FUSED_SPLITK = os.environ.get('GIST_GEMM_FUSED_SPLITK', '0') != '0'       # A/B switches for profiles/
 FUSED_ROWSUM = os.environ.get('GIST_GEMM_FUSED_ROWSUM', '1') != '0'
 BACKGROUND_DW = os.environ.get('GIST_GEMM_BACKGROUND_DW', '1') != '0'
+DZ_FIRST = os.environ.get('GIST_DZ_FIRST', '1') != '0'
 FUSED_LN = os.environ.get('GIST_GEMM_FUSED_LN', '1') != '0'
 _GEMM_COUNTERS = {}
 
@@ -834,9 +835,12 @@ def _side_stream(device):
     return st
 
 
-def _weight_grad_branch(device, fn, keep):
-    """Run fn() (returns tensors) on the side stream, forked from the current stream; registers the
-    join.  Falls back to the current stream when overlap is disabled or outside a backward pass.
+def _weight_grad_branch(device, fn, keep, after=None):
+    """Run fn() (returns tensors) on the side stream, forked from the current stream — or, with
+    ``after`` (an event recorded on the current stream when fn's inputs were ready), from that earlier
+    point: the caller can then enqueue its own latency-critical kernels FIRST and the branch afterwards
+    without making the branch wait for them.  Registers the join.  Falls back to the current stream when
+    overlap is disabled or outside a backward pass.
 
     ``keep``: every tensor fn() reads.  They were allocated on the main stream; the caching
     allocator would hand their memory to the next main-stream allocation as soon as autograd drops
@@ -861,7 +865,10 @@ def _weight_grad_branch(device, fn, keep):
         torch.autograd.Variable._execution_engine.queue_callback(join)
     except RuntimeError:            # not inside a backward pass: nothing would join the branch
         return fn()
-    side.wait_stream(cur)
+    if after is not None:
+        side.wait_event(after)
+    else:
+        side.wait_stream(cur)
     with torch.cuda.stream(side):
         out = fn()
         ev.record(side)
@@ -959,7 +966,15 @@ class _SageLinear(torch.autograd.Function):
                 return gemm(dy, z, a_mn=True, b_mn=True, A_lo=dy_lo, B_lo=z_lo, rowsum=True, flags=bgf)
             return (gemm(dy, z, a_mn=True, b_mn=True, A_lo=dy_lo, B_lo=z_lo, flags=bgf) if need_dW else None,
                     colsum(dy) if need_db and not db_here else None)
-        if need_dW or (need_db and not db_here):      # forked first: the branch depends on dy only
+        # The branch depends on dy only.  Its fork point is recorded NOW, but its kernels are enqueued
+        # AFTER this layer's dz GEMM and K2 (DZ_FIRST): a replayed graph hands nodes to the GPU in creation
+        # order, and a dW launch created first takes the SMs the latency-critical dz GEMM then waits for
+        # (measured in the replayed step: dz 24 us beside an earlier-created dW, 10 us alone).
+        dy_ready = None
+        if DZ_FIRST and OVERLAP_WEIGHT_GRADS and ctx.needs_input_grad[1] and (need_dW or need_db):
+            dy_ready = torch.cuda.Event()
+            dy_ready.record(torch.cuda.current_stream(dy.device))
+        if dy_ready is None and (need_dW or (need_db and not db_here)):
             dW, db = _weight_grad_branch(dy.device, weight_grads, (dy, dy_lo, z, z_lo))
         if db_here:
             db = colsum(dy)
@@ -974,6 +989,8 @@ class _SageLinear(torch.autograd.Function):
             # dh = dz[:, :d] + A^T (inv_deg ⊙ dz[:, d:])
             spmm_raw(colptr, row, n, n, dz[:, d:], dh, src_scale=g.inv_in_degree(), addend=dz[:, :d],
                      schedule=g.seg_schedule(transpose=True))
+        if dy_ready is not None:
+            dW, db = _weight_grad_branch(dy.device, weight_grads, (dy, dy_lo, z, z_lo), after=dy_ready)
         return None, dh, dW, db, None, None, None, None, None
 
 
@@ -1256,6 +1273,65 @@ class _GatAggregate(torch.autograd.Function):
                                         ptr(dout), _ld(dout), ptr(dz), _ld(dz), ptr(dattn), ptr(ws), wsb,
                                         stream_ptr(dev)), 'gat_backward_f32')
         return None, dz, dattn, None
+
+
+class _GatAggregateHeads(torch.autograd.Function):
+    """All H heads of a MultiHeadGATLayer in one launch per kernel: z [n, H*D] (head h = columns
+    [h D, (h+1) D), the heads' projections being ONE GEMM), attn [H, 2D] -> out [n, H*D]."""
+
+    @staticmethod
+    def forward(ctx, g, z, attn, heads, negative_slope):
+        z = _mat(z, 'z')
+        n, W = z.shape
+        D = W // heads
+        assert n == g.number_of_nodes() and W == D * heads and tuple(attn.shape) == (heads, 2 * D)
+        attn = attn.contiguous()
+        dev = z.device
+        lib = _lib.load()
+        scores = torch.empty((heads, n, 2), dtype=torch.float32, device=dev)
+        out = _padded_empty(n, W, dev)
+        lse = torch.empty((heads, n), dtype=torch.float32, device=dev)
+        check(lib.gist_gat_scores_heads_f32(ptr(z), _ld(z), n, D, heads, ptr(attn), ptr(scores), stream_ptr(dev)),
+              'gat_scores_heads_f32')
+        prof = GAT_PROFILE
+        if prof is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        check(lib.gist_gat_aggregate_heads_f32(ptr(g.rowptr), ptr(g.col_buffer), n, ptr(z), _ld(z), D, heads, ptr(scores),
+                                               negative_slope, ptr(out), _ld(out), ptr(lse), stream_ptr(dev)),
+              'gat_aggregate_heads_f32')
+        if prof is not None:
+            ev1.record()
+            prof.append(dict(ev0=ev0, ev1=ev1, rowptr=g.rowptr, n=n, D=D, heads=heads))
+        ctx.g, ctx.slope, ctx.heads = g, negative_slope, heads
+        ctx.save_for_backward(z, attn, scores, lse, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, attn, scores, lse, out = ctx.saved_tensors
+        g, heads = ctx.g, ctx.heads
+        dout = _mat(dout, 'dout')
+        n, W = z.shape
+        D = W // heads
+        dev = z.device
+        lib = _lib.load()
+        colptr, row = g.csc()
+        dz = _padded_empty(n, W, dev)
+        dattn = torch.empty((heads, 2 * D), dtype=torch.float32, device=dev)
+        wsb = lib.gist_gat_backward_heads_workspace_bytes(n, D, heads)
+        ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=dev)
+        check(lib.gist_gat_backward_heads_f32(ptr(g.rowptr), ptr(g.col_buffer), ptr(colptr), ptr(row), n, ptr(z), _ld(z),
+                                              D, heads, ptr(scores), ptr(lse), ptr(attn), ctx.slope, ptr(out), _ld(out),
+                                              ptr(dout), _ld(dout), ptr(dz), _ld(dz), ptr(dattn), ptr(ws), wsb,
+                                              stream_ptr(dev)), 'gat_backward_heads_f32')
+        return None, dz, dattn, None, None
+
+
+def gat_aggregate_heads(g, z, attn, heads, negative_slope=0.01):
+    """z [n, heads * D], attn [heads, 2D] -> [n, heads * D] (see _GatAggregateHeads)."""
+    require_cuda(z, attn, g.rowptr)
+    return _GatAggregateHeads.apply(g, z, attn, int(heads), float(negative_slope))
 
 
 def gat_aggregate(g, z, attn, negative_slope=0.01):

@@ -336,7 +336,9 @@ int gist_gemm_3xtf32(const float *A, const float *A_lo, int64_t lda, int64_t lda
 /* Extended epilogue of K4 — what the training step needs besides the product, done where the product is
  * produced instead of in kernels of their own (every field optional; ex == NULL or all-zero: the plain
  * contraction).  A_lo == B_lo == NULL selects single-pass TF32, both given 3xTF32.
- *   tile_counters / n_counters : uint32 array, ZERO on entry and left zero (one counter per output
+ *   tile_counters / n_counters : (honoured only by builds with -DGIST_GEMM_INKERNEL_SPLITK, see
+ *       gist_gemm_has_inkernel_splitk(); the default build ignores them and runs the two-kernel split-K,
+ *       which measured faster) uint32 array, ZERO on entry and left zero (one counter per output
  *       tile; n_counters >= ceil(M/128) * ceil(N/64) always suffices).  With it a split-K launch is ONE
  *       kernel: every split writes its partial tile to the workspace and the CTA that arrives last at
  *       the tile's counter adds the partials in split order and runs the epilogue (deterministic, same
@@ -363,6 +365,7 @@ typedef struct gist_gemm_ex {
     uint32_t ln_flags;
     const gist_dropout_t *drop;
 } gist_gemm_ex_t;
+int gist_gemm_has_inkernel_splitk(void);
 size_t gist_gemm_ex_workspace_bytes(int32_t M, int32_t N, int32_t K, uint32_t flags, int32_t three_pass,
                                     const gist_gemm_ex_t *ex);
 int gist_gemm_ex_f32(const float *A, const float *A_lo, int64_t lda, int64_t lda_lo, int32_t a_layout,
@@ -496,6 +499,21 @@ int gist_adam_multi_f32(int32_t n_tensors, float *const *params, const float *co
  *   lse[v]    = logsumexp_u e_uv                    (kept for the backward; 0 if no in-edges)
  * No per-edge tensor is materialised.  D <= 1024.
  */
+/* All `heads` attention heads of a MultiHeadGATLayer (cluster_gcn/modules.py:67-76) in one launch per
+ * kernel: z / out / dout / dz are [n, heads * D] (head h = columns [h D, (h + 1) D): the projections of all
+ * heads are one GEMM), attn [heads, 2D], scores [heads, n, 2], lse [heads, n], dattn [heads, 2D].  heads = 1
+ * is the single-head API below. */
+int gist_gat_scores_heads_f32(const float *z, int64_t ldz, int32_t n, int32_t D, int32_t heads, const float *attn,
+                              float *scores, gist_stream_t stream);
+int gist_gat_aggregate_heads_f32(const int32_t *rowptr, const int32_t *col, int32_t n, const float *z, int64_t ldz,
+                                 int32_t D, int32_t heads, const float *scores, float negative_slope, float *out,
+                                 int64_t ldo, float *lse, gist_stream_t stream);
+size_t gist_gat_backward_heads_workspace_bytes(int32_t n, int32_t D, int32_t heads);
+int gist_gat_backward_heads_f32(const int32_t *rowptr, const int32_t *col, const int32_t *colptr, const int32_t *row,
+                                int32_t n, const float *z, int64_t ldz, int32_t D, int32_t heads, const float *scores,
+                                const float *lse, const float *attn, float negative_slope, const float *out,
+                                int64_t ldo, const float *dout, int64_t lddo, float *dz, int64_t lddz, float *dattn,
+                                void *workspace, size_t workspace_bytes, gist_stream_t stream);
 int gist_gat_scores_f32(const float *z, int64_t ldz, int32_t n, int32_t D, const float *attn,
                         float *scores /* [n,2], 8-byte aligned */, gist_stream_t stream);
 int gist_gat_aggregate_f32(const int32_t *rowptr, const int32_t *col, int32_t n, const float *z,

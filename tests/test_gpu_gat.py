@@ -102,3 +102,44 @@ def test_gat_softmax_properties_large():
     mean = ops.gspmm(g, z, None, g.inv_in_degree())
     assert_close(out, mean, 1e-5, 'uniform attention == mean aggregation')
     assert gb.GATLayer  # exported
+
+
+@pytest.mark.parametrize('dims', [(64, 32, 4), (602, 128, 4), (30, 6, 2), (100, 41, 3)])
+def test_multi_head_layer_batched_heads_equal_per_head_launches(dims, monkeypatch):
+    """MultiHeadGATLayer with all heads in one projection GEMM + one K6 launch per kernel (heads = grid
+    dimension) against the per-head form (one GEMM + three launches per head), forward and every gradient,
+    and against the fp64 oracle."""
+    import gist_b200 as gb
+    from gist_b200 import modules
+    from oracle import gist_oracle as O
+    fin, D, H = dims
+    n = 900
+    src, dst = random_graph(n, 12000, seed=fin + D, isolated=4)
+    g = _graph(src, dst, n)
+    og = O.OGraph(src, dst, n)
+    torch.manual_seed(H)
+    layer = gb.MultiHeadGATLayer(fin, D, H).cuda()
+    x = torch.randn(n, fin, device='cuda')
+    wy = torch.randn(n, D, device='cuda')
+    res = {}
+    for batched in (True, False):
+        monkeypatch.setattr(modules, 'BATCH_HEADS', batched)
+        layer.zero_grad(set_to_none=True)
+        xg = x.clone().requires_grad_(True)
+        y = layer(g, xg)
+        (y * wy).sum().backward()
+        res[batched] = (y.detach(), xg.grad, [p.grad.clone() for p in layer.parameters()])
+    assert_close(res[True][0], res[False][0], 1e-5, 'out')
+    assert_close(res[True][1], res[False][1], 1e-4, 'dx')
+    for a, b in zip(res[True][2], res[False][2]):
+        assert_close(a, b, 1e-4, 'param grad')
+    x64 = x.double().cpu().requires_grad_(True)
+    heads = [(hd.fc.weight.detach().double().cpu().requires_grad_(True), hd.attn_fc.weight.detach().double().cpu().requires_grad_(True))
+             for hd in layer.heads]
+    ref = O.multi_head_gat_layer(og, x64, heads)
+    (ref * wy.double().cpu()).sum().backward()
+    assert_close(res[True][0], ref, 1e-5, 'out vs oracle')
+    assert_close(res[True][1], x64.grad, 1e-4, 'dx vs oracle')
+    for hd, (fw, aw) in zip(layer.heads, heads):
+        assert_close(hd.fc.weight.grad, fw.grad, 1e-4, 'dfc vs oracle')
+        assert_close(hd.attn_fc.weight.grad, aw.grad, 1e-4, 'dattn vs oracle')

@@ -256,6 +256,8 @@ def test_in_kernel_splitk_equals_two_kernel_splitk(shape, x3, layout, monkeypatc
     tile counters (left at zero); bias / ReLU run in the reducing CTA."""
     import ctypes
     from gist_b200 import _lib, ops
+    if not _lib.load().gist_gemm_has_inkernel_splitk():
+        pytest.skip('library built without -DGIST_GEMM_INKERNEL_SPLITK (the default)')
     M, N, K = shape
     a_mn, b_mn = layout
     torch.manual_seed(M + 3 * N + K)
@@ -293,7 +295,9 @@ def test_in_kernel_splitk_equals_two_kernel_splitk(shape, x3, layout, monkeypatc
 def test_rowsum_on_the_tensor_core_is_the_bias_gradient(shape, x3, inkernel, monkeypatch):
     """dW = dy^T z with db = colsum(dy) from the same launch: an extra 16-column MMA against a tile of
     ones per K step (in n-tile 0), reduced with the split-K partials."""
-    from gist_b200 import ops
+    from gist_b200 import _lib, ops
+    if inkernel and not _lib.load().gist_gemm_has_inkernel_splitk():
+        pytest.skip('library built without -DGIST_GEMM_INKERNEL_SPLITK (the default)')
     monkeypatch.setattr(ops, 'FUSED_SPLITK', inkernel)        # partial row sums folded in-kernel / by the second pass
     M, N, K = shape               # M = out features, N = in features, K = batch rows
     torch.manual_seed(M + N + K)
@@ -322,7 +326,9 @@ def test_rowsum_on_the_tensor_core_is_the_bias_gradient(shape, x3, inkernel, mon
 def test_layernorm_epilogue_matches_the_row_kernel(shape, relu, inkernel, monkeypatch):
     """y = act(LN(z W^T + b)) from the projection's epilogue (one tile holds the row) vs the projection
     followed by ln_act_fwd_kernel, and vs fp64; the saved (pre-norm, stats) drive the same backward."""
-    from gist_b200 import ops
+    from gist_b200 import _lib, ops
+    if inkernel and not _lib.load().gist_gemm_has_inkernel_splitk():
+        pytest.skip('library built without -DGIST_GEMM_INKERNEL_SPLITK (the default)')
     monkeypatch.setattr(ops, 'FUSED_SPLITK', inkernel)        # split shapes: LN in the last-arriver fold / in the second pass
     M, N, K = shape
     torch.manual_seed(M + N + K)
@@ -350,7 +356,7 @@ def test_layernorm_epilogue_matches_the_row_kernel(shape, relu, inkernel, monkey
 def test_fused_gemm_epilogues_on_parallel_streams_do_not_share_counters(monkeypatch):
     """The weight-gradient branch runs split-K GEMMs beside the training branch: tile counters are per stream."""
     from gist_b200 import ops
-    monkeypatch.setattr(ops, 'FUSED_SPLITK', True)
+    monkeypatch.setattr(ops, 'FUSED_SPLITK', True)        # (a no-op in the default build: counters are then unused)
     torch.manual_seed(0)
     dy = torch.randn(2586, 256, device='cuda')
     z = torch.randn(2586, 1204, device='cuda')
