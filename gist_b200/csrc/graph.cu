@@ -396,7 +396,10 @@ extern "C" int gist_slice_multi_f32(int32_t scatter, int32_t n_jobs, const gist_
             total_elems += j.n_rows * j.n_cols;
             ++last;
         }
-        const int64_t target_blocks = 16LL * kNumSMs;
+        // a few waves for small rounds; for the ultra-wide slices (10^8 elements) ~16 rows x 256 columns per CTA,
+        // so that the scattered 4-byte writes of a row block have thousands of CTAs in flight to hide behind
+        int64_t target_blocks = 16LL * kNumSMs;
+        if (total_elems / 4096 > target_blocks) target_blocks = total_elems / 4096;
         for (int i = first; i < last; ++i) {
             const gist_slice_job_t &j = jobs[i];
             if (j.n_rows == 0 || j.n_cols == 0) continue;

@@ -110,9 +110,12 @@ class GATLayer(nn.Module):
 
 
 PARALLEL_HEADS = True
-# all heads of a layer as ONE projection GEMM + one K6 launch per kernel (heads = grid dimension) instead of
-# a GEMM + three K6 launches per head on per-head streams (GIST_GAT_BATCH_HEADS=0: round 1's form)
-BATCH_HEADS = os.environ.get('GIST_GAT_BATCH_HEADS', '1') != '0'
+# All heads of a layer as ONE projection GEMM + one K6 launch per kernel (heads = grid dimension) instead of
+# a GEMM + three K6 launches per head on per-head streams.  OPT-IN (GIST_GAT_BATCH_HEADS=1): it halves the
+# launches of the config-5 step (39 vs 76 per step) but measured SLOWER, 0.868 vs 0.799 ms/step
+# (profiles/r2_bench_gat*.json): the per-head streams overlap the heads' tail-bound hub rows and their
+# small GEMMs, one batched launch serialises the projection in front of the aggregation.
+BATCH_HEADS = os.environ.get('GIST_GAT_BATCH_HEADS', '0') != '0'
 _HEAD_STREAMS = {}
 
 
