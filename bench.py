@@ -544,13 +544,16 @@ def run_gist(a):
     # DRAM bytes per SpMM launch from the committed `ncu --set full` capture of the same command
     # (profiles/README.md); null when the workload is not the one that was captured
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, 'profiles', 'r1_spmm_step_traffic.json')
+    tp = os.path.join(ROOT, 'profiles', 'r2_spmm_step_traffic.json')
     if a.shape == 'reddit' and a.scale == 1.0 and a.n_hidden == 256 and world == 1 and os.path.exists(tp):
         tj = json.load(open(tp))
-        traffic, traffic_src = tj['traffic_bytes_per_launch'], 'profiles/r1_spmm_step_traffic.json: ' + tj['source']
+        traffic, traffic_src = tj['traffic_bytes_per_launch'], 'profiles/r2_spmm_step_traffic.json: ' + tj['source']
     achieved = alg_b / 1e9 / (spmm_ms / 1e3) if spmm_ms > 0 else 0.0
     roofline = {
-        'bound': 'hbm', 'kernel': 'spmm_seg_kernel + spmm_csr_kernel (all %d SpMM launches/step, fwd + transpose)' % (len(prof) // max(prof_steps, 1)),
+        'bound': 'hbm', 'effective_bound': 'L2 / gather latency: a cluster batch\'s operand (<= 6 MB) is L2-resident, so the '
+                                           'algorithmic gather bytes never reach HBM (see traffic and dram_frac)',
+        'dram_frac': (round(traffic / (spmm_ms * 1e-3 / n_l) / 1e9 / peak, 4) if traffic and spmm_ms > 0 else None),
+        'kernel': 'spmm_seg_kernel + spmm_csr_kernel (all %d SpMM launches/step, fwd + transpose)' % (len(prof) // max(prof_steps, 1)),
         'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4),
         'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
         'bytes_per_launch': round(alg_b / n_l), 'compulsory_bytes_per_launch': round(comp_b / n_l),
@@ -678,6 +681,20 @@ def run_gist(a):
                                'algorithmic_bytes': ab, 'compulsory_bytes': cb,
                                'ms_by_variant': {k: round(v, 3) for k, v in best.items()},
                                'flush': 'operand (%.0f MB) larger than L2' % (4 * n * d / 1e6)}
+            fp = os.path.join(ROOT, 'profiles', 'r2_spmm_fullgraph_traffic.json')
+            if a.shape == 'reddit' and a.scale == 1.0 and os.path.exists(fp):
+                # the same launch under `ncu --set full` (committed capture): what actually moved
+                fl_ = json.load(open(fp))['launches']
+                cap = fl_[0] if d == in_feats else (fl_[1] if len(fl_) > 1 else None)
+                if cap:
+                    dram = cap['dram_read_bytes'] + cap['dram_write_bytes']
+                    full['d%d' % d].update({
+                        'traffic': round(dram), 'traffic_over_compulsory': round(dram / cb, 1),
+                        'dram_frac': round(dram / 1e9 / (cap['us'] / 1e6) / peak, 4),
+                        'l2_to_sm_TBps': cap.get('xbar_to_l1_TBps'), 'l2_hit_pct': cap.get('l2_hit_pct'),
+                        'traffic_source': 'profiles/r2_spmm_fullgraph_traffic.json (ncu --set full of this launch: %.2f ms under the profiler)' % (cap['us'] / 1e3),
+                        'effective_bound': 'L2->SM crossbar / gather latency: frac counts every gathered byte (SURVEY 8d no-reuse model), '
+                                           'dram_frac what reached HBM'})
             del x, y
 
     # ---- evaluate() on the full graph (a12; outside the reference's epoch timer) ---------
