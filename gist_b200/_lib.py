@@ -86,6 +86,9 @@ SIGNATURES = {
     'gist_gat_backward_f32': (ctypes.c_int, [_P, _P, _P, _P, _I32, _P, _I64, _I32, _P, _P, _P, _F32, _P, _I64,
                                              _P, _I64, _P, _I64, _P, _P, _SZ, _P]),
     'gist_adam_multi_f32': (ctypes.c_int, [_I32, _P, _P, _P, _P, _P, _F32, _F32, _F32, _F32, _F32, _P, _P, _P]),
+    'gist_adam_multi_ex_f32': (ctypes.c_int, [_I32, _P, _P, _P, _P, _P, _F32, _F32, _F32, _F32, _F32, _P, _P, _P, _P, _P]),
+    'gist_set_pdl': (ctypes.c_int, [_I32]),
+    'gist_get_pdl': (ctypes.c_int, []),
 }
 
 SPMM_RELU, SPMM_NARROW, SPMM_WIDE = 1, 2, 4
@@ -198,3 +201,13 @@ def require_cuda(*tensors):
 
 def launch_count():
     return int(load().gist_launch_count())
+
+
+def set_pdl(enabled):
+    """Programmatic dependent launch for the training step's kernel chain (gist_set_pdl); process-wide.
+    Set it BEFORE a step is captured: the attribute is recorded into the graph's edges."""
+    check(load().gist_set_pdl(1 if enabled else 0), 'set_pdl')
+
+
+def get_pdl():
+    return bool(load().gist_get_pdl())

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <utility>
 
 #include "../../include/gist_b200.h"
 
@@ -23,6 +24,46 @@ inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------- programmatic dependent launch ----
+// The training step is a chain of ~25 dependent kernels of 3-20 us each, so what a kernel costs
+// besides its bytes — grid launch, barrier / TMEM set-up, descriptor prefetch — sits on the critical
+// path once per link.  With programmatic stream serialization (gist_set_pdl / GIST_PDL=1) kernel k+1
+// is made resident while kernel k drains and runs its prologue there; it blocks in
+// griddepcontrol.wait until kernel k has COMPLETED and its writes are visible, so the data
+// dependency is exactly the stream-order one.  Rules every kernel launched through launch_pdl
+// follows: pdl_wait() comes before the first global-memory access (reads AND writes: the previous
+// kernel may still be reading what this one overwrites) and before any early return; pdl_trigger()
+// comes after it, so at most one dependent grid is ever pre-launched.  Under stream capture the
+// attribute becomes a programmatic edge of the graph.
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+    pdl_wait();
+    pdl_trigger();
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (pdl_enabled()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 // ---------------------------------------------------------------- 3xTF32 ----
 // lo = tf32_rn(x - trunc_tf32(x)); *hi_out = trunc_tf32(x).  trunc_tf32 clears the 13 low

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) ln_act_fwd_kernel(const float *__restrict
                                                          int d, float eps, int relu,
                                                          float *__restrict__ y, int64_t ldy,
                                                          float2 *__restrict__ stats) {
+    pdl_sync();
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= n) return;
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(256) ln_act_bwd_kernel(const float *__restrict
                                                          const float2 *__restrict__ stats, int n, int d,
                                                          int relu, float *__restrict__ dx, int64_t lddx,
                                                          float *__restrict__ dx_lo, int64_t ld_lo) {
+    pdl_sync();
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= n) return;
@@ -446,7 +448,26 @@ __global__ void __launch_bounds__(256) ce_fused_kernel(const float *__restrict__
     __shared__ int s_cnt[8];
     __shared__ float s_loss[8];
     __shared__ bool s_last;
+    pdl_sync();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // This warp's row first: its loads are requested BEFORE the counting loop below and the barrier
+    // behind it, so the kernel is one round of loads, not a chain of them (the launch is latency-bound:
+    // 2 k rows of 41 classes).  Rows of up to 64 classes live in two registers per lane; wider rows are
+    // re-read from L1 in the loops further down.
+    const int r = blockIdx.x * 8 + warp;
+    const bool fast = C <= 64;
+    const float *xr = logits + (int64_t)(r < n ? r : 0) * ld;
+    float x0 = -INFINITY, x1 = -INFINITY;
+    int64_t y = -1;
+    bool m = false;
+    if (r < n) {
+        if (fast) {
+            if (lane < C) x0 = __ldg(xr + lane);
+            if (lane + 32 < C) x1 = __ldg(xr + lane + 32);
+        }
+        y = __ldg(labels + r);
+        m = mask ? (__ldg(mask + r) != 0) : true;
+    }
     // rows that count: masked in AND labelled with a class index (see ce_reduce_kernel).  All loads of
     // a thread are independent (unrolled), so the loop is a couple of L2 round trips, not a chain.
     int cnt = 0;
@@ -470,24 +491,41 @@ __global__ void __launch_bounds__(256) ce_fused_kernel(const float *__restrict__
 #pragma unroll
     for (int w = 0; w < 8; ++w) cnt += s_cnt[w];
     const float inv = 1.f / (float)cnt;         // cnt == 0: inf, and no row is masked in
-    const int r = blockIdx.x * 8 + warp;
     float row_loss = 0.f;
     if (r < n) {
-        const float *xr = logits + (int64_t)r * ld;
-        float mx = -INFINITY;
-        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, __ldg(xr + c));
+        float mx = fmaxf(x0, x1);
+        if (!fast) {
+            mx = -INFINITY;
+            for (int c = lane; c < C; c += 32) mx = fmaxf(mx, __ldg(xr + c));
+        }
         mx = warp_max(mx);
         float se = 0.f;
-        for (int c = lane; c < C; c += 32) se += expf(__ldg(xr + c) - mx);
+        if (fast) {
+            if (lane < C) se += expf(x0 - mx);
+            if (lane + 32 < C) se += expf(x1 - mx);
+        } else {
+            for (int c = lane; c < C; c += 32) se += expf(__ldg(xr + c) - mx);
+        }
         se = warp_sum(se);
         const float l = mx + logf(se);
-        const int64_t y = labels[r];
-        const bool m = (mask ? (mask[r] != 0) : true) && (uint64_t)y < (uint64_t)C;
-        if (m) row_loss = l - __ldg(xr + y);
+        m = m && (uint64_t)y < (uint64_t)C;
+        if (m) {
+            float xy;
+            if (fast) {     // the label's logit sits in lane y % 32, register y / 32
+                const float a = __shfl_sync(0xffffffffu, x0, (int)(y & 31)), b2 = __shfl_sync(0xffffffffu, x1, (int)(y & 31));
+                xy = y < 32 ? a : b2;
+            } else {
+                xy = __ldg(xr + y);
+            }
+            row_loss = l - xy;
+        }
         float *dr = dlogits + (int64_t)r * ldd;
         for (int c = lane; c < ldd_fill; c += 32) {     // columns [C, ldd_fill) are row padding: zeroed
             float v = 0.f;
-            if (c < C && m) v = (expf(__ldg(xr + c) - l) - (c == y ? 1.f : 0.f)) * inv;
+            if (c < C && m) {
+                const float xc = fast ? (c < 32 ? x0 : x1) : __ldg(xr + c);
+                v = (expf(xc - l) - (c == y ? 1.f : 0.f)) * inv;
+            }
             dr[c] = v;
             if (dlo) dlo[(int64_t)r * ldd + c] = tf32_lo(v);
         }
@@ -523,6 +561,7 @@ struct AdamTensor {
     const float *g;
     float *m;
     float *v;
+    float *lo;          // optional: 3xTF32 low half of the UPDATED parameter (same flat layout as p)
     int64_t n;
     int32_t block0;     // first CTA of this tensor
     int32_t vec4;       // all four arrays 16-byte aligned
@@ -542,7 +581,9 @@ struct AdamArgs {
 // finish, after every CTA has read it.
 __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__ AdamArgs a,
                                                          float *__restrict__ step, int advance_step,
-                                                         unsigned int *__restrict__ counter) {
+                                                         unsigned int *__restrict__ counter,
+                                                         int64_t *__restrict__ tick) {
+    pdl_sync();
     int ti = 0;
 #pragma unroll 1
     for (int k = 1; k < a.n_tensors; ++k)
@@ -569,6 +610,8 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
         *reinterpret_cast<float4 *>(T.m + i0) = m;
         *reinterpret_cast<float4 *>(T.v + i0) = v;
         *reinterpret_cast<float4 *>(T.p + i0) = p;
+        if (T.lo)
+            *reinterpret_cast<float4 *>(T.lo + i0) = make_float4(tf32_lo(p.x), tf32_lo(p.y), tf32_lo(p.z), tf32_lo(p.w));
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -579,6 +622,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
                 T.m[i] = m;
                 T.v[i] = v;
                 T.p[i] = p;
+                if (T.lo) T.lo[i] = tf32_lo(p);
             }
         }
     }
@@ -590,6 +634,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
             if (prev == gridDim.x - 1) {
                 *step = t;
                 *counter = 0u;
+                if (tick) *tick += 1;       // the dropout clock of the next training step (gist_counter_add_i64)
             }
         }
     }
@@ -649,10 +694,11 @@ extern "C" int gist_layernorm_act_fwd_f32(const float *x, int64_t ldx, int32_t n
     const int relu = (flags & GIST_ACT_RELU) ? 1 : 0;
     const unsigned grid = (unsigned)((n + 7) / 8);
     cudaStream_t s = (cudaStream_t)stream;
-    if (v4) ln_act_fwd_kernel<true><<<grid, 256, 0, s>>>(x, ldx, n, d, eps, relu, y, ldy, reinterpret_cast<float2 *>(stats));
-    else ln_act_fwd_kernel<false><<<grid, 256, 0, s>>>(x, ldx, n, d, eps, relu, y, ldy, reinterpret_cast<float2 *>(stats));
+    float2 *st2 = reinterpret_cast<float2 *>(stats);
+    const cudaError_t le = v4 ? launch_pdl(ln_act_fwd_kernel<true>, dim3(grid), dim3(256), 0, s, x, ldx, n, d, eps, relu, y, ldy, st2)
+                              : launch_pdl(ln_act_fwd_kernel<false>, dim3(grid), dim3(256), 0, s, x, ldx, n, d, eps, relu, y, ldy, st2);
     count_launch();
-    return last_error();
+    return le == cudaSuccess ? last_error() : (int)le;
 }
 
 extern "C" int gist_layernorm_act_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx,
@@ -669,10 +715,10 @@ extern "C" int gist_layernorm_act_bwd_f32(const float *dy, int64_t lddy, const f
     const unsigned grid = (unsigned)((n + 7) / 8);
     cudaStream_t s = (cudaStream_t)stream;
     const float2 *st = reinterpret_cast<const float2 *>(stats);
-    if (v4) ln_act_bwd_kernel<true><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, st, n, d, relu, dx, lddx, dx_lo, ld_lo);
-    else ln_act_bwd_kernel<false><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, st, n, d, relu, dx, lddx, dx_lo, ld_lo);
+    const cudaError_t le = v4 ? launch_pdl(ln_act_bwd_kernel<true>, dim3(grid), dim3(256), 0, s, dy, lddy, x, ldx, st, n, d, relu, dx, lddx, dx_lo, ld_lo)
+                              : launch_pdl(ln_act_bwd_kernel<false>, dim3(grid), dim3(256), 0, s, dy, lddy, x, ldx, st, n, d, relu, dx, lddx, dx_lo, ld_lo);
     count_launch();
-    return last_error();
+    return le == cudaSuccess ? last_error() : (int)le;
 }
 
 extern "C" size_t gist_tensor_layernorm_workspace_bytes(int32_t n, int32_t d) {
@@ -812,20 +858,22 @@ extern "C" int gist_masked_ce_fused_f32(const float *logits, int64_t ld, int32_t
     if (!logits || !labels || !dlogits || !loss_out || !workspace || !sync || ld < C || fill_cols < C ||
         ldd < fill_cols || workspace_bytes < gist_masked_ce_fused_workspace_bytes(n))
         return GIST_ERR_BADARG;
-    ce_fused_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(logits, ld, n, C, labels, mask, dlogits, ldd,
-                                                                  fill_cols, dlogits_lo, (float *)workspace, sync,
-                                                                  loss_out);
+    const cudaError_t le = launch_pdl(ce_fused_kernel, dim3((unsigned)((n + 7) / 8)), dim3(256), 0, (cudaStream_t)stream,
+                                      logits, ld, n, C, labels, mask, dlogits, ldd, (int)fill_cols, dlogits_lo,
+                                      (float *)workspace, sync, loss_out);
     count_launch();
-    return last_error();
+    return le == cudaSuccess ? last_error() : (int)le;
 }
 
-extern "C" int gist_adam_multi_f32(int32_t n_tensors, float *const *params, const float *const *grads,
-                                   float *const *exp_avg, float *const *exp_avg_sq, const int64_t *numel,
-                                   float lr, float beta1, float beta2, float eps, float weight_decay,
-                                   float *step, uint32_t *counter, gist_stream_t stream) {
+extern "C" int gist_adam_multi_ex_f32(int32_t n_tensors, float *const *params, const float *const *grads,
+                                      float *const *exp_avg, float *const *exp_avg_sq, const int64_t *numel,
+                                      float lr, float beta1, float beta2, float eps, float weight_decay,
+                                      float *step, uint32_t *counter, float *const *params_lo, int64_t *tick,
+                                      gist_stream_t stream) {
     if (n_tensors < 0) return GIST_ERR_BADARG;
     if (n_tensors == 0) return GIST_OK;
     if (!params || !grads || !exp_avg || !exp_avg_sq || !numel || !step || !counter) return GIST_ERR_BADARG;
+    if (tick && !aligned(tick, 8)) return GIST_ERR_ALIGN;
     cudaStream_t s = (cudaStream_t)stream;
     int n_live = 0;
     for (int i = 0; i < n_tensors; ++i) {
@@ -834,7 +882,7 @@ extern "C" int gist_adam_multi_f32(int32_t n_tensors, float *const *params, cons
         if (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i]) return GIST_ERR_BADARG;
         ++n_live;
     }
-    // non-empty tensors in launches of up to kAdamMaxTensors; only the last launch advances `step`
+    // non-empty tensors in launches of up to kAdamMaxTensors; only the last launch advances `step` (and `tick`)
     int i = 0, done = 0;
     while (done < n_live) {
         AdamArgs a;
@@ -844,19 +892,31 @@ extern "C" int gist_adam_multi_f32(int32_t n_tensors, float *const *params, cons
         for (; i < n_tensors && k < kAdamMaxTensors; ++i) {
             if (numel[i] == 0) continue;
             a.t[k].p = params[i]; a.t[k].g = grads[i]; a.t[k].m = exp_avg[i]; a.t[k].v = exp_avg_sq[i];
+            a.t[k].lo = params_lo ? params_lo[i] : nullptr;
             a.t[k].n = numel[i]; a.t[k].block0 = (int32_t)blocks;
             a.t[k].vec4 = (aligned(params[i], 16) && aligned(grads[i], 16) && aligned(exp_avg[i], 16) &&
-                           aligned(exp_avg_sq[i], 16)) ? 1 : 0;
+                           aligned(exp_avg_sq[i], 16) && (!a.t[k].lo || aligned(a.t[k].lo, 16))) ? 1 : 0;
             blocks += (numel[i] + kAdamChunk - 1) / kAdamChunk;
             if (blocks > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
             ++k;
         }
         a.n_tensors = k;
         done += k;
-        adam_multi_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, step, done >= n_live ? 1 : 0, counter);
+        const int last = done >= n_live ? 1 : 0;
+        const cudaError_t le = launch_pdl(adam_multi_kernel, dim3((unsigned)blocks), dim3(256), 0, s, a, step, last, counter,
+                                          last ? tick : (int64_t *)nullptr);
         count_launch();
+        if (le != cudaSuccess) return (int)le;
         const int st = last_error();
         if (st != GIST_OK) return st;
     }
     return GIST_OK;
+}
+
+extern "C" int gist_adam_multi_f32(int32_t n_tensors, float *const *params, const float *const *grads,
+                                   float *const *exp_avg, float *const *exp_avg_sq, const int64_t *numel,
+                                   float lr, float beta1, float beta2, float eps, float weight_decay,
+                                   float *step, uint32_t *counter, gist_stream_t stream) {
+    return gist_adam_multi_ex_f32(n_tensors, params, grads, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps,
+                                  weight_decay, step, counter, nullptr, nullptr, stream);
 }

@@ -318,6 +318,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_base_slot;
+    // everything above touched shared memory, TMEM and kernel parameters only: under programmatic
+    // dependent launch it ran while the previous kernel of the stream was draining
+    pdl_sync();
     if (threadIdx.x == 0) trace_stamp(p, 1);
 
     if (warp == 0) {
@@ -805,6 +808,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restr
                                                             float *__restrict__ C, int64_t ldc, int main_blocks,
                                                             const float *__restrict__ rs_part,
                                                             float *__restrict__ rs_out) {
+    pdl_sync();
     if ((int)blockIdx.x >= main_blocks) {
         rowsum_fold(rs_part, splits, M, rs_out, ((int)blockIdx.x - main_blocks) * 256 + (int)threadIdx.x);
         return;
@@ -843,69 +847,94 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restr
     }
 }
 
-// Split-K second pass WITH the layer norm (gist_gemm_ex_t.ln_out; N <= 128): one warp per row adds the
-// row's partials in split order (lane = 4 columns), adds the bias, and normalises the complete row with
-// warp shuffles: C = pre-norm values, y = act(LN(C)), stats = (mean, rstd).  Replaces splitk_reduce_kernel
-// + ln_act_fwd_kernel behind a layer's projection.
+// Split-K second pass WITH the layer norm (gist_gemm_ex_t.ln_out; N <= 128 * VPL, VPL = 1 or 2): one warp
+// per row adds the row's partials in split order (lane = 4 columns of every 128-column group), adds the
+// bias, and normalises the complete row with warp shuffles: C = pre-norm values, y = act(LN(C)), stats =
+// (mean, rstd).  Replaces splitk_reduce_kernel + ln_act_fwd_kernel behind a layer's projection.  The
+// moments are summed per lane in column order and folded with the same xor tree for either VPL.
+template <int VPL>
 __global__ void __launch_bounds__(256) splitk_reduce_ln_kernel(const float *__restrict__ part, int64_t ldp, int splits,
                                                                int M, int N, const float *__restrict__ bias, float eps,
                                                                int relu, float *__restrict__ C, int64_t ldc,
                                                                float *__restrict__ y, int64_t ldy,
                                                                float2 *__restrict__ stats) {
+    pdl_sync();
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= M) return;
-    const int c = lane * 4;
-    const bool on = c < N;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t sstride = (int64_t)M * ldp;
-    const float *p0 = part + (int64_t)r * ldp + c;
-    if (on) {
-        int s = 0;
-        for (; s + 4 <= splits; s += 4) {
-            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)s * sstride));
-            const float4 v1 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)(s + 1) * sstride));
-            const float4 v2 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)(s + 2) * sstride));
-            const float4 v3 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)(s + 3) * sstride));
-            acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
-            acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
-            acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
-            acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+    float x[VPL][4];
+#pragma unroll
+    for (int g = 0; g < VPL; ++g) {
+        const int c = g * 128 + lane * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < N) {
+            const float *p0 = part + (int64_t)r * ldp + c;
+            int s = 0;
+            for (; s + 4 <= splits; s += 4) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)s * sstride));
+                const float4 v1 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)(s + 1) * sstride));
+                const float4 v2 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)(s + 2) * sstride));
+                const float4 v3 = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)(s + 3) * sstride));
+                acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+                acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+                acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+                acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+            }
+            for (; s < splits; ++s) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)s * sstride));
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
         }
-        for (; s < splits; ++s) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(p0 + (int64_t)s * sstride));
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
+        x[g][0] = acc.x; x[g][1] = acc.y; x[g][2] = acc.z; x[g][3] = acc.w;
     }
-    float x[4] = {acc.x, acc.y, acc.z, acc.w};
     float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (c + k < N) {
-            if (bias) x[k] += __ldg(bias + c + k);
-            sum += x[k];
-        } else {
-            x[k] = 0.f;
+    for (int g = 0; g < VPL; ++g)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = g * 128 + lane * 4 + k;
+            if (c < N) {
+                if (bias) x[g][k] += __ldg(bias + c);
+                sum += x[g][k];
+            } else {
+                x[g][k] = 0.f;
+            }
         }
-    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum / (float)N;
     float q = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (c + k < N) q += (x[k] - mean) * (x[k] - mean);
+    for (int g = 0; g < VPL; ++g)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (g * 128 + lane * 4 + k < N) q += (x[g][k] - mean) * (x[g][k] - mean);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q / (float)N + eps);
     if (lane == 0 && stats) stats[r] = make_float2(mean, rstd);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (c + k < N) {
-            float o = (x[k] - mean) * rstd;
-            if (relu) o = fmaxf(o, 0.f);
-            C[(int64_t)r * ldc + c + k] = x[k];
-            y[(int64_t)r * ldy + c + k] = o;
+    for (int g = 0; g < VPL; ++g) {
+        const int c = g * 128 + lane * 4;
+        if (c >= N) continue;
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o[k] = (x[g][k] - mean) * rstd;
+            if (relu) o[k] = fmaxf(o[k], 0.f);
+        }
+        float *cr = C + (int64_t)r * ldc + c, *yr = y + (int64_t)r * ldy + c;
+        if (c + 4 <= N && ((reinterpret_cast<uintptr_t>(cr) | reinterpret_cast<uintptr_t>(yr)) & 15) == 0) {
+            *reinterpret_cast<float4 *>(cr) = make_float4(x[g][0], x[g][1], x[g][2], x[g][3]);
+            *reinterpret_cast<float4 *>(yr) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (c + k < N) {
+                    cr[k] = x[g][k];
+                    yr[k] = o[k];
+                }
         }
     }
 }
@@ -954,6 +983,7 @@ struct SplitArgs {
 };
 
 __global__ void __launch_bounds__(256) split_tf32_multi_kernel(const __grid_constant__ SplitArgs a) {
+    pdl_sync();
     int ti = 0;
 #pragma unroll 1
     for (int k = 1; k < a.n_tensors; ++k)
@@ -1062,9 +1092,10 @@ static int launch_gemm(const GemmMaps &m, const GemmParams &p, cudaStream_t s) {
     const int n_work = p.tiles_m * p.tiles_n * p.splits;
     const int cap = p.background ? max(sm_count() / 3, 1) : sm_count();
     const int grid = n_work < cap ? n_work : cap;
-    gemm_tf32_kernel<BN, A_MN, B_MN, NT, LN><<<grid, kGemmThreads, smem, s>>>(m.a, m.b, m.al, m.bl, p);
+    const cudaError_t le = launch_pdl(gemm_tf32_kernel<BN, A_MN, B_MN, NT, LN>, dim3(grid), dim3(kGemmThreads), smem, s,
+                                      m.a, m.b, m.al, m.bl, p);
     count_launch();
-    return last_error();
+    return le == cudaSuccess ? last_error() : (int)le;
 }
 
 template <int BN, int NT>
@@ -1203,9 +1234,11 @@ extern "C" size_t gist_gemm_3xtf32_workspace_bytes(int32_t M, int32_t N, int32_t
 // tile-width restrictions of the extended epilogue, folded into the planner's flags
 static uint32_t ex_plan_flags(int32_t N, uint32_t flags, const gist_gemm_ex_t *ex) {
     if (!ex) return flags;
-    if (ex->ln_out) {          // one tile must hold the whole row
+    if (ex->ln_out && N <= 128) {          // one tile must hold the whole row
         flags &= ~(GIST_GEMM_TILE_N64 | GIST_GEMM_TILE_N128 | GIST_GEMM_TILE_N256);
         flags |= N <= 64 ? GIST_GEMM_TILE_N64 : GIST_GEMM_TILE_N128;
+    } else if (ex->ln_out) {               // 128 < N <= 256: the norm runs in the split-K second pass (or behind the GEMM)
+        flags |= kPlanNo256;
     } else if (ex->rowsum) {
         if (flags & GIST_GEMM_TILE_N256) flags = (flags & ~GIST_GEMM_TILE_N256) | GIST_GEMM_TILE_N128;
         flags |= kPlanNo256;
@@ -1221,17 +1254,22 @@ static int gemm_impl(const float *A, const float *A_lo, int64_t lda, int64_t lda
                      const gist_gemm_ex_t *ex = nullptr) {
     const bool x3 = A_lo != nullptr;
     if (ex) {
-        if (ex->ln_out && (N > 128 || a_layout != GIST_GEMM_K_MAJOR || b_layout != GIST_GEMM_K_MAJOR || !x3 ||
+        if (ex->ln_out && (N > 256 || a_layout != GIST_GEMM_K_MAJOR || b_layout != GIST_GEMM_K_MAJOR || !x3 ||
                            ex->ld_ln < N || (ex->ln_stats && !aligned(ex->ln_stats, 8))))
-            return GIST_ERR_UNSUPPORTED;     // LayerNorm epilogue: y = z W^T, 3xTF32, rows of <= 128
+            return GIST_ERR_UNSUPPORTED;     // LayerNorm epilogue: y = z W^T, 3xTF32, rows of <= 256 (<= 128 in one tile)
+        if (ex->ln_out && N > 128 && !ex->ln_stats) return GIST_ERR_BADARG;
         if (ex->ln_out && ex->rowsum) return GIST_ERR_UNSUPPORTED;
         if (ex->rowsum && (a_layout != GIST_GEMM_MN_MAJOR || b_layout != GIST_GEMM_MN_MAJOR))
             return GIST_ERR_UNSUPPORTED;     // row sums are compiled into the dy^T z layout only
         if (ex->tile_counters && !aligned(ex->tile_counters, 4)) return GIST_ERR_ALIGN;
         flags = ex_plan_flags(N, flags, ex);
     }
+    // 128 < N <= 256 with the layer norm: no tile holds the row, so the norm rides in the two-kernel
+    // split-K's second pass when the planner splits K, and runs as the row-wise kernel behind the GEMM
+    // (same launches as the unfused form) when it does not
+    const bool wide_ln = ex && ex->ln_out && N > 128;
 #ifdef GIST_GEMM_INKERNEL_SPLITK
-    const bool inkernel = ex && ex->tile_counters;
+    const bool inkernel = ex && ex->tile_counters && !wide_ln;
 #else
     const bool inkernel = false;
 #endif
@@ -1294,9 +1332,9 @@ static int gemm_impl(const float *A, const float *A_lo, int64_t lda, int64_t lda
         p.rowsum = pl.bn <= 128 ? ex->rowsum : nullptr;
         if (ex->rowsum && !p.rowsum) return GIST_ERR_UNSUPPORTED;
         if (ex->ln_out) {
-            if (pl.bn < N) return GIST_ERR_UNSUPPORTED;
+            if (pl.bn < N && !wide_ln) return GIST_ERR_UNSUPPORTED;
             p.relu = 0;      // the activation belongs to the normalised output
-            if (!(pl.splits > 1 && !inkernel)) {      // in the GEMM's own epilogue; else in the split-K second pass
+            if (!(pl.splits > 1 && !inkernel) && !wide_ln) {      // in the GEMM's own epilogue; else in the split-K second pass
                 p.ln_y = ex->ln_out; p.ld_ln = ex->ld_ln; p.ln_stats = reinterpret_cast<float2 *>(ex->ln_stats);
                 p.ln_eps = ex->ln_eps; p.ln_relu = (ex->ln_flags & GIST_ACT_RELU) ? 1 : 0;
             }
@@ -1326,21 +1364,32 @@ static int gemm_impl(const float *A, const float *A_lo, int64_t lda, int64_t lda
         m.bl = m.b;
         st = launch_tile<1>(pl.bn, a_mn, b_mn, m, p, s);
     }
-    if (st != GIST_OK || pl.splits == 1 || inkernel) return st;
+    if (st != GIST_OK) return st;
+    if (wide_ln && pl.splits == 1)      // unsplit: the row-wise kernel behind the GEMM (csrc/fused.cu)
+        return gist_layernorm_act_fwd_f32(C, ldc, M, N, ex->ln_eps, ex->ln_flags, ex->ln_out, ex->ld_ln, ex->ln_stats,
+                                          stream);
+    if (pl.splits == 1 || inkernel) return st;
+    cudaError_t le;
     if (ex && ex->ln_out) {
-        splitk_reduce_ln_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(
-            reinterpret_cast<const float *>(workspace), pl.ldp, pl.splits, M, N, bias, ex->ln_eps,
-            (ex->ln_flags & GIST_ACT_RELU) ? 1 : 0, C, ldc, ex->ln_out, ex->ld_ln, reinterpret_cast<float2 *>(ex->ln_stats));
+        const int ln_relu = (ex->ln_flags & GIST_ACT_RELU) ? 1 : 0;
+        float2 *stats = reinterpret_cast<float2 *>(ex->ln_stats);
+        const float *part = reinterpret_cast<const float *>(workspace);
+        if (N <= 128)
+            le = launch_pdl(splitk_reduce_ln_kernel<1>, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, s, part, pl.ldp,
+                            pl.splits, M, N, bias, ex->ln_eps, ln_relu, C, ldc, ex->ln_out, ex->ld_ln, stats);
+        else
+            le = launch_pdl(splitk_reduce_ln_kernel<2>, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, s, part, pl.ldp,
+                            pl.splits, M, N, bias, ex->ln_eps, ln_relu, C, ldc, ex->ln_out, ex->ld_ln, stats);
     } else {
         const int64_t items = (int64_t)M * ((N + 3) / 4);
         const int main_blocks = (int)((items + 255) / 256);
         const int rs_blocks = p.rowsum ? (M + 255) / 256 : 0;       // row sums ride in the tail blocks of the fold
-        splitk_reduce_kernel<<<(unsigned)(main_blocks + rs_blocks), 256, 0, s>>>(
-            reinterpret_cast<const float *>(workspace), pl.ldp, pl.splits, M, N, bias, p.relu, C, ldc, main_blocks,
-            p.ws_rowsum, p.rowsum);
+        le = launch_pdl(splitk_reduce_kernel, dim3((unsigned)(main_blocks + rs_blocks)), dim3(256), 0, s,
+                        reinterpret_cast<const float *>(workspace), pl.ldp, pl.splits, M, N, bias, p.relu, C, ldc,
+                        main_blocks, (const float *)p.ws_rowsum, p.rowsum);
     }
     count_launch();
-    return last_error();
+    return le == cudaSuccess ? last_error() : (int)le;
 }
 
 extern "C" int gist_gemm_tf32(const float *A, int64_t lda, int32_t a_layout, const float *B, int64_t ldb,
@@ -1434,9 +1483,9 @@ extern "C" int gist_split_tf32_multi_f32(int32_t n_tensors, const float *const *
         if (blocks > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
     }
     if (blocks == 0) return GIST_OK;
-    split_tf32_multi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    const cudaError_t le = launch_pdl(split_tf32_multi_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a);
     count_launch();
-    return last_error();
+    return le == cudaSuccess ? last_error() : (int)le;
 }
 
 extern "C" int gist_gemm_tn_tf32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C,

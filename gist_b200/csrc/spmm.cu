@@ -12,11 +12,25 @@
 //     broadcasts them with shuffles and issues U independent VEC-wide gathers
 //     before touching the accumulators (memory-level parallelism);
 //   * edges are accumulated in CSR order -> deterministic, no atomics.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gist {
 
 std::atomic<uint64_t> g_launches{0};
+
+// programmatic dependent launch (common.cuh): -1 = not decided yet (GIST_PDL in the environment)
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+    int v = g_pdl.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char *e = getenv("GIST_PDL");
+        v = (e && e[0] && e[0] != '0') ? 1 : 0;
+        g_pdl.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
 
 struct SpmmParams {
     const int32_t *rowptr;
@@ -441,6 +455,7 @@ __global__ void __launch_bounds__(256, SEG_CTAS) spmm_seg_kernel(const __grid_co
     const int lg = lane % LPR;
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
     const int lane0 = grp * LPR;
+    pdl_sync();
     if constexpr (EX) record_drop_step(p);
     // The number of segments is known on the device only (the host sizes its buffers from the
     // batch's edge CAPACITY, several times the actual count), so the grid is a fixed number of
@@ -782,15 +797,17 @@ static int launch_spmm_seg(const SpmmParams &p0, int64_t max_segments, cudaStrea
     if (grid > ceil_div64(max_work, 8)) grid = ceil_div64(max_work, 8);
     p.seg_blocks = 0;
     const bool ex = p.y_lo || p.self_lo || p.drop.p != 0.f;
+    const dim3 g((unsigned)grid), b(256);
+    cudaError_t le;
     if (p.src_scale) {
-        if (ex) spmm_seg_kernel<VEC, LPR, VPL, true, true><<<(unsigned)grid, 256, 0, stream>>>(p);
-        else spmm_seg_kernel<VEC, LPR, VPL, true, false><<<(unsigned)grid, 256, 0, stream>>>(p);
+        le = ex ? launch_pdl(spmm_seg_kernel<VEC, LPR, VPL, true, true>, g, b, 0, stream, p)
+                : launch_pdl(spmm_seg_kernel<VEC, LPR, VPL, true, false>, g, b, 0, stream, p);
     } else {
-        if (ex) spmm_seg_kernel<VEC, LPR, VPL, false, true><<<(unsigned)grid, 256, 0, stream>>>(p);
-        else spmm_seg_kernel<VEC, LPR, VPL, false, false><<<(unsigned)grid, 256, 0, stream>>>(p);
+        le = ex ? launch_pdl(spmm_seg_kernel<VEC, LPR, VPL, false, true>, g, b, 0, stream, p)
+                : launch_pdl(spmm_seg_kernel<VEC, LPR, VPL, false, false>, g, b, 0, stream, p);
     }
     count_launch();
-    return last_error();
+    return le == cudaSuccess ? last_error() : (int)le;
 }
 
 template <int VEC>
@@ -1069,6 +1086,13 @@ extern "C" int gist_degree_norm_f32(const int32_t *rowptr, int32_t n, int32_t mo
 extern "C" int gist_abi_version(void) { return GIST_ABI_VERSION; }
 
 extern "C" uint64_t gist_launch_count(void) { return g_launches.load(); }
+
+extern "C" int gist_set_pdl(int32_t enabled) {
+    g_pdl.store(enabled ? 1 : 0, std::memory_order_relaxed);
+    return GIST_OK;
+}
+
+extern "C" int gist_get_pdl(void) { return pdl_enabled() ? 1 : 0; }
 
 extern "C" int gist_set_device(int device) {
     cudaError_t e = cudaSetDevice(device);

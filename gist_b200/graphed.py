@@ -40,6 +40,12 @@ _KEYS = ('feat', 'label', 'train_mask')
 PREP_CTAS_PER_SM = int(os.environ.get('GIST_PREP_CTAS', '0'))
 TRAIN_FIRST = os.environ.get('GIST_TRAIN_FIRST', '0') != '0'
 PREP_BALANCED = os.environ.get('GIST_PREP_BALANCED', '0') != '0'
+# Fused tail of the step (pipelined 3xTF32 trainer): the Adam launch also writes the weights' 3xTF32 low
+# halves and ticks the dropout clock, the cross entropy writes the loss into the trainer's slot — the
+# step's dependency chain loses the loss copy, the clock tick and the weight split (adam -> copy -> tick
+# -> [next graph] split -> first GEMM: 17.6 us from the end of Adam to the start of the first GEMM in
+# the round-2 timeline, of which 2.4 us is the split's own work).
+FUSED_TAIL = os.environ.get('GIST_FUSED_TAIL', '1') != '0'
 
 
 class GraphedClusterTrainer:
@@ -54,8 +60,18 @@ class GraphedClusterTrainer:
         self.cap = max(cluster_iter.max_batch_edges(), 1)
         nbuf = 2 if self.pipeline else 1
         self.nids = [torch.full((self.n_pad,), -1, dtype=torch.int64, device=self.dev) for _ in range(nbuf)]
-        self.loss = [torch.zeros((), dtype=torch.float32, device=self.dev) for _ in range(nbuf)]
+        self._loss2 = [torch.zeros(2, dtype=torch.float32, device=self.dev) for _ in range(nbuf)]   # (loss, 1 / #rows)
+        self.loss = [b[0] for b in self._loss2]
         self.opt = make_optimizer(model.parameters(), lr, weight_decay)
+        self.fused_tail = (FUSED_TAIL and self.pipeline and not TRAIN_FIRST
+                           and ops.get_matmul_precision() == '3xtf32')
+        if self.fused_tail:
+            # one persistent low-half buffer per TMA-addressable weight, written by the Adam launch
+            for p in model.parameters():
+                if p.dim() == 2 and p.numel() > 0 and p.is_contiguous() and ops._tma_ok(p):
+                    lo = torch.empty_like(p, memory_format=torch.contiguous_format).detach()
+                    ops.register_persistent_lo(p, lo)
+                    self.opt.lo_map[p] = lo
         self.graphs = None
         self.clusters = [None, None]    # pipelined: the two cluster buffer sets
         self.k = 0                      # steps issued so far
@@ -153,12 +169,21 @@ class GraphedClusterTrainer:
                                                                      background=PREP_CTAS_PER_SM or (1 if PREP_BALANCED else 0))
         return sg
 
-    def _train(self, cluster, loss_out):
+    def _train(self, cluster, j, before_update=None):
+        """One training step on ``cluster``; the loss lands in loss[j] (written by the cross-entropy
+        kernel itself).  ``before_update``: called between the backward pass and the optimizer."""
         self.opt.zero_grad(set_to_none=True)
         pred = self.model(cluster)          # (the dropout clock is ticked by the caller: auto_tick off)
-        loss = loss_and_backward(pred, cluster.ndata['label'], cluster.ndata['train_mask'])
+        loss_and_backward(pred, cluster.ndata['label'], cluster.ndata['train_mask'], loss_out=self._loss2[j])
+        if before_update is not None:
+            before_update()
         self.opt.step()
-        loss_out.copy_(loss)
+
+    def _sync_lo(self):
+        """Persistent weight low halves valid before the next step runs (a GIST dispatch, a restore or a
+        load_state_dict wrote the weights since the last one): one split launch on the current stream."""
+        if self.fused_tail and not ops.persistent_lo_valid():
+            ops.refresh_persistent_lo()
 
     def capture(self):
         """Warm up on a real batch, capture, then restore parameters / optimizer state so the
@@ -197,9 +222,10 @@ class GraphedClusterTrainer:
         s = torch.cuda.Stream(device=self.dev, priority=hi_p) if self.pipeline else torch.cuda.Stream(device=self.dev)
         s.wait_stream(main)
         with torch.cuda.stream(s):
+            self._sync_lo()
             for _ in range(3):
                 clock.tick()
-                self._train(self._build(self.nids[0]), self.loss[0])
+                self._train(self._build(self.nids[0]), 0)
         main.wait_stream(s)
         torch.cuda.synchronize(self.dev)
         self.graphs = []
@@ -234,11 +260,20 @@ class GraphedClusterTrainer:
                     # the GPU in creation order, a few microseconds apart at the head of the graph
                     if not TRAIN_FIRST:
                         prepare()
-                    self._train(self.clusters[j], self.loss[j])
-                    if TRAIN_FIRST:
-                        prepare()
-                    cap_main.wait_stream(side)
-                    clock.tick()
+                    if self.fused_tail:
+                        # the preparation branch (which reads the clock) joins BEFORE the optimizer, whose
+                        # launch then ticks the clock: the step ends with the Adam node
+                        self.opt.tick = clock.step
+                        try:
+                            self._train(self.clusters[j], j, before_update=lambda: cap_main.wait_stream(side))
+                        finally:
+                            self.opt.tick = None
+                    else:
+                        self._train(self.clusters[j], j)
+                        if TRAIN_FIRST:
+                            prepare()
+                        cap_main.wait_stream(side)
+                        clock.tick()
                 self.gist_launches_per_step = _lib.launch_count() - l0
                 self.graphs.append(gph)
         else:
@@ -246,7 +281,7 @@ class GraphedClusterTrainer:
             gph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gph):
                 clock.tick()
-                self._train(self._build(self.nids[0]), self.loss[0])
+                self._train(self._build(self.nids[0]), 0)
             self.gist_launches_per_step = _lib.launch_count() - l0   # this library's kernel nodes per replay
             self.graphs.append(gph)
 
@@ -254,12 +289,15 @@ class GraphedClusterTrainer:
         """A fresh Adam, as the reference builds at every dispatch (…distrib.py:405-407), but in
         place: moments and step counters are zeroed so the captured graph's pointers stay valid."""
         self.opt.reset_state()
+        if self.fused_tail:
+            ops.refresh_persistent_lo()     # a dispatch may have written the weights through p.data
 
     def _issue(self):
         """Enqueue step k; returns the buffer index j whose loss[j] the step writes."""
         if self.graphs is None:
             self.capture()
         main = torch.cuda.current_stream(self.dev)
+        self._sync_lo()
         if not self.pipeline:
             if self.k > 0:
                 self._upload(0, after=self._ev_done[0])  # graph k-1 was the last reader of nids[0]

@@ -5,6 +5,7 @@ Every function here enqueues hand-written sm_100a kernels from
 non-CUDA inputs raise ``GistLibraryError``.
 """
 import ctypes
+import weakref
 import os
 
 import torch
@@ -242,6 +243,7 @@ def slice_gather(src, ridx=None, cidx=None, out=None):
     assert tuple(o2.shape) == (nr, nc) and (o2.stride(1) == 1 or nc == 1)
     check(_lib.load().gist_slice_gather_f32(ptr(s2), _ld(s2), ptr(ridx), nr, ptr(cidx), nc, ptr(o2),
                                             _ld(o2), stream_ptr(src.device)), 'slice_gather_f32')
+    note_raw_write(out)
     return out.reshape(nc) if one_d and out.dim() == 2 else out
 
 
@@ -257,6 +259,7 @@ def slice_scatter_(dst, src, ridx=None, cidx=None):
     assert nc == (cidx.shape[0] if cidx is not None else d2.shape[1])
     check(_lib.load().gist_slice_scatter_f32(ptr(s2), _ld(s2), ptr(ridx), nr, ptr(cidx), nc, ptr(d2),
                                              _ld(d2), stream_ptr(dst.device)), 'slice_scatter_f32')
+    note_raw_write(dst)
     return dst
 
 
@@ -285,6 +288,7 @@ def slice_multi(jobs, scatter):
         arr[k] = _lib.SliceJob(s2.data_ptr(), _ld(s2), ridx.data_ptr() if ridx is not None else None, nr,
                                cidx.data_ptr() if cidx is not None else None, nc, d2.data_ptr(), _ld(d2))
         dev = dst.device
+        note_raw_write(dst)
     check(_lib.load().gist_slice_multi_f32(1 if scatter else 0, len(jobs), arr, stream_ptr(dev)), 'slice_multi_f32')
 
 
@@ -487,13 +491,100 @@ def _lo_take(t):
     return None
 
 
+# Low halves that OUTLIVE a forward pass: a trainer that owns the parameter updates
+# (GraphedClusterTrainer: the fused Adam launch writes tf32_lo(p) beside every updated p) registers one
+# persistent buffer per weight; _weight_lo() then needs no split launch at the head of the step.
+# Validity is checked at every use: an entry is served only while (a) no kernel of this library has
+# written a registered weight through its raw pointer since the last refresh (note_raw_write: the K5
+# slice kernels of a GIST dispatch) and (b) the parameter's Tensor._version is the one recorded at the
+# last refresh (torch in-place ops: copy_, load_state_dict ...).  Otherwise the ordinary split runs.
+# The owning trainer refreshes (one launch) before its next step.  Writes through ``p.data`` bypass
+# both checks: a trainer refreshes at every optimizer reset (every GIST dispatch) for that reason.
+class _PersistEntry:
+    __slots__ = ('ref', 'lo', 'ver', 'shape', 'stride')
+
+    def __init__(self, p, lo):
+        self.ref, self.lo, self.ver = weakref.ref(p), lo, -1
+        self.shape, self.stride = tuple(p.shape), tuple(p.stride())
+
+
+_WEIGHT_LO_PERSIST = {}                 # data_ptr -> _PersistEntry
+_PERSIST_EPOCH = [0, -1]                # [raw-write epoch, epoch the buffers were last refreshed at]
+
+
+def register_persistent_lo(p, lo):
+    """``p``: the parameter (the tensor object whose _version is watched); ``lo``: contiguous, same shape."""
+    assert p.dim() == 2 and _tma_ok(p) and p.is_contiguous() and lo.shape == p.shape and lo.is_contiguous()
+    _WEIGHT_LO_PERSIST[p.data_ptr()] = _PersistEntry(p, lo)
+    _PERSIST_EPOCH[1] = -1
+
+
+def unregister_persistent_lo(p):
+    _WEIGHT_LO_PERSIST.pop(p.data_ptr(), None)
+
+
+def note_raw_write(t):
+    """A kernel of this library wrote tensor ``t`` through its raw pointer (no Tensor._version bump)."""
+    if _WEIGHT_LO_PERSIST and t is not None and t.data_ptr() in _WEIGHT_LO_PERSIST:
+        _PERSIST_EPOCH[0] += 1
+
+
+def _persist_live():
+    dead = [k for k, e in _WEIGHT_LO_PERSIST.items() if e.ref() is None]
+    for k in dead:
+        del _WEIGHT_LO_PERSIST[k]
+    return list(_WEIGHT_LO_PERSIST.values())
+
+
+def persistent_lo_valid():
+    if _PERSIST_EPOCH[0] != _PERSIST_EPOCH[1]:
+        return False
+    return all(e.ref()._version == e.ver for e in _persist_live())
+
+
+def refresh_persistent_lo():
+    """Re-split every registered weight on the current stream (one launch per 16 weights)."""
+    es = _persist_live()
+    for i in range(0, len(es), 16):
+        split_tf32_multi([e.ref().detach() for e in es[i:i + 16]], [e.lo for e in es[i:i + 16]])
+    for e in es:
+        e.ver = e.ref()._version
+    _PERSIST_EPOCH[1] = _PERSIST_EPOCH[0]
+
+
+def _persistent_lo(Wv):
+    e = _WEIGHT_LO_PERSIST.get(Wv.data_ptr())
+    if e is None or _PERSIST_EPOCH[0] != _PERSIST_EPOCH[1]:
+        return None
+    p = e.ref()
+    if p is None or p._version != e.ver or tuple(Wv.shape) != e.shape or tuple(Wv.stride()) != e.stride:
+        return None
+    return e.lo
+
+
+def split_tf32_multi(ws, los):
+    """lo_i = tf32(w_i - trunc_tf32(w_i)) for up to 16 matrices in ONE launch (gist_split_tf32_multi_f32)."""
+    n = len(ws)
+    if n == 0:
+        return
+    assert n <= 16
+    X, LO = (ctypes.c_void_p * n)(), (ctypes.c_void_p * n)()
+    LDX, LDL = (ctypes.c_int64 * n)(), (ctypes.c_int64 * n)()
+    R, C = (ctypes.c_int32 * n)(), (ctypes.c_int32 * n)()
+    for i, (w, lo) in enumerate(zip(ws, los)):
+        X[i], LO[i], LDX[i], LDL[i], R[i], C[i] = w.data_ptr(), lo.data_ptr(), _ld(w), _ld(lo), w.shape[0], w.shape[1]
+    check(_lib.load().gist_split_tf32_multi_f32(n, X, LDX, R, C, LO, LDL, stream_ptr(ws[0].device)),
+          'split_tf32_multi_f32')
+
+
 def presplit_weights(params):
     """3xTF32 low halves of every TMA-addressable 2-D fp32 tensor in ``params`` with ONE launch
     (gist_split_tf32_multi_f32), left for the layers to pick up: each entry is consumed by the first
-    _weight_lo() of that tensor, so nothing outlives the forward pass that asked for it."""
+    _weight_lo() of that tensor, so nothing outlives the forward pass that asked for it.  Weights with a
+    registered persistent low half (register_persistent_lo) are skipped."""
     _WEIGHT_LO.clear()
     ws = [p.data if isinstance(p, torch.nn.Parameter) else p for p in params]
-    ws = [w for w in ws if w.dim() == 2 and w.numel() > 0 and _tma_ok(w)][:16]
+    ws = [w for w in ws if w.dim() == 2 and w.numel() > 0 and _tma_ok(w) and _persistent_lo(w) is None][:16]
     if not ws:
         return
     n = len(ws)
@@ -514,6 +605,9 @@ def clear_presplit():
 
 
 def _weight_lo(Wv):
+    lo = _persistent_lo(Wv)
+    if lo is not None:
+        return lo
     e = _WEIGHT_LO.pop(Wv.data_ptr(), None)
     if e is not None and e[1].shape == Wv.shape and e[0].stride() == Wv.stride():
         return e[1]
@@ -589,6 +683,7 @@ FUSED_ROWSUM = os.environ.get('GIST_GEMM_FUSED_ROWSUM', '1') != '0'
 BACKGROUND_DW = os.environ.get('GIST_GEMM_BACKGROUND_DW', '1') != '0'
 DZ_FIRST = os.environ.get('GIST_DZ_FIRST', '1') != '0'
 FUSED_LN = os.environ.get('GIST_GEMM_FUSED_LN', '1') != '0'
+FUSED_LN_WIDE = os.environ.get('GIST_GEMM_FUSED_LN_WIDE', '1') != '0'     # rows of 129..256: in the split-K second pass
 _GEMM_COUNTERS = {}
 
 
@@ -673,8 +768,10 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, relu=False, out=None, flags
 
 
 def ln_fusable(M, N, x3, a_mn=False, b_mn=False):
-    """Does K4's LayerNorm epilogue apply (one tile holds the row; include/gist_b200.h gist_gemm_ex_t)?"""
-    return FUSED_LN and x3 and not a_mn and not b_mn and 0 < N <= 128 and M > 0
+    """Does K4's LayerNorm fusion apply (include/gist_b200.h gist_gemm_ex_t)?  N <= 128: one tile holds the
+    row (GEMM epilogue or split-K second pass); 128 < N <= 256: the split-K second pass normalises the row
+    (when K is not split the library runs the row-wise kernel behind the GEMM itself)."""
+    return FUSED_LN and x3 and not a_mn and not b_mn and 0 < N <= (256 if FUSED_LN_WIDE else 128) and M > 0
 
 
 def gemm_dropmask(A, B, drop, *, a_mn=False, b_mn=False, out=None, A_lo=None, B_lo=None):
@@ -1189,12 +1286,14 @@ def _ce_sync(device):
 
 
 @torch.no_grad()
-def masked_ce_loss_and_grad(logits, labels, mask=None):
+def masked_ce_loss_and_grad(logits, labels, mask=None, out=None):
     """(loss, dlogits) of ``CrossEntropyLoss()(logits[mask], labels[mask])`` in ONE launch — the
     trainers' replacement for ``loss = ...; loss.backward()`` (…distrib.py:413-415): call
     ``logits.backward(dlogits)`` to run the rest of the backward pass.  dlogits is the gradient for
-    an upstream gradient of 1; its 3xTF32 low half is handed to the consuming linear backward."""
-    require_cuda(logits, labels, mask)
+    an upstream gradient of 1; its 3xTF32 low half is handed to the consuming linear backward.
+    ``out``: a caller-owned fp32 tensor of 2 elements the kernel writes (loss, 1 / #rows) into — a
+    trainer's persistent loss slot, so no copy node follows the step."""
+    require_cuda(logits, labels, mask, out)
     logits = _mat(logits.detach(), 'logits')
     n, C = logits.shape
     assert n > 0
@@ -1209,7 +1308,9 @@ def masked_ce_loss_and_grad(logits, labels, mask=None):
     buf = torch.empty((n, ldd), dtype=torch.float32, device=dev)
     x3 = _MATMUL_PRECISION == '3xtf32'
     buf_lo = torch.empty((n, ldd), dtype=torch.float32, device=dev) if x3 else None
-    out = torch.empty(2, dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+    assert out.dtype == torch.float32 and out.shape == (2,) and out.is_contiguous()
     wsb = lib.gist_masked_ce_fused_workspace_bytes(n)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     check(lib.gist_masked_ce_fused_f32(ptr(logits), _ld(logits), n, C, ptr(labels), ptr(mask), ptr(buf), ldd, ldd,

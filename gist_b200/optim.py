@@ -20,6 +20,9 @@ class Adam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self._counter = None
         self._steps = {}        # id(group) -> device float step counter
+        # fused tail of a training step (gist_adam_multi_ex_f32), set by the trainer that owns the step:
+        self.lo_map = {}        # parameter -> persistent contiguous tensor receiving tf32_lo(updated parameter)
+        self.tick = None        # device int64 incremented by the launch (the dropout clock of the next step)
 
     def reset_state(self):
         """Zero moments and step counters IN PLACE (a 'fresh' optimizer whose buffers keep their
@@ -35,10 +38,9 @@ class Adam(torch.optim.Optimizer):
     def step(self, closure=None):
         assert closure is None
         lib = _lib.load()
-        for group in self.param_groups:
+        live = [g for g in self.param_groups if any(p.grad is not None for p in g['params'])]
+        for group in live:
             ps = [p for p in group['params'] if p.grad is not None]
-            if not ps:
-                continue
             dev = ps[0].device
             require_cuda(*ps)
             if self._counter is None:
@@ -47,7 +49,7 @@ class Adam(torch.optim.Optimizer):
                 self._steps[id(group)] = torch.zeros((), dtype=torch.float32, device=dev)
             step = self._steps[id(group)]
             n = len(ps)
-            P, G, M, V = ((ctypes.c_void_p * n)() for _ in range(4))
+            P, G, M, V, LO = ((ctypes.c_void_p * n)() for _ in range(5))
             N = (ctypes.c_int64 * n)()
             keep = []
             for i, p in enumerate(ps):
@@ -63,8 +65,15 @@ class Adam(torch.optim.Optimizer):
                 P[i], G[i] = p.data_ptr(), g.data_ptr()
                 M[i], V[i] = st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr()
                 N[i] = p.numel()
+                lo = self.lo_map.get(p)
+                if lo is not None:
+                    assert lo.is_contiguous() and lo.numel() == p.numel() and lo.dtype == torch.float32
+                    LO[i] = lo.data_ptr()
             b1, b2 = group['betas']
-            check(lib.gist_adam_multi_f32(n, P, G, M, V, N, group['lr'], b1, b2, group['eps'],
-                                          group['weight_decay'], _lib.ptr(step),
-                                          _lib.ptr(self._counter), stream_ptr(dev)), 'adam_multi_f32')
+            last = group is live[-1]
+            check(lib.gist_adam_multi_ex_f32(n, P, G, M, V, N, group['lr'], b1, b2, group['eps'],
+                                             group['weight_decay'], _lib.ptr(step), _lib.ptr(self._counter),
+                                             LO if self.lo_map else None,
+                                             _lib.ptr(self.tick) if last else None, stream_ptr(dev)),
+                  'adam_multi_ex_f32')
         return None

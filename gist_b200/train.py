@@ -14,15 +14,19 @@ def masked_cross_entropy(pred, labels, mask):
     return ops.masked_cross_entropy(pred, labels, mask.bool())
 
 
-def loss_and_backward(pred, labels, mask):
+def loss_and_backward(pred, labels, mask, loss_out=None):
     """``loss = CrossEntropyLoss()(pred[mask], labels[mask]); loss.backward()`` (…distrib.py:413-415)
     with the loss and its gradient seed d loss / d pred produced by one kernel: the backward pass
-    starts from ``pred`` directly.  Returns the detached 0-d loss."""
+    starts from ``pred`` directly.  Returns the detached 0-d loss (``loss_out``: a persistent 2-float
+    buffer the kernel writes the loss into; the returned tensor is then its element 0)."""
     if pred.shape[0] == 0:
         loss = masked_cross_entropy(pred, labels, mask)
         loss.backward()
+        if loss_out is not None:
+            loss_out[0].copy_(loss.detach())
+            return loss_out[0]
         return loss.detach()
-    loss, dpred = ops.masked_ce_loss_and_grad(pred, labels, mask.bool())
+    loss, dpred = ops.masked_ce_loss_and_grad(pred, labels, mask.bool(), out=loss_out)
     pred.backward(dpred)
     return loss
 

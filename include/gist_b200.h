@@ -92,6 +92,18 @@ int gist_set_device(int device);
  * gpu_launches evidence). */
 uint64_t gist_launch_count(void);
 
+/* Programmatic dependent launch for the kernels of the training step's critical chain (K4 and its
+ * split-K second pass, the layer-norm kernels, the segment SpMM, the fused cross entropy, Adam, the
+ * 3xTF32 weight split): launched with cudaLaunchAttributeProgrammaticStreamSerialization, each of
+ * them becomes resident and runs its prologue while its predecessor on the stream drains, and blocks
+ * in griddepcontrol.wait — before its first global-memory access — until the predecessor has
+ * completed.  Results are unchanged (same stream-order dependencies); under stream capture the
+ * attribute becomes a programmatic edge of the graph.  Process-wide switch; the initial value comes
+ * from GIST_PDL in the environment (default off).  There is no reference counterpart: the reference
+ * launches one eager PyTorch kernel after the other (cluster_gcn_ist_distrib.py:408-417). */
+int gist_set_pdl(int32_t enabled);
+int gist_get_pdl(void);
+
 /* ------------------------------------------------------------------------
  * K1 / K2  CSR SpMM with fused epilogue.
  *
@@ -348,9 +360,11 @@ int gist_gemm_3xtf32(const float *A, const float *A_lo, int64_t lda, int64_t lda
  *       as one extra 16-column MMA per K step against a tile of ones.  Tiles are then <= 128 wide;
  *       both operands MN-major only (the dy^T z layout), GIST_ERR_UNSUPPORTED otherwise.
  *   ln_out / ld_ln / ln_stats / ln_eps / ln_flags : LayerNorm without affine (+ ReLU with
- *       GIST_ACT_RELU) over the rows of C (modules.py:234-236) when one tile holds the row (N <= 128;
- *       y = z W^T layout, 3xTF32): C receives the pre-norm values (+ bias), ln_out the normalised /
- *       activated ones, ln_stats [M][2] = (mean, rstd) for gist_layernorm_act_bwd_f32.
+ *       GIST_ACT_RELU) over the rows of C (modules.py:234-236), y = z W^T layout, 3xTF32, N <= 256:
+ *       C receives the pre-norm values (+ bias), ln_out the normalised / activated ones, ln_stats
+ *       [M][2] = (mean, rstd) for gist_layernorm_act_bwd_f32.  N <= 128: one tile holds the row and the
+ *       norm runs in the GEMM's own epilogue (or in the split-K second pass); 128 < N <= 256: in the
+ *       split-K second pass when the planner splits K, else as the row-wise kernel behind the GEMM.
  *   drop : as in gist_gemm_dropmask_f32 (forces a single K split).
  * Workspace: gist_gemm_ex_workspace_bytes with the same arguments.  GIST_ERR_UNSUPPORTED when a
  * requested fusion does not apply to the shape / layout (the caller runs the separate kernel). */
@@ -486,6 +500,20 @@ int gist_adam_multi_f32(int32_t n_tensors, float *const *params, const float *co
                         float *const *exp_avg, float *const *exp_avg_sq, const int64_t *numel, float lr,
                         float beta1, float beta2, float eps, float weight_decay, float *step,
                         uint32_t *counter, gist_stream_t stream);
+
+/* gist_adam_multi_f32 plus the two things that follow optimizer.step() at the tail of a training step
+ * (cluster_gcn_ist_distrib.py:417 is the last statement of the reference's loop body), done by the same
+ * launch instead of as two more links of the step's dependency chain:
+ *   params_lo : HOST array (or NULL) of optional device pointers — the 3xTF32 low half
+ *               tf32(p - trunc_tf32(p)) of every UPDATED parameter, same flat layout as the parameter
+ *               (what gist_split_tf32_multi_f32 would compute at the head of the next step);
+ *   tick      : device int64 (or NULL), incremented once by the last CTA of the last launch — the
+ *               dropout clock of the next step (gist_counter_add_i64).  The caller orders everything that
+ *               still reads the clock (the batch-preparation branch) before this call. */
+int gist_adam_multi_ex_f32(int32_t n_tensors, float *const *params, const float *const *grads,
+                           float *const *exp_avg, float *const *exp_avg_sq, const int64_t *numel, float lr,
+                           float beta1, float beta2, float eps, float weight_decay, float *step,
+                           uint32_t *counter, float *const *params_lo, int64_t *tick, gist_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * K6  graph attention (GAT) message passing: fused edge-softmax + weighted SpMM.

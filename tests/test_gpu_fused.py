@@ -207,3 +207,59 @@ def test_adam_cuda_graph_replay_advances_step():
         q.grad = g.double()
         b.step()
     assert _rel(p, q) < 2e-6
+
+
+@pytest.mark.parametrize('graphed', [False, True])
+def test_adam_fused_tail_writes_low_halves_and_ticks_the_clock(graphed):
+    """gist_adam_multi_ex_f32: the update itself is bit-identical to the plain launch, lo = tf32_lo(updated p)
+    (what gist_split_tf32_multi_f32 computes at the head of the next step) and the clock advances by one per
+    step — eagerly and from a replayed graph."""
+    from gist_b200 import ops
+    from gist_b200.optim import Adam
+    torch.manual_seed(3)
+    shapes = [(256, 1204), (256,), (32, 64), (41, 512), (41,), (3, 8)]
+    ps = [torch.randn(*s, device='cuda').requires_grad_(True) for s in shapes]
+    qs = [p.detach().clone().requires_grad_(True) for p in ps]
+    a, b = Adam(ps, lr=1e-2, weight_decay=5e-4), Adam(qs, lr=1e-2, weight_decay=5e-4)
+    los = {p: torch.full_like(p, float('nan')).detach() for p in ps if p.dim() == 2}
+    a.lo_map = dict(los)
+    a.tick = torch.full((1,), 7, dtype=torch.int64, device='cuda')
+    gs = [torch.randn_like(p) for p in ps]
+    for p, q, g in zip(ps, qs, gs):
+        p.grad, q.grad = g.clone(), g.clone()
+    n_steps = 4
+    if graphed:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            a.step()
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            a.step()
+        for _ in range(n_steps - 1):
+            graph.replay()
+    else:
+        for _ in range(n_steps):
+            a.step()
+    for _ in range(n_steps):
+        b.step()
+    torch.cuda.synchronize()
+    assert int(a.tick.item()) == 7 + n_steps
+    for p, q in zip(ps, qs):
+        assert torch.equal(p, q)
+    for p, lo in los.items():
+        assert torch.equal(lo, ops.split_tf32(p.detach()))
+
+
+def test_masked_ce_writes_the_loss_into_the_callers_slot():
+    from gist_b200 import ops
+    torch.manual_seed(4)
+    logits = torch.randn(2141, 41, device='cuda') * 3
+    labels = torch.randint(0, 41, (2141,), device='cuda')
+    mask = torch.rand(2141, device='cuda') < 0.6
+    ref, dref = ops.masked_ce_loss_and_grad(logits, labels, mask)
+    slot = torch.zeros(2, device='cuda')
+    loss, dl = ops.masked_ce_loss_and_grad(logits, labels, mask, out=slot)
+    assert loss.data_ptr() == slot.data_ptr() and torch.equal(loss, ref) and torch.equal(dl, dref)
+    assert abs(slot[1].item() - 1.0 / int(mask.sum())) < 1e-9

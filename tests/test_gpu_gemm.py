@@ -320,7 +320,10 @@ def test_rowsum_on_the_tensor_core_is_the_bias_gradient(shape, x3, inkernel, mon
 
 
 @pytest.mark.parametrize('shape', [(2590, 32, 1204), (2590, 32, 64), (2586, 64, 128), (2586, 128, 256), (1000, 41, 512),
-                                   (300, 100, 72), (129, 7, 36)])
+                                   (300, 100, 72), (129, 7, 36),
+                                   # rows of 129..256: the norm rides in the split-K second pass (K split) or
+                                   # runs as the row kernel behind the GEMM (K not split)
+                                   (2141, 256, 1204), (2141, 256, 512), (2590, 200, 1204), (300, 132, 64), (20000, 256, 96)])
 @pytest.mark.parametrize('relu', [True, False])
 @pytest.mark.parametrize('inkernel', [False, True])
 def test_layernorm_epilogue_matches_the_row_kernel(shape, relu, inkernel, monkeypatch):
