@@ -35,10 +35,15 @@ SIGNATURES = {
     'gist_exclusive_scan_i32': (ctypes.c_int, [_P, _I32, _P, _P, _SZ, _P]),
     'gist_cluster_batch_build': (ctypes.c_int, [_P, _P, _I32, _P, _I32, _P, _P, _P, _I64, _P, _P,
                                                 _P, _SZ, _P]),
+    'gist_cluster_batch_build_v2_workspace_bytes': (_SZ, [_I32, _I64]),
+    'gist_cluster_batch_build_v2': (ctypes.c_int, [_P, _P, _I32, _P, _I32, _P, _P, _P, _I64, _P, _P, _I64,
+                                                   _P, _SZ, _P]),
     'gist_gather_rows': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _P]),
     'gist_slice_gather_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
     'gist_slice_scatter_f32': (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
     'gist_slice_multi_f32': (ctypes.c_int, [_I32, _I32, _P, _P]),
+    'gist_slice_scatter_rows_f32': (ctypes.c_int, [_I32, _P, _P]),
+    'gist_index_invert_i32': (ctypes.c_int, [_P, _I64, _P, _I64, _P]),
     'gist_gemm_tf32_workspace_bytes': (_SZ, [_I32, _I32, _I32, _U32]),
     'gist_gemm_tf32': (ctypes.c_int, [_P, _I64, _I32, _P, _I64, _I32, _P, _I64, _I32, _I32, _I32, _P, _U32,
                                       _P, _SZ, _P]),
@@ -129,6 +134,12 @@ class SliceJob(ctypes.Structure):
     """gist_slice_job_t"""
     _fields_ = [('src', ctypes.c_void_p), ('ld_src', ctypes.c_int64), ('ridx', ctypes.c_void_p), ('n_rows', ctypes.c_int64),
                 ('cidx', ctypes.c_void_p), ('n_cols', ctypes.c_int64), ('dst', ctypes.c_void_p), ('ld_dst', ctypes.c_int64)]
+
+
+class SliceRowsJob(ctypes.Structure):
+    """gist_slice_rows_job_t"""
+    _fields_ = [('src', ctypes.c_void_p), ('ld_src', ctypes.c_int64), ('ridx', ctypes.c_void_p), ('n_rows', ctypes.c_int64),
+                ('inv_col', ctypes.c_void_p), ('dst', ctypes.c_void_p), ('ld_dst', ctypes.c_int64), ('dst_cols', ctypes.c_int64)]
 
 
 class GemmEx(ctypes.Structure):

@@ -274,6 +274,149 @@ __global__ void __launch_bounds__(256) batch_fill_kernel(const int32_t *__restri
     }
 }
 
+// ------------------------------------------------- batch builder, v2 ----
+// v1 gives every batch row one warp (hub rows one CTA): the launch is as long as its unluckiest CTA
+// — a parent row of 15 k edges is 15 rounds of two dependent loads for each of 8 warps, behind up to 8
+// rounds of ordinary rows — so count and fill take 23-36 us each for ~1 M parent edges (4 MB) that the
+// chip could walk in a few microseconds.  v2 cuts every parent row into CHUNKS of 128 edges (one round
+// of 4 x 32 independent col -> node_map loads) and gives every chunk a warp of a chip-wide grid:
+//   mark + chunks per row -> scan (chunk_ptr) -> count per chunk -> one-CTA scan of the chunk counts
+//   (+ rowptr, 1 / degree) -> fill per chunk -> unmark.
+// Chunks of a row are consecutive and a chunk's hits keep their order, so the CSR is identical to v1's
+// (parent order preserved).  The walks stay latency-bound, but every warp's share is ONE round.
+constexpr int kChunk = 32 * kBuildUnroll;
+
+__global__ void batch_mark_chunks_kernel(const int64_t *__restrict__ nids, int32_t n_b,
+                                         int32_t *__restrict__ node_map, const int32_t *__restrict__ prow,
+                                         int32_t *__restrict__ nck) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_b) {
+        const int64_t p = nids[i];
+        int c = 0;
+        if (p >= 0) {
+            node_map[p] = i;
+            c = (prow[p + 1] - prow[p] + kChunk - 1) / kChunk;
+        }
+        nck[i] = c;
+    }
+}
+
+// chunk c belongs to the last row i with chunk_ptr[i] <= c (rows without chunks are skipped by construction);
+// 32 probes per round: three rounds for 4 k rows instead of twelve dependent loads
+__device__ __forceinline__ int chunk_row_search(const int32_t *__restrict__ chunk_ptr, int n_b, int c, int lane) {
+    int lo = 0, hi = n_b;
+    while (hi - lo > 1) {
+        const int step = (hi - lo + 31) / 32;
+        const int idx = lo + (lane + 1) * step;
+        const bool le = idx < hi && __ldg(chunk_ptr + idx) <= c;
+        const int k = __popc(__ballot_sync(0xffffffffu, le));
+        lo += k * step;
+        hi = min(hi, lo + step);
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) chunk_count_kernel(const int32_t *__restrict__ prow,
+                                                          const int32_t *__restrict__ pcol,
+                                                          const int64_t *__restrict__ nids, int32_t n_b,
+                                                          const int32_t *__restrict__ node_map,
+                                                          const int32_t *__restrict__ chunk_ptr, int32_t max_chunks,
+                                                          int32_t *__restrict__ chunk_row,
+                                                          int32_t *__restrict__ chunk_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int n_warps = gridDim.x * 8;
+    const int T = min(__ldg(chunk_ptr + n_b), max_chunks);
+    for (int c = blockIdx.x * 8 + (threadIdx.x >> 5); c < T; c += n_warps) {
+        const int row = chunk_row_search(chunk_ptr, n_b, c, lane);
+        const int64_t pnode = nids[row];
+        const int rs = prow[pnode], re = prow[pnode + 1];
+        const int eb = rs + (c - __ldg(chunk_ptr + row)) * kChunk;
+        const int cnt = count_range(pcol, node_map, eb, min(re, eb + kChunk), lane);
+        if (lane == 0) {
+            chunk_row[c] = row;
+            chunk_cnt[c] = cnt;
+        }
+    }
+}
+
+// One CTA: exclusive scan of the chunk counts in place (chunk_cnt[T] = total), then the batch's rowptr
+// (row i starts where its first chunk does) and 1 / degree.
+constexpr int kChunkScanThreads = 1024;
+__global__ void __launch_bounds__(kChunkScanThreads) chunk_scan_rows_kernel(
+    const int32_t *__restrict__ chunk_ptr, int32_t n_b, int32_t max_chunks, int32_t *__restrict__ chunk_cnt,
+    int32_t *__restrict__ out_rowptr, float *__restrict__ out_inv_deg, int64_t col_capacity,
+    int32_t *__restrict__ overflow_flag) {
+    __shared__ int s_warp[kChunkScanThreads / 32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T_all = chunk_ptr[n_b];
+    const int T = min(T_all, max_chunks);
+    const int per = (T + kChunkScanThreads - 1) / kChunkScanThreads;
+    const int b = min(T, tid * per), e = min(T, b + per);
+    int sum = 0;
+    for (int k = b; k < e; ++k) sum += chunk_cnt[k];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        s_warp[lane] = wi - w;          // exclusive offset of warp `lane`
+        if (lane == 31) s_total = wi;
+    }
+    __syncthreads();
+    int run = s_warp[warp] + incl - sum;
+    for (int k = b; k < e; ++k) {
+        const int v = chunk_cnt[k];
+        chunk_cnt[k] = run;
+        run += v;
+    }
+    const int total = s_total;
+    if (tid == 0) {
+        chunk_cnt[T] = total;
+        if (overflow_flag && (total > col_capacity || T_all > max_chunks)) *overflow_flag = 1;
+    }
+    __syncthreads();                    // the positions (global memory, this CTA's own writes) are complete
+    for (int i = tid; i <= n_b; i += kChunkScanThreads) out_rowptr[i] = chunk_cnt[min(chunk_ptr[i], T)];
+    if (out_inv_deg) {
+        __syncthreads();
+        for (int i = tid; i < n_b; i += kChunkScanThreads) {
+            const int dg = out_rowptr[i + 1] - out_rowptr[i];
+            out_inv_deg[i] = dg > 0 ? 1.0f / (float)dg : 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) chunk_fill_kernel(const int32_t *__restrict__ prow,
+                                                         const int32_t *__restrict__ pcol,
+                                                         const int64_t *__restrict__ nids, int32_t n_b,
+                                                         const int32_t *__restrict__ node_map,
+                                                         const int32_t *__restrict__ chunk_ptr, int32_t max_chunks,
+                                                         const int32_t *__restrict__ chunk_row,
+                                                         const int32_t *__restrict__ chunk_pos,
+                                                         int32_t *__restrict__ out_col, int64_t col_capacity) {
+    const int lane = threadIdx.x & 31;
+    const int n_warps = gridDim.x * 8;
+    const int T = min(__ldg(chunk_ptr + n_b), max_chunks);
+    for (int c = blockIdx.x * 8 + (threadIdx.x >> 5); c < T; c += n_warps) {
+        const int row = __ldg(chunk_row + c);
+        const int64_t pnode = nids[row];
+        const int rs = prow[pnode], re = prow[pnode + 1];
+        const int eb = rs + (c - __ldg(chunk_ptr + row)) * kChunk;
+        fill_range(pcol, node_map, eb, min(re, eb + kChunk), lane, (int64_t)__ldg(chunk_pos + c), out_col, col_capacity);
+    }
+}
+
 // ----------------------------------------------------------- row gather ----
 template <typename V>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const char *__restrict__ src,
@@ -373,6 +516,89 @@ __global__ void __launch_bounds__(256) slice_multi_kernel(const __grid_constant_
     }
 }
 
+// Row-streaming merge (gist_slice_scatter_rows_f32): a CTA owns kRowsPerCta destination rows of one job and
+// walks them left to right, one 32-byte sector (8 floats) per thread per step; the inverse column map of a
+// sector is loaded once and serves all of the CTA's rows.
+constexpr int kRowsPerCta = 4;
+struct SliceRowsJobDev {
+    const float *src;
+    float *dst;
+    const int64_t *ridx;
+    const int32_t *inv;
+    int64_t ld_src, ld_dst;
+    int32_t n_rows, dst_cols;
+    int32_t block0, pad;
+};
+struct SliceRowsJobsDev {
+    SliceRowsJobDev j[kSliceMaxJobs];
+    int32_t n_jobs;
+};
+
+__global__ void __launch_bounds__(256) slice_scatter_rows_kernel(const __grid_constant__ SliceRowsJobsDev a) {
+    int lo = 0, hi = a.n_jobs - 1;          // last job whose block0 <= blockIdx.x
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)blockIdx.x >= a.j[mid].block0) lo = mid;
+        else hi = mid - 1;
+    }
+    const SliceRowsJobDev &J = a.j[lo];
+    const int r0 = ((int)blockIdx.x - J.block0) * kRowsPerCta;
+    const float *srow[kRowsPerCta];
+    float *drow[kRowsPerCta];
+#pragma unroll
+    for (int k = 0; k < kRowsPerCta; ++k) {
+        const int r = min(r0 + k, J.n_rows - 1);                // rows past the end repeat the last one, never stored
+        const int64_t rr = J.ridx ? __ldg(J.ridx + r) : (int64_t)r;
+        srow[k] = J.src + (int64_t)r * J.ld_src;
+        drow[k] = J.dst + rr * J.ld_dst;
+    }
+    const int n_live = min(kRowsPerCta, J.n_rows - r0);
+    for (int c0 = threadIdx.x * 8; c0 < J.dst_cols; c0 += 256 * 8) {
+        int iv[8];
+        if (c0 + 8 <= J.dst_cols) {
+            const int4 i0 = __ldg(reinterpret_cast<const int4 *>(J.inv + c0));
+            const int4 i1 = __ldg(reinterpret_cast<const int4 *>(J.inv + c0 + 4));
+            iv[0] = i0.x; iv[1] = i0.y; iv[2] = i0.z; iv[3] = i0.w;
+            iv[4] = i1.x; iv[5] = i1.y; iv[6] = i1.z; iv[7] = i1.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) iv[i] = (c0 + i < J.dst_cols) ? __ldg(J.inv + c0 + i) : -1;
+        }
+        int any = -1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) any = max(any, iv[i]);
+        if (any < 0) continue;                                  // nothing lands on this sector
+        const bool whole = c0 + 8 <= J.dst_cols;
+#pragma unroll
+        for (int k = 0; k < kRowsPerCta; ++k) {
+            if (k >= n_live) break;
+            float *d = drow[k] + c0;
+            if (whole) {
+                float4 v0 = *reinterpret_cast<const float4 *>(d);
+                float4 v1 = *reinterpret_cast<const float4 *>(d + 4);
+                float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (iv[i] >= 0) v[i] = srow[k][iv[i]];      // plain load: src may be peer memory
+                *reinterpret_cast<float4 *>(d) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (iv[i] >= 0) d[i] = srow[k][iv[i]];
+            }
+        }
+    }
+}
+
+__global__ void index_invert_kernel(const int64_t *__restrict__ idx, int64_t n, int32_t *__restrict__ inv, int64_t size) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        const int64_t c = idx[k];
+        if (c >= 0 && c < size) inv[c] = (int32_t)k;
+    }
+}
+
 }  // namespace gist
 
 using namespace gist;
@@ -431,6 +657,52 @@ extern "C" int gist_slice_multi_f32(int32_t scatter, int32_t n_jobs, const gist_
     return GIST_OK;
 }
 
+extern "C" int gist_slice_scatter_rows_f32(int32_t n_jobs, const gist_slice_rows_job_t *jobs, gist_stream_t stream) {
+    if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return GIST_ERR_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int done = 0;
+    while (done < n_jobs) {
+        SliceRowsJobsDev a;
+        a.n_jobs = 0;
+        int64_t blocks = 0;
+        for (; done < n_jobs && a.n_jobs < kSliceMaxJobs; ++done) {
+            const gist_slice_rows_job_t &j = jobs[done];
+            if (j.n_rows < 0 || j.dst_cols < 0) return GIST_ERR_BADARG;
+            if (j.n_rows == 0 || j.dst_cols == 0) continue;
+            if (!j.src || !j.dst || !j.inv_col || j.n_rows > 0x7fffffffLL || j.dst_cols > 0x7fffffffLL ||
+                j.ld_dst < j.dst_cols)
+                return GIST_ERR_BADARG;
+            if (!aligned(j.dst, 32) || j.ld_dst % 8 || !aligned(j.inv_col, 16)) return GIST_ERR_ALIGN;
+            SliceRowsJobDev &d = a.j[a.n_jobs++];
+            d.src = j.src; d.dst = j.dst; d.ridx = j.ridx; d.inv = j.inv_col;
+            d.ld_src = j.ld_src; d.ld_dst = j.ld_dst;
+            d.n_rows = (int32_t)j.n_rows; d.dst_cols = (int32_t)j.dst_cols;
+            d.block0 = (int32_t)blocks; d.pad = 0;
+            blocks += (j.n_rows + kRowsPerCta - 1) / kRowsPerCta;
+            if (blocks > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
+        }
+        if (a.n_jobs == 0) continue;
+        slice_scatter_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
+        count_launch();
+        const int st = last_error();
+        if (st != GIST_OK) return st;
+    }
+    return GIST_OK;
+}
+
+extern "C" int gist_index_invert_i32(const int64_t *idx, int64_t n, int32_t *inv, int64_t size, gist_stream_t stream) {
+    if (n < 0 || size < 0 || (size > 0 && !inv) || (n > 0 && !idx) || size > 0x7fffffffLL) return GIST_ERR_BADARG;
+    if (size == 0) return GIST_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(inv, 0xFF, (size_t)size * sizeof(int32_t), s);
+    if (e != cudaSuccess) return (int)e;
+    if (n > 0) {
+        index_invert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(idx, n, inv, size);
+        count_launch();
+    }
+    return last_error();
+}
+
 extern "C" size_t gist_scan_workspace_bytes(int32_t n) {
     if (n <= 4 * kScanTile) return 0;
     const size_t n_tiles = ((size_t)n + kScanTile - 1) / kScanTile;
@@ -474,6 +746,61 @@ extern "C" int gist_cluster_batch_build(const int32_t *parent_rowptr, const int3
                                             overflow_flag);
     batch_mark_kernel<<<g_thread, tb, 0, s>>>(nids, n_b, node_map, 0);
     count_launch(2);
+    return last_error();
+}
+
+static size_t align16(size_t x) { return (x + 15) / 16 * 16; }
+
+extern "C" size_t gist_cluster_batch_build_v2_workspace_bytes(int32_t n_b, int64_t max_chunks) {
+    if (n_b < 0 || max_chunks < 0) return 0;
+    return align16(((size_t)n_b + 1) * 4) + align16((size_t)max_chunks * 4) + align16(((size_t)max_chunks + 1) * 4) +
+           align16(gist_scan_workspace_bytes(n_b));
+}
+
+extern "C" int gist_cluster_batch_build_v2(const int32_t *parent_rowptr, const int32_t *parent_col,
+                                           int32_t n_parent, const int64_t *nids, int32_t n_b,
+                                           int32_t *node_map, int32_t *out_rowptr, int32_t *out_col,
+                                           int64_t col_capacity, float *out_inv_deg, int32_t *overflow_flag,
+                                           int64_t max_chunks, void *workspace, size_t workspace_bytes,
+                                           gist_stream_t stream) {
+    if (n_parent < 0 || n_b < 0 || col_capacity < 0 || max_chunks < 0 || max_chunks > 0x3fffffffLL) return GIST_ERR_BADARG;
+    if (!out_rowptr) return GIST_ERR_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_b == 0) {
+        cudaError_t e = cudaMemsetAsync(out_rowptr, 0, sizeof(int32_t), s);
+        return e == cudaSuccess ? GIST_OK : (int)e;
+    }
+    if (!parent_rowptr || !nids || !node_map) return GIST_ERR_BADARG;
+    if (col_capacity > 0 && !out_col) return GIST_ERR_BADARG;
+    if (!workspace || !aligned(workspace, 16) ||
+        workspace_bytes < gist_cluster_batch_build_v2_workspace_bytes(n_b, max_chunks))
+        return GIST_ERR_WORKSPACE;
+    char *w = reinterpret_cast<char *>(workspace);
+    int32_t *chunk_ptr = reinterpret_cast<int32_t *>(w);
+    w += align16(((size_t)n_b + 1) * 4);
+    int32_t *chunk_row = reinterpret_cast<int32_t *>(w);
+    w += align16((size_t)max_chunks * 4);
+    int32_t *chunk_cnt = reinterpret_cast<int32_t *>(w);
+    w += align16(((size_t)max_chunks + 1) * 4);
+    void *scan_ws = w;
+    const size_t scan_ws_bytes = gist_scan_workspace_bytes(n_b);
+    const int tb = 256;
+    const int g_thread = (n_b + tb - 1) / tb;
+    int64_t g_chunk = (max_chunks + 7) / 8;
+    if (g_chunk > 8LL * kNumSMs) g_chunk = 8LL * kNumSMs;
+    if (g_chunk < 1) g_chunk = 1;
+    batch_mark_chunks_kernel<<<g_thread, tb, 0, s>>>(nids, n_b, node_map, parent_rowptr, chunk_ptr);
+    count_launch();
+    int st = scan_launch(chunk_ptr, n_b, chunk_ptr, scan_ws, scan_ws_bytes, s);
+    if (st != GIST_OK) return st;
+    chunk_count_kernel<<<(unsigned)g_chunk, tb, 0, s>>>(parent_rowptr, parent_col, nids, n_b, node_map, chunk_ptr,
+                                                       (int32_t)max_chunks, chunk_row, chunk_cnt);
+    chunk_scan_rows_kernel<<<1, kChunkScanThreads, 0, s>>>(chunk_ptr, n_b, (int32_t)max_chunks, chunk_cnt, out_rowptr,
+                                                           out_inv_deg, col_capacity, overflow_flag);
+    chunk_fill_kernel<<<(unsigned)g_chunk, tb, 0, s>>>(parent_rowptr, parent_col, nids, n_b, node_map, chunk_ptr,
+                                                      (int32_t)max_chunks, chunk_row, chunk_cnt, out_col, col_capacity);
+    batch_mark_kernel<<<g_thread, tb, 0, s>>>(nids, n_b, node_map, 0);
+    count_launch(4);
     return last_error();
 }
 

@@ -23,6 +23,12 @@ NID = '_ID'
 
 # A/B switch for the segment-balanced cluster-batch SpMM (GIST_SPMM_SEG=0: one row per group)
 SEG_ENABLED = os.environ.get('GIST_SPMM_SEG', '1') != '0'
+# K3 variant: 'rows' = one warp per batch row (gist_cluster_batch_build), 'chunks' = one warp per 128-edge chunk of
+# the batch's parent rows (gist_cluster_batch_build_v2; same CSR).  Chunks need a bound on the batch's parent-degree
+# sum (``walk_capacity``; it covers in-edge rows, so the CSC pass of a directed graph keeps the row kernel); very
+# large node sets keep the row kernel too (the chunk counts are scanned by one CTA).
+BUILDER = os.environ.get('GIST_BUILDER', 'rows')
+MAX_CHUNKS_V2 = 1 << 17
 
 class GistError(RuntimeError):
     """Counterpart of dgl.DGLError."""
@@ -240,8 +246,12 @@ class GistGraph:
             self._cache['node_map'] = torch.full((self._n,), -1, dtype=torch.int32, device=self.device)
         return self._cache['node_map']
 
-    def subgraph(self, nids, col_capacity=None, gather_ndata=True, ndata_keys=None, out=None):
+    def subgraph(self, nids, col_capacity=None, gather_ndata=True, ndata_keys=None, out=None, walk_capacity=None):
         """Node-induced subgraph built on the device (K3).  new node i <-> nids[i].
+
+        ``col_capacity``: capacity of the edge array (default: the ids' parent-degree sum, one sync).
+        ``walk_capacity``: a bound on the ids' parent-degree sum, if the caller has one (ClusterIter: the sum
+        of the parts' degree sums) — what the chunked builder sizes its chunk arrays from.
 
         ``out``: a subgraph previously returned for the same number of ids, capacity and
         ndata keys; its buffers are overwritten in place (fixed addresses: what the pipelined
@@ -260,6 +270,7 @@ class GistGraph:
         if col_capacity is None:
             deg = (self.rowptr[1:] - self.rowptr[:-1])
             col_capacity = int(deg[nids.clamp_min(0)].sum().item()) if n_b else 0
+            walk_capacity = col_capacity
 
         if out is not None:
             assert out.number_of_nodes() == n_b and out.col_buffer.shape[0] == max(col_capacity, 1)
@@ -272,6 +283,16 @@ class GistGraph:
                 rowptr = torch.empty(n_b + 1, dtype=torch.int32, device=dev)
                 col = torch.empty(max(col_capacity, 1), dtype=torch.int32, device=dev)
                 inv = torch.empty(max(n_b, 1), dtype=torch.float32, device=dev) if want_inv else None
+            max_chunks = (walk_capacity // 128 + n_b + 1) if walk_capacity is not None else None
+            if (BUILDER == 'chunks' and max_chunks is not None and max_chunks <= MAX_CHUNKS_V2 and n_b > 0
+                    and prow is self.rowptr):      # the in-edge pass: the rows walk_capacity bounds
+                wsb = lib.gist_cluster_batch_build_v2_workspace_bytes(n_b, max_chunks)
+                ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+                _lib.check(lib.gist_cluster_batch_build_v2(
+                    _lib.ptr(prow), _lib.ptr(pcol), self._n, _lib.ptr(nids), n_b, _lib.ptr(self._node_map()),
+                    _lib.ptr(rowptr), _lib.ptr(col), col_capacity, _lib.ptr(inv), None, max_chunks,
+                    _lib.ptr(ws), wsb, _lib.stream_ptr(dev)), 'cluster_batch_build_v2')
+                return rowptr, col, inv
             wsb = lib.gist_scan_workspace_bytes(n_b)
             ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=dev)
             _lib.check(lib.gist_cluster_batch_build(

@@ -152,7 +152,7 @@ class GraphedClusterTrainer:
     # ------------------------------------------------------------------ step --
     def _build(self, nids, out=None):
         prev = out._cache.get(SAGE_PRE0) if out is not None else None
-        sg = self.it.g.subgraph(nids, col_capacity=self.cap, ndata_keys=_KEYS, out=out)
+        sg = self.it.g.subgraph(nids, col_capacity=self.cap, ndata_keys=_KEYS, out=out, walk_capacity=self.cap)
         sg.seg_schedule()                   # segment schedule of the batch: built here, used by every SpMM
         sg.seg_schedule(transpose=True)
         if self.pre_aggregate:

@@ -291,6 +291,18 @@ class DistributedGNNWrapper(torch.nn.Module):
             else:
                 self.sub_model.layers[L].linear.bias.data = self.base_model.layers[L].linear.bias.data.clone()
 
+    @staticmethod
+    def _stream_merge(dst, w, ridx, cidx):
+        """Row-streaming merge for this slice?  GIST_MERGE=rows / scatter forces it on (where it applies) / off;
+        default: slices of >= 2^20 elements landing on >= 1/16 of the columns of rows of >= 32 KB — the sites'
+        row sets are disjoint (create_partition splits a permutation), which the kernel relies on."""
+        mode = os.environ.get('GIST_MERGE', 'auto')
+        if mode == 'scatter' or not ops.slice_scatter_rows_ok(dst, ridx, cidx):
+            return False
+        if mode == 'rows':
+            return True
+        return w.numel() >= (1 << 20) and dst.shape[1] >= 8192 and 16 * cidx.numel() >= dst.shape[1]
+
     def _merge(self, gathered, parts):
         """Scatter every site's packed slices into the local full-model replica.  ``gathered``: [m, numel]
         tensor or a list of m flat views (peer buffers)."""
@@ -299,7 +311,7 @@ class DistributedGNNWrapper(torch.nn.Module):
         shapes = [(tuple(lyr.linear.weight.shape), tuple(lyr.linear.bias.shape))
                   for lyr in self.sub_model.layers]
         last_bias = None
-        jobs = []
+        jobs, row_jobs = [], []
         for site in range(m):
             off = 0
             row = gathered[site]
@@ -309,7 +321,12 @@ class DistributedGNNWrapper(torch.nn.Module):
                 b = row[off:off + bn]; off += bn
                 ridx, cidx = self._slice_for(l, site, parts)
                 base = self.base_model.layers[l].linear
-                if self._cuda_slices:
+                if self._cuda_slices and self._stream_merge(base.weight.data, w, ridx, cidx):
+                    # ultra-wide layer: whole sectors of the site's rows in ascending order (one launch for all
+                    # sites) instead of one 32-byte sector per scattered element
+                    inv = ops.index_invert(cidx, base.weight.shape[1])
+                    row_jobs.append((w, ridx, inv, base.weight.data))
+                elif self._cuda_slices:
                     jobs.append((w, ridx, cidx, base.weight.data))
                 else:
                     self._scatter_(base.weight.data, w, ridx, cidx)
@@ -321,4 +338,6 @@ class DistributedGNNWrapper(torch.nn.Module):
                     self._scatter_(base.bias.data, b, None, ridx)
         if jobs:
             ops.slice_multi(jobs, scatter=True)          # all sites x all tensors: one launch
+        if row_jobs:
+            ops.slice_scatter_rows_(row_jobs)
         self.base_model.layers[L].linear.bias.data = last_bias / m

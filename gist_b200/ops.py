@@ -292,6 +292,45 @@ def slice_multi(jobs, scatter):
     check(_lib.load().gist_slice_multi_f32(1 if scatter else 0, len(jobs), arr, stream_ptr(dev)), 'slice_multi_f32')
 
 
+def index_invert(idx, size, out=None):
+    """inv[size] int32 with inv[idx[k]] = k and -1 elsewhere (gist_index_invert_i32)."""
+    require_cuda(idx, out)
+    assert idx.dtype == torch.int64 and idx.is_contiguous()
+    if out is None:
+        out = torch.empty(size, dtype=torch.int32, device=idx.device)
+    assert out.dtype == torch.int32 and out.numel() == size and out.is_contiguous()
+    check(_lib.load().gist_index_invert_i32(ptr(idx), idx.numel(), ptr(out), size, stream_ptr(idx.device)),
+          'index_invert_i32')
+    return out
+
+
+def slice_scatter_rows_ok(dst, ridx, cidx):
+    """Can gist_slice_scatter_rows_f32 serve this destination / slice (a 2-D slice of whole-sector rows)?"""
+    return (dst.dim() == 2 and dst.is_cuda and dst.dtype == torch.float32 and dst.stride(1) == 1
+            and dst.data_ptr() % 32 == 0 and dst.stride(0) % 8 == 0 and ridx is not None and cidx is not None)
+
+
+def slice_scatter_rows_(jobs):
+    """dst[ridx[r], cidx[c]] = src[r, c] for jobs (src, ridx, inv_col, dst) whose row sets are disjoint per
+    destination, as ONE row-streaming launch (gist_slice_scatter_rows_f32): whole 32-byte sectors in ascending
+    address order instead of 4-byte scatters.  ``inv_col`` = index_invert(cidx, dst.shape[1])."""
+    if not jobs:
+        return
+    arr = (_lib.SliceRowsJob * len(jobs))()
+    dev = None
+    for k, (src, ridx, inv, dst) in enumerate(jobs):
+        require_cuda(src, ridx, inv, dst)
+        assert src.dim() == 2 and dst.dim() == 2 and src.dtype == torch.float32 and dst.dtype == torch.float32
+        assert (src.shape[1] <= 1 or src.stride(1) == 1) and dst.stride(1) == 1
+        assert inv.dtype == torch.int32 and inv.numel() == dst.shape[1] and inv.is_contiguous()
+        assert ridx is None or (ridx.dtype == torch.int64 and ridx.is_contiguous() and ridx.numel() == src.shape[0])
+        arr[k] = _lib.SliceRowsJob(src.data_ptr(), _ld(src), ridx.data_ptr() if ridx is not None else None, src.shape[0],
+                                   inv.data_ptr(), dst.data_ptr(), _ld(dst), dst.shape[1])
+        dev = dst.device
+        note_raw_write(dst)
+    check(_lib.load().gist_slice_scatter_rows_f32(len(jobs), arr, stream_ptr(dev)), 'slice_scatter_rows_f32')
+
+
 # --------------------------------------------------------------------------
 # autograd
 # --------------------------------------------------------------------------

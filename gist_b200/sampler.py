@@ -182,7 +182,7 @@ class ClusterIter(object):
                     self._pin_ev[slot] = torch.cuda.Event()
                 self._pin_ev[slot].record()
                 self.h2d_bytes += n_b * 8
-            result = self.g.subgraph(nids, col_capacity=cap)
+            result = self.g.subgraph(nids, col_capacity=cap, walk_capacity=cap)
             self.n += 1
             return result
         else:

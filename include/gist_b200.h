@@ -228,6 +228,22 @@ int gist_cluster_batch_build(const int32_t *parent_rowptr, const int32_t *parent
                              int64_t col_capacity, float *out_inv_deg, int32_t *overflow_flag,
                              void *scan_ws, size_t scan_ws_bytes, gist_stream_t stream);
 
+/* gist_cluster_batch_build with the parent rows cut into chunks of 128 edges and one warp per CHUNK
+ * instead of one warp per row (hub rows: one CTA): the same CSR, bit for bit, but the two walks over
+ * the batch's parent rows (~1 M edges for a Reddit-shape batch) are one round of loads per warp on a
+ * chip-wide grid instead of a launch as long as its unluckiest CTA.
+ * max_chunks : capacity of the chunk arrays, >= sum_i ceil(parent_degree(nids[i]) / 128); any bound W
+ *              on the batch's parent-degree sum gives W / 128 + n_b.  More chunks than that set
+ *              *overflow_flag (if given) and the result is truncated.
+ * workspace  : gist_cluster_batch_build_v2_workspace_bytes(n_b, max_chunks) bytes, 16-byte aligned.
+ * Replaces the same reference calls as gist_cluster_batch_build. */
+size_t gist_cluster_batch_build_v2_workspace_bytes(int32_t n_b, int64_t max_chunks);
+int gist_cluster_batch_build_v2(const int32_t *parent_rowptr, const int32_t *parent_col, int32_t n_parent,
+                                const int64_t *nids, int32_t n_b, int32_t *node_map, int32_t *out_rowptr,
+                                int32_t *out_col, int64_t col_capacity, float *out_inv_deg,
+                                int32_t *overflow_flag, int64_t max_chunks, void *workspace,
+                                size_t workspace_bytes, gist_stream_t stream);
+
 /* dst[i, :] = src[idx[i], :] for rows of row_bytes bytes (features, labels,
  * masks — the ndata row-gather of DGLGraph.subgraph). Strides in bytes. */
 int gist_gather_rows(const void *src, int64_t src_stride_bytes, const int64_t *idx, int64_t n,
@@ -269,6 +285,31 @@ typedef struct gist_slice_job {
     int64_t ld_dst;
 } gist_slice_job_t;
 int gist_slice_multi_f32(int32_t scatter, int32_t n_jobs, const gist_slice_job_t *jobs, gist_stream_t stream);
+
+/* The merge of the ULTRA-WIDE layers (sync_model, cluster_gcn_ist_distrib.py:285-367; hidden 32768 split
+ * 8 ways: every site's [4096, 8192] slice goes to random columns of its 4096 rows of a [32768, 65536]
+ * replica): as 4-byte scatters that is one 32-byte sector per element, touched in random order over an
+ * 8.6 GB matrix (measured: 11 ms at ~1 TB/s of DRAM traffic).  Here a CTA owns a few destination ROWS and
+ * walks them left to right: per 32-byte sector it looks up which source column (if any) lands on each of
+ * its 8 elements (inv_col), skips sectors nothing lands on, and otherwise reads the sector, patches it and
+ * writes it back whole — the same bytes in ascending address order, whole sectors only.
+ *   dst[ridx[r], cc] = src[r, inv_col[cc]]   for every cc with inv_col[cc] >= 0       (ridx NULL = identity)
+ * inv_col: int32 [dst_cols], the inverse of the slice's column index (gist_index_invert_i32), -1 where no
+ * source column lands.  Jobs that share a destination must own DISJOINT ROWS (the sites' output-dimension
+ * partitions are): sectors are rewritten whole.  dst rows 32-byte aligned (dst, ld_dst % 8 == 0). */
+typedef struct gist_slice_rows_job {
+    const float *src;       /* [n_rows, ld_src] */
+    int64_t ld_src;
+    const int64_t *ridx;    /* [n_rows] destination rows, or NULL */
+    int64_t n_rows;
+    const int32_t *inv_col; /* [dst_cols] */
+    float *dst;
+    int64_t ld_dst;
+    int64_t dst_cols;
+} gist_slice_rows_job_t;
+int gist_slice_scatter_rows_f32(int32_t n_jobs, const gist_slice_rows_job_t *jobs, gist_stream_t stream);
+/* inv[0 .. size) = -1, then inv[idx[k]] = k for k in [0, n) (idx unique, in range). */
+int gist_index_invert_i32(const int64_t *idx, int64_t n, int32_t *inv, int64_t size, gist_stream_t stream);
 
 
 /* ------------------------------------------------------------------------
