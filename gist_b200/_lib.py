@@ -74,6 +74,7 @@ SIGNATURES = {
                                             _P, _P, _P, _P, _I64, _P, _I64, _U32, _P, _P]),
     'gist_spmm_schedule_workspace_bytes': (_SZ, [_I32]),
     'gist_spmm_schedule_build': (ctypes.c_int, [_P, _I32, _I32, _P, _P, _I64, _P, _SZ, _P]),
+    'gist_spmm_schedule_build_meta': (ctypes.c_int, [_P, _I32, _I32, _P, _P, _P, _I64, _P, _SZ, _P]),
     'gist_gemm_has_inkernel_splitk': (ctypes.c_int, []),
     'gist_gat_scores_heads_f32': (ctypes.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P, _P]),
     'gist_gat_aggregate_heads_f32': (ctypes.c_int, [_P, _P, _I32, _P, _I64, _I32, _I32, _P, _F32, _P, _I64, _P, _P]),
@@ -106,6 +107,7 @@ GEMM_RELU, GEMM_NO_SPLITK, GEMM_TILE_N64, GEMM_TILE_N128, GEMM_TILE_N256 = 1, 2,
 GEMM_BACKGROUND = 32
 GEMM_K_MAJOR, GEMM_MN_MAJOR = 0, 1
 ACT_RELU = 1
+SPMM_SCHED_PREFETCH = 1
 
 
 
@@ -119,7 +121,7 @@ class SpmmSchedule(ctypes.Structure):
     """gist_spmm_schedule_t"""
     _fields_ = [('seg_ptr', ctypes.c_void_p), ('seg_row', ctypes.c_void_p), ('seg_len', ctypes.c_int32),
                 ('max_segments', ctypes.c_int64), ('counters', ctypes.c_void_p), ('workspace', ctypes.c_void_p),
-                ('ld_workspace', ctypes.c_int64)]
+                ('ld_workspace', ctypes.c_int64), ('seg_meta', ctypes.c_void_p), ('flags', ctypes.c_uint32)]
 
 
 class SpmmEx(ctypes.Structure):
@@ -139,7 +141,8 @@ class SliceJob(ctypes.Structure):
 class SliceRowsJob(ctypes.Structure):
     """gist_slice_rows_job_t"""
     _fields_ = [('src', ctypes.c_void_p), ('ld_src', ctypes.c_int64), ('ridx', ctypes.c_void_p), ('n_rows', ctypes.c_int64),
-                ('inv_col', ctypes.c_void_p), ('dst', ctypes.c_void_p), ('ld_dst', ctypes.c_int64), ('dst_cols', ctypes.c_int64)]
+                ('n_cols', ctypes.c_int64), ('inv_col', ctypes.c_void_p), ('dst', ctypes.c_void_p), ('ld_dst', ctypes.c_int64),
+                ('dst_cols', ctypes.c_int64)]
 
 
 class GemmEx(ctypes.Structure):

@@ -1,6 +1,8 @@
 // K3 (cluster-batch builder), exclusive scan, row gather and K5 (GIST slice
 // gather / scatter).  All HBM/L2-bound integer and copy work: coalesced index
 // streams, one warp per adjacency row, order-preserving ballot compaction.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gist {
@@ -519,7 +521,8 @@ __global__ void __launch_bounds__(256) slice_multi_kernel(const __grid_constant_
 // Row-streaming merge (gist_slice_scatter_rows_f32): a CTA owns kRowsPerCta destination rows of one job and
 // walks them left to right, one 32-byte sector (8 floats) per thread per step; the inverse column map of a
 // sector is loaded once and serves all of the CTA's rows.
-constexpr int kRowsPerCta = 4;
+constexpr int kRowsL2 = 4, kRowsStaged = 2;
+constexpr size_t kStageSmemMax = 72 * 1024;     // per CTA: three staged CTAs per SM
 struct SliceRowsJobDev {
     const float *src;
     float *dst;
@@ -527,14 +530,20 @@ struct SliceRowsJobDev {
     const int32_t *inv;
     int64_t ld_src, ld_dst;
     int32_t n_rows, dst_cols;
-    int32_t block0, pad;
+    int32_t block0, n_cols;
 };
 struct SliceRowsJobsDev {
     SliceRowsJobDev j[kSliceMaxJobs];
     int32_t n_jobs;
 };
 
+// STAGED: the CTA's source rows are copied into shared memory first (coalesced) and patched in from there.
+// Every source element is used once, at a random moment of the CTA's sweep over its destination rows, so
+// without staging a source sector has to survive in L2 for the CTA's whole life next to the destination
+// stream — at the ultra-wide size the resident CTAs' source rows alone are ~110 MB.
+template <int ROWS, bool STAGED>
 __global__ void __launch_bounds__(256) slice_scatter_rows_kernel(const __grid_constant__ SliceRowsJobsDev a) {
+    extern __shared__ float s_src[];        // STAGED: [ROWS][n_cols]
     int lo = 0, hi = a.n_jobs - 1;          // last job whose block0 <= blockIdx.x
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -542,6 +551,7 @@ __global__ void __launch_bounds__(256) slice_scatter_rows_kernel(const __grid_co
         else hi = mid - 1;
     }
     const SliceRowsJobDev &J = a.j[lo];
+    constexpr int kRowsPerCta = ROWS;
     const int r0 = ((int)blockIdx.x - J.block0) * kRowsPerCta;
     const float *srow[kRowsPerCta];
     float *drow[kRowsPerCta];
@@ -553,6 +563,20 @@ __global__ void __launch_bounds__(256) slice_scatter_rows_kernel(const __grid_co
         drow[k] = J.dst + rr * J.ld_dst;
     }
     const int n_live = min(kRowsPerCta, J.n_rows - r0);
+    if constexpr (STAGED) {
+#pragma unroll
+        for (int k = 0; k < kRowsPerCta; ++k) {
+            float *sk = s_src + (size_t)k * J.n_cols;
+            if ((J.n_cols & 3) == 0 && (reinterpret_cast<uintptr_t>(srow[k]) & 15) == 0) {
+                for (int c = threadIdx.x * 4; c < J.n_cols; c += 256 * 4)
+                    *reinterpret_cast<float4 *>(sk + c) = *reinterpret_cast<const float4 *>(srow[k] + c);
+            } else {
+                for (int c = threadIdx.x; c < J.n_cols; c += 256) sk[c] = srow[k][c];
+            }
+            srow[k] = sk;
+        }
+        __syncthreads();
+    }
     for (int c0 = threadIdx.x * 8; c0 < J.dst_cols; c0 += 256 * 8) {
         int iv[8];
         if (c0 + 8 <= J.dst_cols) {
@@ -664,25 +688,44 @@ extern "C" int gist_slice_scatter_rows_f32(int32_t n_jobs, const gist_slice_rows
     while (done < n_jobs) {
         SliceRowsJobsDev a;
         a.n_jobs = 0;
-        int64_t blocks = 0;
+        int64_t blocks = 0, max_cols = 0;
         for (; done < n_jobs && a.n_jobs < kSliceMaxJobs; ++done) {
             const gist_slice_rows_job_t &j = jobs[done];
-            if (j.n_rows < 0 || j.dst_cols < 0) return GIST_ERR_BADARG;
-            if (j.n_rows == 0 || j.dst_cols == 0) continue;
+            if (j.n_rows < 0 || j.dst_cols < 0 || j.n_cols < 0) return GIST_ERR_BADARG;
+            if (j.n_rows == 0 || j.dst_cols == 0 || j.n_cols == 0) continue;
             if (!j.src || !j.dst || !j.inv_col || j.n_rows > 0x7fffffffLL || j.dst_cols > 0x7fffffffLL ||
-                j.ld_dst < j.dst_cols)
+                j.n_cols > 0x7fffffffLL || j.ld_dst < j.dst_cols || j.ld_src < j.n_cols)
                 return GIST_ERR_BADARG;
             if (!aligned(j.dst, 32) || j.ld_dst % 8 || !aligned(j.inv_col, 16)) return GIST_ERR_ALIGN;
             SliceRowsJobDev &d = a.j[a.n_jobs++];
             d.src = j.src; d.dst = j.dst; d.ridx = j.ridx; d.inv = j.inv_col;
             d.ld_src = j.ld_src; d.ld_dst = j.ld_dst;
             d.n_rows = (int32_t)j.n_rows; d.dst_cols = (int32_t)j.dst_cols;
-            d.block0 = (int32_t)blocks; d.pad = 0;
-            blocks += (j.n_rows + kRowsPerCta - 1) / kRowsPerCta;
-            if (blocks > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
+            d.n_cols = (int32_t)j.n_cols;
+            if (j.n_cols > max_cols) max_cols = j.n_cols;
         }
         if (a.n_jobs == 0) continue;
-        slice_scatter_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
+        // source rows staged in shared memory when two of them fit a third of an SM's shared memory
+        const size_t smem = (size_t)kRowsStaged * (size_t)max_cols * sizeof(float);
+        const bool staged = smem <= kStageSmemMax && !getenv("GIST_MERGE_NO_STAGE");
+        const int rows_per_cta = staged ? kRowsStaged : kRowsL2;
+        for (int k = 0; k < a.n_jobs; ++k) {
+            a.j[k].block0 = (int32_t)blocks;
+            blocks += (a.j[k].n_rows + rows_per_cta - 1) / rows_per_cta;
+            if (blocks > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
+        }
+        if (staged) {
+            static bool configured = false;
+            if (!configured) {
+                cudaError_t e = cudaFuncSetAttribute(slice_scatter_rows_kernel<kRowsStaged, true>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageSmemMax);
+                if (e != cudaSuccess) return (int)e;
+                configured = true;
+            }
+            slice_scatter_rows_kernel<kRowsStaged, true><<<(unsigned)blocks, 256, smem, s>>>(a);
+        } else {
+            slice_scatter_rows_kernel<kRowsL2, false><<<(unsigned)blocks, 256, 0, s>>>(a);
+        }
         count_launch();
         const int st = last_error();
         if (st != GIST_OK) return st;

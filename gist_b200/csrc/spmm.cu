@@ -67,6 +67,8 @@ struct SpmmParams {
     int32_t seg_blocks;          // CTAs per feature chunk
     uint32_t *seg_count;         // [chunks][n_dst] arrival counters, zero between launches
     float *seg_ws;               // [#segments][ld_ws] partial sums of multi-segment rows
+    const int4 *seg_meta;        // optional [#segments] {row, first edge, first segment of the row, (edges << 20) | segments of the row}
+    uint32_t seg_flags;          // GIST_SPMM_SCHED_PREFETCH: request the next work item before processing the current one
     int32_t ld_ws;
 };
 
@@ -477,23 +479,30 @@ __global__ void __launch_bounds__(256, SEG_CTAS) spmm_seg_kernel(const __grid_co
     // queue on one address (same-address atomics are served one at a time by their L2 slice) —
     // and the queue hands out items W, W + 1, ...  A fetch takes SEG_BATCH consecutive items
     // (1: measured 4 -> 40 us, 16 -> 108 us vs 23 us; the tail of a batch outweighs the atomics).
+    static_assert(SEG_BATCH == 1, "one item per queue fetch (larger batches measured slower)");
     const unsigned q_total = total > n_warps ? total - n_warps : 0u;                     // items behind the queue
-    const unsigned q_total_b = (q_total + SEG_BATCH - 1u) / SEG_BATCH * SEG_BATCH;
-    unsigned work = blockIdx.x * 8u + (threadIdx.x >> 5), work_end = work + 1u;
-    if (work >= total) work_end = work;                  // fewer items than warps: straight to the failing fetch
+    unsigned work = blockIdx.x * 8u + (threadIdx.x >> 5);
+    bool have = work < total;                            // fewer items than warps: straight to the failing fetch
+    // GIST_SPMM_SCHED_PREFETCH: the fetch of the NEXT item is issued before the current one is processed —
+    // the atomic's round trip (the queue head lives in one L2 slice) hides behind a segment of gathers
+    // instead of sitting between two items; every warp still makes exactly one failing fetch
+    const bool prefetch = (p.seg_flags & GIST_SPMM_SCHED_PREFETCH) != 0u;
+    unsigned pre = 0u;
+    if (prefetch && lane == 0) pre = atomicAdd(head, 1u);
     while (true) {
-        if (work == work_end) {
-            if (lane == 0) work = atomicAdd(head, (unsigned)SEG_BATCH);
-            work = __shfl_sync(0xffffffffu, work, 0);
+        if (!have) {
+            if (!prefetch && lane == 0) pre = atomicAdd(head, 1u);
+            work = __shfl_sync(0xffffffffu, pre, 0);
             if (work >= q_total) {
                 // W failing fetches follow the last successful one; the last of them re-arms the head
-                if (work == q_total_b + (n_warps - 1u) * SEG_BATCH && lane == 0) *head = 0u;
+                if (work == q_total + (n_warps - 1u) && lane == 0) *head = 0u;
                 break;
             }
-            work_end = min(work + SEG_BATCH, q_total) + n_warps;
             work += n_warps;
+            if (prefetch && lane == 0) pre = atomicAdd(head, 1u);
         }
-        const unsigned item = work++;
+        have = false;
+        const unsigned item = work;
         const int chunk = (int)item / wipc;
         const int seg = ((int)item - chunk * wipc) * GPW + grp;
         if (seg >= n_seg) continue;                        // whole group skips together
@@ -511,12 +520,20 @@ __global__ void __launch_bounds__(256, SEG_CTAS) spmm_seg_kernel(const __grid_co
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[k][i] = 0.f;
 
-        const int v = __ldg(p.seg_row + seg);
-        const int s0 = __ldg(p.seg_ptr + v);
-        const int nseg = __ldg(p.seg_ptr + v + 1) - s0;
-        const int rs = __ldg(p.rowptr + v), re = __ldg(p.rowptr + v + 1);
-        const int eb = min(re, rs + (seg - s0) * p.seg_len);
-        const int ee = min(re, eb + p.seg_len);
+        int v, s0, nseg, eb, ee;
+        if (p.seg_meta) {       // one 16-byte record instead of seg_row -> (seg_ptr, rowptr): one round trip less per item
+            const int4 mt = __ldg(p.seg_meta + seg);
+            v = mt.x; eb = mt.y; s0 = mt.z;
+            nseg = mt.w & 0xFFFFF;
+            ee = eb + (int)((unsigned)mt.w >> 20);
+        } else {
+            v = __ldg(p.seg_row + seg);
+            s0 = __ldg(p.seg_ptr + v);
+            nseg = __ldg(p.seg_ptr + v + 1) - s0;
+            const int rs = __ldg(p.rowptr + v), re = __ldg(p.rowptr + v + 1);
+            eb = min(re, rs + (seg - s0) * p.seg_len);
+            ee = min(re, eb + p.seg_len);
+        }
         gather_range<VEC, LPR, VPL, HAS_SS>(p, eb, ee, lg, lane0, gmask, c, cv, acc);
         if (nseg == 1) {
             epilogue<VEC, VPL, EX>(p, v, c, cv, acc);
@@ -829,11 +846,21 @@ __global__ void seg_count_kernel(const int32_t *__restrict__ rowptr, int32_t n, 
 }
 
 __global__ void seg_fill_kernel(const int32_t *__restrict__ seg_ptr, int32_t n, int64_t capacity,
-                                int32_t *__restrict__ seg_row) {
+                                int32_t *__restrict__ seg_row, const int32_t *__restrict__ rowptr, int32_t seg_len,
+                                int4 *__restrict__ seg_meta) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     const int s0 = seg_ptr[v], s1 = seg_ptr[v + 1];
     for (int s = s0; s < s1 && s < capacity; ++s) seg_row[s] = v;
+    if (seg_meta) {
+        const int rs = rowptr[v], re = rowptr[v + 1];
+        const int nseg = s1 - s0;
+        for (int s = s0; s < s1 && s < capacity; ++s) {
+            const int eb = min(re, rs + (s - s0) * seg_len);
+            const int len = min(re, eb + seg_len) - eb;
+            seg_meta[s] = make_int4(v, eb, s0, (int)(((unsigned)len << 20) | (unsigned)nseg));
+        }
+    }
 }
 
 template <int VEC, int LPR, int VPL>
@@ -992,6 +1019,8 @@ extern "C" int gist_spmm_csr_ex_f32(const int32_t *rowptr, const int32_t *col, i
     p.seg_len = p.seg_blocks = p.ld_ws = 0;
     p.seg_count = nullptr;
     p.seg_ws = nullptr;
+    p.seg_meta = nullptr;
+    p.seg_flags = 0u;
     const gist_spmm_schedule_t *sch = ex ? ex->schedule : nullptr;
     if (sch) {
         if (!sch->seg_ptr || !sch->seg_row || !sch->counters || !sch->workspace || sch->seg_len <= 0 ||
@@ -1000,6 +1029,9 @@ extern "C" int gist_spmm_csr_ex_f32(const int32_t *rowptr, const int32_t *col, i
         if (sch->ld_workspace > 0x7fffffffLL) return GIST_ERR_UNSUPPORTED;
         p.seg_ptr = sch->seg_ptr; p.seg_row = sch->seg_row; p.seg_len = sch->seg_len;
         p.seg_count = sch->counters; p.seg_ws = sch->workspace; p.ld_ws = (int32_t)sch->ld_workspace;
+        if (sch->seg_meta && !aligned(sch->seg_meta, 16)) return GIST_ERR_ALIGN;
+        p.seg_meta = reinterpret_cast<const int4 *>(sch->seg_meta);
+        p.seg_flags = sch->flags;
         p.heavy_deg = 0x7fffffff;
         cudaStream_t s2 = (cudaStream_t)stream;
         // slab kernel: the whole batch's column slab in shared memory (needs 128-bit alignment everywhere
@@ -1055,7 +1087,16 @@ extern "C" size_t gist_spmm_schedule_workspace_bytes(int32_t n) { return gist_sc
 extern "C" int gist_spmm_schedule_build(const int32_t *rowptr, int32_t n, int32_t seg_len, int32_t *seg_ptr,
                                         int32_t *seg_row, int64_t max_segments, void *scan_ws,
                                         size_t scan_ws_bytes, gist_stream_t stream) {
+    return gist_spmm_schedule_build_meta(rowptr, n, seg_len, seg_ptr, seg_row, nullptr, max_segments, scan_ws,
+                                         scan_ws_bytes, stream);
+}
+
+extern "C" int gist_spmm_schedule_build_meta(const int32_t *rowptr, int32_t n, int32_t seg_len, int32_t *seg_ptr,
+                                             int32_t *seg_row, int32_t *seg_meta, int64_t max_segments,
+                                             void *scan_ws, size_t scan_ws_bytes, gist_stream_t stream) {
     if (n < 0 || seg_len <= 0 || max_segments < n) return GIST_ERR_BADARG;
+    // the packed record holds <= 4095 edges and < 2^20 segments per row
+    if (seg_meta && (seg_len > 4095 || max_segments >= (1LL << 20) || !aligned(seg_meta, 16))) return GIST_ERR_UNSUPPORTED;
     if (!seg_ptr) return GIST_ERR_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
     if (n == 0) {
@@ -1068,7 +1109,8 @@ extern "C" int gist_spmm_schedule_build(const int32_t *rowptr, int32_t n, int32_
     count_launch();
     int st = gist_exclusive_scan_i32(seg_ptr, n, seg_ptr, scan_ws, scan_ws_bytes, stream);   // in place
     if (st != GIST_OK) return st;
-    seg_fill_kernel<<<(n + 255) / 256, 256, 0, s>>>(seg_ptr, n, max_segments, seg_row);
+    seg_fill_kernel<<<(n + 255) / 256, 256, 0, s>>>(seg_ptr, n, max_segments, seg_row, rowptr, seg_len,
+                                                    reinterpret_cast<int4 *>(seg_meta));
     count_launch();
     return last_error();
 }

@@ -27,7 +27,7 @@ SEG_ENABLED = os.environ.get('GIST_SPMM_SEG', '1') != '0'
 # the batch's parent rows (gist_cluster_batch_build_v2; same CSR).  Chunks need a bound on the batch's parent-degree
 # sum (``walk_capacity``; it covers in-edge rows, so the CSC pass of a directed graph keeps the row kernel); very
 # large node sets keep the row kernel too (the chunk counts are scanned by one CTA).
-BUILDER = os.environ.get('GIST_BUILDER', 'rows')
+BUILDER = os.environ.get('GIST_BUILDER', 'chunks')
 MAX_CHUNKS_V2 = 1 << 17
 
 class GistError(RuntimeError):

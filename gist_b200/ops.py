@@ -68,7 +68,8 @@ def spmm_raw(rowptr, col, n_dst, n_src, X, out, *, src_scale=None, dst_scale=Non
             ws = torch.empty((schedule.max_segments, ld_ws), dtype=torch.float32, device=X.device)
             cnt = schedule.counters(max(1, (d + 7) // 8))       # one arrival counter per (feature chunk, row); 8-float chunks are the narrowest
             sch = _lib.SpmmSchedule(ptr(schedule.seg_ptr), ptr(schedule.seg_row), schedule.seg_len,
-                                    schedule.max_segments, ptr(cnt), ptr(ws), ld_ws)
+                                    schedule.max_segments, ptr(cnt), ptr(ws), ld_ws, ptr(schedule.seg_meta),
+                                    _lib.SPMM_SCHED_PREFETCH if SEG_PREFETCH else 0)
         ex = _lib.SpmmEx(ptr(out_lo), _ld(out_lo) if out_lo is not None else 0,
                          ptr(self_lo), _ld(self_lo) if self_lo is not None else 0,
                          ctypes.pointer(drop) if drop is not None else None, drop_col0_out, drop_col0_self,
@@ -101,6 +102,11 @@ def _slab_ok(X, n_src):
     return (X.data_ptr() % 16 == 0 and _ld(X) % 4 == 0 and 0 < n_src * 32 <= SLAB_SMEM_BYTES and n_src < 65536)
 
 
+# A/B switches of the segment kernel's per-item overheads (profiles/): packed segment records, queue prefetch
+SEG_META = os.environ.get('GIST_SEG_META', '1') != '0'
+SEG_PREFETCH = os.environ.get('GIST_SEG_PREFETCH', '1') != '0'
+
+
 class SegSchedule:
     """Segment schedule of one CSR (gist_spmm_schedule_t minus the per-launch workspace)."""
 
@@ -110,6 +116,9 @@ class SegSchedule:
         dev = rowptr.device
         self.seg_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
         self.seg_row = torch.empty(self.max_segments, dtype=torch.int32, device=dev)
+        # packed per-segment records (one 16-byte load per warp item); the format holds < 2^20 segments
+        self.seg_meta = (torch.empty((self.max_segments, 4), dtype=torch.int32, device=dev)
+                         if SEG_META and self.max_segments < (1 << 20) and seg_len <= 4095 else None)
         # work-queue head + arrival counters (zeroed once; the kernel leaves them zero).  The first
         # stream that launches on this schedule owns the set allocated here; any other stream gets
         # its own (see counters()).  Sized for the widest scheduled launch of a Reddit-shape batch
@@ -124,9 +133,9 @@ class SegSchedule:
         lib = _lib.load()
         wsb = lib.gist_spmm_schedule_workspace_bytes(self.n)
         ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=rowptr.device)
-        check(lib.gist_spmm_schedule_build(ptr(rowptr), self.n, self.seg_len, ptr(self.seg_ptr), ptr(self.seg_row),
-                                           self.max_segments, ptr(ws), wsb, stream_ptr(rowptr.device)),
-              'spmm_schedule_build')
+        check(lib.gist_spmm_schedule_build_meta(ptr(rowptr), self.n, self.seg_len, ptr(self.seg_ptr), ptr(self.seg_row),
+                                                ptr(self.seg_meta), self.max_segments, ptr(ws), wsb,
+                                                stream_ptr(rowptr.device)), 'spmm_schedule_build_meta')
 
     def counters(self, chunks):
         """Zeroed work-queue head + arrival counters for `chunks` feature chunks (the kernel leaves
@@ -325,7 +334,7 @@ def slice_scatter_rows_(jobs):
         assert inv.dtype == torch.int32 and inv.numel() == dst.shape[1] and inv.is_contiguous()
         assert ridx is None or (ridx.dtype == torch.int64 and ridx.is_contiguous() and ridx.numel() == src.shape[0])
         arr[k] = _lib.SliceRowsJob(src.data_ptr(), _ld(src), ridx.data_ptr() if ridx is not None else None, src.shape[0],
-                                   inv.data_ptr(), dst.data_ptr(), _ld(dst), dst.shape[1])
+                                   src.shape[1], inv.data_ptr(), dst.data_ptr(), _ld(dst), dst.shape[1])
         dev = dst.device
         note_raw_write(dst)
     check(_lib.load().gist_slice_scatter_rows_f32(len(jobs), arr, stream_ptr(dev)), 'slice_scatter_rows_f32')

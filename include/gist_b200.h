@@ -159,7 +159,13 @@ typedef struct gist_spmm_schedule {
     uint32_t *counters;
     float *workspace;
     int64_t ld_workspace;
+    /* optional (NULL / 0 = the behaviour above): */
+    const int32_t *seg_meta; /* [max_segments][4] from gist_spmm_schedule_build_meta, 16-byte aligned: per segment
+                                {row, first edge, first segment of the row, (edges << 20) | segments of the row} — a
+                                warp item then starts with ONE 16-byte load instead of seg_row -> (seg_ptr, rowptr) */
+    uint32_t flags;          /* GIST_SPMM_SCHED_* */
 } gist_spmm_schedule_t;
+#define GIST_SPMM_SCHED_PREFETCH 1u /* fetch the next work item from the queue before processing the current one */
 
 typedef struct gist_spmm_ex {
     float *y_lo;
@@ -175,6 +181,11 @@ size_t gist_spmm_schedule_workspace_bytes(int32_t n);
 int gist_spmm_schedule_build(const int32_t *rowptr, int32_t n, int32_t seg_len, int32_t *seg_ptr,
                              int32_t *seg_row, int64_t max_segments, void *scan_ws, size_t scan_ws_bytes,
                              gist_stream_t stream);
+/* The same, also filling seg_meta ([max_segments][4] int32, 16-byte aligned; NULL = skip).  The packed record
+ * needs seg_len <= 4095 and max_segments < 2^20 (GIST_ERR_UNSUPPORTED otherwise: use the plain schedule). */
+int gist_spmm_schedule_build_meta(const int32_t *rowptr, int32_t n, int32_t seg_len, int32_t *seg_ptr,
+                                  int32_t *seg_row, int32_t *seg_meta, int64_t max_segments, void *scan_ws,
+                                  size_t scan_ws_bytes, gist_stream_t stream);
 int gist_spmm_csr_ex_f32(const int32_t *rowptr, const int32_t *col, int32_t n_dst, int32_t n_src,
                          const float *X, int64_t ldx, int32_t d,
                          float *Y, int64_t ldy,
@@ -292,7 +303,9 @@ int gist_slice_multi_f32(int32_t scatter, int32_t n_jobs, const gist_slice_job_t
  * 8.6 GB matrix (measured: 11 ms at ~1 TB/s of DRAM traffic).  Here a CTA owns a few destination ROWS and
  * walks them left to right: per 32-byte sector it looks up which source column (if any) lands on each of
  * its 8 elements (inv_col), skips sectors nothing lands on, and otherwise reads the sector, patches it and
- * writes it back whole — the same bytes in ascending address order, whole sectors only.
+ * writes it back whole — the same bytes in ascending address order, whole sectors only.  When two source
+ * rows fit 72 KB the CTA stages them in shared memory first: every source element is used once, at a random
+ * moment of the sweep, and would otherwise have to survive in L2 next to the destination stream.
  *   dst[ridx[r], cc] = src[r, inv_col[cc]]   for every cc with inv_col[cc] >= 0       (ridx NULL = identity)
  * inv_col: int32 [dst_cols], the inverse of the slice's column index (gist_index_invert_i32), -1 where no
  * source column lands.  Jobs that share a destination must own DISJOINT ROWS (the sites' output-dimension
@@ -302,6 +315,7 @@ typedef struct gist_slice_rows_job {
     int64_t ld_src;
     const int64_t *ridx;    /* [n_rows] destination rows, or NULL */
     int64_t n_rows;
+    int64_t n_cols;         /* source columns (every value of inv_col is < n_cols) */
     const int32_t *inv_col; /* [dst_cols] */
     float *dst;
     int64_t ld_dst;

@@ -275,11 +275,15 @@ def test_chunked_builder_gives_the_same_csr_as_the_row_builder(case, monkeypatch
     assert (g._node_map() == -1).all()
 
 
-@pytest.mark.parametrize('shape', [(64, 48, 96), (300, 1204, 1208), (41, 100, 104), (128, 8192, 8192)])
-def test_row_streaming_scatter_equals_indexing(shape):
+@pytest.mark.parametrize('staged', [True, False])
+@pytest.mark.parametrize('shape', [(64, 48, 96), (300, 1204, 1208), (41, 100, 104), (128, 8192, 8192), (37, 40000, 40000)])
+def test_row_streaming_scatter_equals_indexing(shape, staged, monkeypatch):
     """gist_slice_scatter_rows_f32 (whole sectors of the owned rows, left to right) against torch indexing:
-    several jobs with disjoint rows on one destination, ragged column counts, identity rows."""
+    several jobs with disjoint rows on one destination, ragged column counts, identity rows; source rows staged
+    in shared memory (when two fit 72 KB) or read through L2."""
     from gist_b200 import ops
+    if not staged:
+        monkeypatch.setenv('GIST_MERGE_NO_STAGE', '1')
     R, C, ld = shape
     torch.manual_seed(R + C)
     buf = torch.randn(R, ld, device='cuda')

@@ -6,7 +6,8 @@ from collections import defaultdict
 
 for f in sys.argv[1:]:
     rows = list(csv.DictReader(open(f)))
-    starts = [i for i, r in enumerate(rows) if 'split_tf32_multi' in r['name']]
+    # one Adam launch per step (the fused tail removed the per-step weight split that used to mark a step)
+    starts = [i for i, r in enumerate(rows) if 'adam_multi' in r['name']]
     if len(starts) < 3:
         print(f, 'too few steps')
         continue
