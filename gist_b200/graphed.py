@@ -46,6 +46,7 @@ PREP_BALANCED = os.environ.get('GIST_PREP_BALANCED', '0') != '0'
 # -> [next graph] split -> first GEMM: 17.6 us from the end of Adam to the start of the first GEMM in
 # the round-2 timeline, of which 2.4 us is the split's own work).
 FUSED_TAIL = os.environ.get('GIST_FUSED_TAIL', '1') != '0'
+STAGE_IDS_AHEAD = os.environ.get('GIST_STAGE_IDS_AHEAD', '1') != '0'
 
 
 class GraphedClusterTrainer:
@@ -102,6 +103,7 @@ class GraphedClusterTrainer:
         self._ring = torch.zeros(nbuf, dtype=torch.float32).pin_memory()
         self._ring_busy = [False] * nbuf
         self._pending = None
+        self._staged = [False, False]   # ids for the next use of nids[j] are already on their way
         g.is_symmetric()                # decided once, outside capture (it syncs)
         self._load_epoch()
 
@@ -201,6 +203,7 @@ class GraphedClusterTrainer:
         finally:
             clock.auto_tick = auto_tick
         self.k = 0
+        self._staged = [False, False]
         with torch.no_grad():
             for p, q in zip(params, saved):
                 p.copy_(q)
@@ -310,15 +313,25 @@ class GraphedClusterTrainer:
         else:
             j = self.k & 1
             # ids of batch k+1 (built during this step) go into nids[j], last read by graph k-2.
-            # The host runs at least one step ahead of the GPU, so this copy overlaps graph k-1.
-            # (Fetching the row here, after any dispatch of step k and before the next one, keeps
-            # the epoch-end shuffle in the reference's position in the Python random stream.)
-            self._upload(j, after=self._ev_done[j] if self.k >= 2 else None)
+            # Normally they were staged one step ago (below); otherwise — first steps, first row of an
+            # epoch — the copy is issued here.  (Fetching an epoch's FIRST row here, after any dispatch of
+            # step k and before the next one, keeps the epoch-end shuffle in the reference's position in
+            # the Python random stream.)
+            if not self._staged[j]:
+                self._upload(j, after=self._ev_done[j] if self.k >= 2 else None)
+            self._staged[j] = False
             main.wait_event(self._ev_ids[j])
             if self._ring_busy[j]:
                 main.wait_event(self._ev_ring[j])        # loss[j] of step k-2 has been copied out
             self.graphs[j].replay()
             self._ev_done[j].record(main)
+            # Stage the ids graph k+1 will read (nids[1-j], last read by graph k-1) NOW, so the copy runs
+            # while graph k does: issued at the head of step k+1 instead, its few microseconds sit between
+            # two graphs, because a replay waits for its ids as a whole.  Rows of the current epoch only:
+            # they are already in the id table, no shuffle is pulled forward.
+            if STAGE_IDS_AHEAD and self.i < len(self.it):
+                self._upload(1 - j, after=self._ev_done[1 - j] if self.k >= 1 else None)
+                self._staged[1 - j] = True
         self.k += 1
         self.replays += 1
         return j
