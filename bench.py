@@ -767,6 +767,7 @@ def run_gist(a):
                                    'MMAs per K step, fp32 accumulate in TMEM; ~1e-6 relative vs fp64',
                          'fp32': 'cuBLAS fp32 sgemm via torch'}[a.matmul],
                 'loss_after': round(final_loss, 4),
+                'step_options': _step_options(),
             },
             'roofline': roofline, 'roofline_gemm': roofline_gemm, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
             'sync': sync, 'replay_timeline': timeline,
@@ -777,6 +778,14 @@ def run_gist(a):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _step_options():
+    """The A/B switches the captured step ran with (environment-controlled; defaults = the measured best)."""
+    from gist_b200 import _lib, graph as gg, graphed, ops
+    return {'builder': gg.BUILDER, 'fused_tail': graphed.FUSED_TAIL, 'layernorm_in_splitk_pass_up_to_256': ops.FUSED_LN_WIDE,
+            'segment_records': ops.SEG_META, 'queue_prefetch': ops.SEG_PREFETCH, 'ids_staged_ahead': graphed.STAGE_IDS_AHEAD,
+            'programmatic_dependent_launch': _lib.get_pdl(), 'merge': os.environ.get('GIST_MERGE', 'auto')}
 
 
 def cpu_baseline(a, train_g, steps_per_epoch, it, threads=None):
