@@ -220,3 +220,43 @@ def test_synth_shapes():
     assert torch.equal(ds.src, ds2.src) and torch.equal(ds.feat, ds2.feat)
     dl = synth.make('cora', seed=0, self_loops=True)
     assert dl.src.shape[0] == 10556 + 2708
+
+
+def test_persistent_weight_low_halves_are_served_only_while_valid(monkeypatch):
+    """ops' registry of persistent 3xTF32 low halves (the fused Adam launch keeps them current): an entry is
+    served only while no raw-pointer writer of this library (note_raw_write) and no torch in-place op
+    (Tensor._version) has touched the weight since the last refresh; dead parameters drop out."""
+    import gc
+    import torch
+    from gist_b200 import ops
+    calls = []
+    monkeypatch.setattr(ops, '_tma_ok', lambda t: t.dim() == 2)
+    monkeypatch.setattr(ops, 'split_tf32_multi', lambda ws, los: calls.append(len(ws)))
+    monkeypatch.setattr(ops, '_WEIGHT_LO_PERSIST', {})
+    monkeypatch.setattr(ops, '_PERSIST_EPOCH', [0, -1])
+    p = torch.nn.Parameter(torch.randn(8, 12))
+    q = torch.nn.Parameter(torch.randn(4, 12))
+    lo_p, lo_q = torch.zeros(8, 12), torch.zeros(4, 12)
+    ops.register_persistent_lo(p, lo_p)
+    ops.register_persistent_lo(q, lo_q)
+    assert not ops.persistent_lo_valid() and ops._persistent_lo(p.data) is None     # never refreshed
+    ops.refresh_persistent_lo()
+    assert calls == [2] and ops.persistent_lo_valid()
+    assert ops._persistent_lo(p) is lo_p and ops._persistent_lo(p.data) is lo_p and ops._persistent_lo(q) is lo_q
+    assert ops._persistent_lo(torch.randn(8, 12)) is None                          # some other tensor
+    with torch.no_grad():
+        p.mul_(2.0)                                                                 # torch in-place op: version bump
+    assert not ops.persistent_lo_valid() and ops._persistent_lo(p) is None
+    assert ops._persistent_lo(q) is lo_q                                            # q itself is untouched
+    ops.refresh_persistent_lo()
+    assert ops._persistent_lo(p) is lo_p
+    ops.note_raw_write(torch.randn(3, 3))                                           # not a registered weight: nothing happens
+    assert ops.persistent_lo_valid()
+    ops.note_raw_write(q.data)                                                      # a K5 kernel wrote q through its pointer
+    assert not ops.persistent_lo_valid() and ops._persistent_lo(q) is None and ops._persistent_lo(p) is None
+    ops.refresh_persistent_lo()
+    assert ops.persistent_lo_valid() and calls == [2, 2, 2]
+    del p
+    gc.collect()
+    ops.refresh_persistent_lo()
+    assert calls[-1] == 1 and len(ops._WEIGHT_LO_PERSIST) == 1                      # the dead parameter dropped out
