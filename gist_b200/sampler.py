@@ -128,15 +128,24 @@ class ClusterIter(object):
         if out is None:
             out = np.empty((self.max, n_pad), dtype=np.int64)
         assert out.shape == (self.max, n_pad) and out.dtype == np.int64
+        # One concatenation + one slice copy per ROW (not per part): this runs on the host at every epoch
+        # boundary of the graph trainer, whose end-to-end loop is at most one step ahead of the GPU — per-part
+        # copies (1500 of them on the Reddit shape, ~1.5 ms) stalled the step pipeline once per epoch.
         out.fill(-1)
         bs = self.batch_size
+        used = self.par_li[:min(self.max * bs, self.psize)]
+        if not used:
+            return torch.from_numpy(out)
+        ends = np.cumsum(np.fromiter((len(p) for p in used), dtype=np.int64, count=len(used)))
+        allv = np.concatenate(used)
+        lo = 0
         for i in range(self.max):
-            pos = 0
-            row = out[i]
-            for s in range(i * bs, min((i + 1) * bs, self.psize)):
-                p = self.par_li[s]
-                row[pos:pos + len(p)] = p
-                pos += len(p)
+            last = min((i + 1) * bs, len(used))
+            if last <= i * bs:
+                break
+            hi = int(ends[last - 1])
+            out[i, :hi - lo] = allv[lo:hi]
+            lo = hi
         return torch.from_numpy(out)
 
     def end_epoch(self):

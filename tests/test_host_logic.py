@@ -260,3 +260,26 @@ def test_persistent_weight_low_halves_are_served_only_while_valid(monkeypatch):
     gc.collect()
     ops.refresh_persistent_lo()
     assert calls[-1] == 1 and len(ops._WEIGHT_LO_PERSIST) == 1                      # the dead parameter dropped out
+
+
+def test_padded_epoch_ids_row_copies_equal_the_per_part_form():
+    """ClusterIter.padded_epoch_ids (one slice copy per batch row) against the literal per-part loop, including a
+    part count that is not a multiple of the batch size and empty parts."""
+    from types import SimpleNamespace
+    from gist_b200.sampler import ClusterIter
+    rng = np.random.RandomState(4)
+    for psize, bs in [(1500, 20), (37, 5), (7, 3), (4, 8), (1, 1)]:
+        par_li = [np.sort(rng.choice(100000, int(s), replace=False)).astype(np.int64) for s in rng.randint(0, 40, psize)]
+        mx = max(psize // bs, 1) if psize >= bs else 1
+        it = SimpleNamespace(par_li=par_li, batch_size=bs, psize=psize, max=mx)
+        n_pad = int(sum(sorted((len(p) for p in par_li), reverse=True)[:bs])) + 3
+        ref = np.full((mx, n_pad), -1, dtype=np.int64)
+        for i in range(mx):
+            pos = 0
+            for s in range(i * bs, min((i + 1) * bs, psize)):
+                ref[i, pos:pos + len(par_li[s])] = par_li[s]
+                pos += len(par_li[s])
+        got = ClusterIter.padded_epoch_ids(it, n_pad).numpy()
+        assert np.array_equal(got, ref), (psize, bs)
+        buf = np.zeros((mx, n_pad), dtype=np.int64)
+        assert ClusterIter.padded_epoch_ids(it, n_pad, out=buf).numpy() is not None and np.array_equal(buf, ref)
