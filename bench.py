@@ -213,7 +213,7 @@ def replay_timeline(loop, steps, record):
             return 'spmm'
         if 'gemm_tf32' in n or 'splitk' in n:
             return 'gemm'
-        if 'batch_' in n or 'gather_' in n or 'scan_' in n or 'seg_' in n:
+        if 'batch_' in n or 'chunk_' in n or 'gather_' in n or 'scan_' in n or 'seg_' in n:
             return 'batch_build'
         if 'gat_' in n:
             return 'gat'
