@@ -10,7 +10,8 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'gist_b200', 'csrc', 'libgist_b200.so')
 WATCH = ['UTCHMMA', 'UTCQMMA', 'UTCIMMA', 'UTCMMA', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'HMMA', 'HGMMA',
-         'SYNCS', 'FADD2', 'FFMA2', 'IMAD.WIDE.U32', 'LDG.E.128', 'LDG.E.64', 'ATOMG', 'SHFL', 'MEMBAR', 'ERRBAR']
+         'SYNCS', 'FADD2', 'FFMA2', 'IMAD.WIDE.U32', 'LDG.E.128', 'LDG.E.64', 'ATOMG', 'SHFL', 'MEMBAR', 'ERRBAR',
+         'ACQBULK', 'PREEXIT']      # griddepcontrol.wait / .launch_dependents (programmatic dependent launch)
 
 
 def main():
