@@ -253,7 +253,13 @@ __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
 // named barrier among the 128 epilogue threads (barrier 0 is __syncthreads)
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BN, bool A_MN, bool B_MN, int NT, bool LN = false>
+// MASK: the dropout-mask epilogue (gist_gemm_dropmask_f32) is compiled in.  The 3xTF32 epilogue holds the tile's
+// row in registers and stores it fully unrolled, so the Philox code is replicated per 4-column group: the
+// BN = 128 instantiations were 11.0 k SASS instructions with it against 4.6 k for the LayerNorm variant, which
+// never masks (profiles/r2c_sass_evidence.txt) — and a one-tile CTA runs its epilogue once, cold (carrying the
+// unused in-kernel split-K code there cost the replayed step 4.7 %).  Only the dz = mask * (dy W) launches use the
+// MASK = true instantiations; every other launch has p.drop.p == 0 and takes the lean ones — same arithmetic.
+template <int BN, bool A_MN, bool B_MN, int NT, bool LN = false, bool MASK = true>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmBl,
@@ -480,7 +486,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool fused = !legacy;
             const int ncols = min(BN, p.N - n0);     // warp-uniform
             // one 32-column segment of the finished row: bias / ReLU, then 128-bit or scalar stores
-            const bool masked = fused && p.drop.p != 0.f;
+            const bool masked = MASK && fused && p.drop.p != 0.f;
             const int64_t dstep = masked ? drop_step(p.drop) : 0;
             auto store32 = [&](const float (&v)[32], int c) {
                 if (row >= p.M) return;
@@ -1078,13 +1084,13 @@ struct GemmMaps {
     CUtensorMap a, b, al, bl;     // al / bl = the x_lo operands (NT == 3); copies of a / b otherwise
 };
 
-template <int BN, bool A_MN, bool B_MN, int NT, bool LN = false>
+template <int BN, bool A_MN, bool B_MN, int NT, bool LN = false, bool MASK = true>
 static int launch_gemm(const GemmMaps &m, const GemmParams &p, cudaStream_t s) {
     constexpr size_t smem = GemmCfg<BN, NT>::kSmemBytes;
     static_assert(GemmCfg<BN, NT>::kStages >= 2, "operand ring needs at least two stages");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN, NT, LN>,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN, NT, LN, MASK>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
@@ -1092,16 +1098,26 @@ static int launch_gemm(const GemmMaps &m, const GemmParams &p, cudaStream_t s) {
     const int n_work = p.tiles_m * p.tiles_n * p.splits;
     const int cap = p.background ? max(sm_count() / 3, 1) : sm_count();
     const int grid = n_work < cap ? n_work : cap;
-    const cudaError_t le = launch_pdl(gemm_tf32_kernel<BN, A_MN, B_MN, NT, LN>, dim3(grid), dim3(kGemmThreads), smem, s,
+    const cudaError_t le = launch_pdl(gemm_tf32_kernel<BN, A_MN, B_MN, NT, LN, MASK>, dim3(grid), dim3(kGemmThreads), smem, s,
                                       m.a, m.b, m.al, m.bl, p);
     count_launch();
     return le == cudaSuccess ? last_error() : (int)le;
 }
 
+template <int BN, int NT, bool MASK>
+static int launch_layout_m(bool a_mn, bool b_mn, const GemmMaps &m, const GemmParams &p, cudaStream_t s) {
+    if (a_mn) return b_mn ? launch_gemm<BN, true, true, NT, false, MASK>(m, p, s)
+                          : launch_gemm<BN, true, false, NT, false, MASK>(m, p, s);
+    return b_mn ? launch_gemm<BN, false, true, NT, false, MASK>(m, p, s)
+                : launch_gemm<BN, false, false, NT, false, MASK>(m, p, s);
+}
+
 template <int BN, int NT>
 static int launch_layout(bool a_mn, bool b_mn, const GemmMaps &m, const GemmParams &p, cudaStream_t s) {
-    if (a_mn) return b_mn ? launch_gemm<BN, true, true, NT>(m, p, s) : launch_gemm<BN, true, false, NT>(m, p, s);
-    return b_mn ? launch_gemm<BN, false, true, NT>(m, p, s) : launch_gemm<BN, false, false, NT>(m, p, s);
+    if constexpr (NT == 3) {       // lean epilogue unless this launch applies a dropout mask (see gemm_tf32_kernel)
+        if (p.drop.p == 0.f) return launch_layout_m<BN, NT, false>(a_mn, b_mn, m, p, s);
+    }
+    return launch_layout_m<BN, NT, true>(a_mn, b_mn, m, p, s);
 }
 
 template <int NT>
@@ -1356,8 +1372,8 @@ static int gemm_impl(const float *A, const float *A_lo, int64_t lda, int64_t lda
         if (st != GIST_OK) return st;
         st = map_b(&m.bl, B_lo, ldb_lo);
         if (st != GIST_OK) return st;
-        if (p.ln_y) st = pl.bn == 64 ? launch_gemm<64, false, false, 3, true>(m, p, s)
-                                     : launch_gemm<128, false, false, 3, true>(m, p, s);
+        if (p.ln_y) st = pl.bn == 64 ? launch_gemm<64, false, false, 3, true, false>(m, p, s)
+                                     : launch_gemm<128, false, false, 3, true, false>(m, p, s);
         else st = launch_tile<3>(pl.bn, a_mn, b_mn, m, p, s);
     } else {
         m.al = m.a;
