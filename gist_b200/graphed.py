@@ -71,8 +71,7 @@ class GraphedClusterTrainer:
             for p in model.parameters():
                 if p.dim() == 2 and p.numel() > 0 and p.is_contiguous() and ops._tma_ok(p):
                     lo = torch.empty_like(p, memory_format=torch.contiguous_format).detach()
-                    ops.register_persistent_lo(p, lo)
-                    self.opt.lo_map[p] = lo
+                    self.opt.lo_map[p] = ops.register_persistent_lo(p, lo)
         self.graphs = None
         self.clusters = [None, None]    # pipelined: the two cluster buffer sets
         self.k = 0                      # steps issued so far

@@ -561,10 +561,16 @@ _PERSIST_EPOCH = [0, -1]                # [raw-write epoch, epoch the buffers we
 
 
 def register_persistent_lo(p, lo):
-    """``p``: the parameter (the tensor object whose _version is watched); ``lo``: contiguous, same shape."""
+    """``p``: the parameter (the tensor object whose _version is watched); ``lo``: contiguous, same shape.
+    Returns the buffer to write: ``lo``, or the one already registered for this very parameter (two trainers
+    over one model must keep ONE low half current, not two of which only the newer is served)."""
     assert p.dim() == 2 and _tma_ok(p) and p.is_contiguous() and lo.shape == p.shape and lo.is_contiguous()
+    e = _WEIGHT_LO_PERSIST.get(p.data_ptr())
+    if e is not None and e.ref() is p and e.lo.shape == p.shape:
+        return e.lo
     _WEIGHT_LO_PERSIST[p.data_ptr()] = _PersistEntry(p, lo)
     _PERSIST_EPOCH[1] = -1
+    return lo
 
 
 def unregister_persistent_lo(p):

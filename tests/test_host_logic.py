@@ -237,8 +237,9 @@ def test_persistent_weight_low_halves_are_served_only_while_valid(monkeypatch):
     p = torch.nn.Parameter(torch.randn(8, 12))
     q = torch.nn.Parameter(torch.randn(4, 12))
     lo_p, lo_q = torch.zeros(8, 12), torch.zeros(4, 12)
-    ops.register_persistent_lo(p, lo_p)
-    ops.register_persistent_lo(q, lo_q)
+    assert ops.register_persistent_lo(p, lo_p) is lo_p
+    assert ops.register_persistent_lo(q, lo_q) is lo_q
+    assert ops.register_persistent_lo(p, torch.zeros(8, 12)) is lo_p       # a second owner of the same parameter shares it
     assert not ops.persistent_lo_valid() and ops._persistent_lo(p.data) is None     # never refreshed
     ops.refresh_persistent_lo()
     assert calls == [2] and ops.persistent_lo_valid()
